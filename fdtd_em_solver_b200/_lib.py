@@ -1,0 +1,139 @@
+"""ctypes binding of libfdtd2d.so (include/fdtd2d.h) and its in-tree build.
+
+The library is the only compute path.  If it is missing and cannot be built,
+or no CUDA device is present, callers get an exception -- there is no CPU
+fallback (the numpy restatement in oracle/ is test infrastructure only).
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC_DIR = os.path.join(HERE, "csrc")
+INCLUDE_DIR = os.path.join(ROOT, "include")
+LIB_PATH = os.path.join(HERE, "libfdtd2d.so")
+
+F64, F32 = 0, 1
+SRC_POINT, SRC_RIGHT, SRC_LEFT, SRC_UP, SRC_DOWN = 0, 1, 2, 3, 4
+KERNEL_EXACT, KERNEL_STREAM = 0, 1
+DIRECTION_KIND = {None: SRC_POINT, "right": SRC_RIGHT, "left": SRC_LEFT, "up": SRC_UP, "down": SRC_DOWN}
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+
+
+class Config(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+                ("pitch", C.c_int64), ("dtype", C.c_int32), ("device", C.c_int32), ("reflect", C.c_int32 * 4),
+                ("kernel", C.c_int32), ("tile_rows", C.c_int32), ("vec", C.c_int32), ("block_warps", C.c_int32),
+                ("courant", C.c_double), ("one_minus_courant", C.c_double)]
+
+
+class Source(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("row", C.c_int64), ("col", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("cell_updates", C.c_int64), ("kernel_launches", C.c_int64),
+                ("halo_bytes_sent", C.c_int64), ("last_run_ms", C.c_double)]
+
+
+# name -> (restype, argtypes); must list every symbol include/fdtd2d.h declares
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+SIGNATURES = {
+    "fdtd_default_pitch": (C.c_int64, [C.c_int64, C.c_int32]),
+    "fdtd_local_rows": (C.c_int64, [C.POINTER(Config)]),
+    "fdtd_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "fdtd_destroy": (C.c_int, [_P]),
+    "fdtd_last_error": (C.c_char_p, [_P]),
+    "fdtd_bind_buffers": (C.c_int, [_P] * 9),
+    "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "fdtd_fill_synthetic_coeffs": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double]),
+    "fdtd_set_fields": (C.c_int, [_P, _P, _P, _P]),
+    "fdtd_get_fields": (C.c_int, [_P, _P, _P, _P]),
+    "fdtd_zero_fields": (C.c_int, [_P]),
+    "fdtd_set_sources": (C.c_int, [_P, C.c_int32, C.POINTER(Source), C.c_int64, _P, _P, _P, _P]),
+    "fdtd_set_reflectors": (C.c_int, [_P, C.c_int32, _P]),
+    "fdtd_set_probes": (C.c_int, [_P, C.c_int32, _P]),
+    "fdtd_probe_fetch": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "fdtd_probe_clear": (C.c_int, [_P]),
+    "fdtd_step": (C.c_int, [_P, C.c_int64]),
+    "fdtd_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "fdtd_set_tuning": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fdtd_sync": (C.c_int, [_P]),
+    "fdtd_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "fdtd_current_generation": (C.c_int, [_P]),
+    "fdtd_comm_unique_id": (C.c_int, [_P]),
+    "fdtd_comm_init": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "fdtd_halo_exchange": (C.c_int, [_P]),
+    "fdtd_halo_rows": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+}
+
+
+def sources():
+    return [os.path.join(SRC_DIR, "fdtd2d.cu")]
+
+
+def _stale():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR)] + [os.path.join(INCLUDE_DIR, "fdtd2d.h")]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> fdtd_em_solver_b200/libfdtd2d.so (in tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libfdtd2d.so (and there is no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE_DIR] + sources() + ["-o", LIB_PATH + ".tmp"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load (building first if the sources are newer) and type the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        build()
+    except RuntimeError:
+        if not os.path.isfile(LIB_PATH):
+            raise
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)            # AttributeError if the .so lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class FdtdError(RuntimeError):
+    pass
+
+
+def check(lib, handle, rc):
+    if rc == 0:
+        return
+    msg = lib.fdtd_last_error(handle)
+    msg = msg.decode() if msg else ""
+    if rc == -4:
+        raise IndexError(msg)              # the reference raises IndexError for a short pulse table (App. A-Q10)
+    raise FdtdError("libfdtd2d error %d: %s" % (rc, msg))

@@ -1,0 +1,725 @@
+// libfdtd2d.so -- host side of the C ABI declared in include/fdtd2d.h.
+// Replaces the reference's Solver.update / Solver.solve loops
+// (/root/reference/solver.py:169-257, :270-337) with launches of the fused
+// sm_100a kernels in kernels.cuh.  No CPU fallback exists: every entry point
+// that computes needs a CUDA device.
+#include "fdtd2d.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using fdtd::RectI;
+using fdtd::StepParams;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- NCCL, bound at run time so that single-GPU use never needs it -------------------------
+typedef struct ncclComm* ncclComm_t;
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+#define FDTD_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(lib, sym)); \
+        if (!field) { err = std::string("missing NCCL symbol ") + sym; lib = nullptr; return false; }
+        FDTD_SYM(GetUniqueId, "ncclGetUniqueId") FDTD_SYM(CommInitRank, "ncclCommInitRank")
+        FDTD_SYM(CommDestroy, "ncclCommDestroy") FDTD_SYM(Send, "ncclSend") FDTD_SYM(Recv, "ncclRecv")
+        FDTD_SYM(GroupStart, "ncclGroupStart") FDTD_SYM(GroupEnd, "ncclGroupEnd")
+        FDTD_SYM(GetErrorString, "ncclGetErrorString")
+#undef FDTD_SYM
+        return true;
+    }
+} g_nccl;
+
+}  // namespace
+
+struct fdtd_ctx {
+    fdtd_config cfg{};
+    int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0;
+    size_t esize = 8;
+    void* gen[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [generation][h,ex,ey]
+    void* epc = nullptr; void* muc = nullptr;
+    bool bound = false;
+    int cur = 0;
+
+    int n_src = 0;
+    fdtd_source src[64];
+    int64_t table_len = 0;
+    std::vector<double> mag, magz, last;
+    std::vector<uint8_t> active;
+
+    int n_rect = 0;
+    RectI rh[FDTD_MAX_RECT], rex[FDTD_MAX_RECT], rey[FDTD_MAX_RECT];
+
+    int n_probe = 0;
+    int probe_i[FDTD_MAX_PROBE], probe_j[FDTD_MAX_PROBE];
+    double* probe_dev = nullptr;
+    int64_t probe_cap = 0, probe_count = 0;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    double* snap_dev[2] = {nullptr, nullptr};
+    void* stage = nullptr; size_t stage_bytes = 0;
+
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    fdtd_stats stats{};
+    std::string err;
+};
+
+namespace {
+
+int fail(fdtd_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(c, FDTD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define NCK(call) do { int r_ = (call); if (r_ != 0) \
+    return fail(c, FDTD_ERR_COMM, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+
+int64_t norm_index(int64_t v, int64_t len) {        // python slice.indices(), step 1
+    if (v < 0) { v += len; if (v < 0) v = 0; }
+    if (v > len) v = len;
+    return v;
+}
+
+RectI norm_rect(const int64_t* r, int64_t nrows, int64_t ncols) {
+    RectI o;
+    o.r0 = (int)norm_index(r[0], nrows); o.r1 = (int)norm_index(r[1], nrows);
+    o.c0 = (int)norm_index(r[2], ncols); o.c1 = (int)norm_index(r[3], ncols);
+    return o;
+}
+
+template <typename T>
+T* plane(void* base, fdtd_ctx* c, int64_t global_row) {
+    return reinterpret_cast<T*>(base) + (global_row - c->row_off) * c->pitch;
+}
+
+int ensure_stage(fdtd_ctx* c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+// global host rows [g0, g0+n) x ncols (ld host_ld) -> device plane `base`
+template <typename T>
+int h2d_plane(fdtd_ctx* c, void* base, const double* host, int64_t host_ld, int64_t g0, int64_t n, int64_t ncols) {
+    if (n <= 0) return 0;
+    T* dst = plane<T>(base, c, g0);
+    if (!host) { CK(cudaMemset2DAsync(dst, c->pitch * sizeof(T), 0, ncols * sizeof(T), n, c->stream)); return 0; }
+    const double* src = host + g0 * host_ld;
+    if (sizeof(T) == 8) {
+        CK(cudaMemcpy2DAsync(dst, c->pitch * 8, src, host_ld * 8, ncols * 8, n, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(32 << 20) / (ncols * 8));
+    if (int rc = ensure_stage(c, (size_t)std::min(chunk, n) * ncols * 8)) return rc;
+    for (int64_t a = 0; a < n; a += chunk) {
+        const int64_t m = std::min(chunk, n - a);
+        CK(cudaMemcpy2DAsync(c->stage, ncols * 8, src + a * host_ld, host_ld * 8, ncols * 8, m,
+                             cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)m);
+        fdtd::plane_from_f64<T><<<grid, 256, 0, c->stream>>>(dst + a * c->pitch, c->pitch,
+                                                             (const double*)c->stage, ncols, (int)m, (int)ncols);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+template <typename T>
+int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int64_t g0, int64_t n, int64_t ncols) {
+    if (n <= 0 || !host) return 0;
+    const T* src = plane<T>(const_cast<void*>(base), c, g0);
+    double* dst = host + g0 * host_ld;
+    if (sizeof(T) == 8) {
+        CK(cudaMemcpy2DAsync(dst, host_ld * 8, src, c->pitch * 8, ncols * 8, n, cudaMemcpyDeviceToHost, c->stream));
+        return 0;
+    }
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(32 << 20) / (ncols * 8));
+    if (int rc = ensure_stage(c, (size_t)std::min(chunk, n) * ncols * 8)) return rc;
+    fdtd::PatchList none; none.n = 0;
+    for (int64_t a = 0; a < n; a += chunk) {
+        const int64_t m = std::min(chunk, n - a);
+        dim3 block(64, 4), grid((unsigned)((ncols + 63) / 64), (unsigned)((m + 3) / 4));
+        fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>((double*)c->stage, ncols, src + a * c->pitch, c->pitch,
+                                                             (int)m, (int)ncols, 0, none);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(dst + a * host_ld, host_ld * 8, c->stage, ncols * 8, ncols * 8, m,
+                             cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+template <typename T>
+int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step) {
+    const int a = c->cur, b = c->cur ^ 1;
+    P.h = (const T*)c->gen[a][0]; P.ex = (const T*)c->gen[a][1]; P.ey = (const T*)c->gen[a][2];
+    P.muc = (const T*)c->muc; P.epc = (const T*)c->epc;
+    P.hn = (T*)c->gen[b][0]; P.exn = (T*)c->gen[b][1]; P.eyn = (T*)c->gen[b][2];
+    P.pitch = c->pitch;
+    P.NR = (int)c->cfg.rows; P.NC = (int)c->cfg.cols;
+    P.row_off = (int)c->row_off; P.lrows = (int)c->lrows;
+    P.tile_rows = c->cfg.tile_rows;
+    P.absorb_u = !c->cfg.reflect[0]; P.absorb_d = !c->cfg.reflect[1];
+    P.absorb_l = !c->cfg.reflect[2]; P.absorb_r = !c->cfg.reflect[3];
+    P.S = (T)c->cfg.courant; P.oms = (T)c->cfg.one_minus_courant;
+    P.n_src = 0; P.last_mag = T(0);
+    if (c->n_src > 0) {
+        if (step < 0 || step >= c->table_len)
+            return fail(c, FDTD_ERR_RANGE, "step " + std::to_string(step) + " outside the source tables (length " +
+                                               std::to_string(c->table_len) + ")");
+        for (int p = 0; p < c->n_src; ++p) {
+            if (!c->active[(size_t)p * c->table_len + step]) continue;
+            if (P.n_src >= FDTD_MAX_SRC) return fail(c, FDTD_ERR_ARG, "more than 16 pulses active in one call");
+            fdtd::SrcStep<T>& q = P.src[P.n_src++];
+            q.kind = c->src[p].kind; q.row = (int)c->src[p].row; q.col = (int)c->src[p].col; q.pad = 0;
+            q.mag = (T)c->mag[(size_t)p * c->table_len + step];
+            q.magz = (T)c->magz[(size_t)p * c->table_len + step];
+        }
+        P.last_mag = (T)c->last[step];
+    }
+    P.n_rect = c->n_rect;
+    for (int r = 0; r < c->n_rect; ++r) { P.rh[r] = c->rh[r]; P.rex[r] = c->rex[r]; P.rey[r] = c->rey[r]; }
+    P.n_probe = c->n_probe;
+    for (int k = 0; k < c->n_probe; ++k) { P.probe_i[k] = c->probe_i[k]; P.probe_j[k] = c->probe_j[k]; }
+    P.probe_out = nullptr;
+    return 0;
+}
+
+template <typename T, int V>
+void launch_stream(const StepParams<T>& P, int WARPS, cudaStream_t s) {
+    const int ncol_tiles = (P.NC + 1 + 32 * V * WARPS - 1) / (32 * V * WARPS);
+    const int nrow_tiles = (P.row_hi - P.row_lo + P.tile_rows - 1) / P.tile_rows;
+    dim3 grid((unsigned)ncol_tiles, (unsigned)nrow_tiles);
+    fdtd::step_stream<T, V><<<grid, WARPS * 32, 0, s>>>(P);
+}
+
+template <typename T>
+int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, cudaStream_t s) {
+    if (row_hi <= row_lo) return 0;
+    P.row_lo = (int)row_lo; P.row_hi = (int)row_hi;
+    if (c->cfg.kernel == FDTD_KERNEL_EXACT) {
+        dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)(row_hi - row_lo));
+        fdtd::step_exact<T><<<grid, 256, 0, s>>>(P);
+    } else {
+        const int v = c->cfg.vec, w = c->cfg.block_warps;
+        constexpr int VA = sizeof(T) == 8 ? 2 : 4, VB = 2 * VA;
+        if (w < 1 || w > 8) return fail(c, FDTD_ERR_ARG, "block_warps must be 1..8");
+        if (v == VA) launch_stream<T, VA>(P, w, s);
+        else if (v == VB) launch_stream<T, VB>(P, w, s);
+        else return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
+    }
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensure_probe_capacity(fdtd_ctx* c, int64_t extra_steps) {
+    if (c->n_probe == 0) return 0;
+    const int64_t need = c->probe_count + extra_steps;
+    if (need <= c->probe_cap) return 0;
+    const int64_t cap = std::max<int64_t>(need, c->probe_cap * 2);
+    double* nb = nullptr;
+    CK(cudaMalloc(&nb, (size_t)cap * c->n_probe * 3 * sizeof(double)));
+    CK(cudaMemsetAsync(nb, 0, (size_t)cap * c->n_probe * 3 * sizeof(double), c->stream));
+    if (c->probe_dev) {
+        CK(cudaMemcpyAsync(nb, c->probe_dev, (size_t)c->probe_count * c->n_probe * 3 * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->probe_dev);
+    }
+    c->probe_dev = nb; c->probe_cap = cap;
+    return 0;
+}
+
+int nccl_dtype(fdtd_ctx* c) { return c->cfg.dtype == FDTD_F64 ? 8 : 7; }
+
+// Exchange the halo rows of generation g on `s` (3 rows down, 1 row up).
+int exchange(fdtd_ctx* c, int g, cudaStream_t s) {
+    if (!c->comm) return 0;
+    const int64_t NC = c->cfg.cols;
+    const size_t es = c->esize;
+    auto row = [&](int f, int64_t grow) { return (char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * es; };
+    const bool has_up = c->rank > 0, has_down = c->rank + 1 < c->nranks;
+    const int dt = nccl_dtype(c);
+    NCK(g_nccl.GroupStart());
+    if (has_down) {
+        NCK(g_nccl.Send(row(0, c->cfg.row_end - 1), (size_t)NC, dt, c->rank + 1, c->comm, s));
+        NCK(g_nccl.Send(row(1, c->cfg.row_end - 1), (size_t)NC, dt, c->rank + 1, c->comm, s));
+        NCK(g_nccl.Send(row(2, c->cfg.row_end - 1), (size_t)NC + 1, dt, c->rank + 1, c->comm, s));
+        NCK(g_nccl.Recv(row(1, c->cfg.row_end), (size_t)NC, dt, c->rank + 1, c->comm, s));
+        c->stats.halo_bytes_sent += (int64_t)((3 * NC + 1) * es);
+    }
+    if (has_up) {
+        NCK(g_nccl.Send(row(1, c->cfg.row_begin), (size_t)NC, dt, c->rank - 1, c->comm, s));
+        NCK(g_nccl.Recv(row(0, c->cfg.row_begin - 1), (size_t)NC, dt, c->rank - 1, c->comm, s));
+        NCK(g_nccl.Recv(row(1, c->cfg.row_begin - 1), (size_t)NC, dt, c->rank - 1, c->comm, s));
+        NCK(g_nccl.Recv(row(2, c->cfg.row_begin - 1), (size_t)NC + 1, dt, c->rank - 1, c->comm, s));
+        c->stats.halo_bytes_sent += (int64_t)(NC * es);
+    }
+    NCK(g_nccl.GroupEnd());
+    return 0;
+}
+
+template <typename T>
+int step_impl(fdtd_ctx* c, int64_t step) {
+    StepParams<T> P;
+    if (int rc = fill_params<T>(c, P, step)) return rc;
+    if (c->n_probe) {
+        if (int rc = ensure_probe_capacity(c, 1)) return rc;
+        P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    }
+    const int64_t lo = c->cfg.row_begin;
+    const int64_t hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);   // last slab also owns ex[rows]
+    if (!c->comm) {
+        if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
+    } else {
+        // interface strips first, halo exchange on the comm stream, interior meanwhile
+        const int64_t tr = c->cfg.tile_rows;
+        const bool has_up = c->rank > 0, has_down = c->rank + 1 < c->nranks;
+        int64_t a = has_up ? std::min(lo + tr, hi) : lo;
+        int64_t b = has_down ? std::max(a, c->cfg.row_end - tr) : hi;
+        if (int rc = launch_rows<T>(c, P, lo, a, c->stream)) return rc;
+        if (int rc = launch_rows<T>(c, P, b, hi, c->stream)) return rc;
+        CK(cudaEventRecord(c->ev_bnd, c->stream));
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+        if (int rc = exchange(c, c->cur ^ 1, c->comm_stream)) return rc;
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+        if (int rc = launch_rows<T>(c, P, a, b, c->stream)) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+    }
+    c->cur ^= 1;
+    if (c->n_probe) c->probe_count++;
+    c->stats.steps++;
+    c->stats.cell_updates += c->owned * c->cfg.cols;
+    return 0;
+}
+
+int step_any(fdtd_ctx* c, int64_t step) {
+    return c->cfg.dtype == FDTD_F64 ? step_impl<double>(c, step) : step_impl<float>(c, step);
+}
+
+template <typename T>
+int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, int64_t total_calls) {
+    fdtd::PatchList pl; pl.n = 0;
+    if (next_step < total_calls && next_step < c->table_len) {
+        for (int p = 0; p < c->n_src; ++p) {
+            if (c->src[p].kind != FDTD_SRC_POINT || !c->active[(size_t)p * c->table_len + next_step]) continue;
+            if (pl.n >= FDTD_MAX_SRC) return fail(c, FDTD_ERR_ARG, "too many point sources for a snapshot");
+            pl.p[pl.n].row = (int)c->src[p].row; pl.p[pl.n].col = (int)c->src[p].col;
+            // the stored array has dtype T: the reference writes into the array itself
+            pl.p[pl.n].value = (double)(T)c->mag[(size_t)p * c->table_len + next_step];
+            pl.n++;
+        }
+    }
+    const int64_t rows = c->owned, cols = c->cfg.cols;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_free[slot], 0));
+    dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 3) / 4));
+    fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>(c->snap_dev[slot], cols,
+        plane<T>(c->gen[c->cur][0], c, c->cfg.row_begin), c->pitch, (int)rows, (int)cols, (int)c->cfg.row_begin, pl);
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_packed[slot], c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[slot], 0));
+    CK(cudaMemcpyAsync(host_dst, c->snap_dev[slot], (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_free[slot], c->copy_stream));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int64_t fdtd_default_pitch(int64_t cols, int32_t /*dtype*/) { return ((cols + 1 + 31) / 32) * 32; }
+
+int64_t fdtd_local_rows(const fdtd_config* cfg) {
+    if (!cfg) return 0;
+    return (cfg->row_end - cfg->row_begin) + (cfg->row_begin > 0 ? 1 : 0) + 1;
+}
+
+const char* fdtd_last_error(fdtd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
+    fdtd_ctx* c = nullptr;
+    if (!cfg || !out) return fail(c, FDTD_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->rows < 3 || cfg->cols < 3) return fail(c, FDTD_ERR_ARG, "grid must be at least 3x3");
+    if (cfg->rows > 0x7ffffff0LL || cfg->cols > 0x7ffffff0LL) return fail(c, FDTD_ERR_ARG, "grid too large");
+    if (cfg->row_begin < 0 || cfg->row_end > cfg->rows || cfg->row_end - cfg->row_begin < 1)
+        return fail(c, FDTD_ERR_ARG, "bad slab row range");
+    const bool whole = cfg->row_begin == 0 && cfg->row_end == cfg->rows;
+    if (!whole && cfg->row_end - cfg->row_begin < 2) return fail(c, FDTD_ERR_ARG, "a slab must own at least 2 rows");
+    if (cfg->dtype != FDTD_F64 && cfg->dtype != FDTD_F32) return fail(c, FDTD_ERR_ARG, "bad dtype");
+    if (cfg->kernel != FDTD_KERNEL_EXACT && cfg->kernel != FDTD_KERNEL_STREAM) return fail(c, FDTD_ERR_ARG, "bad kernel");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, FDTD_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                          " (libfdtd2d has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(c, FDTD_ERR_ARG, "bad device ordinal");
+    c = new fdtd_ctx();
+    c->cfg = *cfg;
+    c->esize = cfg->dtype == FDTD_F64 ? 8 : 4;
+    c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
+    if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
+    c->cfg.pitch = c->pitch;
+    c->halo_top = cfg->row_begin > 0 ? 1 : 0;
+    c->row_off = cfg->row_begin - c->halo_top;
+    c->owned = cfg->row_end - cfg->row_begin;
+    c->lrows = fdtd_local_rows(cfg);
+    if (c->cfg.tile_rows <= 0) c->cfg.tile_rows = 64;
+    if (c->cfg.vec <= 0) c->cfg.vec = cfg->dtype == FDTD_F64 ? 2 : 4;
+    if (c->cfg.block_warps <= 0) c->cfg.block_warps = 4;
+    auto bail = [&](cudaError_t ee, const char* what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(ee);
+        delete c; c = nullptr; return fail(nullptr, FDTD_ERR_CUDA, m);
+    };
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    cudaEventCreate(&c->ev_t0); cudaEventCreate(&c->ev_t1);
+    cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
+    for (int s = 0; s < 2; ++s) {
+        cudaEventCreateWithFlags(&c->ev_packed[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming);
+    }
+    *out = c;
+    return 0;
+}
+
+int fdtd_destroy(fdtd_handle c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->probe_dev) cudaFree(c->probe_dev);
+    if (c->stage) cudaFree(c->stage);
+    for (int s = 0; s < 2; ++s) {
+        if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
+        if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
+        if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
+    }
+    for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream}) if (s) cudaStreamDestroy(s);
+    delete c;
+    return 0;
+}
+
+int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
+                      void* eps_coef, void* mu_coef) {
+    if (!c) return FDTD_ERR_ARG;
+    void* all[8] = {h0, h1, ex0, ex1, ey0, ey1, eps_coef, mu_coef};
+    for (void* p : all) {
+        if (!p) return fail(c, FDTD_ERR_ARG, "null device buffer");
+        if (reinterpret_cast<uintptr_t>(p) % 128) return fail(c, FDTD_ERR_ARG, "device buffers must be 128-byte aligned");
+    }
+    c->gen[0][0] = h0; c->gen[1][0] = h1; c->gen[0][1] = ex0; c->gen[1][1] = ex1; c->gen[0][2] = ey0; c->gen[1][2] = ey1;
+    c->epc = eps_coef; c->muc = mu_coef;
+    c->bound = true; c->cur = 0;
+    return 0;
+}
+
+#define NEED_BOUND() do { if (!c) return FDTD_ERR_ARG; if (!c->bound) return fail(c, FDTD_ERR_STATE, "buffers not bound"); \
+    CK(cudaSetDevice(c->cfg.device)); } while (0)
+
+int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_coef, int64_t host_ld) {
+    NEED_BOUND();
+    if (!eps_coef || !mu_coef || host_ld < c->cfg.cols) return fail(c, FDTD_ERR_ARG, "bad coefficient arrays");
+    const int64_t g0 = c->row_off, n = c->cfg.row_end - c->row_off;
+    int rc;
+    if (c->cfg.dtype == FDTD_F64) {
+        if ((rc = h2d_plane<double>(c, c->epc, eps_coef, host_ld, g0, n, c->cfg.cols))) return rc;
+        if ((rc = h2d_plane<double>(c, c->muc, mu_coef, host_ld, g0, n, c->cfg.cols))) return rc;
+    } else {
+        if ((rc = h2d_plane<float>(c, c->epc, eps_coef, host_ld, g0, n, c->cfg.cols))) return rc;
+        if ((rc = h2d_plane<float>(c, c->muc, mu_coef, host_ld, g0, n, c->cfg.cols))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, double epsilon0, double mu0) {
+    NEED_BOUND();
+    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)c->lrows);
+    if (c->cfg.dtype == FDTD_F64)
+        fdtd::synth_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0);
+    else
+        fdtd::synth_coeffs<float><<<grid, 256, 0, c->stream>>>((float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0);
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fdtd_zero_fields(fdtd_handle c) {
+    NEED_BOUND();
+    for (int g = 0; g < 2; ++g)
+        for (int f = 0; f < 3; ++f)
+            CK(cudaMemsetAsync(c->gen[g][f], 0, (size_t)c->lrows * c->pitch * c->esize, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->cur = 0;
+    return 0;
+}
+
+int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const double* ey) {
+    NEED_BOUND();
+    const int64_t g0 = c->row_off, n = c->cfg.row_end - c->row_off, NC = c->cfg.cols;
+    const int a = c->cur;
+    int rc;
+    if (c->cfg.dtype == FDTD_F64) {
+        if ((rc = h2d_plane<double>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = h2d_plane<double>(c, c->gen[a][1], ex, NC, g0, n + 1, NC))) return rc;
+        if ((rc = h2d_plane<double>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    } else {
+        if ((rc = h2d_plane<float>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = h2d_plane<float>(c, c->gen[a][1], ex, NC, g0, n + 1, NC))) return rc;
+        if ((rc = h2d_plane<float>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fdtd_get_fields(fdtd_handle c, double* hh, double* ex, double* ey) {
+    NEED_BOUND();
+    const int64_t g0 = c->cfg.row_begin, n = c->owned, NC = c->cfg.cols;
+    const int64_t nex = n + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
+    const int a = c->cur;
+    int rc;
+    if (c->cfg.dtype == FDTD_F64) {
+        if ((rc = d2h_plane<double>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = d2h_plane<double>(c, c->gen[a][1], ex, NC, g0, nex, NC))) return rc;
+        if ((rc = d2h_plane<double>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    } else {
+        if ((rc = d2h_plane<float>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = d2h_plane<float>(c, c->gen[a][1], ex, NC, g0, nex, NC))) return rc;
+        if ((rc = d2h_plane<float>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fdtd_set_sources(fdtd_handle c, int32_t n, const fdtd_source* src, int64_t table_len,
+                     const double* mag, const double* mag_z, const uint8_t* active, const double* last_mag) {
+    if (!c) return FDTD_ERR_ARG;
+    if (n < 0 || n > 64) return fail(c, FDTD_ERR_ARG, "at most 64 pulses");
+    if (n > 0 && (!src || !mag || !mag_z || !active || !last_mag || table_len <= 0))
+        return fail(c, FDTD_ERR_ARG, "null source table");
+    for (int p = 0; p < n; ++p) {
+        const fdtd_source& s = src[p];
+        const bool bad_kind = s.kind < FDTD_SRC_POINT || s.kind > FDTD_SRC_DOWN;
+        bool bad = bad_kind || s.row < 0 || s.col < 0 || s.row >= c->cfg.rows || s.col >= c->cfg.cols;
+        if (s.kind == FDTD_SRC_UP && s.row + 1 >= c->cfg.rows) bad = true;    // h[1+row,:] must exist (solver.py:198)
+        if (bad) return fail(c, FDTD_ERR_ARG, "pulse " + std::to_string(p) + " lies outside the grid");
+    }
+    c->n_src = n; c->table_len = n ? table_len : 0;
+    for (int p = 0; p < n; ++p) c->src[p] = src[p];
+    const size_t tot = (size_t)n * (size_t)c->table_len;
+    c->mag.assign(mag, mag + tot); c->magz.assign(mag_z, mag_z + tot);
+    c->active.assign(active, active + tot);
+    c->last.assign(last_mag, last_mag + (n ? table_len : 0));
+    return 0;
+}
+
+int fdtd_set_reflectors(fdtd_handle c, int32_t n, const int64_t* rects) {
+    if (!c) return FDTD_ERR_ARG;
+    if (n < 0 || n > FDTD_MAX_RECT) return fail(c, FDTD_ERR_ARG, "at most 24 reflector rectangles");
+    if (n > 0 && !rects) return fail(c, FDTD_ERR_ARG, "null rectangle list");
+    c->n_rect = n;
+    const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
+    for (int r = 0; r < n; ++r) {
+        c->rh[r] = norm_rect(rects + 4 * r, NR, NC);
+        c->rex[r] = norm_rect(rects + 4 * r, NR + 1, NC);
+        c->rey[r] = norm_rect(rects + 4 * r, NR, NC + 1);
+    }
+    return 0;
+}
+
+int fdtd_set_probes(fdtd_handle c, int32_t n, const int64_t* ij) {
+    if (!c) return FDTD_ERR_ARG;
+    if (n < 0 || n > FDTD_MAX_PROBE) return fail(c, FDTD_ERR_ARG, "at most 16 probes");
+    cudaSetDevice(c->cfg.device);
+    if (c->probe_dev) { cudaStreamSynchronize(c->stream); cudaFree(c->probe_dev); c->probe_dev = nullptr; }
+    c->probe_cap = 0; c->probe_count = 0;
+    for (int k = 0; k < n; ++k) {
+        if (ij[2 * k] < 0 || ij[2 * k] >= c->cfg.rows || ij[2 * k + 1] < 0 || ij[2 * k + 1] >= c->cfg.cols)
+            return fail(c, FDTD_ERR_ARG, "probe outside the grid");
+        c->probe_i[k] = (int)ij[2 * k]; c->probe_j[k] = (int)ij[2 * k + 1];
+    }
+    c->n_probe = n;
+    return 0;
+}
+
+int fdtd_probe_fetch(fdtd_handle c, double* out, int64_t max_records, int64_t* n_records) {
+    if (!c) return FDTD_ERR_ARG;
+    CK(cudaSetDevice(c->cfg.device));
+    const int64_t n = std::min(max_records, c->probe_count);
+    if (n_records) *n_records = c->probe_count;
+    if (n > 0 && out && c->n_probe) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(out, c->probe_dev, (size_t)n * c->n_probe * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int fdtd_probe_clear(fdtd_handle c) {
+    if (!c) return FDTD_ERR_ARG;
+    c->probe_count = 0;
+    return 0;
+}
+
+int fdtd_step(fdtd_handle c, int64_t step) {
+    NEED_BOUND();
+    return step_any(c, step);
+}
+
+int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
+             double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots) {
+    NEED_BOUND();
+    if (n_snapshots) *n_snapshots = 0;
+    if (n_steps < 0) return fail(c, FDTD_ERR_ARG, "negative step count");
+    const bool snaps = snapshot_every > 0 && snapshots_host != nullptr;
+    if (snaps) {
+        for (int s = 0; s < 2; ++s)
+            if (!c->snap_dev[s]) CK(cudaMalloc(&c->snap_dev[s], (size_t)c->owned * c->cfg.cols * 8));
+    }
+    if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
+    int64_t k = 0;
+    int rc = 0;
+    CK(cudaEventRecord(c->ev_t0, c->stream));
+    for (int64_t n = first_step; n < first_step + n_steps; ++n) {
+        if ((rc = step_any(c, n))) break;
+        if (snaps && (n + 1) % snapshot_every == 0) {
+            if (k >= max_snapshots) { rc = fail(c, FDTD_ERR_ARG, "snapshot buffer too small"); break; }
+            double* dst = snapshots_host + (size_t)k * c->owned * c->cfg.cols;
+            rc = c->cfg.dtype == FDTD_F64 ? snapshot_impl<double>(c, (int)(k & 1), dst, n + 1, total_calls)
+                                          : snapshot_impl<float>(c, (int)(k & 1), dst, n + 1, total_calls);
+            if (rc) break;
+            ++k;
+        }
+    }
+    cudaEventRecord(c->ev_t1, c->stream);
+    cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);
+    cudaError_t e3 = cudaStreamSynchronize(c->comm_stream);
+    if (n_snapshots) *n_snapshots = k;
+    if (rc) return rc;
+    for (cudaError_t e : {e1, e2, e3})
+        if (e != cudaSuccess) return fail(c, FDTD_ERR_CUDA, std::string("fdtd_run: ") + cudaGetErrorString(e));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+    c->stats.last_run_ms = ms;
+    return 0;
+}
+
+int fdtd_set_tuning(fdtd_handle c, int32_t tile_rows, int32_t vec, int32_t block_warps) {
+    if (!c) return FDTD_ERR_ARG;
+    const int va = c->cfg.dtype == FDTD_F64 ? 2 : 4;
+    if (vec && vec != va && vec != 2 * va) return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
+    if (block_warps < 0 || block_warps > 8 || tile_rows < 0) return fail(c, FDTD_ERR_ARG, "bad tuning");
+    if (tile_rows) c->cfg.tile_rows = tile_rows;
+    if (vec) c->cfg.vec = vec;
+    if (block_warps) c->cfg.block_warps = block_warps;
+    return 0;
+}
+
+int fdtd_sync(fdtd_handle c) {
+    if (!c) return FDTD_ERR_ARG;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->comm_stream));
+    return 0;
+}
+
+int fdtd_get_stats(fdtd_handle c, fdtd_stats* out) {
+    if (!c || !out) return FDTD_ERR_ARG;
+    *out = c->stats;
+    return 0;
+}
+
+int fdtd_current_generation(fdtd_handle c) { return c ? c->cur : FDTD_ERR_ARG; }
+
+int fdtd_comm_unique_id(void* out128) {
+    fdtd_ctx* c = nullptr;
+    if (!out128) return fail(c, FDTD_ERR_ARG, "null id buffer");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(c, FDTD_ERR_COMM, err);
+    NcclId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    std::memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+int fdtd_comm_init(fdtd_handle c, const void* unique_id128, int32_t rank, int32_t nranks) {
+    if (!c || !unique_id128) return FDTD_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, FDTD_ERR_ARG, "bad rank/nranks");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(c, FDTD_ERR_COMM, err);
+    CK(cudaSetDevice(c->cfg.device));
+    NcclId id;
+    std::memcpy(id.internal, unique_id128, 128);
+    NCK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->rank = rank; c->nranks = nranks;
+    return 0;
+}
+
+int fdtd_halo_exchange(fdtd_handle c) {
+    NEED_BOUND();
+    if (!c->comm) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    if (int rc = exchange(c, c->cur, c->comm_stream)) return rc;
+    CK(cudaStreamSynchronize(c->comm_stream));
+    return 0;
+}
+
+int fdtd_halo_rows(fdtd_handle c, void* send_down[3], void* recv_up[3], void** send_up, void** recv_down,
+                   int64_t counts[3]) {
+    NEED_BOUND();
+    const int g = c->cur;
+    auto row = [&](int f, int64_t grow) { return (void*)((char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * c->esize); };
+    for (int f = 0; f < 3; ++f) {
+        if (send_down) send_down[f] = row(f, c->cfg.row_end - 1);
+        if (recv_up) recv_up[f] = c->halo_top ? row(f, c->cfg.row_begin - 1) : nullptr;
+    }
+    if (send_up) *send_up = row(1, c->cfg.row_begin);
+    if (recv_down) *recv_down = row(1, c->cfg.row_end);
+    if (counts) { counts[0] = c->cfg.cols; counts[1] = c->cfg.cols; counts[2] = c->cfg.cols + 1; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// Device code of libfdtd2d.so: the fused 2D Yee leapfrog step for sm_100a.
+//
+// Two kernels compute the SAME function (one call of the reference's
+// Solver.update, /root/reference/solver.py:169-257), from generation A of the
+// fields into generation B (ping-pong):
+//
+//   step_exact   one thread per cell; every output value is the closed form of
+//                the reference's statement sequence, written
+//                as the recursive functions of struct Exact.  Slow (it re-reads
+//                its stencil from L1/L2) but obviously right: the in-repo GPU
+//                reference, and the per-cell fix-up used by step_stream.
+//   step_stream  production path.  Each warp owns a (tile_rows x 32*V) tile and
+//                marches down its rows with ex[i,:] and hn[i-1,:] carried in
+//                registers, hn[i,j-1] by warp shuffle and a one-column halo
+//                recomputed by lane 0.  Each field/coefficient word is read once
+//                with 128-bit loads; H and E updates are fused.  Tiles that
+//                touch a wall, a source line, a reflector or a probe ("mixed"
+//                tiles) run the same loop with guarded loads and overwrite their
+//                special cells with Exact -- walls, sources and reflectors are
+//                tile predicates of the one launch, not extra launches.
+//
+// Arithmetic: explicit round-to-nearest intrinsics, never contracted to FMA
+// (numpy rounds after every ufunc); the association order is the reference's.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FDTD_MAX_SRC 16
+#define FDTD_MAX_RECT 24
+#define FDTD_MAX_PROBE 16
+
+namespace fdtd {
+
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+
+template <typename T>
+struct SrcStep {          // one ACTIVE pulse of this call, in list order
+    int kind, row, col, pad;
+    T mag;                // pulse.magnitude(step)
+    T magz;               // pulse.magnitude(step) * sqrt(MU/EPSILON)
+};
+
+struct RectI { int r0, r1, c0, c1; };   // already clipped to the array it applies to
+
+template <typename T>
+struct StepParams {
+    const T* h; const T* ex; const T* ey; const T* muc; const T* epc;   // generation A + coefficients
+    T* hn; T* exn; T* eyn;                                              // generation B
+    double* probe_out;        // this call's record: n_probe x (h,ex,ey)
+    long long pitch;
+    int NR, NC;               // global h shape
+    int row_off;              // global row of local row 0
+    int lrows;                // local rows allocated
+    int row_lo, row_hi;       // rows of the (NR+1)-row index space this launch writes
+    int tile_rows;
+    int absorb_u, absorb_d, absorb_l, absorb_r;
+    int n_src, n_rect, n_probe;
+    T S, oms;                 // C*dt/ds and 1 - C*dt/ds
+    T last_mag;               // magnitude of the last active pulse in list order
+    SrcStep<T> src[FDTD_MAX_SRC];
+    RectI rh[FDTD_MAX_RECT], rex[FDTD_MAX_RECT], rey[FDTD_MAX_RECT];
+    int probe_i[FDTD_MAX_PROBE], probe_j[FDTD_MAX_PROBE];
+};
+
+__device__ __forceinline__ bool inside(const RectI& r, int i, int j) {
+    return i >= r.r0 && i < r.r1 && j >= r.c0 && j < r.c1;
+}
+
+// ---------------------------------------------------------------------------
+// Closed-form semantics of one update() call.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Exact {
+    const StepParams<T>& P;
+    __device__ explicit Exact(const StepParams<T>& p) : P(p) {}
+
+    __device__ __forceinline__ T ld(const T* a, int i, int j) const {
+        return __ldg(a + (long long)(i - P.row_off) * P.pitch + j);
+    }
+
+    // h after the hard point-source writes of solver.py:176-180
+    __device__ __noinline__ T h_old(int i, int j) const {
+        T v = ld(P.h, i, j);
+        for (int s = 0; s < P.n_src; ++s)
+            if (P.src[s].kind == 0 && P.src[s].row == i && P.src[s].col == j) v = P.src[s].mag;
+        return v;
+    }
+
+    // new h before the wall overwrite: solver.py:182, :184-200, :203-204
+    __device__ __noinline__ T hn_pre(int i, int j) const {
+        const T ho = h_old(i, j);
+        const T mu = ld(P.muc, i, j);
+        const T dex = sub(ld(P.ex, i + 1, j), ld(P.ex, i, j));
+        const T eyc = ld(P.ey, i, j), eyr = ld(P.ey, i, j + 1);
+        T v = add(ho, mul(mu, sub(dex, sub(eyr, eyc))));
+        for (int s = 0; s < P.n_src; ++s) {
+            const SrcStep<T>& q = P.src[s];
+            if (q.kind == 1) { if (j == q.col) v = add(ho, mul(mu, sub(dex, sub(eyr, add(eyc, q.magz))))); }
+            else if (q.kind == 2) { if (j == q.col) v = add(v, mul(mu, P.last_mag)); }
+            else if (q.kind == 3) { if (i == q.row + 1) v = sub(v, mul(mu, P.last_mag)); }
+            else if (q.kind == 4) { if (i == q.row) v = sub(v, mul(mu, P.last_mag)); }
+        }
+        for (int r = 0; r < P.n_rect; ++r) if (inside(P.rh[r], i, j)) v = T(0);
+        return v;
+    }
+
+    // ex after solver.py:207 (rows 0 and NR untouched)
+    __device__ __noinline__ T ex_pre(int i, int j) const {
+        const T e = ld(P.ex, i, j);
+        if (i >= 1 && i <= P.NR - 1) return add(e, mul(ld(P.epc, i, j), sub(hn_pre(i, j), hn_pre(i - 1, j))));
+        return e;
+    }
+
+    // ey after solver.py:208 and the TF/SF re-application of :211-217
+    __device__ __noinline__ T ey_pre(int i, int j) const {
+        T v = ld(P.ey, i, j);
+        if (j >= 1 && j <= P.NC - 1) v = sub(v, mul(ld(P.epc, i, j), sub(hn_pre(i, j), hn_pre(i, j - 1))));
+        for (int s = 0; s < P.n_src; ++s) {
+            const SrcStep<T>& q = P.src[s];
+            if (q.kind == 1 && j == q.col) {
+                const int jm = (j == 0) ? P.NC - 1 : j - 1;     // python's h[:, col-1] wraps at col 0
+                v = sub(v, mul(ld(P.epc, i, j), sub(sub(hn_pre(i, j), q.mag), hn_pre(i, jm))));
+            }
+        }
+        return v;
+    }
+
+    // ex / ey after the up and down walls (solver.py:220-227)
+    __device__ __noinline__ T ex_ud(int i, int j) const {
+        if (P.absorb_u && i == 0) return add(mul(ld(P.ex, 0, j), P.oms), mul(ex_pre(1, j), P.S));
+        if (P.absorb_d && i == P.NR) return add(mul(ld(P.ex, P.NR, j), P.oms), mul(ex_pre(P.NR - 1, j), P.S));
+        return ex_pre(i, j);
+    }
+    __device__ __noinline__ T ey_ud(int i, int j) const {
+        if (P.absorb_u && i == 0) return add(mul(ey_pre(0, j), P.oms), mul(ey_pre(1, j), P.S));
+        if (P.absorb_d && i == P.NR - 1) return add(mul(ey_pre(P.NR - 1, j), P.oms), mul(ey_pre(P.NR - 2, j), P.S));
+        return ey_pre(i, j);
+    }
+
+    // final values: left/right walls (solver.py:228-235), reflector zeroing (:238-242)
+    __device__ __noinline__ T h_final(int i, int j) const {
+        T v = hn_pre(i, j);
+        if (P.absorb_u && i == 0) v = add(mul(h_old(0, j), P.oms), mul(h_old(1, j), P.S));
+        if (P.absorb_d && i == P.NR - 1) v = add(mul(h_old(P.NR - 1, j), P.oms), mul(h_old(P.NR - 2, j), P.S));
+        if (P.absorb_l && j == 0) v = add(mul(h_old(i, 0), P.oms), mul(h_old(i, 1), P.S));
+        if (P.absorb_r && j == P.NC - 1) v = add(mul(h_old(i, P.NC - 1), P.oms), mul(h_old(i, P.NC - 2), P.S));
+        return v;
+    }
+    __device__ __noinline__ T ex_final(int i, int j) const {
+        T v;
+        if (P.absorb_l && j == 0) v = add(mul(ex_ud(i, 0), P.oms), mul(ex_ud(i, 1), P.S));
+        else if (P.absorb_r && j == P.NC - 1) v = add(mul(ex_ud(i, P.NC - 1), P.oms), mul(ex_ud(i, P.NC - 2), P.S));
+        else v = ex_ud(i, j);
+        for (int r = 0; r < P.n_rect; ++r) if (inside(P.rex[r], i, j)) v = T(0);
+        return v;
+    }
+    __device__ __noinline__ T ey_final(int i, int j) const {
+        T v;
+        if (P.absorb_l && j == 0) v = add(mul(ey_ud(i, 0), P.oms), mul(ey_ud(i, 1), P.S));
+        else if (P.absorb_r && j == P.NC) v = add(mul(ey_ud(i, P.NC), P.oms), mul(ey_ud(i, P.NC - 1), P.S));
+        else v = ey_ud(i, j);
+        for (int r = 0; r < P.n_rect; ++r) if (inside(P.rey[r], i, j)) v = T(0);
+        return v;
+    }
+
+    // Is the plain interior formula wrong for any of h/ex/ey at index (i,j)?
+    __device__ __noinline__ bool special(int i, int j) const {
+        if (i <= 0 || i >= P.NR - 1 || j <= 0 || j >= P.NC - 1) return true;
+        for (int s = 0; s < P.n_src; ++s) {
+            const SrcStep<T>& q = P.src[s];
+            if (q.kind == 0) { if ((j == q.col && (i == q.row || i - 1 == q.row)) || (i == q.row && j - 1 == q.col)) return true; }
+            else if (q.kind <= 2) { if (j == q.col || j - 1 == q.col) return true; }
+            else if (q.kind == 3) { if (i == q.row + 1 || i == q.row + 2) return true; }
+            else { if (i == q.row || i == q.row + 1) return true; }
+        }
+        for (int r = 0; r < P.n_rect; ++r) {
+            if (inside(P.rh[r], i, j) || inside(P.rh[r], i - 1, j) || inside(P.rh[r], i, j - 1)) return true;
+            if (inside(P.rex[r], i, j) || inside(P.rey[r], i, j)) return true;
+        }
+        return false;
+    }
+
+    __device__ __noinline__ void probe(int i, int j, T hv, T exv, T eyv) const {
+        for (int k = 0; k < P.n_probe; ++k)
+            if (P.probe_i[k] == i && P.probe_j[k] == j) {
+                P.probe_out[3 * k + 0] = (double)hv;
+                P.probe_out[3 * k + 1] = (double)exv;
+                P.probe_out[3 * k + 2] = (double)eyv;
+            }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) step_exact(const __grid_constant__ StepParams<T> P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = P.row_lo + blockIdx.y;
+    if (j > P.NC || i >= P.row_hi) return;
+    const Exact<T> X(P);
+    const long long o = (long long)(i - P.row_off) * P.pitch + j;
+    T hv = T(0), exv = T(0), eyv = T(0);
+    if (i < P.NR && j < P.NC) { hv = X.h_final(i, j); P.hn[o] = hv; }
+    if (j < P.NC) { exv = X.ex_final(i, j); P.exn[o] = exv; }
+    if (i < P.NR) { eyv = X.ey_final(i, j); P.eyn[o] = eyv; }
+    if (P.n_probe) X.probe(i, j, hv, exv, eyv);
+}
+
+// ---------------------------------------------------------------------------
+// Streaming kernel.
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+struct Row {              // everything one lane loads for row i
+    T h[V], mu[V], ep[V], exn[V], ey[V];
+    T halo;               // lanes 0..4: h,mu,ex[i+1],ey at column jw-1; ey at column jw+W
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void ldvec(T (&r)[V], const T* p) {
+    constexpr int N16 = V * (int)sizeof(T) / 16;
+    constexpr int E16 = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int c = 0; c < N16; ++c) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(p) + c);
+        if constexpr (sizeof(T) == 8) {
+            r[c * E16 + 0] = __hiloint2double(q.y, q.x);
+            r[c * E16 + 1] = __hiloint2double(q.w, q.z);
+        } else {
+            r[c * E16 + 0] = __int_as_float(q.x); r[c * E16 + 1] = __int_as_float(q.y);
+            r[c * E16 + 2] = __int_as_float(q.z); r[c * E16 + 3] = __int_as_float(q.w);
+        }
+    }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void stvec(T* p, const T (&r)[V]) {
+    constexpr int N16 = V * (int)sizeof(T) / 16;
+    constexpr int E16 = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int c = 0; c < N16; ++c) {
+        int4 q;
+        if constexpr (sizeof(T) == 8) {
+            q.x = __double2loint(r[c * E16 + 0]); q.y = __double2hiint(r[c * E16 + 0]);
+            q.z = __double2loint(r[c * E16 + 1]); q.w = __double2hiint(r[c * E16 + 1]);
+        } else {
+            q.x = __float_as_int(r[c * E16 + 0]); q.y = __float_as_int(r[c * E16 + 1]);
+            q.z = __float_as_int(r[c * E16 + 2]); q.w = __float_as_int(r[c * E16 + 3]);
+        }
+        reinterpret_cast<int4*>(p)[c] = q;
+    }
+}
+
+template <typename T, int V, bool MIXED>
+__device__ __forceinline__ void zero(T (&r)[V]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[v] = T(0);
+}
+
+template <typename T, int V, bool MIXED>
+struct Tile {
+    const StepParams<T>& P;
+    int jw, lane, j;
+    const T* halo_base; int halo_col; bool halo_on;
+
+    __device__ Tile(const StepParams<T>& p, int jw_, int lane_) : P(p), jw(jw_), lane(lane_), j(jw_ + lane_ * V) {
+        constexpr int W = 32 * V;
+        halo_base = lane == 0 ? P.h : lane == 1 ? P.muc : lane == 2 ? P.ex : P.ey;
+        halo_col = (lane == 4) ? jw + W : jw - 1;
+        halo_on = lane < 5 && halo_col >= 0 && halo_col < P.pitch;
+    }
+    __device__ __forceinline__ bool row_ok(int i) const { return !MIXED || (i >= P.row_off && i < P.row_off + P.lrows); }
+    __device__ __forceinline__ bool col_ok() const { return !MIXED || (j < P.pitch); }
+    __device__ __forceinline__ long long off(int i) const { return (long long)(i - P.row_off) * P.pitch; }
+
+    __device__ __forceinline__ void ld(T (&r)[V], const T* a, int i) const {
+        if (row_ok(i) && col_ok()) ldvec<T, V>(r, a + off(i) + j);
+        else zero<T, V, MIXED>(r);
+    }
+    // lanes 0,1,3,4 read row i; lane 2 reads ex row i+1
+    __device__ __forceinline__ T ld_halo(int i) const {
+        const int ii = i + (lane == 2 ? 1 : 0);
+        if (halo_on && row_ok(ii)) return __ldg(halo_base + off(ii) + halo_col);
+        return T(0);
+    }
+    __device__ __forceinline__ void load(Row<T, V>& r, int i) const {
+        ld(r.h, P.h, i); ld(r.mu, P.muc, i); ld(r.ep, P.epc, i); ld(r.exn, P.ex, i + 1); ld(r.ey, P.ey, i);
+        r.halo = ld_halo(i);
+    }
+};
+
+// plain interior hn for V consecutive columns + the halo column (meaningful on lane 0)
+template <typename T, int V>
+__device__ __forceinline__ void plain_hn(T (&hn)[V], T& hn_halo, const T (&h)[V], const T (&mu)[V], const T (&exn)[V],
+                                         const T (&exc)[V], const T (&ey)[V], T halo, T exc_halo, T& exn_halo) {
+    const unsigned full = 0xffffffffu;
+    const T h_l = __shfl_sync(full, halo, 0), mu_l = __shfl_sync(full, halo, 1);
+    exn_halo = __shfl_sync(full, halo, 2);
+    const T ey_l = __shfl_sync(full, halo, 3), ey_far = __shfl_sync(full, halo, 4);
+    T ey_next = __shfl_down_sync(full, ey[0], 1);
+    if ((threadIdx.x & 31) == 31) ey_next = ey_far;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : ey_next;
+        hn[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
+    }
+    hn_halo = add(h_l, mul(mu_l, sub(sub(exn_halo, exc_halo), sub(ey[0], ey_l))));
+}
+
+template <typename T, int V, bool MIXED>
+__device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    const unsigned full = 0xffffffffu;
+    const Tile<T, V, MIXED> t(P, jw, lane);
+    const int j = t.j;
+
+    // prologue: exc = ex[ta], hnp = plain hn(ta-1)
+    T exc[V], hnp[V], exc_halo;
+    {
+        T h[V], mu[V], exm[V], ey[V], hh, dummy;
+        t.ld(h, P.h, ta - 1); t.ld(mu, P.muc, ta - 1); t.ld(exm, P.ex, ta - 1); t.ld(exc, P.ex, ta); t.ld(ey, P.ey, ta - 1);
+        const T halo = t.ld_halo(ta - 1);
+        plain_hn<T, V>(hnp, hh, h, mu, exc, exm, ey, halo, T(0), dummy);
+        exc_halo = dummy;                  // lane 2 loaded ex[ta, jw-1]
+    }
+
+    Row<T, V> cur;
+    t.load(cur, ta);
+    for (int i = ta; i < tb; ++i) {
+        Row<T, V> nxt;
+        if (i + 1 < tb) t.load(nxt, i + 1);
+
+        T hn[V], hn_halo, exn_halo;
+        plain_hn<T, V>(hn, hn_halo, cur.h, cur.mu, cur.exn, exc, cur.ey, cur.halo, exc_halo, exn_halo);
+        T hn_left = __shfl_up_sync(full, hn[V - 1], 1);
+        if (lane == 0) hn_left = hn_halo;
+
+        T ho[V], exo[V], eyo[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T hl = (v == 0) ? hn_left : hn[v > 0 ? v - 1 : 0];
+            ho[v] = hn[v];
+            exo[v] = add(exc[v], mul(cur.ep[v], sub(hn[v], hnp[v])));
+            eyo[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn[v], hl)));
+        }
+
+        const long long o = t.off(i) + j;
+        if constexpr (!MIXED) {
+            stvec<T, V>(P.hn + o, ho); stvec<T, V>(P.exn + o, exo); stvec<T, V>(P.eyn + o, eyo);
+        } else {
+            const Exact<T> X(P);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int jj = j + v;
+                if (jj > P.NC) continue;
+                const bool sp = X.special(i, jj);
+                if (i < P.NR && jj < P.NC) { if (sp) ho[v] = X.h_final(i, jj); P.hn[o + v] = ho[v]; }
+                if (jj < P.NC) { if (sp) exo[v] = X.ex_final(i, jj); P.exn[o + v] = exo[v]; }
+                if (i < P.NR) { if (sp) eyo[v] = X.ey_final(i, jj); P.eyn[o + v] = eyo[v]; }
+                if (P.n_probe) X.probe(i, jj, ho[v], exo[v], eyo[v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { exc[v] = cur.exn[v]; hnp[v] = hn[v]; }
+        exc_halo = exn_halo;
+        cur = nxt;
+    }
+}
+
+// Does anything non-plain touch index rows [ta,tb) x cols [ja,jb)?  (hn of one row up / one column left included)
+template <typename T>
+__device__ bool tile_is_mixed(const StepParams<T>& P, int ta, int tb, int ja, int jb) {
+    if (ta <= 0 || tb > P.NR - 1 || ja <= 0 || jb > P.NC - 1) return true;
+    const int ra = ta - 1, ca = ja - 1;     // hn region [ra,tb) x [ca,jb)
+    for (int s = 0; s < P.n_src; ++s) {
+        const SrcStep<T>& q = P.src[s];
+        if (q.kind == 0) { if (q.row >= ra && q.row < tb && q.col >= ca && q.col < jb) return true; }
+        else if (q.kind <= 2) { if (q.col >= ca && q.col < jb) return true; }
+        else if (q.kind == 3) { if (q.row + 1 >= ra && q.row + 1 < tb) return true; }
+        else { if (q.row >= ra && q.row < tb) return true; }
+    }
+    for (int r = 0; r < P.n_rect; ++r) {
+        const RectI& a = P.rh[r];
+        if (a.r0 < tb && a.r1 > ra && a.c0 < jb && a.c1 > ca) return true;
+        const RectI& b = P.rex[r];
+        if (b.r0 < tb && b.r1 > ta && b.c0 < jb && b.c1 > ja) return true;
+        const RectI& c = P.rey[r];
+        if (c.r0 < tb && c.r1 > ta && c.c0 < jb && c.c1 > ja) return true;
+    }
+    for (int k = 0; k < P.n_probe; ++k)
+        if (P.probe_i[k] >= ta && P.probe_i[k] < tb && P.probe_j[k] >= ja && P.probe_j[k] < jb) return true;
+    return false;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) step_stream(const __grid_constant__ StepParams<T> P) {
+    constexpr int W = 32 * V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jw = (blockIdx.x * (blockDim.x >> 5) + warp) * W;
+    if (jw > P.NC) return;                                   // index space has NC+1 columns
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    if (tile_is_mixed(P, ta, tb, jw, jw + W)) run_tile<T, V, true>(P, ta, tb, jw, lane);
+    else run_tile<T, V, false>(P, ta, tb, jw, lane);
+}
+
+// ---------------------------------------------------------------------------
+// Small service kernels.
+// ---------------------------------------------------------------------------
+// host double plane (dense, ld = cols) staged on the device -> pitched T plane
+template <typename T>
+__global__ void plane_from_f64(T* dst, long long pitch, const double* src, long long src_ld, int rows, int cols) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j < cols && i < rows) dst[(long long)i * pitch + j] = (T)src[(long long)i * src_ld + j];
+}
+
+// pitched T plane -> dense double plane, with the snapshot aliasing patches applied
+struct Patch { int row, col; double value; };
+struct PatchList { int n; Patch p[FDTD_MAX_SRC]; };
+
+template <typename T>
+__global__ void plane_to_f64(double* dst, long long dst_ld, const T* src, long long pitch, int rows, int cols,
+                             int row_global0, const __grid_constant__ PatchList patches) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= cols || i >= rows) return;
+    double v = (double)src[(long long)i * pitch + j];
+    for (int k = 0; k < patches.n; ++k)
+        if (patches.p[k].row == row_global0 + i && patches.p[k].col == j) v = patches.p[k].value;
+    dst[(long long)i * dst_ld + j] = v;
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// SURVEY.md 8(d) C5 recipe; same operation order as oracle.restated.synthetic_coefficients
+template <typename T>
+__global__ void synth_coeffs(T* epc, T* muc, long long pitch, int lrows, int cols, int row_off, int NR, long long NC,
+                             unsigned long long seed, double dtds, double eps0, double mu0) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    const int i = row_off + l;
+    if (j >= cols || l >= lrows || i >= NR) return;
+    const unsigned long long bits = splitmix64(seed + (unsigned long long)i * (unsigned long long)NC + (unsigned long long)j);
+    const double u = __dmul_rn((double)(bits >> 11), 1.1102230246251565e-16);      // 2^-53
+    const double eps_r = __dadd_rn(1.0, __dmul_rn(3.0, u));
+    const double eps = __dmul_rn(eps_r, eps0);
+    const double mu = __dmul_rn(1.0, mu0);
+    epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
+    muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
+}
+
+}  // namespace fdtd

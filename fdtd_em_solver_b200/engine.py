@@ -1,0 +1,237 @@
+"""Device engine: torch tensors as device buffers + the libfdtd2d C ABI.
+
+This is the layer the drop-in `Solver` (solver.py) and bench.py sit on.  It
+replaces the arrays and loops of the reference's Solver.solve / Solver.update
+(/root/reference/solver.py:169-257, :270-337); all arithmetic happens in the
+CUDA library.  There is deliberately no CPU implementation here.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+# solver.py:9-11, same expressions -> same float64 bits
+C0 = 2.99 * (10 ** 8)
+MU = 1.26 * (10 ** (-6))
+EPSILON = 8.85 * (10 ** (-12))
+IMPEDANCE = math.sqrt(MU / EPSILON)
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def build_source_tables(pulses, times):
+    """Host-side evaluation of what solver.py:176-217 reads from the pulses.
+
+    `pulses`: objects with get_direction/get_row/get_col/get_start_time/get_end_time/magnitude
+    (the reference's Pulse API) or with .direction/.row/.col/.start/.end/.table.
+    Returns (sources, mag, magz, active, last, first_bad) where first_bad is the
+    first call index at which the reference would raise IndexError (a pulse
+    still active past the end of its own table)."""
+    times = np.asarray(times, dtype=np.float64)
+    n_calls = len(times)
+    n = len(pulses)
+    mag = np.zeros((n, n_calls))
+    active = np.zeros((n, n_calls), dtype=np.uint8)
+    srcs = (L.Source * max(n, 1))()
+    first_bad = None
+    for p, pulse in enumerate(pulses):
+        if hasattr(pulse, "get_direction"):
+            d, r, c = pulse.get_direction(), pulse.get_row(), pulse.get_col()
+            t0, t1, table = pulse.get_start_time(), pulse.get_end_time(), pulse._magnitude_vector
+        else:
+            d, r, c, t0, t1, table = pulse.direction, pulse.row, pulse.col, pulse.start, pulse.end, pulse.table
+        table = np.asarray(table, dtype=np.float64)
+        m = min(len(table), n_calls)
+        mag[p, :m] = table[:m]
+        active[p] = (t0 < times) & (times < t1)
+        if len(table) < n_calls:
+            bad = np.nonzero(active[p, len(table):])[0]
+            if len(bad):
+                b = len(table) + int(bad[0])
+                first_bad = b if first_bad is None else min(first_bad, b)
+        srcs[p].kind, srcs[p].row, srcs[p].col = L.DIRECTION_KIND[d], int(r), int(c)
+    magz = mag * IMPEDANCE
+    last = np.zeros(n_calls)
+    for p in range(n):                       # later pulses in list order win (solver.py:178)
+        last = np.where(active[p] != 0, mag[p], last)
+    return srcs, mag, magz, active, last, first_bad
+
+
+class Engine:
+    def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
+                 reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
+                 tile_rows=0, vec=0, block_warps=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
+                               "sm_100a kernels (no CPU fallback)")
+        self.torch = torch
+        self.lib = L.load()
+        cols = rows if cols is None else cols
+        row_end = rows if row_end is None else row_end
+        self.rows, self.cols, self.row_begin, self.row_end = int(rows), int(cols), int(row_begin), int(row_end)
+        self.owned = self.row_end - self.row_begin
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype("float64"), np.dtype("float32")):
+            raise ValueError("dtype must be float64 or float32")
+        cfg = L.Config()
+        cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = self.rows, self.cols, self.row_begin, self.row_end
+        cfg.pitch = 0
+        cfg.dtype = L.F64 if self.dtype == np.float64 else L.F32
+        cfg.device = int(device)
+        for k in range(4):
+            cfg.reflect[k] = 1 if reflect[k] else 0
+        cfg.kernel = L.KERNEL_STREAM if kernel == "stream" else L.KERNEL_EXACT
+        cfg.tile_rows, cfg.vec, cfg.block_warps = int(tile_rows), int(vec), int(block_warps)
+        cfg.courant = float(courant)
+        cfg.one_minus_courant = float(1 - courant) if one_minus_courant is None else float(one_minus_courant)
+        self.cfg = cfg
+        self.pitch = int(self.lib.fdtd_default_pitch(self.cols, cfg.dtype))
+        self.lrows = int(self.lib.fdtd_local_rows(C.byref(cfg)))
+        self.handle = C.c_void_p()
+        L.check(self.lib, None, self.lib.fdtd_create(C.byref(cfg), C.byref(self.handle)))
+        tdt = torch.float64 if self.dtype == np.float64 else torch.float32
+        dev = torch.device("cuda", int(device))
+        self.device = dev
+        # the ONLY role torch plays: owner of the device buffers
+        self.buffers = [torch.zeros((self.lrows, self.pitch), dtype=tdt, device=dev) for _ in range(8)]
+        torch.cuda.synchronize(dev)
+        L.check(self.lib, self.handle, self.lib.fdtd_bind_buffers(self.handle, *[C.c_void_p(b.data_ptr()) for b in self.buffers]))
+        self.first_bad = None
+        self._keep = None
+
+    # ---- static inputs -------------------------------------------------------------------
+    def upload_coefficients(self, eps_coef, mu_coef):
+        e, m = _f64(eps_coef), _f64(mu_coef)
+        if e.shape != (self.rows, self.cols) or m.shape != (self.rows, self.cols):
+            raise ValueError("coefficient arrays must be (rows, cols)")
+        L.check(self.lib, self.handle, self.lib.fdtd_upload_coeffs(self.handle, _ptr(e), _ptr(m), self.cols))
+
+    def fill_synthetic_coefficients(self, seed, dt_over_ds):
+        L.check(self.lib, self.handle, self.lib.fdtd_fill_synthetic_coeffs(self.handle, int(seed), float(dt_over_ds),
+                                                                          EPSILON, MU))
+
+    def set_sources(self, pulses, times):
+        srcs, mag, magz, active, last, self.first_bad = build_source_tables(pulses, times)
+        self._keep = (srcs, mag, magz, active, last)
+        L.check(self.lib, self.handle, self.lib.fdtd_set_sources(
+            self.handle, len(pulses), srcs, len(times), _ptr(mag), _ptr(magz), _ptr(active), _ptr(last)))
+
+    def set_reflectors(self, rects):
+        a = np.ascontiguousarray(np.asarray(rects, dtype=np.int64).reshape(-1, 4))
+        L.check(self.lib, self.handle, self.lib.fdtd_set_reflectors(self.handle, len(a), _ptr(a)))
+
+    def set_probes(self, cells):
+        a = np.ascontiguousarray(np.asarray(cells, dtype=np.int64).reshape(-1, 2))
+        self.n_probes = len(a)
+        L.check(self.lib, self.handle, self.lib.fdtd_set_probes(self.handle, len(a), _ptr(a)))
+
+    # ---- fields ----------------------------------------------------------------------------
+    def set_fields(self, h=None, ex=None, ey=None):
+        h, ex, ey = _f64(h), _f64(ex), _f64(ey)
+        for a, shape in ((h, (self.rows, self.cols)), (ex, (self.rows + 1, self.cols)), (ey, (self.rows, self.cols + 1))):
+            if a is not None and a.shape != shape:
+                raise ValueError("field shape %s, expected %s" % (a.shape, shape))
+        L.check(self.lib, self.handle, self.lib.fdtd_set_fields(self.handle, _ptr(h), _ptr(ex), _ptr(ey)))
+
+    def zero_fields(self):
+        L.check(self.lib, self.handle, self.lib.fdtd_zero_fields(self.handle))
+
+    def get_fields(self, which="hxy", out=None):
+        """Global-shaped float64 arrays; only the owned rows are written (others stay as given / zero)."""
+        out = out or {}
+        h = out.get("h", np.zeros((self.rows, self.cols))) if "h" in which else None
+        ex = out.get("ex", np.zeros((self.rows + 1, self.cols))) if "x" in which else None
+        ey = out.get("ey", np.zeros((self.rows, self.cols + 1))) if "y" in which else None
+        L.check(self.lib, self.handle, self.lib.fdtd_get_fields(self.handle, _ptr(h), _ptr(ex), _ptr(ey)))
+        return h, ex, ey
+
+    # ---- time stepping -----------------------------------------------------------------------
+    def step(self, n):
+        if self.first_bad is not None and n >= self.first_bad:
+            raise IndexError("index %d is out of bounds for the pulse magnitude table" % n)
+        L.check(self.lib, self.handle, self.lib.fdtd_step(self.handle, int(n)))
+
+    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None, pinned=True):
+        """Steps [first_step, first_step+n_steps); returns the float64 snapshot stack (or None)."""
+        first_step, n_steps = int(first_step), int(n_steps)
+        total_calls = first_step + n_steps if total_calls is None else int(total_calls)
+        bad = None
+        if self.first_bad is not None and first_step + n_steps > self.first_bad:
+            bad = self.first_bad
+            n_steps = max(0, bad - first_step)
+        snaps, n_snaps, host = None, 0, None
+        if snapshot_every:
+            k = int(snapshot_every)
+            n_snaps = (first_step + n_steps) // k - first_step // k
+            if n_snaps:
+                t = self.torch.empty((n_snaps, self.owned, self.cols), dtype=self.torch.float64,
+                                     pin_memory=bool(pinned))
+                host = t
+                snaps = t.numpy()
+        got = C.c_int64(0)
+        L.check(self.lib, self.handle, self.lib.fdtd_run(
+            self.handle, first_step, n_steps, int(snapshot_every), _ptr(snaps) if snaps is not None else None,
+            n_snaps, total_calls, C.byref(got)))
+        self._last_host = host
+        if bad is not None:
+            raise IndexError("index %d is out of bounds for the pulse magnitude table" % bad)
+        return snaps
+
+    def set_tuning(self, tile_rows=0, vec=0, block_warps=0):
+        L.check(self.lib, self.handle, self.lib.fdtd_set_tuning(self.handle, int(tile_rows), int(vec), int(block_warps)))
+
+    def sync(self):
+        L.check(self.lib, self.handle, self.lib.fdtd_sync(self.handle))
+
+    def probes(self):
+        n = C.c_int64(0)
+        L.check(self.lib, self.handle, self.lib.fdtd_probe_fetch(self.handle, None, 0, C.byref(n)))
+        out = np.zeros((n.value, getattr(self, "n_probes", 0), 3))
+        if out.size:
+            L.check(self.lib, self.handle, self.lib.fdtd_probe_fetch(self.handle, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def clear_probes(self):
+        L.check(self.lib, self.handle, self.lib.fdtd_probe_clear(self.handle))
+
+    def stats(self):
+        s = L.Stats()
+        L.check(self.lib, self.handle, self.lib.fdtd_get_stats(self.handle, C.byref(s)))
+        return dict(steps=s.steps, cell_updates=s.cell_updates, kernel_launches=s.kernel_launches,
+                    halo_bytes_sent=s.halo_bytes_sent, last_run_ms=s.last_run_ms)
+
+    # ---- multi-GPU ---------------------------------------------------------------------------
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        L.check(self.lib, self.handle, self.lib.fdtd_comm_init(self.handle, C.cast(buf, C.c_void_p), rank, nranks))
+
+    def halo_exchange(self):
+        L.check(self.lib, self.handle, self.lib.fdtd_halo_exchange(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.fdtd_destroy(self.handle)
+            self.handle = None
+        self.buffers = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id():
+    lib = L.load()
+    buf = (C.c_char * 128)()
+    L.check(lib, None, lib.fdtd_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)

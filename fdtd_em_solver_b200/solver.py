@@ -1,0 +1,580 @@
+"""Drop-in `solver` module: same public surface as the reference's solver.py
+(Solver / MaterialArray / Pulse, constants C, MU, EPSILON), with the time-step
+path running on the GPU through libfdtd2d.so.
+
+What stays host-side Python (thin, numpy): grid sizing (reference
+solver.py:93-105), pulse tables (:480-550), material painting (:352-466),
+index conversion (:107-124, :343-345), persistence (:67-91, :303).
+What moved to the device: Solver.update (:169-257) and the run loops of
+Solver.solve (:288-292, :319-337) -- see engine.py / csrc/.
+
+Extra, optional constructor keywords (defaults keep reference scripts
+unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact".
+"""
+import json
+import math
+import sys
+
+import numpy as np
+
+from .engine import Engine
+
+C = 2.99 * (10 ** 8)
+MU = 1.26 * (10 ** (-6))
+EPSILON = 8.85 * (10 ** (-12))
+
+VERBOSE = True
+
+
+def _say(*a):
+    if VERBOSE:
+        print(*a)
+
+
+def _pyplot():
+    import matplotlib.pyplot as plt      # imported lazily: matplotlib is optional on a GPU box
+    return plt
+
+
+class Solver:
+    """reference solver.py:14-349."""
+
+    def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
+                 dtype="float64", device=0, kernel="stream"):
+        self.points_per_wavelength = points_per_wavelength
+        self.stability = stability
+        self.n_max = math.sqrt(eps_r_max * mu_r_max)
+
+        self.omega_max = 0
+        self.lambda_min = None
+        self.length_x = self.length_y = simulation_size
+        self.ds = self.dt = None
+
+        self.steps = None
+        self.end_time = simulation_time
+        self.size = None
+        self.time_vector = None
+
+        self.time = 0
+        self.step = 0
+        self.h_list = []
+
+        self.material = None
+        self.eps_coefficient_arr = None
+        self.mu_coefficient_arr = None
+
+        self.reflect = False
+        self.reflectors = []
+        self.boundaries = [False, False, False, False]     # up, down, left, right; True = reflect
+        self.pulses = []
+        self.pulses_max = None
+
+        self.save_file_name = None
+        self.save_file = False
+        self.save_dict_json = dict()
+        self.step_frequency = 5
+
+        self.recorded_energies = []
+        self.energy_vector = []
+
+        # device side
+        self._dtype, self._device, self._kernel = dtype, device, kernel
+        self._engine = None
+        self._engine_key = None
+        self._host = None           # (h, ex, ey) host copies valid for the current step, or None
+        self._pending = None        # host fields to upload before the next step
+        self._probe_seen = 0
+
+    # ------------------------------------------------------------------ sizing
+    def update_constants(self):
+        """reference solver.py:93-105; also re-zeroes the fields."""
+        self.lambda_min = math.pi * 2 * C / (self.n_max * self.omega_max)
+        self.ds = self.lambda_min / self.points_per_wavelength
+        self.dt = min(self.ds * self.stability / C, math.pi / self.omega_max)
+        self.size = int(self.length_x / self.ds)
+        n = self.size
+        self._pending = (np.zeros((n, n)), np.zeros((n + 1, n)), np.zeros((n, n + 1)))
+        self._host = self._pending
+        self.steps = int(self.end_time / self.dt)
+
+    def convert(self, si_unit):
+        return int((si_unit / self.length_x) * self.size)
+
+    # field views: host copies of the device state (the reference keeps them on the host)
+    def _fetch(self):
+        if self._host is None:
+            self._host = self._engine.get_fields()
+        return self._host
+
+    h = property(lambda self: None if self.size is None else self._fetch()[0])
+    ex = property(lambda self: None if self.size is None else self._fetch()[1])
+    ey = property(lambda self: None if self.size is None else self._fetch()[2])
+
+    def _set_field(self, k, value):
+        cur = list(self._fetch())
+        cur[k] = np.array(value, dtype=np.float64)
+        self._host = self._pending = tuple(cur)
+
+    h = h.setter(lambda self, v: self._set_field(0, v))
+    ex = ex.setter(lambda self, v: self._set_field(1, v))
+    ey = ey.setter(lambda self, v: self._set_field(2, v))
+
+    # ------------------------------------------------------------------ scene
+    def create_material(self):
+        self.material = MaterialArray(self.size, self.length_x, self.length_y)
+        return self.material
+
+    def set_reflect_square(self, upper_left, lower_right):
+        top, left = (self.convert(v) for v in upper_left)
+        bottom, right = (self.convert(v) for v in lower_right)
+        self.reflect = True
+        self.reflectors.append([top, bottom, left, right])
+
+    def set_reflect_boundaries(self, up=True, down=True, left=True, right=True):
+        self.boundaries = [up, down, left, right]
+
+    def _grow(self, omega):
+        if omega > self.omega_max:
+            self.omega_max = omega
+            self.update_constants()
+
+    def _add(self, kind, location, start_time, direction, **kw):
+        pulse = Pulse(dt=self.dt, location=[self.convert(v) for v in location], start_time=start_time, type=kind,
+                      sim_end_time=self.end_time, direction=direction, real_location=location, **kw)
+        self.pulses.append(pulse)
+        return pulse
+
+    def add_oscillating_pulse(self, sigma_w, location, omega_0, start_time=0, direction=None):
+        self._grow(3 * sigma_w + omega_0)
+        return self._add("oscillate", location, start_time, direction, sigma_w=sigma_w, omega_0=omega_0)
+
+    def add_gaussian_pulse(self, sigma_w, location, start_time=0, direction=None):
+        self._grow(3 * sigma_w)
+        return self._add("gd", location, start_time, direction, sigma_w=sigma_w)
+
+    def add_sinusoidal_pulse(self, omega_0, location, start_time=0, direction=None):
+        self._grow(omega_0)
+        return self._add("sinusoidal", location, start_time, direction, omega_0=omega_0)
+
+    def ready(self):
+        return len(self.pulses) > 0
+
+    def record_energy(self, location):
+        row, col = (self.convert(v) for v in location)
+        self.recorded_energies.append({"i": row, "j": col, "location": location, "energies": []})
+
+    def save(self, file_name):
+        self.save_file_name = file_name
+        self.save_file = True
+
+    def reset(self):
+        self.step = 0
+        self.update_constants()
+
+    def assign_pulse_max(self):
+        self.pulses_max = max(p.pulse_maxima() for p in self.pulses)
+        _say('Solver max:', self.pulses_max)
+
+    # ------------------------------------------------------------------ device plumbing
+    def _coefficients(self):
+        """reference solver.py:278-279."""
+        self.eps_coefficient_arr = (self.dt / self.ds) * (1 / self.material.eps_arr)
+        self.mu_coefficient_arr = (self.dt / self.ds) * (1 / self.material.mu_arr)
+
+    def _sync_engine(self, times):
+        """(Re)build the device state from the host-side description when it changed."""
+        courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
+        key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant)
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                if self._pending is None:
+                    self._pending = self._fetch()
+                self._engine.close()
+            self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
+                                  device=self._device, reflect=self.boundaries, kernel=self._kernel)
+            self._engine_key = key
+            self._static_key = None
+            self._probe_seen = 0
+            self._steps_seen = 0
+        e = self._engine
+        static = (id(self.eps_coefficient_arr), id(self.mu_coefficient_arr),
+                  tuple(map(tuple, self.reflectors)) if self.reflect else (),
+                  tuple((d["i"], d["j"]) for d in self.recorded_energies),
+                  tuple(id(p) for p in self.pulses), np.asarray(times).tobytes())
+        if static != self._static_key:
+            e.upload_coefficients(self.eps_coefficient_arr, self.mu_coefficient_arr)
+            e.set_reflectors(self.reflectors if self.reflect else [])
+            e.set_probes([(d["i"], d["j"]) for d in self.recorded_energies])
+            e.set_sources(self.pulses, times)
+            self._static_key = static
+            self._probe_seen = 0
+        if self._pending is not None:
+            e.set_fields(*self._pending)
+            self._pending = None
+
+    def _collect_probes(self):
+        """Energy formula of reference solver.py:251-255, evaluated on the host from raw device probes."""
+        if not self.recorded_energies:
+            return
+        raw = self._engine.probes()
+        eps, mu = self.material.eps_arr, self.material.mu_arr
+        for rec in raw[self._probe_seen:]:
+            for k, d in enumerate(self.recorded_energies):
+                i, j = d["i"], d["j"]
+                hv, exv, eyv = (np.float64(v) for v in rec[k])
+                d["energies"].append(0.5 * ((eps[i][j] * (exv ** 2 + eyv ** 2) + mu[i][j] * hv ** 2)))
+        self._probe_seen = len(raw)
+
+    def _run_device(self, times, snapshot_every=0):
+        """The loops of solver.py:288-292 / :331-337 for calls self.step .. len(times)-1."""
+        self._sync_engine(times)
+        first = self.step
+        n = len(times) - first
+        self._host = None
+        try:
+            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times))
+        finally:
+            done = self._engine.stats()["steps"]
+            self.step = first + (done - self._steps_seen)
+            self._steps_seen = done
+            self._collect_probes()
+        return stack
+
+    def update(self, time):
+        """One leapfrog step (reference solver.py:169-257); returns the new h as a host array."""
+        if self.eps_coefficient_arr is None:
+            self._coefficients()
+        table_times = self.time_vector if self.time_vector is not None else np.arange(0, self.end_time, self.dt)
+        on_axis = self.step < len(table_times) and table_times[self.step] == time
+        if on_axis:
+            self._sync_engine(table_times)
+            self._engine.step(self.step)
+        else:
+            # off-axis call: gate on the caller's `time`, index tables with self.step (solver.py:177-178)
+            times = np.full(self.step + 1, float(time))
+            for p in self.pulses:
+                if p.get_start_time() < time < p.get_end_time():
+                    p.magnitude(self.step)          # IndexError exactly where the reference raises it
+            self._static_key = None
+            self._sync_engine(times)
+            self._engine.step(self.step)
+            self._static_key = None
+        self._steps_seen = self._engine.stats()["steps"]
+        self.step += 1
+        self._host = None
+        self._collect_probes()
+        return self.h
+
+    # ------------------------------------------------------------------ run loops
+    def solve(self, realtime=True, step_frequency=5, solve_only=False):
+        if not self.ready():
+            raise Exception('No pulse added')
+
+        _say("Matrix size: {}".format(self.size))
+        _say("Number of time steps:", self.steps)
+
+        self._coefficients()
+        self.assign_pulse_max()
+        self.time_vector = np.arange(0, self.end_time, self.dt)
+        self.step_frequency = step_frequency
+
+        if solve_only:
+            self._loop(0)
+            return
+
+        if realtime and not self.save_file:
+            self.plot_and_show()
+        else:
+            if not self.save_file:
+                raise Exception("Must create a save file name for non-realtime simulation")
+            self.plot_and_save(step_frequency=step_frequency)
+            _say("Saving to npy file...")
+            np.save(self.save_file_name, self._stack if self._stack is not None else self.h_list)
+            _say("Saving to txt file...")
+            self.save_to_json()
+            _say("Complete!")
+
+    def _loop(self, snapshot_every):
+        if self.step == 0:
+            stack = self._run_device(self.time_vector, snapshot_every)
+        else:                       # solve() called again without reset(): replay the reference literally
+            stack = None
+            frames = []
+            for t in self.time_vector:
+                self.update(t)
+                if snapshot_every and self.step % snapshot_every == 0:
+                    frames.append(self.h)
+            if frames:
+                stack = np.array(frames)
+        if self.steps and VERBOSE:
+            sys.stdout.write("\r%d%%" % (100 * self.step // self.steps))
+            sys.stdout.flush()
+        return stack
+
+    def plot_and_save(self, step_frequency):
+        """reference solver.py:331-337: headless loop + snapshot capture every `step_frequency` calls."""
+        stack = self._loop(step_frequency if self.save_file else 0)
+        fresh = not self.h_list
+        if stack is not None:
+            self.h_list.extend(stack[k] for k in range(len(stack)))
+        self._stack = stack if fresh else None
+
+    _stack = None
+
+    def plot_and_show(self):
+        """reference solver.py:309-329: one update per animation frame."""
+        plt = _pyplot()
+        import matplotlib.animation as animation
+        fig, ax1 = plt.subplots(figsize=(6, 6))
+        im = ax1.imshow(self.h, animated=True, extent=[0, self.length_x, self.length_y, 0], vmax=self.pulses_max,
+                        vmin=-self.pulses_max, aspect='auto', cmap='seismic')
+        ax1.set_aspect('equal', 'box')
+        ax1.xaxis.set_ticks_position('top')
+        ax1.xaxis.set_label_position('top')
+        fig.colorbar(im, ax=ax1)
+
+        def animate(time):
+            if self.step % self.step_frequency == 0:
+                fig.suptitle("Time Step = {}".format(self.step))
+            im.set_array(self.update(time))
+            return im,
+
+        self._anim = animation.FuncAnimation(fig, animate, frames=self.time_vector, interval=1, blit=False,
+                                             repeat=False)
+        plt.show()
+
+    # ------------------------------------------------------------------ persistence
+    def save_to_json(self):
+        """reference solver.py:67-91 -- same keys, same order, same file name."""
+        d = self.save_dict_json
+        for key in ('dt', 'ds', 'length_x', 'length_y', 'stability', 'omega_max', 'end_time', 'step_frequency'):
+            d[key] = getattr(self, key)
+        d['material'] = self.material.eps_arr.tolist()
+        d['pulses'] = [{'sigma_w': 0 if p.sigma_w is None else p.sigma_w, 'omega_0': p.omega_0,
+                        'omega_max': p.get_omega_max(), 'location': p.real_location, 'type': p.get_type()}
+                       for p in self.pulses]
+        with open(self.save_file_name + '.txt', 'w') as outfile:
+            json.dump(d, outfile)
+
+
+class MaterialArray:
+    """reference solver.py:352-475: host-side painting of absolute eps/mu per cell."""
+
+    def __init__(self, size, real_size_x, real_size_y, eps_array=None):
+        self.eps_arr = np.full((size, size), 1.0) * EPSILON if eps_array is None else eps_array
+        self.mu_arr = np.full((size, size), 1.0) * MU
+        self.size = size
+        self.length_x = real_size_x
+        self.length_y = real_size_y
+
+    def convert(self, si_unit):
+        if si_unit == self.length_x:
+            return self.size
+        return int((si_unit / self.length_x) * self.size)
+
+    def _fill(self, rows, cols, epsilon_rel, mu_rel):
+        self.eps_arr[rows, cols] = epsilon_rel * EPSILON
+        self.mu_arr[rows, cols] = mu_rel * MU
+
+    def set_material_rect(self, upper_left, lower_right, epsilon_rel, mu_rel=1, convert=True):
+        """Rows end-exclusive, columns end-INCLUSIVE (reference solver.py:374-375)."""
+        if convert:
+            upper_left = [self.convert(v) for v in upper_left]
+            lower_right = [self.convert(v) for v in lower_right]
+        self._fill(slice(upper_left[0], lower_right[0]), slice(upper_left[1], lower_right[1] + 1), epsilon_rel, mu_rel)
+
+    def set_material_convex(self, center: tuple, radius, thickness, epsilon_rel, mu_rel=1, convert=True):
+        """Two circular caps facing each other (reference solver.py:377-409), vectorised.
+
+        The reference indexes cell by cell inside try/except IndexError, so indices
+        in [-size, size) are legal (negative ones wrap) and anything else is skipped."""
+        if convert:
+            displacer = self.convert(radius - (thickness / 2))
+            ci, cj = self.convert(center[0]), self.convert(center[1])
+            radius = self.convert(radius)
+        else:
+            displacer = radius - thickness // 2
+            ci, cj = center[0], center[1]
+        n = self.size
+        i = np.arange(-radius, radius)[:, None]
+        for js, shift in ((np.arange(-radius, -displacer), displacer), (np.arange(displacer, radius), -displacer)):
+            j = js[None, :]
+            rr, cc = np.broadcast_arrays(ci + i, cj + j + shift)
+            keep = (i ** 2 + j ** 2 < radius ** 2) & (rr >= -n) & (rr < n) & (cc >= -n) & (cc < n)
+            self._fill(rr[keep] % n, cc[keep] % n, epsilon_rel, mu_rel)
+
+    def set_fixed_length_waveguide(self, upper_left, waveguide_length, curved_portion_ratio, thickness, epsilon_rel,
+                                   mu_rel=1):
+        straight = (waveguide_length * (1 - curved_portion_ratio)) / 2
+        bend = curved_portion_ratio * waveguide_length / (math.pi / 2)
+        self.set_waveguide(upper_left, thickness, straight, bend + thickness / 2, epsilon_rel, mu_rel=mu_rel,
+                           convert=True)
+
+    def set_quarter_circle(self, center, radius, epsilon_rel, mu_rel=1, thickness=0, convert=True):
+        """Upper-right quarter annulus (reference solver.py:418-432)."""
+        ci, cj = center[0], center[1]
+        if convert:
+            ci, cj = self.convert(ci), self.convert(cj)
+            radius = self.convert(radius)
+            thickness = self.convert(thickness)
+        print("latest one   ")
+        di = np.arange(-ci, self.size - ci)[:, None]
+        dj = np.arange(-cj, self.size - cj)[None, :]
+        d2 = di ** 2 + dj ** 2
+        mask = (radius ** 2 > d2) & (d2 > (radius - thickness) ** 2) & (di < 0) & (dj > 0)
+        self.eps_arr[mask] = epsilon_rel * EPSILON
+        self.mu_arr[mask] = mu_rel * MU
+
+    def set_waveguide(self, start_point, thickness, rect_length, radius, epsilon_rel, mu_rel=1, convert=True):
+        """Straight - quarter bend - straight (reference solver.py:446-466)."""
+        i0, j0 = start_point[0], start_point[1]
+        if convert:
+            i0, j0, thickness, rect_length, radius = (self.convert(v) for v in (i0, j0, thickness, rect_length, radius))
+        self.set_material_rect((i0, j0), (i0 + thickness, j0 + rect_length), epsilon_rel, mu_rel=mu_rel, convert=False)
+        bend_center = (i0 + radius, j0 + rect_length)
+        self.set_quarter_circle(bend_center, radius, epsilon_rel, thickness=thickness, mu_rel=mu_rel, convert=False)
+        leg = (bend_center[0], bend_center[1] + radius - thickness)
+        self.set_material_rect(leg, (leg[0] + rect_length, leg[1] + thickness), epsilon_rel, mu_rel=mu_rel,
+                               convert=False)
+
+    def plot(self):
+        plt = _pyplot()
+        fig, ax = plt.subplots()
+        image = ax.imshow(self.eps_arr, extent=([0, self.length_x, self.length_y, 0]), vmax=(np.max(self.eps_arr)),
+                          vmin=0, aspect='auto')
+        ax.set_aspect('equal', 'box')
+        ax.set_title('Material (epsilon relative)')
+        fig.colorbar(image, ax=ax)
+        plt.show()
+
+
+def _envelope(t, sigma_t, mid):
+    return (1 / (sigma_t * np.sqrt(2 * math.pi))) * (np.exp(-((t - mid) ** 2) / (2 * (sigma_t ** 2))))
+
+
+class Pulse:
+    """reference solver.py:478-642: the source waveform, tabulated once on the host."""
+
+    TYPES = ("gd", "oscillate", "sinusoidal")
+    DIRECTIONS = ("up", "down", "left", "right", None)
+
+    def __init__(self, dt, start_time, type, sim_end_time, sigma_w=None, location=None, real_location=None, omega_0=0,
+                 direction=None, step_frequency=1):
+        _say("--- Pulse Info ---")
+        self.omega_0 = omega_0
+        self.dt = dt
+        self._start_time = start_time
+        self._sim_end_time = sim_end_time
+        self._index_location = location
+        self.real_location = real_location
+        self._type = type
+        self.plot_title = "Oscillating pulse" if type == "oscillate" else "Gaussian derivative"
+        self.step_frequency = step_frequency
+        self.sigma_w = sigma_w
+
+        if sigma_w is not None:
+            self.sigma_t = 1 / sigma_w
+            self.pulse_mid = 3 * self.sigma_t
+            self._end_time = start_time + self.pulse_mid * 3
+            self._omega_max = 3 * sigma_w + omega_0
+            _say("Pulse type: {}, sigma_w: {}, omega_0: {}, omega_max: {}".format(type, sigma_w, omega_0,
+                                                                                 self._omega_max))
+        else:
+            self._end_time = sim_end_time
+            self._omega_max = omega_0
+            _say("Pulse type: {}, omega_0: {}".format(type, omega_0))
+
+        self._direction = direction
+        self._end_step = int(1 + (self._end_time // dt))
+        self._time_vector = np.arange(0, sim_end_time, dt)
+        self._magnitude_vector = None
+        self.create_magnitude_vector()
+        self._maximum = self.pulse_maxima()
+        self.fft_amplitude = None
+        self.fft_frequencies = None
+
+        if type not in self.TYPES:
+            raise Exception("Pulse type not recognised: {}".format(type))
+        if direction not in self.DIRECTIONS:
+            raise Exception("Pulse direction not recognised: {}".format(self.get_direction))
+        if type == "oscillate" and not omega_0:
+            raise Exception("Missing arguments f_0: {}".format(omega_0))
+
+    def magnitude(self, timestep):
+        return self._magnitude_vector[timestep]
+
+    def pulse_maxima(self):
+        return np.max(self._magnitude_vector)
+
+    def create_magnitude_vector(self):
+        t = self._time_vector
+        if self._type == "sinusoidal":
+            self._magnitude_vector = np.sin(t * self.omega_0)
+            return
+        if self._type == "gd":
+            self._magnitude_vector = (-t + self.pulse_mid) * _envelope(t, self.sigma_t, self.pulse_mid)
+        elif self._type == "oscillate":
+            self._magnitude_vector = np.cos(t * self.omega_0) * _envelope(t, self.sigma_t, self.pulse_mid)
+        _say("Pulse duration: {} seconds, {} steps".format(t[-1], len(t)))
+
+    # ---- analysis of the source waveform (host, out of the hot path) ----
+    def plot_time(self, scaled_plot=True, show=True, title=False):
+        plt = _pyplot()
+        plt.plot(self._time_vector, self._magnitude_vector)
+        if title:
+            plt.suptitle(self.plot_title)
+        if self._type == "oscillate":
+            local = np.arange(0, self._end_time, self.dt)
+            plt.plot(local, _envelope(local, self.sigma_t, self.pulse_mid))
+        plt.xlabel("Time (seconds)")
+        plt.ylabel("Magnitude")
+        if scaled_plot:
+            plt.xlim(0, self._end_time)
+        if show:
+            plt.show()
+
+    def plot_frequency(self, show=True, title=False):
+        plt = _pyplot()
+        plt.xlabel("Frequency (rad/s)")
+        plt.ylabel("Amplitude")
+        if title:
+            plt.suptitle(self.plot_title)
+        w = np.linspace(self._omega_max, 1000)
+        if self._type == "oscillate":
+            plt.plot(w, self.sigma_t * 0.5 * (np.exp((-(w - self.omega_0) ** 2 / (2 * self.sigma_w ** 2))) +
+                                              np.exp((-(w + self.omega_0) ** 2 / (2 * self.sigma_w ** 2)))))
+        elif self._type == "gd":
+            plt.plot(w, np.abs(w) * self.sigma_t * np.exp(-((w ** 2) / (2 * self.sigma_w ** 2))))
+        if show:
+            plt.show()
+
+    def fft(self):
+        samples = self._magnitude_vector[::self.step_frequency]
+        padded = np.concatenate((samples, np.zeros(2 ** 14 - len(samples))))
+        freqs = 2 * np.pi * np.fft.fftfreq(len(padded), d=self.dt * self.step_frequency)
+        keep = np.logical_and(freqs > 0, freqs < self._omega_max)
+        self.fft_amplitude = np.abs(np.fft.fft(padded)[keep])
+        self.fft_frequencies = freqs[keep]
+        _say("Number of frequency points:", len(self.fft_frequencies))
+
+    def plot_frequency_fft(self, show=True, title=False):
+        plt = _pyplot()
+        if self.fft_amplitude is None:
+            self.fft()
+        plt.plot(self.fft_frequencies, self.fft_amplitude)
+        if title:
+            plt.suptitle(self.plot_title)
+        if show:
+            plt.ylabel("Amplitude")
+            plt.xlabel("Frequency (rad/s)")
+            plt.show()
+
+    def get_maximum(self): return self._maximum
+    def get_start_time(self): return self._start_time
+    def get_direction(self): return self._direction
+    def get_end_time(self): return self._end_time
+    def get_end_step(self): return self._end_step
+    def get_omega_max(self): return self._omega_max
+    def get_row(self): return self._index_location[0]
+    def get_col(self): return self._index_location[1]
+    def get_type(self): return self._type

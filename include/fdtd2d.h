@@ -1,0 +1,164 @@
+/* fdtd2d.h -- C ABI of the B200-native 2D Yee time-stepper (libfdtd2d.so).
+ *
+ * The reference (jmanchuck/FDTD-EM-Solver) has no FFI layer: its hot path is the
+ * Python method Solver.update (solver.py:169-257) driven by the loops in
+ * Solver.solve (solver.py:288-292, :331-337).  This header is the boundary a
+ * maintainer binds (ctypes/cffi) to replace exactly that
+ * path; each entry point cites the reference lines it stands in for.
+ *
+ * Conventions: every function returns 0 on success and a negative fdtd_status
+ * on failure; fdtd_last_error() gives the message.  No C++ exceptions, no
+ * exit(), no torch types.  Device buffers are owned by the caller (raw device
+ * pointers, e.g. torch tensors' data_ptr()); the library owns only its small
+ * parameter tables, streams/events and snapshot staging.
+ *
+ * Geometry.  Global grid: h (rows, cols), ex (rows+1, cols), ey (rows, cols+1)
+ * as in solver.py:101-103, but rows != cols is allowed.  A context owns the
+ * y-slab of global rows [row_begin,row_end).  Every device array of a context
+ * has the same shape (fdtd_local_rows() x pitch elements, C order):
+ *   local row l  <->  global row  row_begin - halo_top + l,
+ *   halo_top = (row_begin > 0) ? 1 : 0       (old h/ex/ey/mu_coef of the row above),
+ *   the last local row holds ex[row_end] (halo from the slab below, or the
+ *   real last ex row when row_end == rows).
+ * pitch >= cols+1 and a multiple of 32 elements (fdtd_default_pitch()).
+ */
+#ifndef FDTD2D_H
+#define FDTD2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdtd_ctx* fdtd_handle;
+
+enum fdtd_status {
+    FDTD_OK = 0,
+    FDTD_ERR_ARG = -1,      /* bad argument / unsupported geometry          */
+    FDTD_ERR_CUDA = -2,     /* a CUDA runtime call failed                   */
+    FDTD_ERR_STATE = -3,    /* call order (buffers not bound, ...)          */
+    FDTD_ERR_RANGE = -4,    /* step outside the uploaded source tables      */
+    FDTD_ERR_COMM = -5      /* NCCL halo transport failed / unavailable     */
+};
+
+enum fdtd_dtype { FDTD_F64 = 0, FDTD_F32 = 1 };
+
+/* Pulse.get_direction(): None / "right" / "left" / "up" / "down" (solver.py:484, :176-217). */
+enum fdtd_source_kind { FDTD_SRC_POINT = 0, FDTD_SRC_RIGHT = 1, FDTD_SRC_LEFT = 2, FDTD_SRC_UP = 3, FDTD_SRC_DOWN = 4 };
+
+enum fdtd_kernel {
+    FDTD_KERNEL_EXACT = 0,   /* one thread per cell, closed-form restatement of solver.py:169-242 (in-repo GPU reference) */
+    FDTD_KERNEL_STREAM = 1   /* fused H+E streaming kernel, the production path                                         */
+};
+
+typedef struct fdtd_config {
+    int64_t rows, cols;            /* solver.py:98 `size` (both), rectangular allowed               */
+    int64_t row_begin, row_end;    /* owned y-slab; 0,rows on one GPU                               */
+    int64_t pitch;                 /* elements per row of every device array; 0 = default           */
+    int32_t dtype;                 /* fdtd_dtype                                                    */
+    int32_t device;                /* CUDA device ordinal                                           */
+    int32_t reflect[4];            /* solver.py:54 boundaries [up,down,left,right], 1=reflect       */
+    int32_t kernel;                /* fdtd_kernel                                                   */
+    int32_t tile_rows;             /* rows marched per warp tile (0 = default)                      */
+    int32_t vec;                   /* elements per thread per row (0 = default; 2/4 f64, 4/8 f32)   */
+    int32_t block_warps;           /* warps per CTA (0 = default)                                   */
+    double courant;                /* (C*dt/ds) evaluated by the host in Python floats, solver.py:221 */
+    double one_minus_courant;      /* (1 - (C*dt/ds)), same                                         */
+} fdtd_config;
+
+typedef struct fdtd_source {
+    int32_t kind;                  /* fdtd_source_kind                                              */
+    int32_t reserved;
+    int64_t row, col;              /* Pulse.get_row()/get_col(), solver.py:635-639 (global indices) */
+} fdtd_source;
+
+typedef struct fdtd_stats {
+    int64_t steps;                 /* leapfrog steps executed since create                          */
+    int64_t cell_updates;          /* owned rows * cols * steps                                     */
+    int64_t kernel_launches;       /* kernels of this library launched since create                 */
+    int64_t halo_bytes_sent;       /* NVLink halo traffic, this rank                                */
+    double  last_run_ms;           /* device time of the last fdtd_run (CUDA events)                */
+} fdtd_stats;
+
+int64_t fdtd_default_pitch(int64_t cols, int32_t dtype);
+int64_t fdtd_local_rows(const fdtd_config* cfg);
+
+/* Solver.update_constants() field allocation + solve() preamble (solver.py:93-105, :270-286). */
+int fdtd_create(const fdtd_config* cfg, fdtd_handle* out);
+int fdtd_destroy(fdtd_handle h);
+const char* fdtd_last_error(fdtd_handle h);          /* h may be NULL: last error of a failed fdtd_create */
+
+/* Device arrays (caller-owned, fdtd_local_rows() x pitch each, zero-filled by the caller or by
+ * fdtd_zero_fields): two generations of h/ex/ey (ping-pong) and the two coefficient planes. */
+int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
+                      void* eps_coef, void* mu_coef);
+
+/* eps_coefficient_arr / mu_coefficient_arr (solver.py:278-279), GLOBAL host arrays (rows x cols,
+ * leading dimension host_ld doubles); the context takes the rows it needs (incl. halo_top). */
+int fdtd_upload_coeffs(fdtd_handle h, const double* eps_coef, const double* mu_coef, int64_t host_ld);
+
+/* C5 synthetic coefficients generated on the device: eps_r = 1 + 3*u(i,j),
+ * u = (splitmix64(seed + i*cols + j) >> 11) * 2^-53, mu_r = 1; same bits as oracle.restated.synthetic_coefficients. */
+int fdtd_fill_synthetic_coeffs(fdtd_handle h, uint64_t seed, double dt_over_ds, double epsilon0, double mu0);
+
+/* self.h / self.ex / self.ey (solver.py:101-103).  GLOBAL host arrays, any pointer may be NULL
+ * (set: zero-fill that field; get: skip it).  set also loads the halo rows; get writes owned rows only. */
+int fdtd_set_fields(fdtd_handle h, const double* hh, const double* ex, const double* ey);
+int fdtd_get_fields(fdtd_handle h, double* hh, double* ex, double* ey);
+int fdtd_zero_fields(fdtd_handle h);                 /* Solver.reset(), solver.py:347-349 */
+
+/* Pulses (solver.py:176-217).  Tables are host arrays evaluated by the caller with the reference's
+ * own expressions: mag[p*table_len+n] = pulse.magnitude(n); mag_z = mag*sqrt(MU/EPSILON);
+ * active[p*table_len+n] = (start < time_vector[n] < end); last_mag[n] = magnitude of the last active
+ * pulse in list order (the stale `magnitude` local of solver.py:178/:196-200). */
+int fdtd_set_sources(fdtd_handle h, int32_t n, const fdtd_source* src, int64_t table_len,
+                     const double* mag, const double* mag_z, const uint8_t* active, const double* last_mag);
+
+/* self.reflectors (solver.py:114-120, :164-167, :238-242): n x [r0,r1,c0,c1] with Python slice semantics. */
+int fdtd_set_reflectors(fdtd_handle h, int32_t n, const int64_t* rects);
+
+/* record_energy cells (solver.py:343-345): raw (h,ex,ey) triples captured after every step (:246-255). */
+int fdtd_set_probes(fdtd_handle h, int32_t n, const int64_t* ij);
+int fdtd_probe_fetch(fdtd_handle h, double* out, int64_t max_records, int64_t* n_records);
+int fdtd_probe_clear(fdtd_handle h);
+
+/* One Solver.update(time) call for call index `step` (= self.step on entry), asynchronous. */
+int fdtd_step(fdtd_handle h, int64_t step);
+
+/* The solve() loops (solver.py:288-292 and :331-337): steps [first_step, first_step+n_steps).
+ * If snapshot_every > 0, after every call with (step+1) % snapshot_every == 0 the owned rows of h are
+ * written as float64 to snapshots_host[k] (owned_rows x cols each, dense), k counting from 0, with the
+ * reference's list-aliasing rule applied (solver.py:337 vs :180: point-source cells hold the NEXT call's
+ * magnitude when that call exists, i.e. step+1 < total_calls, and the pulse is active then).
+ * Returns after all device work and copies completed. */
+int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
+             double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots);
+
+/* Launch geometry of the streaming kernel (0 keeps the current value); results never depend on it. */
+int fdtd_set_tuning(fdtd_handle h, int32_t tile_rows, int32_t vec, int32_t block_warps);
+
+int fdtd_sync(fdtd_handle h);
+int fdtd_get_stats(fdtd_handle h, fdtd_stats* out);
+
+/* Which generation (0/1) currently holds the fields -- for callers that read the torch tensors directly. */
+int fdtd_current_generation(fdtd_handle h);
+
+/* y-slab halo exchange over NCCL (no reference counterpart).  One context per rank.
+ * fdtd_comm_unique_id fills a 128-byte ncclUniqueId on rank 0; broadcast it out-of-band
+ * (torch.distributed) and pass it to fdtd_comm_init on every rank.  Afterwards fdtd_step/fdtd_run
+ * exchange 3 rows down / 1 row up per step, overlapped with the interior update. */
+int fdtd_comm_unique_id(void* out128);
+int fdtd_comm_init(fdtd_handle h, const void* unique_id128, int32_t rank, int32_t nranks);
+/* Exchange the halo rows of the CURRENT generation (after fdtd_set_fields on every rank). */
+int fdtd_halo_exchange(fdtd_handle h);
+/* Row pointers/counts of the current generation for an external transport (torch.distributed):
+ * send_down[3] = owned last rows of h,ex,ey; recv_up[3] = halo_top rows; send_up = ex[row_begin];
+ * recv_down = ex[row_end] slot.  counts in elements. */
+int fdtd_halo_rows(fdtd_handle h, void* send_down[3], void* recv_up[3], void** send_up, void** recv_down,
+                   int64_t counts[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDTD2D_H */

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+fp64 bar: BIT-EXACT (stronger than BASELINE.json's 1e-12 relative L2) on h, ex, ey after
+every call, on snapshots and on probe series.  fp32 bar: 1e-5 relative L2 (tolerance
+written where it is used).
+"""
+import contextlib
+import io
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import restated as R, scenarios as SC
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_for(f, setup, times, **kw):
+    from fdtd_em_solver_b200.engine import Engine
+    rows, cols = f.h.shape
+    S = setup.courant
+    e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, **kw)
+    e.upload_coefficients(setup.eps_coef, setup.mu_coef)
+    e.set_sources(setup.pulses, times)
+    e.set_reflectors(setup.reflectors)
+    e.set_fields(f.h, f.ex, f.ey)
+    return e
+
+
+def _same(e, f, where=""):
+    h, ex, ey = e.get_fields()
+    for name, a, b in (("h", h, f.h), ("ex", ex, f.ex), ("ey", ey, f.ey)):
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError("%s differs %s: %d cells, first %s: got %r want %r" % (
+                name, where, len(bad), bad[0], a[tuple(bad[0])], b[tuple(bad[0])]))
+
+
+WALLS = list(itertools.product([False, True], repeat=4))
+
+
+@pytest.mark.parametrize("kernel,kw", [("exact", {}), ("stream", dict(tile_rows=4, vec=2, block_warps=1)),
+                                      ("stream", dict(tile_rows=5, vec=4, block_warps=2))])
+@pytest.mark.parametrize("shape", [(3, 3), (4, 7), (9, 5), (33, 33), (40, 70), (67, 131)])
+def test_random_cases_every_step_bitwise(kernel, kw, shape):
+    rows, cols = shape
+    for seed in range(4):
+        walls = WALLS[(seed * 5 + rows + cols) % 16]
+        f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=10)
+        e = _engine_for(f, setup, times, kernel=kernel, **kw)
+        for n, t in enumerate(times):
+            R.leapfrog(f, setup, t)
+            e.step(n)
+            _same(e, f, "shape %s seed %d walls %s step %d" % (shape, seed, walls, n))
+        e.close()
+
+
+@pytest.mark.parametrize("walls", WALLS)
+def test_all_wall_combinations(walls):
+    for shape in [(6, 6), (17, 12)]:
+        f, setup, times = SC.random_case(shape[0], shape[1], 11, walls=walls, n_steps=6)
+        e = _engine_for(f, setup, times, kernel="stream", tile_rows=4)
+        for n, t in enumerate(times):
+            R.leapfrog(f, setup, t)
+            e.step(n)
+            _same(e, f, "walls %s step %d" % (walls, n))
+        e.close()
+
+
+@pytest.mark.parametrize("vec,tile_rows,warps", [(2, 64, 4), (4, 32, 8), (2, 16, 2)])
+def test_large_hetero_grid_stream_vs_oracle(vec, tile_rows, warps):
+    """Interior fast tiles + every kind of mixed tile on a grid with many tiles."""
+    f, setup, times = SC.random_case(300, 1100, 5, walls=(False, True, False, False), n_steps=5)
+    e = _engine_for(f, setup, times, kernel="stream", vec=vec, tile_rows=tile_rows, block_warps=warps)
+    for n, t in enumerate(times):
+        R.leapfrog(f, setup, t)
+        e.step(n)
+    _same(e, f, "large grid")
+    e.close()
+
+
+def test_run_loop_snapshots_and_probes_bitwise():
+    """fdtd_run: snapshot cadence + the list-aliasing rule (App. A-Q8) + probe capture."""
+    for k in (1, 3, 5):
+        f, setup, times = SC.random_case(24, 31, 3, n_steps=23)
+        cells = [(0, 0), (5, 7), (23, 30), (12, 0)]
+        f.raw_probes = [(i, j, []) for i, j in cells]
+        e = _engine_for(f, setup, times, kernel="stream", tile_rows=8)
+        e.set_probes(cells)
+        want = np.array(R.run_saving(f, setup, times, k))
+        got = e.run(0, len(times), snapshot_every=k, total_calls=len(times))
+        assert got.shape == want.shape and np.array_equal(got, want)
+        _same(e, f, "after run")
+        raw = e.probes()
+        for c, (i, j, series) in enumerate(f.raw_probes):
+            assert np.array_equal(raw[:, c, :], np.array(series))
+        e.close()
+
+
+@pytest.mark.parametrize("name,n_calls", [("tutorial", None), ("lens", None), ("waveguide", None),
+                                          ("waveguide_mixed_walls", 2500), ("mixed", None), ("doubleslit", 4000)])
+def test_scenarios_through_the_python_api(name, n_calls, tmp_path):
+    """BASELINE.json configs 1-4 through the drop-in Solver API vs the oracle: snapshot stack, final
+    fields and energy probe series, all bitwise."""
+    from fdtd_em_solver_b200 import solver as S, analyser as A
+    sc = SC.spec(name)
+    f, setup, times, info = SC.restate(sc)
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, sc)
+        assert s.size == info["size"] and s.dt == info["dt"] and s.ds == info["ds"] and s.steps == info["steps"]
+        if n_calls is not None:
+            times = times[:n_calls]
+            s.end_time = float(times[-1]) + 0.5 * s.dt            # same truncated time axis on both sides
+            assert np.array_equal(np.arange(0, s.end_time, s.dt), times)
+        s.save(str(tmp_path / name))
+        s.solve(realtime=False, step_frequency=sc["step_frequency"])
+    want = np.array(R.run_saving(f, setup, times, sc["step_frequency"]))
+    got = np.load(str(tmp_path / name) + ".npy")
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(s.h, f.h) and np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)
+    assert s.step == f.step == len(times)
+    for d, (i, j, series) in zip(s.recorded_energies, f.probes):
+        assert (d["i"], d["j"]) == (i, j) and d["energies"] == series
+    with contextlib.redirect_stdout(io.StringIO()):
+        loader = A.FileLoader(str(tmp_path / name))
+    assert loader.size == s.size and np.array_equal(loader.get_matrix(), want)
+    i, j = sc["probe_cells"][0]
+    dc = loader.create_data_collector((i * s.ds * 1.0000001, j * s.ds * 1.0000001))
+    assert np.array_equal(dc.data, want[:, dc.i_pos, dc.j_pos])
+
+
+def test_update_api_step_by_step():
+    """Solver.update(time) called directly, as the realtime animation does (solver.py:319-325)."""
+    from fdtd_em_solver_b200 import solver as S
+    sc = SC.spec("waveguide")
+    f, setup, times, info = SC.restate(sc)
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, sc)
+        s._coefficients()
+        s.time_vector = np.arange(0, s.end_time, s.dt)
+    for t in times[:60]:
+        R.leapfrog(f, setup, t)
+        h = s.update(t)
+        assert np.array_equal(h, f.h)
+    assert np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)
+    assert s.recorded_energies[0]["energies"] == f.probes[0][2]
+
+
+def test_fp32_within_tolerance():
+    """fp32 path vs the fp64 oracle: relative L2 <= 1e-5 per snapshot while the field is in the domain."""
+    from fdtd_em_solver_b200 import solver as S
+    TOL = 1e-5
+    sc = SC.spec("lens")
+    f, setup, times, info = SC.restate(sc)
+    want = np.array(R.run_saving(f, setup, times, 5))
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, sc, dtype="float32")
+        s._coefficients()
+        s.time_vector = times
+        got = s._run_device(times, 5)
+    num = np.sqrt(((got - want) ** 2).sum(axis=(1, 2)))
+    den = np.sqrt((want ** 2).sum(axis=(1, 2)))
+    rel = num[den > 0] / den[den > 0]
+    assert rel.max() <= TOL, rel.max()
+
+
+def test_synthetic_coefficients_match_oracle_bitwise():
+    from fdtd_em_solver_b200.engine import Engine
+    rows, cols, dt, ds = 37, 70, 3.9e-12, 0.011741702542791853
+    e = Engine(rows, cols, courant=0.1)
+    e.fill_synthetic_coefficients(7, dt / ds)
+    epc, muc = R.synthetic_coefficients(rows, cols, dt, ds, seed=7)
+    got_e = e.buffers[6].cpu().numpy()[:rows, :cols]
+    got_m = e.buffers[7].cpu().numpy()[:rows, :cols]
+    assert np.array_equal(got_e, epc) and np.array_equal(got_m, muc)
+    e.close()
+
+
+def test_stale_pulse_raises_index_error_like_the_reference():
+    """App. A-Q10: a pulse created before a re-mesh keeps its short table -> IndexError when indexed past it."""
+    from fdtd_em_solver_b200 import solver as S
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = S.Solver(10, 0.1, 1, 1, 1.0, 4e-9)
+        s.add_gaussian_pulse(2e9, (0.3, 0.3))
+        n_short = len(s.pulses[0]._magnitude_vector)
+        s.add_oscillating_pulse(3e9, (0.5, 0.5), 8e9)
+        s.create_material()
+        assert len(s.pulses[1]._magnitude_vector) > n_short
+        with pytest.raises(IndexError):
+            s.solve(solve_only=True)
+    assert s.step == n_short
