@@ -504,17 +504,23 @@ class Pulse:
         return self._magnitude_vector[timestep]
 
     def pulse_maxima(self):
-        return np.max(self._magnitude_vector)
+        return None if self._magnitude_vector is None else np.max(self._magnitude_vector)
 
     def create_magnitude_vector(self):
         t = self._time_vector
         if self._type == "sinusoidal":
             self._magnitude_vector = np.sin(t * self.omega_0)
             return
+        carrier = None
         if self._type == "gd":
-            self._magnitude_vector = (-t + self.pulse_mid) * _envelope(t, self.sigma_t, self.pulse_mid)
+            carrier = -t + self.pulse_mid
         elif self._type == "oscillate":
-            self._magnitude_vector = np.cos(t * self.omega_0) * _envelope(t, self.sigma_t, self.pulse_mid)
+            carrier = np.cos(t * self.omega_0)
+        if carrier is None:                 # unknown type: the constructor raises right after (reference :523-524)
+            return
+        # association order of reference solver.py:541-545: (carrier * norm) * gaussian, rounded in that order
+        norm = 1 / (self.sigma_t * np.sqrt(2 * math.pi))
+        self._magnitude_vector = carrier * norm * np.exp(-((t - self.pulse_mid) ** 2) / (2 * (self.sigma_t ** 2)))
         _say("Pulse duration: {} seconds, {} steps".format(t[-1], len(t)))
 
     # ---- analysis of the source waveform (host, out of the hot path) ----

@@ -191,3 +191,33 @@ def test_stale_pulse_raises_index_error_like_the_reference():
         with pytest.raises(IndexError):
             s.solve(solve_only=True)
     assert s.step == n_short
+
+
+def test_cuda_against_reference_golden_vectors():
+    """CUDA path vs the fixtures the real reference produced (tests/golden/): bitwise."""
+    from golden_util import load, random_files, setup_of, sha
+    from fdtd_em_solver_b200.engine import Engine
+    for path in random_files():
+        g = load(path)
+        s = setup_of(g)
+        f = R.Fields(g["h0"].copy(), g["ex0"].copy(), g["ey0"].copy())
+        e = _engine_for(f, s, g["times"], kernel="stream", tile_rows=8)
+        for n in range(len(g["times"])):
+            e.step(n)
+            assert np.array_equal(e.get_fields("h")[0], g["h_steps"][n]), (path, n)
+        h, ex, ey = e.get_fields()
+        assert np.array_equal(h, g["h"]) and np.array_equal(ex, g["ex"]) and np.array_equal(ey, g["ey"])
+        e.close()
+    for name in ("tutorial", "lens", "waveguide", "waveguide_mixed_walls", "mixed", "doubleslit"):
+        g = load(name)
+        s = setup_of(g)
+        n = int(g["size"])
+        e = Engine(n, courant=s.courant, one_minus_courant=(1 - s.courant), reflect=s.reflect_walls)
+        e.upload_coefficients(g["eps_coef"], g["mu_coef"])
+        e.set_sources(s.pulses, g["times"])
+        e.set_reflectors(s.reflectors)
+        stack = e.run(0, len(g["times"]), snapshot_every=int(g["step_frequency"]), total_calls=len(g["times"]))
+        h, ex, ey = e.get_fields()
+        assert np.array_equal(h, g["final_h"]) and sha(ex) == str(g["sha_ex"]) and sha(ey) == str(g["sha_ey"]), name
+        assert len(stack) == int(g["n_snapshots"]) and sha(stack) == str(g["sha_stack"]), name
+        e.close()
