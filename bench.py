@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric  : Gcell-updates/s of the 2D Yee leapfrog step (one cell-update = H, Ex, Ey of one cell
+          advanced one step, incl. source / wall handling), fp64 by default (--dtype f32).
+workload: the C5 synthetic slab: 8192 rows x 65536 cols per GPU of the
+          65536 x 65536 heterogeneous-eps grid, y-slab sharded (weak scaling: 8192*N rows at N GPUs),
+          absorbing walls, one point source per slab + one "right" TF/SF line at column 7.
+a step  : ONE leapfrog time step over the whole (sharded) grid.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU); ranks exchange halo rows over NCCL inside the
+C library.  Timing: CUDA events on the library's launch stream around fdtd_run, barrier +
+synchronize on both sides, max over ranks.  Inputs (8 arrays x 4 GiB per GPU) exceed L2 (126 MB),
+so no explicit L2 flush is needed between steps.
+
+`--impl reference` times the reference's CPU path (numpy; the oracle port oracle/restated.py,
+bit-identical to /root/reference/solver.py:169-257 which cannot travel to the GPU box) on the host
+cores, each step a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ROWS_PER_GPU = 8192
+COLS = 65536
+BYTES_PER_CELL = {"f64": 64, "f32": 32}      # 5 words read + 3 written
+METRIC = "Gcell-updates/s (2D Yee leapfrog, C5 synthetic slab)"
+CPU_SAMPLE = (2048, 2048)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, watts = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); watts.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(watts) if watts else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(steps_budget_s=15.0):
+    """The oracle port of the reference numpy step, timed on this host (bounded sample)."""
+    from oracle import restated as R
+    from fdtd_em_solver_b200 import synthetic as SY
+    rows, cols = CPU_SAMPLE
+    epc, muc = R.synthetic_coefficients(rows, cols, SY.DT, SY.DS, seed=0, total_cols=COLS)
+    n_calls = 64
+    pulses = [R.PulseSpec("table", p.direction, p.row, p.col, p.start, p.end, p.table)
+              for p in SY.pulses(rows, cols, n_calls)]
+    S = (SY.C0 * SY.DT / SY.DS)
+    setup = R.Setup(eps_coef=epc, mu_coef=muc, courant=S, pulses=pulses)
+    f = R.Fields.zeros(rows, cols)
+    t = SY.times(n_calls)
+    R.leapfrog(f, setup, t[0])                       # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < n_calls - 1 and (n < 3 or time.perf_counter() - t0 < steps_budget_s):
+        R.leapfrog(f, setup, t[n + 1])
+        n += 1
+    dt = time.perf_counter() - t0
+    return rows * cols * n / dt / 1e9, n, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    value, n, dt = cpu_baseline(steps_budget_s=max(5.0, min(60.0, 0.2 * (args.steps + args.warmup))))
+    sample = "%dx%d sub-grid of the C5 slab recipe, %d numpy steps in %.1f s" % (CPU_SAMPLE + (n, dt))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "note": "numpy elementwise ufuncs are single-threaded; oracle/restated.py is bit-identical "
+                                 "to reference solver.py:169-257 (tests/test_oracle_vs_reference.py)"},
+        "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "C5 synthetic: %d x %d Yee grid (%d rows per GPU, y-slab sharded), heterogeneous eps_r=1+3u "
+                        "(splitmix64), mu_r=1, 4 absorbing walls, 1 point source per slab + 1 TF/SF line at col 7"
+                        % (ROWS_PER_GPU * n_gpus, COLS, ROWS_PER_GPU),
+            "rows": ROWS_PER_GPU * n_gpus, "cols": COLS, "rows_per_gpu": ROWS_PER_GPU,
+            "l2": "inputs_exceed_l2 (8 arrays x %.1f GiB per GPU, no flush needed)"
+                  % (ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
+            "parallelism": "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus if n_gpus > 1 else "1 GPU",
+            "kernel": "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tile-rows", type=int, default=16)
+    ap.add_argument("--vec", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.vec == 0:
+        args.vec = 4 if args.dtype == "f64" else 8
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fdtd_em_solver_b200 import synthetic as SY
+    from fdtd_em_solver_b200.engine import comm_unique_id
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    rows = ROWS_PER_GPU * n_gpus
+    dtype = "float64" if args.dtype == "f64" else "float32"
+    n_calls = 2 * (args.steps + args.warmup) + 64
+    e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
+                          row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
+                          tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps)
+    if world > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        e.comm_init(rank, world, bytes(ident.cpu().numpy().tobytes()))
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ("value") -------------------------------------------------
+    step = 0
+    e.run(step, args.warmup); step += args.warmup
+    fence()
+    launches0 = e.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.perf_counter()
+    e.run(step, args.steps); step += args.steps           # events on the library stream bracket exactly K steps
+    fence()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    st = e.stats()
+    ms = max_over_ranks(st["last_run_ms"])
+    launches = st["kernel_launches"] - launches0
+    cells = rows * COLS
+    value = cells * args.steps / (ms * 1e-3) / 1e9
+    halo_bytes = st["halo_bytes_sent"]
+
+    # ---- end to end through the host-facing API ("e2e") -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        owned = ROWS_PER_GPU
+        tdt = torch.float64
+        lo, hi = (1 if rank > 0 else 0), (1 if rank > 0 else 0) + owned
+        # host-resident inputs of this slab: the two coefficient planes, pinned, float64 (what
+        # Solver.solve hands over, solver.py:278-279); built once outside the timed region
+        eps_slab = torch.empty((owned + 1, COLS), dtype=tdt, pin_memory=True)
+        mu_slab = torch.empty((owned + 1, COLS), dtype=tdt, pin_memory=True)
+        eps_slab[:owned + lo].copy_(e.buffers[6][:owned + lo, :COLS].to(tdt))
+        mu_slab[:owned + lo].copy_(e.buffers[7][:owned + lo, :COLS].to(tdt))
+        h_out = torch.empty((owned, COLS), dtype=tdt, pin_memory=True)
+        torch.cuda.synchronize()
+        import ctypes as C
+        from fdtd_em_solver_b200 import _lib as L
+        # the host keeps only this rank's slab (first stored row = halo row above the slab, if any)
+        L.check(e.lib, e.handle, e.lib.fdtd_set_host_row_origin(e.handle, rank * ROWS_PER_GPU - lo))
+
+        def host_ptr(t):
+            return C.c_void_p(t.data_ptr())
+
+        fence()
+        t0 = time.perf_counter()
+        L.check(e.lib, e.handle, e.lib.fdtd_upload_coeffs(e.handle, host_ptr(eps_slab), host_ptr(mu_slab), COLS))
+        e.zero_fields()
+        e.run(0, args.steps)
+        hp = C.c_void_p(h_out.data_ptr() - lo * COLS * 8)        # h_out row 0 = first OWNED row
+        L.check(e.lib, e.handle, e.lib.fdtd_get_fields(e.handle, hp, None, None))
+        fence()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        h2d = 2 * (owned + lo) * COLS * 8
+        d2h = owned * COLS * 8
+        e2e = {"value": cells * args.steps / sec / 1e9, "unit": "Gcell-updates/s",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "seconds": sec, "checksum_h": float(h_out[:: max(1, owned // 64)].abs().sum()),
+               "what": "fdtd_upload_coeffs from pinned host float64 planes + fdtd_zero_fields + fdtd_run(K) + "
+                       "fdtd_get_fields(h) to pinned host, wall clock incl. all copies; per-GPU bytes"}
+        launches_e2e = e.stats()["kernel_launches"] - st["kernel_launches"]
+    else:
+        launches_e2e = 0
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    bpc = BYTES_PER_CELL[args.dtype]
+    per_gpu_gcells = value / n_gpus
+    achieved = per_gpu_gcells * bpc
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n_gpus),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ROWS_PER_GPU * COLS * bpc,
+                     "kernel": "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
+                         "double" if args.dtype == "f64" else "float", args.vec,
+                         "; 3 launches with halo overlap" if n_gpus > 1 else ""),
+                     "launch_ms": ms / args.steps},
+        "wall_s_timed_region": wall,
+    }
+    if n_gpus > 1:
+        line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
+                        "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.dtype)
+    if os.path.isfile(traffic_file):
+        try:
+            line["roofline"]["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    if n_gpus == 1 and not args.no_cpu:
+        v, n, dt = cpu_baseline()
+        line["cpu_baseline"] = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": "port",
+                                "sample": "%dx%d sub-grid of the C5 recipe, %d numpy steps in %.1f s (host has %d cores; "
+                                          "numpy ufuncs use 1)" % (CPU_SAMPLE + (n, dt, os.cpu_count()))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

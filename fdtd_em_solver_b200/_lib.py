@@ -13,7 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC_DIR = os.path.join(HERE, "csrc")
 INCLUDE_DIR = os.path.join(ROOT, "include")
-LIB_PATH = os.path.join(HERE, "libfdtd2d.so")
+# experiment hooks (tools/sweep.py): alternative builds side by side, e.g.
+#   FDTD_LIB_SUFFIX=_cs FDTD_NVCC_EXTRA='-DFDTD_ST_MOD=".cs"'
+LIB_PATH = os.path.join(HERE, "libfdtd2d%s.so" % os.environ.get("FDTD_LIB_SUFFIX", ""))
+NVCC_EXTRA = os.environ.get("FDTD_NVCC_EXTRA", "").split()
 
 F64, F32 = 0, 1
 SRC_POINT, SRC_RIGHT, SRC_LEFT, SRC_UP, SRC_DOWN = 0, 1, 2, 3, 4
@@ -50,6 +53,7 @@ SIGNATURES = {
     "fdtd_destroy": (C.c_int, [_P]),
     "fdtd_last_error": (C.c_char_p, [_P]),
     "fdtd_bind_buffers": (C.c_int, [_P] * 9),
+    "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),
     "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fdtd_fill_synthetic_coeffs": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "fdtd_set_fields": (C.c_int, [_P, _P, _P, _P]),
@@ -92,7 +96,7 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfdtd2d.so (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE_DIR] + sources() + ["-o", LIB_PATH + ".tmp"]
+    cmd = [nvcc] + NVCC_FLAGS + NVCC_EXTRA + ["-I", INCLUDE_DIR] + sources() + ["-o", LIB_PATH + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

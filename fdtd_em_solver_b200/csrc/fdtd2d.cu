@@ -54,7 +54,7 @@ struct NcclApi {
 
 struct fdtd_ctx {
     fdtd_config cfg{};
-    int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0;
+    int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0, host_row0 = 0;
     size_t esize = 8;
     void* gen[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [generation][h,ex,ey]
     void* epc = nullptr; void* muc = nullptr;
@@ -133,7 +133,7 @@ int h2d_plane(fdtd_ctx* c, void* base, const double* host, int64_t host_ld, int6
     if (n <= 0) return 0;
     T* dst = plane<T>(base, c, g0);
     if (!host) { CK(cudaMemset2DAsync(dst, c->pitch * sizeof(T), 0, ncols * sizeof(T), n, c->stream)); return 0; }
-    const double* src = host + g0 * host_ld;
+    const double* src = host + (g0 - c->host_row0) * host_ld;
     if (sizeof(T) == 8) {
         CK(cudaMemcpy2DAsync(dst, c->pitch * 8, src, host_ld * 8, ncols * 8, n, cudaMemcpyHostToDevice, c->stream));
         return 0;
@@ -158,7 +158,7 @@ template <typename T>
 int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int64_t g0, int64_t n, int64_t ncols) {
     if (n <= 0 || !host) return 0;
     const T* src = plane<T>(const_cast<void*>(base), c, g0);
-    double* dst = host + g0 * host_ld;
+    double* dst = host + (g0 - c->host_row0) * host_ld;
     if (sizeof(T) == 8) {
         CK(cudaMemcpy2DAsync(dst, host_ld * 8, src, c->pitch * 8, ncols * 8, n, cudaMemcpyDeviceToHost, c->stream));
         return 0;
@@ -398,9 +398,25 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->row_off = cfg->row_begin - c->halo_top;
     c->owned = cfg->row_end - cfg->row_begin;
     c->lrows = fdtd_local_rows(cfg);
-    if (c->cfg.tile_rows <= 0) c->cfg.tile_rows = 64;
-    if (c->cfg.vec <= 0) c->cfg.vec = cfg->dtype == FDTD_F64 ? 2 : 4;
-    if (c->cfg.block_warps <= 0) c->cfg.block_warps = 4;
+    {
+        // Launch geometry defaults (tools/sweep.py on the 8192 x 65536 slab): 256-bit lanes, 4 warps per CTA and
+        // SHORT tiles -- 16 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
+        // Small grids (the script configs, N = 139..442) get narrow single-warp tiles so that the launch
+        // still spreads over the 148 SMs.
+        const int va = cfg->dtype == FDTD_F64 ? 2 : 4;
+        const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 15) / 16);
+        const bool small = wide_tiles < 2 * 148;
+        if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 2 * va;
+        if (c->cfg.block_warps <= 0) c->cfg.block_warps = small ? 1 : 4;
+        if (c->cfg.tile_rows <= 0) {
+            c->cfg.tile_rows = 16;
+            if (small) {
+                const int64_t col_tiles = (cfg->cols + 1 + 32 * va - 1) / (32 * va);
+                const int64_t want_row_tiles = std::max<int64_t>(1, 592 / col_tiles);
+                c->cfg.tile_rows = (int)std::min<int64_t>(16, std::max<int64_t>(4, c->owned / want_row_tiles));
+            }
+        }
+    }
     auto bail = [&](cudaError_t ee, const char* what) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(ee);
         delete c; c = nullptr; return fail(nullptr, FDTD_ERR_CUDA, m);
@@ -454,6 +470,13 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
 
 #define NEED_BOUND() do { if (!c) return FDTD_ERR_ARG; if (!c->bound) return fail(c, FDTD_ERR_STATE, "buffers not bound"); \
     CK(cudaSetDevice(c->cfg.device)); } while (0)
+
+int fdtd_set_host_row_origin(fdtd_handle c, int64_t first_global_row) {
+    if (!c) return FDTD_ERR_ARG;
+    if (first_global_row < 0 || first_global_row > c->row_off) return fail(c, FDTD_ERR_ARG, "host arrays must start at or above the slab's first stored row");
+    c->host_row0 = first_global_row;
+    return 0;
+}
 
 int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_coef, int64_t host_ld) {
     NEED_BOUND();

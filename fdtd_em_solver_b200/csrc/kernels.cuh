@@ -28,6 +28,12 @@
 #define FDTD_MAX_SRC 16
 #define FDTD_MAX_RECT 24
 #define FDTD_MAX_PROBE 16
+#ifndef FDTD_LAUNCH_BOUNDS
+#define FDTD_LAUNCH_BOUNDS 256
+#endif
+#ifndef FDTD_CHUNK
+#define FDTD_CHUNK 4
+#endif
 
 namespace fdtd {
 
@@ -168,23 +174,6 @@ struct Exact {
         return v;
     }
 
-    // Is the plain interior formula wrong for any of h/ex/ey at index (i,j)?
-    __device__ __noinline__ bool special(int i, int j) const {
-        if (i <= 0 || i >= P.NR - 1 || j <= 0 || j >= P.NC - 1) return true;
-        for (int s = 0; s < P.n_src; ++s) {
-            const SrcStep<T>& q = P.src[s];
-            if (q.kind == 0) { if ((j == q.col && (i == q.row || i - 1 == q.row)) || (i == q.row && j - 1 == q.col)) return true; }
-            else if (q.kind <= 2) { if (j == q.col || j - 1 == q.col) return true; }
-            else if (q.kind == 3) { if (i == q.row + 1 || i == q.row + 2) return true; }
-            else { if (i == q.row || i == q.row + 1) return true; }
-        }
-        for (int r = 0; r < P.n_rect; ++r) {
-            if (inside(P.rh[r], i, j) || inside(P.rh[r], i - 1, j) || inside(P.rh[r], i, j - 1)) return true;
-            if (inside(P.rex[r], i, j) || inside(P.rey[r], i, j)) return true;
-        }
-        return false;
-    }
-
     __device__ __noinline__ void probe(int i, int j, T hv, T exv, T eyv) const {
         for (int k = 0; k < P.n_probe; ++k)
             if (P.probe_i[k] == i && P.probe_j[k] == j) {
@@ -212,52 +201,45 @@ __global__ void __launch_bounds__(256) step_exact(const __grid_constant__ StepPa
 // ---------------------------------------------------------------------------
 // Streaming kernel.
 // ---------------------------------------------------------------------------
-template <typename T, int V>
-struct Row {              // everything one lane loads for row i
-    T h[V], mu[V], ep[V], exn[V], ey[V];
-    T halo;               // lanes 0..4: h,mu,ex[i+1],ey at column jw-1; ey at column jw+W
-};
+#ifndef FDTD_LD_MOD
+#define FDTD_LD_MOD ".nc"            // inputs are never written by the running kernel (ping-pong)
+#endif
+#ifndef FDTD_ST_MOD
+#define FDTD_ST_MOD ""
+#endif
 
+// V consecutive elements, 128-bit (V*sizeof(T)==16) or 256-bit (==32) per lane
 template <typename T, int V>
 __device__ __forceinline__ void ldvec(T (&r)[V], const T* p) {
-    constexpr int N16 = V * (int)sizeof(T) / 16;
-    constexpr int E16 = 16 / (int)sizeof(T);
-#pragma unroll
-    for (int c = 0; c < N16; ++c) {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(p) + c);
-        if constexpr (sizeof(T) == 8) {
-            r[c * E16 + 0] = __hiloint2double(q.y, q.x);
-            r[c * E16 + 1] = __hiloint2double(q.w, q.z);
-        } else {
-            r[c * E16 + 0] = __int_as_float(q.x); r[c * E16 + 1] = __int_as_float(q.y);
-            r[c * E16 + 2] = __int_as_float(q.z); r[c * E16 + 3] = __int_as_float(q.w);
-        }
-    }
+    if constexpr (sizeof(T) == 8 && V == 2)
+        asm("ld.global" FDTD_LD_MOD ".v2.f64 {%0,%1}, [%2];" : "=d"(r[0]), "=d"(r[1]) : "l"(p));
+    else if constexpr (sizeof(T) == 8 && V == 4)
+        asm("ld.global" FDTD_LD_MOD ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+    else if constexpr (sizeof(T) == 4 && V == 4)
+        asm("ld.global" FDTD_LD_MOD ".v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(p));
+    else
+        asm("ld.global" FDTD_LD_MOD ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
 }
 
 template <typename T, int V>
 __device__ __forceinline__ void stvec(T* p, const T (&r)[V]) {
-    constexpr int N16 = V * (int)sizeof(T) / 16;
-    constexpr int E16 = 16 / (int)sizeof(T);
-#pragma unroll
-    for (int c = 0; c < N16; ++c) {
-        int4 q;
-        if constexpr (sizeof(T) == 8) {
-            q.x = __double2loint(r[c * E16 + 0]); q.y = __double2hiint(r[c * E16 + 0]);
-            q.z = __double2loint(r[c * E16 + 1]); q.w = __double2hiint(r[c * E16 + 1]);
-        } else {
-            q.x = __float_as_int(r[c * E16 + 0]); q.y = __float_as_int(r[c * E16 + 1]);
-            q.z = __float_as_int(r[c * E16 + 2]); q.w = __float_as_int(r[c * E16 + 3]);
-        }
-        reinterpret_cast<int4*>(p)[c] = q;
-    }
+    if constexpr (sizeof(T) == 8 && V == 2)
+        asm volatile("st.global" FDTD_ST_MOD ".v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(r[0]), "d"(r[1]) : "memory");
+    else if constexpr (sizeof(T) == 8 && V == 4)
+        asm volatile("st.global" FDTD_ST_MOD ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]) : "memory");
+    else if constexpr (sizeof(T) == 4 && V == 4)
+        asm volatile("st.global" FDTD_ST_MOD ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+    else
+        asm volatile("st.global" FDTD_ST_MOD ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]),
+                     "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
 }
 
-template <typename T, int V, bool MIXED>
-__device__ __forceinline__ void zero(T (&r)[V]) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) r[v] = T(0);
-}
+template <typename T, int V>
+struct Row {              // everything one lane loads for row i
+    T h[V], mu[V], ep[V], exn[V], ey[V];
+    T halo;               // lanes 0..4: h, mu, ex[i+1], ey at column jw-1; ey at column jw+W
+};
 
 template <typename T, int V, bool MIXED>
 struct Tile {
@@ -277,7 +259,10 @@ struct Tile {
 
     __device__ __forceinline__ void ld(T (&r)[V], const T* a, int i) const {
         if (row_ok(i) && col_ok()) ldvec<T, V>(r, a + off(i) + j);
-        else zero<T, V, MIXED>(r);
+        else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) r[v] = T(0);
+        }
     }
     // lanes 0,1,3,4 read row i; lane 2 reads ex row i+1
     __device__ __forceinline__ T ld_halo(int i) const {
@@ -291,12 +276,38 @@ struct Tile {
     }
 };
 
-// plain interior hn for V consecutive columns + the halo column (meaningful on lane 0)
-template <typename T, int V>
-__device__ __forceinline__ void plain_hn(T (&hn)[V], T& hn_halo, const T (&h)[V], const T (&mu)[V], const T (&exn)[V],
-                                         const T (&exc)[V], const T (&ey)[V], T halo, T exc_halo, T& exn_halo) {
+// h after the point-source writes (solver.py:176-180), operand already in a register
+template <typename T>
+__device__ __forceinline__ T h_old_reg(const StepParams<T>& P, int i, int jj, T h) {
+    for (int s = 0; s < P.n_src; ++s)
+        if (P.src[s].kind == 0 && P.src[s].row == i && P.src[s].col == jj) h = P.src[s].mag;
+    return h;
+}
+
+// hn_pre(i,jj) from register operands: plain curl, then the TF/SF fix-ups in list order, then reflector zeroing
+template <typename T>
+__device__ __forceinline__ T hn_exact_reg(const StepParams<T>& P, int i, int jj, T ho, T mu, T dex, T eyc, T eyr) {
+    T v = add(ho, mul(mu, sub(dex, sub(eyr, eyc))));
+    for (int s = 0; s < P.n_src; ++s) {
+        const SrcStep<T>& q = P.src[s];
+        if (q.kind == 1) { if (jj == q.col) v = add(ho, mul(mu, sub(dex, sub(eyr, add(eyc, q.magz))))); }
+        else if (q.kind == 2) { if (jj == q.col) v = add(v, mul(mu, P.last_mag)); }
+        else if (q.kind == 3) { if (i == q.row + 1) v = sub(v, mul(mu, P.last_mag)); }
+        else if (q.kind == 4) { if (i == q.row) v = sub(v, mul(mu, P.last_mag)); }
+    }
+    for (int r = 0; r < P.n_rect; ++r) if (inside(P.rh[r], i, jj)) v = T(0);
+    return v;
+}
+
+// New h of row i for the lane's V columns and for the halo column jw-1 (meaningful on lane 0).
+// MIXED: exact hn_pre (sources, reflectors) and h_old; otherwise the plain interior curl.
+template <typename T, int V, bool MIXED>
+__device__ __forceinline__ void row_hn(const StepParams<T>& P, int i, int j, int jw, T (&hn)[V], T& hn_halo, T (&ho)[V],
+                                       const T (&h)[V], const T (&mu)[V], const T (&exn)[V], const T (&exc)[V],
+                                       const T (&ey)[V], T halo, T exc_halo, T& exn_halo) {
     const unsigned full = 0xffffffffu;
-    const T h_l = __shfl_sync(full, halo, 0), mu_l = __shfl_sync(full, halo, 1);
+    T h_l = __shfl_sync(full, halo, 0);
+    const T mu_l = __shfl_sync(full, halo, 1);
     exn_halo = __shfl_sync(full, halo, 2);
     const T ey_l = __shfl_sync(full, halo, 3), ey_far = __shfl_sync(full, halo, 4);
     T ey_next = __shfl_down_sync(full, ey[0], 1);
@@ -304,9 +315,22 @@ __device__ __forceinline__ void plain_hn(T (&hn)[V], T& hn_halo, const T (&h)[V]
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : ey_next;
-        hn[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
+        const T dex = sub(exn[v], exc[v]);
+        if constexpr (MIXED) {
+            ho[v] = h_old_reg(P, i, j + v, h[v]);
+            hn[v] = hn_exact_reg(P, i, j + v, ho[v], mu[v], dex, ey[v], eyr);
+        } else {
+            ho[v] = h[v];
+            hn[v] = add(h[v], mul(mu[v], sub(dex, sub(eyr, ey[v]))));
+        }
     }
-    hn_halo = add(h_l, mul(mu_l, sub(sub(exn_halo, exc_halo), sub(ey[0], ey_l))));
+    const T dex_l = sub(exn_halo, exc_halo);
+    if constexpr (MIXED) {
+        h_l = h_old_reg(P, i, jw - 1, h_l);
+        hn_halo = hn_exact_reg(P, i, jw - 1, h_l, mu_l, dex_l, ey_l, ey[0]);
+    } else {
+        hn_halo = add(h_l, mul(mu_l, sub(dex_l, sub(ey[0], ey_l))));
+    }
 }
 
 template <typename T, int V, bool MIXED>
@@ -315,14 +339,13 @@ __device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb,
     const Tile<T, V, MIXED> t(P, jw, lane);
     const int j = t.j;
 
-    // prologue: exc = ex[ta], hnp = plain hn(ta-1)
+    // prologue: exc = ex[ta], hnp = hn_pre(ta-1)
     T exc[V], hnp[V], exc_halo;
     {
-        T h[V], mu[V], exm[V], ey[V], hh, dummy;
+        T h[V], mu[V], exm[V], ey[V], ho[V], hh;
         t.ld(h, P.h, ta - 1); t.ld(mu, P.muc, ta - 1); t.ld(exm, P.ex, ta - 1); t.ld(exc, P.ex, ta); t.ld(ey, P.ey, ta - 1);
         const T halo = t.ld_halo(ta - 1);
-        plain_hn<T, V>(hnp, hh, h, mu, exc, exm, ey, halo, T(0), dummy);
-        exc_halo = dummy;                  // lane 2 loaded ex[ta, jw-1]
+        row_hn<T, V, MIXED>(P, ta - 1, j, jw, hnp, hh, ho, h, mu, exc, exm, ey, halo, T(0), exc_halo);   // lane 2 loaded ex[ta, jw-1]
     }
 
     Row<T, V> cur;
@@ -331,34 +354,85 @@ __device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb,
         Row<T, V> nxt;
         if (i + 1 < tb) t.load(nxt, i + 1);
 
-        T hn[V], hn_halo, exn_halo;
-        plain_hn<T, V>(hn, hn_halo, cur.h, cur.mu, cur.exn, exc, cur.ey, cur.halo, exc_halo, exn_halo);
+        T hn[V], ho[V], hn_halo, exn_halo;
+        row_hn<T, V, MIXED>(P, i, j, jw, hn, hn_halo, ho, cur.h, cur.mu, cur.exn, exc, cur.ey, cur.halo, exc_halo, exn_halo);
         T hn_left = __shfl_up_sync(full, hn[V - 1], 1);
         if (lane == 0) hn_left = hn_halo;
 
-        T ho[V], exo[V], eyo[V];
+        T hout[V], exo[V], eyo[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const T hl = (v == 0) ? hn_left : hn[v > 0 ? v - 1 : 0];
-            ho[v] = hn[v];
-            exo[v] = add(exc[v], mul(cur.ep[v], sub(hn[v], hnp[v])));
-            eyo[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn[v], hl)));
+            hout[v] = hn[v];
+            exo[v] = add(exc[v], mul(cur.ep[v], sub(hn[v], hnp[v])));                     // solver.py:207
+            if constexpr (!MIXED) {
+                eyo[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn[v], hl)));                  // solver.py:208
+            } else {
+                const int jj = j + v;
+                T e = cur.ey[v];
+                if (jj >= 1 && jj <= P.NC - 1) e = sub(e, mul(cur.ep[v], sub(hn[v], hl)));
+                for (int s = 0; s < P.n_src; ++s)                                          // solver.py:211-217
+                    if (P.src[s].kind == 1 && P.src[s].col == jj && jj > 0)
+                        e = sub(e, mul(cur.ep[v], sub(sub(hn[v], P.src[s].mag), hl)));
+                eyo[v] = e;
+            }
         }
 
         const long long o = t.off(i) + j;
         if constexpr (!MIXED) {
-            stvec<T, V>(P.hn + o, ho); stvec<T, V>(P.exn + o, exo); stvec<T, V>(P.eyn + o, eyo);
+            stvec<T, V>(P.hn + o, hout); stvec<T, V>(P.exn + o, exo); stvec<T, V>(P.eyn + o, eyo);
         } else {
+            // left neighbours of this lane's first column, for the right wall (solver.py:232-235)
+            const T ho_lft = __shfl_up_sync(full, ho[V - 1], 1);
+            const T ex_lft = __shfl_up_sync(full, exo[V - 1], 1);
+            const T ey_lft = __shfl_up_sync(full, eyo[V - 1], 1);
+            const bool wall_row = (i <= 0 || i >= P.NR - 1);       // rows 0, NR-1, NR: closed form (up/down walls, edges)
             const Exact<T> X(P);
+            T hw[V], exw[V], eyw[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int jj = j + v;
+                hw[v] = hout[v]; exw[v] = exo[v]; eyw[v] = eyo[v];
                 if (jj > P.NC) continue;
-                const bool sp = X.special(i, jj);
-                if (i < P.NR && jj < P.NC) { if (sp) ho[v] = X.h_final(i, jj); P.hn[o + v] = ho[v]; }
-                if (jj < P.NC) { if (sp) exo[v] = X.ex_final(i, jj); P.exn[o + v] = exo[v]; }
-                if (i < P.NR) { if (sp) eyo[v] = X.ey_final(i, jj); P.eyn[o + v] = eyo[v]; }
-                if (P.n_probe) X.probe(i, jj, ho[v], exo[v], eyo[v]);
+                bool closed = wall_row;
+                if (jj == 0) {
+                    for (int s = 0; s < P.n_src; ++s) if (P.src[s].kind == 1 && P.src[s].col == 0) closed = true;   // wraps to NC-1
+                    if (P.absorb_l && V > 1) {                                             // solver.py:228-231
+                        hw[v] = add(mul(ho[0], P.oms), mul(ho[V > 1 ? 1 : 0], P.S));
+                        exw[v] = add(mul(exo[0], P.oms), mul(exo[V > 1 ? 1 : 0], P.S));
+                        eyw[v] = add(mul(eyo[0], P.oms), mul(eyo[V > 1 ? 1 : 0], P.S));
+                    }
+                }
+                if (P.absorb_r && (jj == P.NC - 1 || jj == P.NC)) {
+                    if (v == 0 && lane == 0) closed = true;                                // neighbour column is in another warp
+                    const T a = (v == 0) ? ho_lft : ho[v > 0 ? v - 1 : 0];
+                    const T b = (v == 0) ? ex_lft : exo[v > 0 ? v - 1 : 0];
+                    const T c = (v == 0) ? ey_lft : eyo[v > 0 ? v - 1 : 0];
+                    if (jj == P.NC - 1) { hw[v] = add(mul(ho[v], P.oms), mul(a, P.S)); exw[v] = add(mul(exo[v], P.oms), mul(b, P.S)); }
+                    else eyw[v] = add(mul(eyo[v], P.oms), mul(c, P.S));
+                }
+                for (int r = 0; r < P.n_rect; ++r) {                                       // solver.py:238-242
+                    if (inside(P.rex[r], i, jj)) exw[v] = T(0);
+                    if (inside(P.rey[r], i, jj)) eyw[v] = T(0);
+                }
+                if (closed) {
+                    if (i < P.NR && jj < P.NC) hw[v] = X.h_final(i, jj);
+                    if (jj < P.NC) exw[v] = X.ex_final(i, jj);
+                    if (i < P.NR) eyw[v] = X.ey_final(i, jj);
+                }
+                if (P.n_probe) X.probe(i, jj, hw[v], exw[v], eyw[v]);
+            }
+            if (i < P.NR && j + V <= P.NC) {                       // whole vector valid in all three arrays
+                stvec<T, V>(P.hn + o, hw); stvec<T, V>(P.exn + o, exw); stvec<T, V>(P.eyn + o, eyw);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int jj = j + v;
+                    if (jj > P.NC) continue;
+                    if (i < P.NR && jj < P.NC) P.hn[o + v] = hw[v];
+                    if (jj < P.NC) P.exn[o + v] = exw[v];
+                    if (i < P.NR) P.eyn[o + v] = eyw[v];
+                }
             }
         }
 #pragma unroll
@@ -366,6 +440,17 @@ __device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb,
         exc_halo = exn_halo;
         cur = nxt;
     }
+}
+
+// Separate (non-inlined) bodies: each gets its own register allocation, so the slow path's calls into
+// Exact cannot push spills into the streaming loop of the fast path.
+template <typename T, int V>
+__device__ __noinline__ void run_tile_mixed(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    run_tile<T, V, true>(P, ta, tb, jw, lane);
+}
+template <typename T, int V>
+__device__ __noinline__ void run_tile_fast(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    run_tile<T, V, false>(P, ta, tb, jw, lane);
 }
 
 // Does anything non-plain touch index rows [ta,tb) x cols [ja,jb)?  (hn of one row up / one column left included)
@@ -394,7 +479,7 @@ __device__ bool tile_is_mixed(const StepParams<T>& P, int ta, int tb, int ja, in
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256) step_stream(const __grid_constant__ StepParams<T> P) {
+__global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_constant__ StepParams<T> P) {
     constexpr int W = 32 * V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int jw = (blockIdx.x * (blockDim.x >> 5) + warp) * W;
@@ -402,8 +487,27 @@ __global__ void __launch_bounds__(256) step_stream(const __grid_constant__ StepP
     const int ta = P.row_lo + blockIdx.y * P.tile_rows;
     const int tb = min(ta + P.tile_rows, P.row_hi);
     if (ta >= tb) return;
-    if (tile_is_mixed(P, ta, tb, jw, jw + W)) run_tile<T, V, true>(P, ta, tb, jw, lane);
-    else run_tile<T, V, false>(P, ta, tb, jw, lane);
+    if (!tile_is_mixed(P, ta, tb, jw, jw + W)) {             // the common case, inlined: no call in its loop
+        run_tile<T, V, false>(P, ta, tb, jw, lane);
+        return;
+    }
+    // Classify in chunks of FDTD_CHUNK rows so that a wall row or a source row makes only its own chunk
+    // "mixed"; consecutive plain chunks are merged into one streaming pass.
+    int r = ta;
+    while (r < tb) {
+        int e = min(r + FDTD_CHUNK, tb);
+        if (tile_is_mixed(P, r, e, jw, jw + W)) {
+            run_tile_mixed<T, V>(P, r, e, jw, lane);
+        } else {
+            while (e < tb) {
+                const int e2 = min(e + FDTD_CHUNK, tb);
+                if (tile_is_mixed(P, e, e2, jw, jw + W)) break;
+                e = e2;
+            }
+            run_tile_fast<T, V>(P, r, e, jw, lane);
+        }
+        r = e;
+    }
 }
 
 // ---------------------------------------------------------------------------

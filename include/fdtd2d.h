@@ -94,6 +94,10 @@ const char* fdtd_last_error(fdtd_handle h);          /* h may be NULL: last erro
 int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
                       void* eps_coef, void* mu_coef);
 
+/* Host arrays handed to fdtd_upload_coeffs / fdtd_set_fields / fdtd_get_fields normally start at global
+ * row 0.  A rank that keeps only its slab on the host declares the global row its host arrays start at. */
+int fdtd_set_host_row_origin(fdtd_handle h, int64_t first_global_row);
+
 /* eps_coefficient_arr / mu_coefficient_arr (solver.py:278-279), GLOBAL host arrays (rows x cols,
  * leading dimension host_ld doubles); the context takes the rows it needs (incl. halo_top). */
 int fdtd_upload_coeffs(fdtd_handle h, const double* eps_coef, const double* mu_coef, int64_t host_ld);
