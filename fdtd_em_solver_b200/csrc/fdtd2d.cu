@@ -75,8 +75,8 @@ struct fdtd_ctx {
     double* probe_dev = nullptr;
     int64_t probe_cap = 0, probe_count = 0;
 
-    cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr, ev_int = nullptr;
     cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     double* snap_dev[2] = {nullptr, nullptr};
     void* stage = nullptr; size_t stage_bytes = 0;
@@ -304,19 +304,26 @@ int step_impl(fdtd_ctx* c, int64_t step) {
     if (!c->comm) {
         if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
     } else {
-        // interface strips first, halo exchange on the comm stream, interior meanwhile
+        // Interface strips on a high-priority stream, their rows sent over NCCL on the comm stream, the
+        // interior on the main stream -- all three overlap.  Dependencies of step n (A -> B):
+        //   edge(n)     after interior(n-1) [it overwrites A strip rows interior(n-1) still reads] and comm(n-1)
+        //   comm(n)     after edge(n)
+        //   interior(n) after edge(n-1) [it reads generation A strip rows that edge(n-1) wrote]; same stream as interior(n-1)
         const int64_t tr = c->cfg.tile_rows;
         const bool has_up = c->rank > 0, has_down = c->rank + 1 < c->nranks;
         int64_t a = has_up ? std::min(lo + tr, hi) : lo;
         int64_t b = has_down ? std::max(a, c->cfg.row_end - tr) : hi;
-        if (int rc = launch_rows<T>(c, P, lo, a, c->stream)) return rc;
-        if (int rc = launch_rows<T>(c, P, b, hi, c->stream)) return rc;
-        CK(cudaEventRecord(c->ev_bnd, c->stream));
+        CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
+        CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0));
+        if (int rc = launch_rows<T>(c, P, lo, a, c->edge_stream)) return rc;
+        if (int rc = launch_rows<T>(c, P, b, hi, c->edge_stream)) return rc;
+        CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
         CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
         if (int rc = exchange(c, c->cur ^ 1, c->comm_stream)) return rc;
         CK(cudaEventRecord(c->ev_comm, c->comm_stream));
         if (int rc = launch_rows<T>(c, P, a, b, c->stream)) return rc;
-        CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        CK(cudaEventRecord(c->ev_int, c->stream));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));      // main-stream order now implies "all owned rows written"
     }
     c->cur ^= 1;
     if (c->n_probe) c->probe_count++;
@@ -424,10 +431,14 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithPriority(&c->edge_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     cudaEventCreate(&c->ev_t0); cudaEventCreate(&c->ev_t1);
     cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming);
     for (int s = 0; s < 2; ++s) {
         cudaEventCreateWithFlags(&c->ev_packed[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming);
@@ -448,8 +459,8 @@ int fdtd_destroy(fdtd_handle c) {
         if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
         if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
     }
-    for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream}) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm, c->ev_int}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream, c->edge_stream}) if (s) cudaStreamDestroy(s);
     delete c;
     return 0;
 }
@@ -655,10 +666,12 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
             ++k;
         }
     }
+    if (c->comm) cudaStreamWaitEvent(c->stream, c->ev_comm, 0);      // the timed region ends after the last halo landed
     cudaEventRecord(c->ev_t1, c->stream);
     cudaError_t e1 = cudaStreamSynchronize(c->stream);
     cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);
     cudaError_t e3 = cudaStreamSynchronize(c->comm_stream);
+    if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(c->edge_stream);
     if (n_snapshots) *n_snapshots = k;
     if (rc) return rc;
     for (cudaError_t e : {e1, e2, e3})
@@ -686,6 +699,7 @@ int fdtd_sync(fdtd_handle c) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->copy_stream));
     CK(cudaStreamSynchronize(c->comm_stream));
+    CK(cudaStreamSynchronize(c->edge_stream));
     return 0;
 }
 

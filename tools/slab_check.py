@@ -1,0 +1,58 @@
+"""Run under torchrun: every rank steps its y-slab (halo rows over NCCL inside libfdtd2d); rank 0 also
+steps the whole grid on its own GPU and the gathered slabs must be bit-identical (fields and checksums)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from fdtd_em_solver_b200.engine import Engine, comm_unique_id
+from fdtd_em_solver_b200 import slab as SL
+from oracle import scenarios as SC           # only to build a seeded random case (inputs), not as a compute path
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict())]:
+    f, setup, times = SC.random_case(rows, cols, 3, walls=(False, False, False, True), n_steps=n_steps)
+    b, e_ = SL.split_rows(rows, world)[rank]
+    S = setup.courant
+    eng = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, row_begin=b,
+                 row_end=e_, device=local, **kw)
+    eng.upload_coefficients(setup.eps_coef, setup.mu_coef)
+    eng.set_sources(setup.pulses, times)
+    eng.set_reflectors(setup.reflectors)
+    eng.set_fields(f.h, f.ex, f.ey)
+    ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        ident.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    eng.comm_init(rank, world, ident.cpu().numpy().tobytes())
+    eng.run(0, n_steps)
+    h, ex, ey = eng.get_fields()
+    parts = [None] * world
+    dist.all_gather_object(parts, (b, e_, h[b:e_], ex[b:e_ + (1 if e_ == rows else 0)], ey[b:e_]))
+    if rank == 0:
+        whole = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, device=local, **kw)
+        whole.upload_coefficients(setup.eps_coef, setup.mu_coef)
+        whole.set_sources(setup.pulses, times)
+        whole.set_reflectors(setup.reflectors)
+        whole.set_fields(f.h, f.ex, f.ey)
+        whole.run(0, n_steps)
+        H, EX, EY = whole.get_fields()
+        gh = np.concatenate([p[2] for p in parts]); gex = np.concatenate([p[3] for p in parts])
+        gey = np.concatenate([p[4] for p in parts])
+        ok = np.array_equal(gh, H) and np.array_equal(gex, EX) and np.array_equal(gey, EY)
+        print("grid %dx%d world %d steps %d: %s  halo bytes/step/rank0 %d" % (
+            rows, cols, world, n_steps, "bit-identical" if ok else "MISMATCH",
+            eng.stats()["halo_bytes_sent"] // n_steps), flush=True)
+        assert ok
+        whole.close()
+    eng.close()
+    dist.barrier()
+if rank == 0:
+    print("SLAB_CHECK_OK", flush=True)
+dist.destroy_process_group()
