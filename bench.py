@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tile-rows", type=int, default=16)
+    ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--vec", type=int, default=0)
     ap.add_argument("--warps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")

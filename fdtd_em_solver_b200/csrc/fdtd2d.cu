@@ -407,16 +407,16 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->lrows = fdtd_local_rows(cfg);
     {
         // Launch geometry defaults (tools/sweep.py on the 8192 x 65536 slab): 256-bit lanes, 4 warps per CTA and
-        // SHORT tiles -- 16 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
+        // SHORT tiles -- 8 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
         // Small grids (the script configs, N = 139..442) get narrow single-warp tiles so that the launch
         // still spreads over the 148 SMs.
         const int va = cfg->dtype == FDTD_F64 ? 2 : 4;
-        const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 15) / 16);
+        const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 7) / 8);
         const bool small = wide_tiles < 2 * 148;
         if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 2 * va;
         if (c->cfg.block_warps <= 0) c->cfg.block_warps = small ? 1 : 4;
         if (c->cfg.tile_rows <= 0) {
-            c->cfg.tile_rows = 16;
+            c->cfg.tile_rows = 8;
             if (small) {
                 const int64_t col_tiles = (cfg->cols + 1 + 32 * va - 1) / (32 * va);
                 const int64_t want_row_tiles = std::max<int64_t>(1, 592 / col_tiles);
