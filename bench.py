@@ -146,7 +146,10 @@ def workload_config(args, n_gpus):
             "l2": "inputs_exceed_l2 (8 arrays x %.1f GiB per GPU, no flush needed)"
                   % (ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
             "parallelism": "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus if n_gpus > 1 else "1 GPU",
-            "kernel": "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)}
+            "kernel": "%s vec=%d tile_rows=%d warps=%d" % (
+                "step2_stream (2 steps per HBM pass) + masked step_stream frame passes" if args.temporal == 2
+                else "step_stream", args.vec, args.tile_rows, args.warps),
+            "temporal_blocking": args.temporal}
 
 
 def main():
@@ -158,13 +161,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--vec", type=int, default=0)
-    ap.add_argument("--warps", type=int, default=4)
+    ap.add_argument("--warps", type=int, default=2)
+    ap.add_argument("--temporal", type=int, default=2, choices=[1, 2],
+                    help="leapfrog steps per HBM pass (2 = temporal blocking, the default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.vec == 0:
-        args.vec = 4 if args.dtype == "f64" else 8
+        args.vec = 4
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +195,7 @@ def main():
     n_calls = 2 * (args.steps + args.warmup) + 64
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
-                          tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps)
+                          tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -294,17 +299,22 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ROWS_PER_GPU * COLS * bpc,
-                     "kernel": "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
+                     "algorithmic_bytes_per_launch": ROWS_PER_GPU * COLS * bpc * args.temporal,
+                     "kernel": ("fdtd::step2_stream<%s,%d>: one launch advances TWO steps (algorithmic bytes are counted per "
+                                "step, so frac > 1 is the temporal-blocking gain; DRAM-level traffic is in `traffic`)"
+                                % ("double" if args.dtype == "f64" else "float", 2 if args.dtype == "f64" else 4))
+                     if args.temporal == 2 else
+                     "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
                          "double" if args.dtype == "f64" else "float", args.vec,
                          "; 3 launches with halo overlap" if n_gpus > 1 else ""),
-                     "launch_ms": ms / args.steps},
+                     "launch_ms": ms / args.steps * (2 if args.temporal == 2 else 1),
+                     "steps_per_launch": args.temporal},
         "wall_s_timed_region": wall,
     }
     if n_gpus > 1:
         line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.dtype)
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s.json" % (args.dtype, "_temporal2" if args.temporal == 2 else ""))
     if os.path.isfile(traffic_file):
         try:
             line["roofline"]["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]

@@ -53,6 +53,8 @@ SIGNATURES = {
     "fdtd_destroy": (C.c_int, [_P]),
     "fdtd_last_error": (C.c_char_p, [_P]),
     "fdtd_bind_buffers": (C.c_int, [_P] * 9),
+    "fdtd_bind_scratch": (C.c_int, [_P, _P, _P, _P]),
+    "fdtd_set_temporal_blocking": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),
     "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fdtd_fill_synthetic_coeffs": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double]),

@@ -56,7 +56,18 @@ struct fdtd_ctx {
     fdtd_config cfg{};
     int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0, host_row0 = 0;
     size_t esize = 8;
-    void* gen[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [generation][h,ex,ey]
+    void* gen[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [generation][h,ex,ey]
+    bool has_scratch = false;       // generation 2 bound (needed by temporal blocking)
+    int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1 or 2)
+    std::vector<uint8_t> map_key;   // active-source signature the frame maps were built for
+    std::vector<uint8_t> h_skip, h_maskB, h_maskC;
+    unsigned char* d_skip = nullptr; unsigned char* d_maskB = nullptr; unsigned char* d_maskC = nullptr;
+    std::vector<int2> h_listB, h_listC;          // compact (block column, row tile) launch lists of the frame passes
+    int2* d_listB = nullptr; int2* d_listC = nullptr;
+    size_t d_list_cap = 0;
+    size_t d_skip_cap = 0, d_mask_cap = 0;
+    int nty = 0, ntx2 = 0, ntx1 = 0;
+    int64_t pair_launch_cells = 0;
     void* epc = nullptr; void* muc = nullptr;
     bool bound = false;
     int cur = 0;
@@ -76,7 +87,7 @@ struct fdtd_ctx {
     int64_t probe_cap = 0, probe_count = 0;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr, edge_stream = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr, ev_int = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr, ev_int = nullptr, ev_p3 = nullptr;
     cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     double* snap_dev[2] = {nullptr, nullptr};
     void* stage = nullptr; size_t stage_bytes = 0;
@@ -180,9 +191,10 @@ int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int6
     return 0;
 }
 
+int next_gen(const fdtd_ctx* c, int g) { return c->has_scratch ? (g + 1) % 3 : (g ^ 1); }
+
 template <typename T>
-int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step) {
-    const int a = c->cur, b = c->cur ^ 1;
+int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step, int a, int b) {
     P.h = (const T*)c->gen[a][0]; P.ex = (const T*)c->gen[a][1]; P.ey = (const T*)c->gen[a][2];
     P.muc = (const T*)c->muc; P.epc = (const T*)c->epc;
     P.hn = (T*)c->gen[b][0]; P.exn = (T*)c->gen[b][1]; P.eyn = (T*)c->gen[b][2];
@@ -213,20 +225,23 @@ int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step) {
     P.n_probe = c->n_probe;
     for (int k = 0; k < c->n_probe; ++k) { P.probe_i[k] = c->probe_i[k]; P.probe_j[k] = c->probe_j[k]; }
     P.probe_out = nullptr;
+    P.tile_mask = nullptr; P.mask_stride = 0; P.tile_list = nullptr;
     return 0;
 }
 
 template <typename T, int V>
-void launch_stream(const StepParams<T>& P, int WARPS, cudaStream_t s) {
+void launch_stream(const StepParams<T>& P, int WARPS, cudaStream_t s, int n_list) {
     const int ncol_tiles = (P.NC + 1 + 32 * V * WARPS - 1) / (32 * V * WARPS);
     const int nrow_tiles = (P.row_hi - P.row_lo + P.tile_rows - 1) / P.tile_rows;
     dim3 grid((unsigned)ncol_tiles, (unsigned)nrow_tiles);
+    if (P.tile_list) grid = dim3((unsigned)n_list, 1);
     fdtd::step_stream<T, V><<<grid, WARPS * 32, 0, s>>>(P);
 }
 
 template <typename T>
-int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, cudaStream_t s) {
+int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, cudaStream_t s, int n_list = 0) {
     if (row_hi <= row_lo) return 0;
+    if (P.tile_list && n_list == 0) return 0;
     P.row_lo = (int)row_lo; P.row_hi = (int)row_hi;
     if (c->cfg.kernel == FDTD_KERNEL_EXACT) {
         dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)(row_hi - row_lo));
@@ -235,8 +250,8 @@ int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, c
         const int v = c->cfg.vec, w = c->cfg.block_warps;
         constexpr int VA = sizeof(T) == 8 ? 2 : 4, VB = 2 * VA;
         if (w < 1 || w > 8) return fail(c, FDTD_ERR_ARG, "block_warps must be 1..8");
-        if (v == VA) launch_stream<T, VA>(P, w, s);
-        else if (v == VB) launch_stream<T, VB>(P, w, s);
+        if (v == VA) launch_stream<T, VA>(P, w, s, n_list);
+        else if (v == VB) launch_stream<T, VB>(P, w, s, n_list);
         else return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
     }
     c->stats.kernel_launches++;
@@ -294,7 +309,8 @@ int exchange(fdtd_ctx* c, int g, cudaStream_t s) {
 template <typename T>
 int step_impl(fdtd_ctx* c, int64_t step) {
     StepParams<T> P;
-    if (int rc = fill_params<T>(c, P, step)) return rc;
+    const int dst = next_gen(c, c->cur);
+    if (int rc = fill_params<T>(c, P, step, c->cur, dst)) return rc;
     if (c->n_probe) {
         if (int rc = ensure_probe_capacity(c, 1)) return rc;
         P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
@@ -319,17 +335,193 @@ int step_impl(fdtd_ctx* c, int64_t step) {
         if (int rc = launch_rows<T>(c, P, b, hi, c->edge_stream)) return rc;
         CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
         CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-        if (int rc = exchange(c, c->cur ^ 1, c->comm_stream)) return rc;
+        if (int rc = exchange(c, dst, c->comm_stream)) return rc;
         CK(cudaEventRecord(c->ev_comm, c->comm_stream));
         if (int rc = launch_rows<T>(c, P, a, b, c->stream)) return rc;
         CK(cudaEventRecord(c->ev_int, c->stream));
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));      // main-stream order now implies "all owned rows written"
     }
-    c->cur ^= 1;
+    c->cur = dst;
     if (c->n_probe) c->probe_count++;
     c->stats.steps++;
     c->stats.cell_updates += c->owned * c->cfg.cols;
     return 0;
+}
+
+// ---- temporal blocking (2 steps per HBM pass) ----------------------------------------------------------
+// Which two-step tiles must NOT be advanced by step2_stream, and which single-step tiles advance them instead.
+template <typename T>
+int build_frame_maps(fdtd_ctx* c, int64_t n) {
+    constexpr int V2 = sizeof(T) == 8 ? 2 : 4;
+    const int OUT = 30 * V2, LD = 32 * V2;
+    const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
+    const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == NR ? 1 : 0);
+    const int TR = c->cfg.tile_rows, W1 = 32 * c->cfg.vec;
+    // signature: which pulses are live in step n or n+1, plus the geometry knobs
+    std::vector<uint8_t> key;
+    for (int p = 0; p < c->n_src; ++p) {
+        uint8_t live = 0;
+        for (int64_t t = n; t <= n + 1; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
+        key.push_back(live);
+    }
+    key.push_back((uint8_t)TR); key.push_back((uint8_t)c->cfg.vec); key.push_back((uint8_t)c->n_rect); key.push_back((uint8_t)c->n_probe);
+    if (key == c->map_key && c->d_skip) return 0;
+    const int nty = (int)((hi - lo + TR - 1) / TR);
+    const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
+    c->nty = nty; c->ntx2 = ntx2; c->ntx1 = ntx1;
+    c->h_skip.assign((size_t)nty * ntx2, 0); c->h_maskB.assign((size_t)nty * ntx1, 0); c->h_maskC.assign((size_t)nty * ntx1, 0);
+    struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
+    std::vector<Box> mods;
+    const int64_t BIG = (int64_t)1 << 40;
+    for (int p = 0; p < c->n_src; ++p) {
+        if (!key[p]) continue;
+        const fdtd_source& q = c->src[p];
+        if (q.kind == FDTD_SRC_POINT) mods.push_back({q.row, q.row, q.col, q.col});
+        else if (q.kind == FDTD_SRC_RIGHT || q.kind == FDTD_SRC_LEFT) mods.push_back({-BIG, BIG, q.col, q.col});
+        else if (q.kind == FDTD_SRC_UP) mods.push_back({q.row + 1, q.row + 1, -BIG, BIG});
+        else mods.push_back({q.row, q.row, -BIG, BIG});
+    }
+    for (int r = 0; r < c->n_rect; ++r)
+        for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
+            if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
+    for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
+    int64_t two_step_cells = 0;
+    for (int ty = 0; ty < nty; ++ty) {
+        const int64_t ta = lo + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hi);
+        const bool rows_ok = ta - 1 >= 1 && tb <= NR - 2 && ta - 2 >= c->cfg.row_begin && tb + 1 <= c->cfg.row_end - 1;
+        for (int tx = 0; tx < ntx2; ++tx) {
+            const int64_t jw = (int64_t)tx * OUT - V2;
+            bool mixed = !rows_ok || jw < 1 || jw + LD - 1 > NC - 2;
+            if (!mixed)
+                for (const Box& m : mods)
+                    if (m.r0 <= tb + 2 && m.r1 >= ta - 3 && m.c0 <= jw + LD && m.c1 >= jw - 1) { mixed = true; break; }
+            if (!mixed) { two_step_cells += (tb - ta) * OUT; continue; }
+            c->h_skip[(size_t)ty * ntx2 + tx] = 1;
+            const int64_t c0 = (int64_t)tx * OUT, c1 = std::min<int64_t>(c0 + OUT - 1, NC);
+            for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) c->h_maskB[(size_t)ty * ntx1 + t1] = 1;
+        }
+    }
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx1; ++tx) {
+            if (!c->h_maskB[(size_t)ty * ntx1 + tx]) continue;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int y = ty + dy, x = tx + dx;
+                    if (y >= 0 && y < nty && x >= 0 && x < ntx1) c->h_maskC[(size_t)y * ntx1 + x] = 1;
+                }
+        }
+    c->pair_launch_cells = two_step_cells;
+    {
+        const int w = c->cfg.block_warps, nbx = (ntx1 + w - 1) / w;
+        c->h_listB.clear(); c->h_listC.clear();
+        for (int ty = 0; ty < nty; ++ty)
+            for (int bx = 0; bx < nbx; ++bx) {
+                bool anyB = false, anyC = false;
+                for (int t = bx * w; t < std::min(ntx1, (bx + 1) * w); ++t) {
+                    anyB |= c->h_maskB[(size_t)ty * ntx1 + t] != 0;
+                    anyC |= c->h_maskC[(size_t)ty * ntx1 + t] != 0;
+                }
+                if (anyB) c->h_listB.push_back(make_int2(bx, ty));
+                if (anyC) c->h_listC.push_back(make_int2(bx, ty));
+            }
+        const size_t need = std::max<size_t>(1, c->h_listC.size());
+        if (c->d_list_cap < need) {
+            if (c->d_listB) cudaFree(c->d_listB);
+            if (c->d_listC) cudaFree(c->d_listC);
+            CK(cudaMalloc(&c->d_listB, need * sizeof(int2))); CK(cudaMalloc(&c->d_listC, need * sizeof(int2)));
+            c->d_list_cap = need;
+        }
+    }
+    if (c->d_skip_cap < c->h_skip.size()) {
+        if (c->d_skip) cudaFree(c->d_skip);
+        CK(cudaMalloc(&c->d_skip, c->h_skip.size())); c->d_skip_cap = c->h_skip.size();
+    }
+    if (c->d_mask_cap < c->h_maskB.size()) {
+        if (c->d_maskB) cudaFree(c->d_maskB);
+        if (c->d_maskC) cudaFree(c->d_maskC);
+        CK(cudaMalloc(&c->d_maskB, c->h_maskB.size())); CK(cudaMalloc(&c->d_maskC, c->h_maskC.size()));
+        c->d_mask_cap = c->h_maskB.size();
+    }
+    // the previous pair's launches may still be reading the old maps
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->edge_stream));
+    CK(cudaMemcpyAsync(c->d_skip, c->h_skip.data(), c->h_skip.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_maskB, c->h_maskB.data(), c->h_maskB.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_maskC, c->h_maskC.data(), c->h_maskC.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_listB.empty())
+        CK(cudaMemcpyAsync(c->d_listB, c->h_listB.data(), c->h_listB.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_listC.empty())
+        CK(cudaMemcpyAsync(c->d_listC, c->h_listC.data(), c->h_listC.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->map_key = key;
+    return 0;
+}
+
+// Steps n and n+1 in one HBM pass: A -> B.  Frame tiles go A -> C (step n) -> B (step n+1) with masked single steps.
+template <typename T>
+int pair_impl(fdtd_ctx* c, int64_t n) {
+    constexpr int V2 = sizeof(T) == 8 ? 2 : 4;
+    if (int rc = build_frame_maps<T>(c, n)) return rc;
+    const int A = c->cur, B = (A + 1) % 3, Cg = (A + 2) % 3;
+    const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
+    if (c->n_probe) if (int rc = ensure_probe_capacity(c, 2)) return rc;
+    // pass 1 (frame + one ring of tiles, A -> C, step n) runs on the high-priority edge stream CONCURRENTLY with
+    // pass 2 (everything else, two steps at once, A -> B) on the main stream; pass 3 (frame, C -> B, step n+1)
+    // follows both.  The frame passes are compact launches over the listed tiles only.
+    // With slabs (fdtd_comm_init) the interface strips are part of the frame: generation C's halo rows are exchanged
+    // after pass 1 and generation B's after pass 3, both on the comm stream, hidden behind the two-step kernel.
+    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this pair
+    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
+    if (c->comm) CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0));      // halos of generation A have landed
+    {
+        StepParams<T> P;
+        if (int rc = fill_params<T>(c, P, n, A, Cg)) return rc;
+        if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+        P.tile_mask = c->d_maskC; P.mask_stride = c->ntx1; P.tile_list = c->d_listC;
+        if (int rc = launch_rows<T>(c, P, lo, hi, c->edge_stream, (int)c->h_listC.size())) return rc;
+        CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+    }
+    if (c->comm) {
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+        if (int rc = exchange(c, Cg, c->comm_stream)) return rc;
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    }
+    {
+        StepParams<T> P;
+        if (int rc = fill_params<T>(c, P, n, A, B)) return rc;
+        P.n_src = 0; P.n_rect = 0; P.n_probe = 0;
+        P.row_lo = (int)lo; P.row_hi = (int)hi;
+        const int w = c->cfg.block_warps;
+        dim3 grid((unsigned)((c->ntx2 + w - 1) / w), (unsigned)c->nty);
+        fdtd::step2_stream<T, V2><<<grid, w * 32, 0, c->stream>>>(P, c->d_skip, c->ntx2);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
+    if (c->comm) CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));           // halos of generation C have landed
+    {
+        StepParams<T> P;
+        if (int rc = fill_params<T>(c, P, n + 1, Cg, B)) return rc;
+        if (c->n_probe) P.probe_out = c->probe_dev + (size_t)(c->probe_count + 1) * c->n_probe * 3;
+        P.tile_mask = c->d_maskB; P.mask_stride = c->ntx1; P.tile_list = c->d_listB;
+        if (int rc = launch_rows<T>(c, P, lo, hi, c->stream, (int)c->h_listB.size())) return rc;
+    }
+    if (c->comm) {
+        CK(cudaEventRecord(c->ev_p3, c->stream));
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_p3, 0));
+        if (int rc = exchange(c, B, c->comm_stream)) return rc;
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    }
+    CK(cudaEventRecord(c->ev_int, c->stream));                  // "all owned rows of generation B written"
+    c->cur = B;
+    if (c->n_probe) c->probe_count += 2;
+    c->stats.steps += 2;
+    c->stats.cell_updates += 2 * c->owned * c->cfg.cols;
+    return 0;
+}
+
+int pair_any(fdtd_ctx* c, int64_t n) {
+    return c->cfg.dtype == FDTD_F64 ? pair_impl<double>(c, n) : pair_impl<float>(c, n);
 }
 
 int step_any(fdtd_ctx* c, int64_t step) {
@@ -413,7 +605,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
         const int va = cfg->dtype == FDTD_F64 ? 2 : 4;
         const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 7) / 8);
         const bool small = wide_tiles < 2 * 148;
-        if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 2 * va;
+        if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 4;     // 4 columns per lane: 256-bit (f64) / 128-bit (f32) accesses
         if (c->cfg.block_warps <= 0) c->cfg.block_warps = small ? 1 : 4;
         if (c->cfg.tile_rows <= 0) {
             c->cfg.tile_rows = 8;
@@ -439,6 +631,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_int, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_p3, cudaEventDisableTiming);
     for (int s = 0; s < 2; ++s) {
         cudaEventCreateWithFlags(&c->ev_packed[s], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming);
@@ -454,12 +647,14 @@ int fdtd_destroy(fdtd_handle c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->probe_dev) cudaFree(c->probe_dev);
     if (c->stage) cudaFree(c->stage);
+    for (unsigned char* m : {c->d_skip, c->d_maskB, c->d_maskC}) if (m) cudaFree(m);
+    for (int2* m : {c->d_listB, c->d_listC}) if (m) cudaFree(m);
     for (int s = 0; s < 2; ++s) {
         if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
         if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
         if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
     }
-    for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm, c->ev_int}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm, c->ev_int, c->ev_p3}) if (e) cudaEventDestroy(e);
     for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream, c->edge_stream}) if (s) cudaStreamDestroy(s);
     delete c;
     return 0;
@@ -476,6 +671,27 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
     c->gen[0][0] = h0; c->gen[1][0] = h1; c->gen[0][1] = ex0; c->gen[1][1] = ex1; c->gen[0][2] = ey0; c->gen[1][2] = ey1;
     c->epc = eps_coef; c->muc = mu_coef;
     c->bound = true; c->cur = 0;
+    return 0;
+}
+
+int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
+    if (!c) return FDTD_ERR_ARG;
+    for (void* p : {h2, ex2, ey2}) {
+        if (!p) return fail(c, FDTD_ERR_ARG, "null device buffer");
+        if (reinterpret_cast<uintptr_t>(p) % 128) return fail(c, FDTD_ERR_ARG, "device buffers must be 128-byte aligned");
+    }
+    if (!c->bound) return fail(c, FDTD_ERR_STATE, "bind the two field generations first");
+    if (c->cur == 2) return fail(c, FDTD_ERR_STATE, "scratch generation currently holds the fields");
+    c->gen[2][0] = h2; c->gen[2][1] = ex2; c->gen[2][2] = ey2;
+    c->has_scratch = true;
+    return 0;
+}
+
+int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
+    if (!c) return FDTD_ERR_ARG;
+    if (steps_per_pass != 1 && steps_per_pass != 2) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1 or 2");
+    if (steps_per_pass == 2 && !c->has_scratch) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch");
+    c->temporal = steps_per_pass;
     return 0;
 }
 
@@ -522,7 +738,7 @@ int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, 
 
 int fdtd_zero_fields(fdtd_handle c) {
     NEED_BOUND();
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < (c->has_scratch ? 3 : 2); ++g)
         for (int f = 0; f < 3; ++f)
             CK(cudaMemsetAsync(c->gen[g][f], 0, (size_t)c->lrows * c->pitch * c->esize, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -655,8 +871,14 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     int64_t k = 0;
     int rc = 0;
     CK(cudaEventRecord(c->ev_t0, c->stream));
+    const bool pairs = c->temporal == 2 && c->has_scratch && c->cfg.kernel == FDTD_KERNEL_STREAM;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
-        if ((rc = step_any(c, n))) break;
+        const bool snap_after_first = snaps && (n + 1) % snapshot_every == 0;
+        if (pairs && n + 1 < first_step + n_steps && !snap_after_first &&
+            (c->n_src == 0 || n + 1 < c->table_len)) {
+            if ((rc = pair_any(c, n))) break;
+            ++n;                                         // two steps done
+        } else if ((rc = step_any(c, n))) break;
         if (snaps && (n + 1) % snapshot_every == 0) {
             if (k >= max_snapshots) { rc = fail(c, FDTD_ERR_ARG, "snapshot buffer too small"); break; }
             double* dst = snapshots_host + (size_t)k * c->owned * c->cfg.cols;

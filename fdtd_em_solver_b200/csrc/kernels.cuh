@@ -71,6 +71,9 @@ struct StepParams {
     SrcStep<T> src[FDTD_MAX_SRC];
     RectI rh[FDTD_MAX_RECT], rex[FDTD_MAX_RECT], rey[FDTD_MAX_RECT];
     int probe_i[FDTD_MAX_PROBE], probe_j[FDTD_MAX_PROBE];
+    const unsigned char* tile_mask;   // optional: [row tile][warp tile] != 0 -> compute, else skip (temporal-blocking frame)
+    const int2* tile_list;            // optional compact launch: blockIdx.x -> (block column, row tile)
+    int mask_stride;
 };
 
 __device__ __forceinline__ bool inside(const RectI& r, int i, int j) {
@@ -279,6 +282,7 @@ struct Tile {
 // h after the point-source writes (solver.py:176-180), operand already in a register
 template <typename T>
 __device__ __forceinline__ T h_old_reg(const StepParams<T>& P, int i, int jj, T h) {
+#pragma unroll 1
     for (int s = 0; s < P.n_src; ++s)
         if (P.src[s].kind == 0 && P.src[s].row == i && P.src[s].col == jj) h = P.src[s].mag;
     return h;
@@ -288,6 +292,7 @@ __device__ __forceinline__ T h_old_reg(const StepParams<T>& P, int i, int jj, T 
 template <typename T>
 __device__ __forceinline__ T hn_exact_reg(const StepParams<T>& P, int i, int jj, T ho, T mu, T dex, T eyc, T eyr) {
     T v = add(ho, mul(mu, sub(dex, sub(eyr, eyc))));
+#pragma unroll 1
     for (int s = 0; s < P.n_src; ++s) {
         const SrcStep<T>& q = P.src[s];
         if (q.kind == 1) { if (jj == q.col) v = add(ho, mul(mu, sub(dex, sub(eyr, add(eyc, q.magz))))); }
@@ -295,8 +300,110 @@ __device__ __forceinline__ T hn_exact_reg(const StepParams<T>& P, int i, int jj,
         else if (q.kind == 3) { if (i == q.row + 1) v = sub(v, mul(mu, P.last_mag)); }
         else if (q.kind == 4) { if (i == q.row) v = sub(v, mul(mu, P.last_mag)); }
     }
+#pragma unroll 1
     for (int r = 0; r < P.n_rect; ++r) if (inside(P.rh[r], i, jj)) v = T(0);
     return v;
+}
+
+// ey after solver.py:208 and :211-217 for one cell, operands in registers (hl = hn_pre(i, jj-1))
+template <typename T>
+__device__ __forceinline__ T ey_exact_reg(const StepParams<T>& P, int jj, T ey, T ep, T hn, T hl) {
+    T e = ey;
+    if (jj >= 1 && jj <= P.NC - 1) e = sub(e, mul(ep, sub(hn, hl)));
+#pragma unroll 1
+    for (int s = 0; s < P.n_src; ++s)
+        if (P.src[s].kind == 1 && P.src[s].col == jj && jj > 0) e = sub(e, mul(ep, sub(sub(hn, P.src[s].mag), hl)));
+    return e;
+}
+
+// Rows 0, NR-1 and NR (up/down walls, solver.py:220-227, and the untouched ex edge rows) for an interior column
+// 1 <= jj <= NC-2: the whole 2x2(+1) stencil is fetched in ONE batch of independent loads and evaluated in registers
+// (the generic Exact recursion costs ~15 dependent memory round trips per cell).  Same operations, same order.
+template <typename T>
+__device__ __noinline__ void wall_row_cell(const StepParams<T>& P, int i, int jj, T& hw, T& exw, T& eyw) {
+    const int r0 = (i == 0) ? 0 : P.NR - 2;
+    const long long o0 = (long long)(r0 - P.row_off) * P.pitch + jj;
+    T h[2][2], mu[2][2], ep[2], ey[2][3], ex[3][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const long long o = o0 + a * P.pitch;
+        h[a][0] = __ldg(P.h + o - 1); h[a][1] = __ldg(P.h + o);
+        mu[a][0] = __ldg(P.muc + o - 1); mu[a][1] = __ldg(P.muc + o);
+        ep[a] = __ldg(P.epc + o);
+        ey[a][0] = __ldg(P.ey + o - 1); ey[a][1] = __ldg(P.ey + o); ey[a][2] = __ldg(P.ey + o + 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { ex[a][0] = __ldg(P.ex + o0 + a * P.pitch - 1); ex[a][1] = __ldg(P.ex + o0 + a * P.pitch); }
+    T ho[2][2], hn[2][2], eyp[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            ho[a][b] = h_old_reg(P, r0 + a, jj - 1 + b, h[a][b]);
+            hn[a][b] = hn_exact_reg(P, r0 + a, jj - 1 + b, ho[a][b], mu[a][b], sub(ex[a + 1][b], ex[a][b]), ey[a][b], ey[a][b + 1]);
+        }
+    const T exp1 = add(ex[1][1], mul(ep[1], sub(hn[1][1], hn[0][1])));          // ex_pre(r0+1, jj)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) eyp[a] = ey_exact_reg(P, jj, ey[a][1], ep[a], hn[a][1], hn[a][0]);
+    if (i == 0) {
+        hw = P.absorb_u ? add(mul(ho[0][1], P.oms), mul(ho[1][1], P.S)) : hn[0][1];
+        exw = P.absorb_u ? add(mul(ex[0][1], P.oms), mul(exp1, P.S)) : ex[0][1];
+        eyw = P.absorb_u ? add(mul(eyp[0], P.oms), mul(eyp[1], P.S)) : eyp[0];
+    } else if (i == P.NR - 1) {
+        hw = P.absorb_d ? add(mul(ho[1][1], P.oms), mul(ho[0][1], P.S)) : hn[1][1];
+        exw = exp1;
+        eyw = P.absorb_d ? add(mul(eyp[1], P.oms), mul(eyp[0], P.S)) : eyp[1];
+    } else {
+        exw = P.absorb_d ? add(mul(ex[2][1], P.oms), mul(exp1, P.S)) : ex[2][1];
+    }
+#pragma unroll 1
+    for (int r = 0; r < P.n_rect; ++r) {
+        if (inside(P.rex[r], i, jj)) exw = T(0);
+        if (inside(P.rey[r], i, jj)) eyw = T(0);
+    }
+}
+
+// Walls (solver.py:220-235), reflector E zeroing (:238-242), closed-form fallbacks, store and probe for ONE cell
+// of a mixed tile.  own = values at (i,jj); lft/rgt = values one column to the left/right (h_old, ex_pre, ey_pre).
+template <typename T>
+__device__ __noinline__ void finish_cell(const StepParams<T>& P, int i, int jj, bool no_left_neighbour, long long o,
+                                         T hn, T ho, T exo, T eyo, T ho_l, T ex_l, T ey_l, T ho_r, T ex_r, T ey_r) {
+    if (jj > P.NC) return;
+    T hw = hn, exw = exo, eyw = eyo;
+    bool closed = (i <= 0 || i >= P.NR - 1);                // rows 0, NR-1, NR: up/down walls and untouched edges
+    if (jj == 0) {
+#pragma unroll 1
+        for (int s = 0; s < P.n_src; ++s) if (P.src[s].kind == 1 && P.src[s].col == 0) closed = true;   // wraps to NC-1
+        if (P.absorb_l) {
+            hw = add(mul(ho, P.oms), mul(ho_r, P.S));
+            exw = add(mul(exo, P.oms), mul(ex_r, P.S));
+            eyw = add(mul(eyo, P.oms), mul(ey_r, P.S));
+        }
+    }
+    if (P.absorb_r && (jj == P.NC - 1 || jj == P.NC)) {
+        if (no_left_neighbour) closed = true;               // the neighbour column belongs to another warp
+        if (jj == P.NC - 1) { hw = add(mul(ho, P.oms), mul(ho_l, P.S)); exw = add(mul(exo, P.oms), mul(ex_l, P.S)); }
+        else eyw = add(mul(eyo, P.oms), mul(ey_l, P.S));
+    }
+#pragma unroll 1
+    for (int r = 0; r < P.n_rect; ++r) {
+        if (inside(P.rex[r], i, jj)) exw = T(0);
+        if (inside(P.rey[r], i, jj)) eyw = T(0);
+    }
+    const Exact<T> X(P);
+    if (closed) {
+        if ((i <= 0 || i >= P.NR - 1) && jj >= 1 && jj <= P.NC - 2) {
+            wall_row_cell<T>(P, i, jj, hw, exw, eyw);
+        } else {                                            // corner columns, TF/SF wrap at column 0, lone last column
+            if (i < P.NR && jj < P.NC) hw = X.h_final(i, jj);
+            if (jj < P.NC) exw = X.ex_final(i, jj);
+            if (i < P.NR) eyw = X.ey_final(i, jj);
+        }
+    }
+    if (i < P.NR && jj < P.NC) P.hn[o] = hw;
+    if (jj < P.NC) P.exn[o] = exw;
+    if (i < P.NR) P.eyn[o] = eyw;
+    if (P.n_probe) X.probe(i, jj, hw, exw, eyw);
 }
 
 // New h of row i for the lane's V columns and for the halo column jw-1 (meaningful on lane 0).
@@ -365,17 +472,8 @@ __device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb,
             const T hl = (v == 0) ? hn_left : hn[v > 0 ? v - 1 : 0];
             hout[v] = hn[v];
             exo[v] = add(exc[v], mul(cur.ep[v], sub(hn[v], hnp[v])));                     // solver.py:207
-            if constexpr (!MIXED) {
-                eyo[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn[v], hl)));                  // solver.py:208
-            } else {
-                const int jj = j + v;
-                T e = cur.ey[v];
-                if (jj >= 1 && jj <= P.NC - 1) e = sub(e, mul(cur.ep[v], sub(hn[v], hl)));
-                for (int s = 0; s < P.n_src; ++s)                                          // solver.py:211-217
-                    if (P.src[s].kind == 1 && P.src[s].col == jj && jj > 0)
-                        e = sub(e, mul(cur.ep[v], sub(sub(hn[v], P.src[s].mag), hl)));
-                eyo[v] = e;
-            }
+            if constexpr (!MIXED) eyo[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn[v], hl)));        // solver.py:208
+            else eyo[v] = ey_exact_reg(P, j + v, cur.ey[v], cur.ep[v], hn[v], hl);
         }
 
         const long long o = t.off(i) + j;
@@ -386,53 +484,12 @@ __device__ __forceinline__ void run_tile(const StepParams<T>& P, int ta, int tb,
             const T ho_lft = __shfl_up_sync(full, ho[V - 1], 1);
             const T ex_lft = __shfl_up_sync(full, exo[V - 1], 1);
             const T ey_lft = __shfl_up_sync(full, eyo[V - 1], 1);
-            const bool wall_row = (i <= 0 || i >= P.NR - 1);       // rows 0, NR-1, NR: closed form (up/down walls, edges)
-            const Exact<T> X(P);
-            T hw[V], exw[V], eyw[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const int jj = j + v;
-                hw[v] = hout[v]; exw[v] = exo[v]; eyw[v] = eyo[v];
-                if (jj > P.NC) continue;
-                bool closed = wall_row;
-                if (jj == 0) {
-                    for (int s = 0; s < P.n_src; ++s) if (P.src[s].kind == 1 && P.src[s].col == 0) closed = true;   // wraps to NC-1
-                    if (P.absorb_l && V > 1) {                                             // solver.py:228-231
-                        hw[v] = add(mul(ho[0], P.oms), mul(ho[V > 1 ? 1 : 0], P.S));
-                        exw[v] = add(mul(exo[0], P.oms), mul(exo[V > 1 ? 1 : 0], P.S));
-                        eyw[v] = add(mul(eyo[0], P.oms), mul(eyo[V > 1 ? 1 : 0], P.S));
-                    }
-                }
-                if (P.absorb_r && (jj == P.NC - 1 || jj == P.NC)) {
-                    if (v == 0 && lane == 0) closed = true;                                // neighbour column is in another warp
-                    const T a = (v == 0) ? ho_lft : ho[v > 0 ? v - 1 : 0];
-                    const T b = (v == 0) ? ex_lft : exo[v > 0 ? v - 1 : 0];
-                    const T c = (v == 0) ? ey_lft : eyo[v > 0 ? v - 1 : 0];
-                    if (jj == P.NC - 1) { hw[v] = add(mul(ho[v], P.oms), mul(a, P.S)); exw[v] = add(mul(exo[v], P.oms), mul(b, P.S)); }
-                    else eyw[v] = add(mul(eyo[v], P.oms), mul(c, P.S));
-                }
-                for (int r = 0; r < P.n_rect; ++r) {                                       // solver.py:238-242
-                    if (inside(P.rex[r], i, jj)) exw[v] = T(0);
-                    if (inside(P.rey[r], i, jj)) eyw[v] = T(0);
-                }
-                if (closed) {
-                    if (i < P.NR && jj < P.NC) hw[v] = X.h_final(i, jj);
-                    if (jj < P.NC) exw[v] = X.ex_final(i, jj);
-                    if (i < P.NR) eyw[v] = X.ey_final(i, jj);
-                }
-                if (P.n_probe) X.probe(i, jj, hw[v], exw[v], eyw[v]);
-            }
-            if (i < P.NR && j + V <= P.NC) {                       // whole vector valid in all three arrays
-                stvec<T, V>(P.hn + o, hw); stvec<T, V>(P.exn + o, exw); stvec<T, V>(P.eyn + o, eyw);
-            } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const int jj = j + v;
-                    if (jj > P.NC) continue;
-                    if (i < P.NR && jj < P.NC) P.hn[o + v] = hw[v];
-                    if (jj < P.NC) P.exn[o + v] = exw[v];
-                    if (i < P.NR) P.eyn[o + v] = eyw[v];
-                }
+                const int l = v > 0 ? v - 1 : 0, r = v + 1 < V ? v + 1 : V - 1;
+                finish_cell<T>(P, i, j + v, v == 0 && lane == 0, o + v, hn[v], ho[v], exo[v], eyo[v],
+                               v == 0 ? ho_lft : ho[l], v == 0 ? ex_lft : exo[l], v == 0 ? ey_lft : eyo[l],
+                               ho[r], exo[r], eyo[r]);
             }
         }
 #pragma unroll
@@ -482,11 +539,14 @@ template <typename T, int V>
 __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_constant__ StepParams<T> P) {
     constexpr int W = 32 * V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jw = (blockIdx.x * (blockDim.x >> 5) + warp) * W;
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (P.tile_list) { const int2 t = P.tile_list[blockIdx.x]; bx = t.x; by = t.y; }
+    const int jw = (bx * (blockDim.x >> 5) + warp) * W;
     if (jw > P.NC) return;                                   // index space has NC+1 columns
-    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int ta = P.row_lo + by * P.tile_rows;
     const int tb = min(ta + P.tile_rows, P.row_hi);
     if (ta >= tb) return;
+    if (P.tile_mask && !P.tile_mask[(long long)by * P.mask_stride + jw / W]) return;
     if (!tile_is_mixed(P, ta, tb, jw, jw + W)) {             // the common case, inlined: no call in its loop
         run_tile<T, V, false>(P, ta, tb, jw, lane);
         return;
@@ -508,6 +568,117 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
         }
         r = e;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Temporal blocking: TWO leapfrog steps per HBM pass (generation A -> generation B = A + 2 steps).
+//
+// Only for tiles whose two-step dependency cone touches no wall, source, reflector or probe; the host
+// marks all other tiles in `skip` and advances them with two masked single-step launches through a third
+// generation (fdtd2d.cu: pair_impl).  Per warp: 32 lanes x V columns are LOADED, stage 1 (step n) is
+// computed for all of them, stage 2 (step n+1) trails one row behind in registers, and only lanes 1..30
+// store: lane 0 and lane 31 are sacrificial halo lanes (their neighbour values are garbage), so the tile
+// stride is 30*V columns and no scalar halo loads exist.  Same rounding order as the single-step kernel, so the
+// result is bit-identical to two single steps.  Algorithmic traffic: 8 words per cell per TWO steps.
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ void run_tile2(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int j = jw + lane * V;
+    const long long pitch = P.pitch;
+    auto at = [&](const T* a, int i) { return a + (long long)(i - P.row_off) * pitch + j; };
+    auto right_of = [&](const T (&x)[V], int v) {            // value in column j+v+1
+        const T nb = __shfl_down_sync(full, x[0], 1);
+        return (v + 1 < V) ? x[v + 1 < V ? v + 1 : 0] : nb;
+    };
+
+    T ex0c[V], hn1p[V], mu_p[V], ep_p[V], ex1p[V], ey1p[V], hn2p[V];
+    {   // prologue: hn1[ta-2] and ex0[ta-1]
+        T h[V], mu[V], exm[V], ey[V];
+        ldvec<T, V>(h, at(P.h, ta - 2)); ldvec<T, V>(mu, at(P.muc, ta - 2)); ldvec<T, V>(exm, at(P.ex, ta - 2));
+        ldvec<T, V>(ex0c, at(P.ex, ta - 1)); ldvec<T, V>(ey, at(P.ey, ta - 2));
+        const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+            hn1p[v] = add(h[v], mul(mu[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
+            mu_p[v] = ep_p[v] = ex1p[v] = ey1p[v] = hn2p[v] = T(0);
+        }
+    }
+    Row<T, V> cur;
+    auto load = [&](Row<T, V>& r, int i) {
+        ldvec<T, V>(r.h, at(P.h, i)); ldvec<T, V>(r.mu, at(P.muc, i)); ldvec<T, V>(r.ep, at(P.epc, i));
+        ldvec<T, V>(r.exn, at(P.ex, i + 1)); ldvec<T, V>(r.ey, at(P.ey, i));
+    };
+    load(cur, ta - 1);
+    for (int i = ta - 1; i <= tb; ++i) {                     // stage-1 row i, stage-2 row i-1
+        Row<T, V> nxt;
+        if (i < tb) load(nxt, i + 1);
+        // ---- stage 1: step n on row i
+        T hn1[V], ex1[V], ey1[V];
+        {
+            const T nb = __shfl_down_sync(full, cur.ey[0], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T eyr = (v + 1 < V) ? cur.ey[v + 1 < V ? v + 1 : 0] : nb;
+                hn1[v] = add(cur.h[v], mul(cur.mu[v], sub(sub(cur.exn[v], ex0c[v]), sub(eyr, cur.ey[v]))));
+            }
+            const T lf = __shfl_up_sync(full, hn1[V - 1], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T hl = (v == 0) ? lf : hn1[v > 0 ? v - 1 : 0];
+                ex1[v] = add(ex0c[v], mul(cur.ep[v], sub(hn1[v], hn1p[v])));
+                ey1[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn1[v], hl)));
+            }
+        }
+        // ---- stage 2: step n+1 on row r = i-1 (its ex1[r+1] is the ex1 just computed)
+        if (i >= ta) {
+            const int r = i - 1;
+            T hn2[V];
+            const T nb = __shfl_down_sync(full, ey1p[0], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T eyr = (v + 1 < V) ? ey1p[v + 1 < V ? v + 1 : 0] : nb;
+                hn2[v] = add(hn1p[v], mul(mu_p[v], sub(sub(ex1[v], ex1p[v]), sub(eyr, ey1p[v]))));
+            }
+            if (r >= ta) {
+                const T lf = __shfl_up_sync(full, hn2[V - 1], 1);
+                T ex2[V], ey2[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const T hl = (v == 0) ? lf : hn2[v > 0 ? v - 1 : 0];
+                    ex2[v] = add(ex1p[v], mul(ep_p[v], sub(hn2[v], hn2p[v])));
+                    ey2[v] = sub(ey1p[v], mul(ep_p[v], sub(hn2[v], hl)));
+                }
+                if (lane >= 1 && lane <= 30) {
+                    const long long o = (long long)(r - P.row_off) * pitch + j;
+                    stvec<T, V>(P.hn + o, hn2); stvec<T, V>(P.exn + o, ex2); stvec<T, V>(P.eyn + o, ey2);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) hn2p[v] = hn2[v];
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            ex0c[v] = cur.exn[v]; hn1p[v] = hn1[v]; mu_p[v] = cur.mu[v]; ep_p[v] = cur.ep[v];
+            ex1p[v] = ex1[v]; ey1p[v] = ey1[v];
+        }
+        cur = nxt;
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step2_stream(const __grid_constant__ StepParams<T> P,
+                                                                   const unsigned char* __restrict__ skip, int skip_stride) {
+    constexpr int OUT = 30 * V;                              // columns stored per warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tx >= skip_stride) return;
+    if (skip[(long long)blockIdx.y * skip_stride + tx]) return;
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    run_tile2<T, V>(P, ta, tb, tx * OUT - V, lane);
 }
 
 // ---------------------------------------------------------------------------

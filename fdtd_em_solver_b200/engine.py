@@ -68,7 +68,7 @@ def build_source_tables(pulses, times):
 class Engine:
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
@@ -107,6 +107,20 @@ class Engine:
         L.check(self.lib, self.handle, self.lib.fdtd_bind_buffers(self.handle, *[C.c_void_p(b.data_ptr()) for b in self.buffers]))
         self.first_bad = None
         self._keep = None
+        self.temporal = 1
+        if temporal == 2:
+            self.enable_temporal_blocking()
+
+    def enable_temporal_blocking(self, steps_per_pass=2):
+        """Two leapfrog steps per HBM pass in run(): needs a third generation of h/ex/ey (3 more buffers)."""
+        torch = self.torch
+        if steps_per_pass == 2 and len(self.buffers) == 8:
+            extra = [torch.zeros((self.lrows, self.pitch), dtype=self.buffers[0].dtype, device=self.device) for _ in range(3)]
+            torch.cuda.synchronize(self.device)
+            L.check(self.lib, self.handle, self.lib.fdtd_bind_scratch(self.handle, *[C.c_void_p(b.data_ptr()) for b in extra]))
+            self.buffers += extra
+        L.check(self.lib, self.handle, self.lib.fdtd_set_temporal_blocking(self.handle, int(steps_per_pass)))
+        self.temporal = int(steps_per_pass)
 
     # ---- static inputs -------------------------------------------------------------------
     def upload_coefficients(self, eps_coef, mu_coef):

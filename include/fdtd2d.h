@@ -94,6 +94,14 @@ const char* fdtd_last_error(fdtd_handle h);          /* h may be NULL: last erro
 int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
                       void* eps_coef, void* mu_coef);
 
+/* Temporal blocking (BASELINE.json north_star (1)): with a THIRD generation of h/ex/ey bound, fdtd_run advances
+ * TWO leapfrog steps per HBM pass wherever the two-step dependency cone touches no wall, source, reflector,
+ * probe or slab interface (kernel step2_stream), and advances the remaining frame of tiles with two masked
+ * single-step launches through the third generation.  Results are bit-identical to single stepping.
+ * With fdtd_comm_init active the slab interface strips belong to the frame and exchange their halo rows every step. */
+int fdtd_bind_scratch(fdtd_handle h, void* h2, void* ex2, void* ey2);
+int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
+
 /* Host arrays handed to fdtd_upload_coeffs / fdtd_set_fields / fdtd_get_fields normally start at global
  * row 0.  A rank that keeps only its slab on the host declares the global row its host arrays start at. */
 int fdtd_set_host_row_origin(fdtd_handle h, int64_t first_global_row);

@@ -221,3 +221,54 @@ def test_cuda_against_reference_golden_vectors():
         assert np.array_equal(h, g["final_h"]) and sha(ex) == str(g["sha_ex"]) and sha(ey) == str(g["sha_ey"]), name
         assert len(stack) == int(g["n_snapshots"]) and sha(stack) == str(g["sha_stack"]), name
         e.close()
+
+
+@pytest.mark.parametrize("shape,tile_rows,warps", [((200, 900), 8, 4), ((131, 517), 4, 2), ((64, 300), 16, 1)])
+def test_temporal_blocking_two_steps_per_pass_bitwise(shape, tile_rows, warps):
+    """fdtd_run with 2 steps per HBM pass (step2_stream + masked frame passes) == oracle, every snapshot/probe."""
+    rows, cols = shape
+    for seed, k in ((1, 0), (2, 3), (3, 5), (4, 2)):
+        f, setup, times = SC.random_case(rows, cols, seed, walls=WALLS[(seed * 3) % 16], n_steps=17)
+        cells = [(0, 0), (rows // 2, cols // 2), (rows - 1, cols - 1), (5, cols // 3)]
+        f.raw_probes = [(i, j, []) for i, j in cells]
+        e = _engine_for(f, setup, times, kernel="stream", tile_rows=tile_rows, block_warps=warps, temporal=2)
+        e.set_probes(cells)
+        launches0 = e.stats()["kernel_launches"]
+        if k:
+            want = np.array(R.run_saving(f, setup, times, k))
+            got = e.run(0, len(times), snapshot_every=k, total_calls=len(times))
+            assert got.shape == want.shape and np.array_equal(got, want), (seed, k)
+        else:
+            R.run(f, setup, times)
+            e.run(0, len(times))
+            assert e.stats()["kernel_launches"] - launches0 == 3 * (len(times) // 2) + len(times) % 2
+        _same(e, f, "temporal blocking seed %d" % seed)
+        raw = e.probes()
+        for c, (i, j, series) in enumerate(f.raw_probes):
+            assert np.array_equal(raw[:, c, :], np.array(series)), (seed, c)
+        e.close()
+
+
+def test_temporal_blocking_interior_only_and_fp32():
+    """No sources/reflectors: almost every tile goes through the two-step kernel.  fp32: identical bits to single steps."""
+    from fdtd_em_solver_b200.engine import Engine
+    f, setup, times = SC.random_case(300, 2000, 9, n_steps=12, with_sources=False, with_rects=False)
+    e = _engine_for(f, setup, times, kernel="stream", tile_rows=8, temporal=2)
+    R.run(f, setup, times)
+    e.run(0, len(times))
+    _same(e, f, "interior two-step")
+    e.close()
+    f, setup, times = SC.random_case(150, 1200, 10, n_steps=10)
+    outs = []
+    for temporal in (1, 2):
+        rows, cols = f.h.shape
+        S = setup.courant
+        e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, dtype="float32",
+                   tile_rows=8, temporal=temporal)
+        e.upload_coefficients(setup.eps_coef, setup.mu_coef); e.set_sources(setup.pulses, times)
+        e.set_reflectors(setup.reflectors); e.set_fields(f.h, f.ex, f.ey)
+        e.run(0, len(times))
+        outs.append(e.get_fields())
+        e.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

@@ -16,7 +16,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict())]:
+for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
+                                (97, 300, 13, dict(tile_rows=4, temporal=2)), (1500, 4100, 25, dict(temporal=2)),
+                                (2000, 9000, 16, dict(temporal=2, block_warps=2))]:
     f, setup, times = SC.random_case(rows, cols, 3, walls=(False, False, False, True), n_steps=n_steps)
     b, e_ = SL.split_rows(rows, world)[rank]
     S = setup.courant
@@ -46,8 +48,8 @@ for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 2
         gh = np.concatenate([p[2] for p in parts]); gex = np.concatenate([p[3] for p in parts])
         gey = np.concatenate([p[4] for p in parts])
         ok = np.array_equal(gh, H) and np.array_equal(gex, EX) and np.array_equal(gey, EY)
-        print("grid %dx%d world %d steps %d: %s  halo bytes/step/rank0 %d" % (
-            rows, cols, world, n_steps, "bit-identical" if ok else "MISMATCH",
+        print("grid %dx%d world %d steps %d %s: %s  halo bytes/step/rank0 %d" % (
+            rows, cols, world, n_steps, kw, "bit-identical" if ok else "MISMATCH",
             eng.stats()["halo_bytes_sent"] // n_steps), flush=True)
         assert ok
         whole.close()

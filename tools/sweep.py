@@ -11,8 +11,9 @@ ap.add_argument("--cols", type=int, default=65536)
 ap.add_argument("--dtype", default="float64")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--configs", default="")
+ap.add_argument("--temporal", type=int, default=1)
 a = ap.parse_args()
-e, times = synthetic.make_engine(a.rows, a.cols, dtype=a.dtype, n_calls=4096)
+e, times = synthetic.make_engine(a.rows, a.cols, dtype=a.dtype, n_calls=4096, temporal=a.temporal)
 bytes_per_cell = 64 if a.dtype == "float64" else 32
 va = 2 if a.dtype == "float64" else 4
 cfgs = [(v, tr, w) for v in (va, 2 * va) for tr in (32, 64, 128, 256) for w in (2, 4, 8)]
@@ -25,5 +26,5 @@ for v, tr, w in cfgs:
     e.run(n, a.steps); n += a.steps
     ms = e.stats()["last_run_ms"] / a.steps
     g = a.rows * a.cols / ms / 1e6
-    print(json.dumps(dict(vec=v, tile_rows=tr, warps=w, ms_per_step=round(ms, 4), gcells=round(g, 2),
+    print(json.dumps(dict(temporal=a.temporal, vec=v, tile_rows=tr, warps=w, ms_per_step=round(ms, 4), gcells=round(g, 2),
                           gbs=round(g * bytes_per_cell, 1))), flush=True)
