@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--vec", type=int, default=0)
-    ap.add_argument("--warps", type=int, default=2)
+    ap.add_argument("--warps", type=int, default=1)
     ap.add_argument("--temporal", type=int, default=2, choices=[1, 2],
                     help="leapfrog steps per HBM pass (2 = temporal blocking, the default)")
     ap.add_argument("--no-e2e", action="store_true")
