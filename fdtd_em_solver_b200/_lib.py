@@ -38,6 +38,13 @@ class Source(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("row", C.c_int64), ("col", C.c_int64)]
 
 
+class Shape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("a", C.c_int64 * 6), ("eps", C.c_double), ("mu", C.c_double)]
+
+
+SHAPE_RECT, SHAPE_QUARTER, SHAPE_CONVEX = 0, 1, 2
+
+
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("cell_updates", C.c_int64), ("kernel_launches", C.c_int64),
                 ("halo_bytes_sent", C.c_int64), ("last_run_ms", C.c_double)]
@@ -57,6 +64,7 @@ SIGNATURES = {
     "fdtd_set_temporal_blocking": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),
     "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "fdtd_paint_coeffs": (C.c_int, [_P, C.c_int32, C.POINTER(Shape), C.c_double, C.c_double, C.c_double]),
     "fdtd_fill_synthetic_coeffs": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "fdtd_set_fields": (C.c_int, [_P, _P, _P, _P]),
     "fdtd_get_fields": (C.c_int, [_P, _P, _P, _P]),

@@ -736,6 +736,36 @@ int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, 
     return 0;
 }
 
+int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double eps_background, double mu_background,
+                      double dt_over_ds) {
+    NEED_BOUND();
+    if (n < 0 || (n > 0 && !shapes)) return fail(c, FDTD_ERR_ARG, "bad shape list");
+    std::vector<fdtd::ShapeDev> host((size_t)std::max(n, 1));
+    for (int k = 0; k < n; ++k) {
+        if (shapes[k].kind < FDTD_SHAPE_RECT || shapes[k].kind > FDTD_SHAPE_CONVEX) return fail(c, FDTD_ERR_ARG, "bad shape kind");
+        host[k].kind = shapes[k].kind; host[k].pad = 0;
+        for (int q = 0; q < 6; ++q) host[k].a[q] = shapes[k].a[q];
+        host[k].eps = shapes[k].eps; host[k].mu = shapes[k].mu;
+    }
+    fdtd::ShapeDev* dev = nullptr;
+    CK(cudaMalloc(&dev, host.size() * sizeof(fdtd::ShapeDev)));
+    CK(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(fdtd::ShapeDev), cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)c->lrows);
+    if (c->cfg.dtype == FDTD_F64)
+        fdtd::paint_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
+    else
+        fdtd::paint_coeffs<float><<<grid, 256, 0, c->stream>>>((float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
+    c->stats.kernel_launches++;
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(c, FDTD_ERR_CUDA, std::string("paint_coeffs: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return 0;
+}
+
 int fdtd_zero_fields(fdtd_handle c) {
     NEED_BOUND();
     for (int g = 0; g < (c->has_scratch ? 3 : 2); ++g)

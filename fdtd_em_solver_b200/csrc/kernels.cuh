@@ -733,4 +733,46 @@ __global__ void synth_coeffs(T* epc, T* muc, long long pitch, int lrows, int col
     muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
 }
 
+struct ShapeDev { int kind, pad; long long a[6]; double eps, mu; };
+
+__device__ __forceinline__ bool convex_hit(const ShapeDev& s, long long r, long long c) {
+    // python: for j in range(-rad,-disp): cell (ci+i, cj+j+disp); for j in range(disp,rad): cell (ci+i, cj+j-disp);
+    // i in range(-rad,rad), i*i+j*j < rad*rad; an index k in [-n,n) addresses k mod n, anything else is skipped
+    const long long ci = s.a[0], cj = s.a[1], rad = s.a[2], disp = s.a[3], n = s.a[4];
+    for (int wr = 0; wr < 2; ++wr) {
+        const long long i = (wr ? r - n : r) - ci;
+        if (i < -rad || i >= rad) continue;
+        for (int wc = 0; wc < 2; ++wc) {
+            const long long cc = wc ? c - n : c;
+            const long long j1 = cc - cj - disp;                  // first cap: j in [-rad, -disp)
+            if (j1 >= -rad && j1 < -disp && i * i + j1 * j1 < rad * rad) return true;
+            const long long j2 = cc - cj + disp;                  // second cap: j in [disp, rad)
+            if (j2 >= disp && j2 < rad && i * i + j2 * j2 < rad * rad) return true;
+        }
+    }
+    return false;
+}
+
+template <typename T>
+__global__ void paint_coeffs(T* epc, T* muc, long long pitch, int lrows, int cols, int row_off, int NR,
+                             const ShapeDev* __restrict__ shapes, int n_shapes, double eps_bg, double mu_bg, double dtds) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    const long long i = (long long)row_off + l;
+    if (j >= cols || l >= lrows || i >= NR) return;
+    double eps = eps_bg, mu = mu_bg;
+    for (int k = 0; k < n_shapes; ++k) {
+        const ShapeDev& s = shapes[k];
+        bool hit;
+        if (s.kind == 0) hit = i >= s.a[0] && i < s.a[1] && j >= s.a[2] && j < s.a[3];
+        else if (s.kind == 1) {
+            const long long x = i - s.a[0], y = (long long)j - s.a[1], d2 = x * x + y * y, in = s.a[2] - s.a[3];
+            hit = s.a[2] * s.a[2] > d2 && d2 > in * in && x < 0 && y > 0;
+        } else hit = convex_hit(s, i, j);
+        if (hit) { eps = s.eps; mu = s.mu; }
+    }
+    epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
+    muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
+}
+
 }  // namespace fdtd

@@ -129,6 +129,18 @@ class Engine:
             raise ValueError("coefficient arrays must be (rows, cols)")
         L.check(self.lib, self.handle, self.lib.fdtd_upload_coeffs(self.handle, _ptr(e), _ptr(m), self.cols))
 
+    def paint_coefficients(self, shapes, dt_over_ds, eps_background=EPSILON, mu_background=MU):
+        """Device-side MaterialArray painting + coefficient build.  `shapes`: [(kind, (a0..), eps_abs, mu_abs), ...]
+        in painting order (see include/fdtd2d.h fdtd_shape)."""
+        arr = (L.Shape * max(len(shapes), 1))()
+        for k, (kind, a, eps, mu) in enumerate(shapes):
+            arr[k].kind = kind
+            for q, v in enumerate(a):
+                arr[k].a[q] = int(v)
+            arr[k].eps, arr[k].mu = float(eps), float(mu)
+        L.check(self.lib, self.handle, self.lib.fdtd_paint_coeffs(self.handle, len(shapes), arr, float(eps_background),
+                                                                 float(mu_background), float(dt_over_ds)))
+
     def fill_synthetic_coefficients(self, seed, dt_over_ds):
         L.check(self.lib, self.handle, self.lib.fdtd_fill_synthetic_coeffs(self.handle, int(seed), float(dt_over_ds),
                                                                           EPSILON, MU))

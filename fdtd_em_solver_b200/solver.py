@@ -40,7 +40,7 @@ class Solver:
     """reference solver.py:14-349."""
 
     def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
-                 dtype="float64", device=0, kernel="stream"):
+                 dtype="float64", device=0, kernel="stream", material_on_device=False):
         self.points_per_wavelength = points_per_wavelength
         self.stability = stability
         self.n_max = math.sqrt(eps_r_max * mu_r_max)
@@ -79,6 +79,7 @@ class Solver:
 
         # device side
         self._dtype, self._device, self._kernel = dtype, device, kernel
+        self._material_on_device = material_on_device
         self._engine = None
         self._engine_key = None
         self._host = None           # (h, ex, ey) host copies valid for the current step, or None
@@ -121,7 +122,7 @@ class Solver:
 
     # ------------------------------------------------------------------ scene
     def create_material(self):
-        self.material = MaterialArray(self.size, self.length_x, self.length_y)
+        self.material = MaterialArray(self.size, self.length_x, self.length_y, on_device=self._material_on_device)
         return self.material
 
     def set_reflect_square(self, upper_left, lower_right):
@@ -177,7 +178,10 @@ class Solver:
 
     # ------------------------------------------------------------------ device plumbing
     def _coefficients(self):
-        """reference solver.py:278-279."""
+        """reference solver.py:278-279 (skipped on the host when the material is painted on the device)."""
+        if not self.material.on_host and self.material.ops_complete:
+            self.eps_coefficient_arr = self.mu_coefficient_arr = ("device", len(self.material.ops))
+            return
         self.eps_coefficient_arr = (self.dt / self.ds) * (1 / self.material.eps_arr)
         self.mu_coefficient_arr = (self.dt / self.ds) * (1 / self.material.mu_arr)
 
@@ -202,7 +206,10 @@ class Solver:
                   tuple((d["i"], d["j"]) for d in self.recorded_energies),
                   tuple(id(p) for p in self.pulses), np.asarray(times).tobytes())
         if static != self._static_key:
-            e.upload_coefficients(self.eps_coefficient_arr, self.mu_coefficient_arr)
+            if isinstance(self.eps_coefficient_arr, tuple):          # painted on the device from the recorded shapes
+                e.paint_coefficients(self.material.ops, self.dt / self.ds)
+            else:
+                e.upload_coefficients(self.eps_coefficient_arr, self.mu_coefficient_arr)
             e.set_reflectors(self.reflectors if self.reflect else [])
             e.set_probes([(d["i"], d["j"]) for d in self.recorded_energies])
             e.set_sources(self.pulses, times)
@@ -217,12 +224,12 @@ class Solver:
         if not self.recorded_energies:
             return
         raw = self._engine.probes()
-        eps, mu = self.material.eps_arr, self.material.mu_arr
+        cells = [self.material.cell(d["i"], d["j"]) for d in self.recorded_energies]
         for rec in raw[self._probe_seen:]:
             for k, d in enumerate(self.recorded_energies):
-                i, j = d["i"], d["j"]
+                eps_ij, mu_ij = cells[k]
                 hv, exv, eyv = (np.float64(v) for v in rec[k])
-                d["energies"].append(0.5 * ((eps[i][j] * (exv ** 2 + eyv ** 2) + mu[i][j] * hv ** 2)))
+                d["energies"].append(0.5 * ((eps_ij * (exv ** 2 + eyv ** 2) + mu_ij * hv ** 2)))
         self._probe_seen = len(raw)
 
     def _run_device(self, times, snapshot_every=0):
@@ -358,30 +365,114 @@ class Solver:
 
 
 class MaterialArray:
-    """reference solver.py:352-475: host-side painting of absolute eps/mu per cell."""
+    """reference solver.py:352-475: painting of absolute eps/mu per cell.
 
-    def __init__(self, size, real_size_x, real_size_y, eps_array=None):
-        self.eps_arr = np.full((size, size), 1.0) * EPSILON if eps_array is None else eps_array
-        self.mu_arr = np.full((size, size), 1.0) * MU
+    Every painter also records its shape (in grid indices) in `self.ops`; with `on_device=True` no host arrays are
+    allocated and the solver paints the coefficient planes on the GPU from that list (fdtd_paint_coeffs) -- the route
+    for grids whose eps/mu arrays do not fit in host RAM.  `eps_arr` / `mu_arr` then materialise lazily on access."""
+
+    def __init__(self, size, real_size_x, real_size_y, eps_array=None, on_device=False):
         self.size = size
         self.length_x = real_size_x
         self.length_y = real_size_y
+        self.ops = []                      # [(kind, (ints...), eps_abs, mu_abs)] in painting order
+        self.ops_complete = eps_array is None
+        self._eps = eps_array
+        self._mu = None
+        if not (on_device and eps_array is None):
+            self._allocate()
+
+    def _allocate(self):
+        if self._eps is None:
+            self._eps = np.full((self.size, self.size), 1.0) * EPSILON
+        self._mu = np.full((self.size, self.size), 1.0) * MU
+
+    def _host(self):
+        """Materialise the host arrays by replaying the recorded shapes (device-painted materials only)."""
+        if self._mu is None:
+            self._allocate()
+            ops, self.ops = self.ops, []
+            for kind, a, eps, mu in ops:
+                self._apply(kind, a, eps / EPSILON, mu / MU, eps, mu)
+            self.ops = ops
+        return self
+
+    eps_arr = property(lambda self: self._host()._eps, lambda self, v: (self._host(), setattr(self, "_eps", v), setattr(self, "ops_complete", False)) and None)
+    mu_arr = property(lambda self: self._host()._mu, lambda self, v: (self._host(), setattr(self, "_mu", v), setattr(self, "ops_complete", False)) and None)
+
+    @property
+    def on_host(self):
+        return self._mu is not None
+
+    def cell(self, i, j):
+        """(eps, mu) of one cell without materialising the arrays (used by the energy probes)."""
+        if self.on_host:
+            return self._eps[i][j], self._mu[i][j]
+        n = self.size
+        i, j = (i + n if i < 0 else i), (j + n if j < 0 else j)
+        eps, mu = np.float64(1.0 * EPSILON), np.float64(1.0 * MU)
+        for kind, a, e, m in self.ops:
+            if kind == 0:
+                hit = a[0] <= i < a[1] and a[2] <= j < a[3]
+            elif kind == 1:
+                x, y = i - a[0], j - a[1]
+                hit = a[2] ** 2 > x * x + y * y > (a[2] - a[3]) ** 2 and x < 0 and y > 0
+            else:
+                ci, cj, rad, disp, _ = a
+                hit = False
+                for ii in (i - ci, i - n - ci):
+                    for cc in (j, j - n):
+                        for jj, lo, hi in ((cc - cj - disp, -rad, -disp), (cc - cj + disp, disp, rad)):
+                            if -rad <= ii < rad and lo <= jj < hi and ii * ii + jj * jj < rad * rad:
+                                hit = True
+            if hit:
+                eps, mu = np.float64(e), np.float64(m)
+        return eps, mu
 
     def convert(self, si_unit):
         if si_unit == self.length_x:
             return self.size
         return int((si_unit / self.length_x) * self.size)
 
-    def _fill(self, rows, cols, epsilon_rel, mu_rel):
-        self.eps_arr[rows, cols] = epsilon_rel * EPSILON
-        self.mu_arr[rows, cols] = mu_rel * MU
+    def _record(self, kind, a, epsilon_rel, mu_rel):
+        eps, mu = epsilon_rel * EPSILON, mu_rel * MU
+        self.ops.append((kind, tuple(int(v) for v in a), eps, mu))
+        if self.on_host:
+            self._apply(kind, a, epsilon_rel, mu_rel, eps, mu)
+
+    def _apply(self, kind, a, epsilon_rel, mu_rel, eps, mu):
+        n = self.size
+        if kind == 0:
+            rows, cols = slice(a[0], a[1]), slice(a[2], a[3])
+        elif kind == 1:
+            di = np.arange(-a[0], n - a[0])[:, None]
+            dj = np.arange(-a[1], n - a[1])[None, :]
+            d2 = di ** 2 + dj ** 2
+            mask = (a[2] ** 2 > d2) & (d2 > (a[2] - a[3]) ** 2) & (di < 0) & (dj > 0)
+            self._eps[mask] = eps
+            self._mu[mask] = mu
+            return
+        else:
+            ci, cj, radius, displacer, _ = a
+            i = np.arange(-radius, radius)[:, None]
+            for js, shift in ((np.arange(-radius, -displacer), displacer), (np.arange(displacer, radius), -displacer)):
+                j = js[None, :]
+                rr, cc = np.broadcast_arrays(ci + i, cj + j + shift)
+                keep = (i ** 2 + j ** 2 < radius ** 2) & (rr >= -n) & (rr < n) & (cc >= -n) & (cc < n)
+                self._eps[rr[keep] % n, cc[keep] % n] = eps
+                self._mu[rr[keep] % n, cc[keep] % n] = mu
+            return
+        self._eps[rows, cols] = eps
+        self._mu[rows, cols] = mu
 
     def set_material_rect(self, upper_left, lower_right, epsilon_rel, mu_rel=1, convert=True):
         """Rows end-exclusive, columns end-INCLUSIVE (reference solver.py:374-375)."""
         if convert:
             upper_left = [self.convert(v) for v in upper_left]
             lower_right = [self.convert(v) for v in lower_right]
-        self._fill(slice(upper_left[0], lower_right[0]), slice(upper_left[1], lower_right[1] + 1), epsilon_rel, mu_rel)
+        r0, r1, _ = slice(upper_left[0], lower_right[0]).indices(self.size)      # python slice clipping
+        c0, c1, _ = slice(upper_left[1], lower_right[1] + 1).indices(self.size)
+        self._record(0, (r0, max(r0, r1), c0, max(c0, c1)), epsilon_rel, mu_rel)
 
     def set_material_convex(self, center: tuple, radius, thickness, epsilon_rel, mu_rel=1, convert=True):
         """Two circular caps facing each other (reference solver.py:377-409), vectorised.
@@ -395,13 +486,7 @@ class MaterialArray:
         else:
             displacer = radius - thickness // 2
             ci, cj = center[0], center[1]
-        n = self.size
-        i = np.arange(-radius, radius)[:, None]
-        for js, shift in ((np.arange(-radius, -displacer), displacer), (np.arange(displacer, radius), -displacer)):
-            j = js[None, :]
-            rr, cc = np.broadcast_arrays(ci + i, cj + j + shift)
-            keep = (i ** 2 + j ** 2 < radius ** 2) & (rr >= -n) & (rr < n) & (cc >= -n) & (cc < n)
-            self._fill(rr[keep] % n, cc[keep] % n, epsilon_rel, mu_rel)
+        self._record(2, (ci, cj, radius, displacer, self.size), epsilon_rel, mu_rel)
 
     def set_fixed_length_waveguide(self, upper_left, waveguide_length, curved_portion_ratio, thickness, epsilon_rel,
                                    mu_rel=1):
@@ -418,12 +503,7 @@ class MaterialArray:
             radius = self.convert(radius)
             thickness = self.convert(thickness)
         print("latest one   ")
-        di = np.arange(-ci, self.size - ci)[:, None]
-        dj = np.arange(-cj, self.size - cj)[None, :]
-        d2 = di ** 2 + dj ** 2
-        mask = (radius ** 2 > d2) & (d2 > (radius - thickness) ** 2) & (di < 0) & (dj > 0)
-        self.eps_arr[mask] = epsilon_rel * EPSILON
-        self.mu_arr[mask] = mu_rel * MU
+        self._record(1, (ci, cj, radius, thickness), epsilon_rel, mu_rel)
 
     def set_waveguide(self, start_point, thickness, rect_length, radius, epsilon_rel, mu_rel=1, convert=True):
         """Straight - quarter bend - straight (reference solver.py:446-466)."""

@@ -73,6 +73,21 @@ typedef struct fdtd_source {
     int64_t row, col;              /* Pulse.get_row()/get_col(), solver.py:635-639 (global indices) */
 } fdtd_source;
 
+/* One MaterialArray painting call, already converted to grid indices (solver.py:368-466), for fdtd_paint_coeffs.
+ *   FDTD_SHAPE_RECT    a = {r0, r1, c0, c1}: rows [r0,r1), cols [c0,c1) after Python slice clipping of
+ *                      eps_arr[ul0:lr0, ul1:lr1+1] (solver.py:374)
+ *   FDTD_SHAPE_QUARTER a = {ci, cj, radius, thickness}: radius^2 > x^2+y^2 > (radius-thickness)^2, x<0, y>0 (solver.py:426-429)
+ *   FDTD_SHAPE_CONVEX  a = {ci, cj, radius, displacer, size}: the two caps of solver.py:393-409 incl. the wrap of
+ *                      negative indices and the skipping of indices >= size                                        */
+enum fdtd_shape_kind { FDTD_SHAPE_RECT = 0, FDTD_SHAPE_QUARTER = 1, FDTD_SHAPE_CONVEX = 2 };
+typedef struct fdtd_shape {
+    int32_t kind;
+    int32_t reserved;
+    int64_t a[6];
+    double eps;                    /* absolute: epsilon_rel * EPSILON, evaluated by the host */
+    double mu;                     /* absolute: mu_rel * MU                                  */
+} fdtd_shape;
+
 typedef struct fdtd_stats {
     int64_t steps;                 /* leapfrog steps executed since create                          */
     int64_t cell_updates;          /* owned rows * cols * steps                                     */
@@ -113,6 +128,12 @@ int fdtd_upload_coeffs(fdtd_handle h, const double* eps_coef, const double* mu_c
 /* C5 synthetic coefficients generated on the device: eps_r = 1 + 3*u(i,j),
  * u = (splitmix64(seed + i*cols + j) >> 11) * 2^-53, mu_r = 1; same bits as oracle.restated.synthetic_coefficients. */
 int fdtd_fill_synthetic_coeffs(fdtd_handle h, uint64_t seed, double dt_over_ds, double epsilon0, double mu0);
+
+/* MaterialArray painting + coefficient build on the device, for grids whose eps/mu arrays do
+ * not fit in host RAM: the shapes are applied in list order over the background, then
+ * eps_coef = dt_over_ds * (1 / eps), mu_coef = dt_over_ds * (1 / mu) exactly as solver.py:278-279 rounds them. */
+int fdtd_paint_coeffs(fdtd_handle h, int32_t n, const fdtd_shape* shapes, double eps_background, double mu_background,
+                      double dt_over_ds);
 
 /* self.h / self.ex / self.ey (solver.py:101-103).  GLOBAL host arrays, any pointer may be NULL
  * (set: zero-fill that field; get: skip it).  set also loads the halo rows; get writes owned rows only. */

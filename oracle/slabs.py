@@ -37,28 +37,17 @@ def local_setup(setup, row_off, lrows_h, rows_total):
     s.pulses = pulses
     rects = []
     for r0, r1, c0, c1 in setup.reflectors:
-        n_h, n_ex = rows_total, rows_total + 1
-        # python slice semantics on the GLOBAL arrays first, then shift (h/ey have n_h rows, ex n_ex)
-        a0, a1, _ = slice(r0, r1).indices(n_ex)
-        rects.append([max(0, a0 - row_off), max(0, a1 - row_off), c0, c1, n_h])
+        # python slice semantics on the GLOBAL arrays first (ex has rows_total+1 rows), then shift to local rows;
+        # the local h/ey arrays end where the global ones do (last slab) or earlier, so numpy clips them the same way
+        a0, a1, _ = slice(r0, r1).indices(rows_total + 1)
+        rects.append([max(0, a0 - row_off), max(0, a1 - row_off), c0, c1])
     s.reflectors = rects
     return s
 
 
-def leapfrog_slab(f, s_local, time, rows_total, row_off):
-    """Like R.leapfrog on the local arrays; reflector rows are clipped per array as the global slices were."""
-    rects = s_local.reflectors
-    lrows_h = f.h.shape[0]
-    s = copy.copy(s_local)
-    # h / ey rectangles must not reach the local ex-only row when the global rectangle stopped at rows_total
-    fixed = []
-    for a0, a1, c0, c1, n_h in rects:
-        fixed.append([a0, a1, c0, c1])
-    s.reflectors = fixed
-    # global h/ey have rows_total rows: a rectangle running to rows_total+1 (ex only) is clipped by numpy
-    # automatically because the local h/ey arrays end at the same global row as the global ones do
-    # (last slab) or earlier (other slabs, where the local ex row beyond is a halo that gets overwritten).
-    return R.leapfrog(f, s, time)
+def leapfrog_slab(f, s_local, time, rows_total=None, row_off=None):
+    """One step of a slab: oracle.restated.leapfrog on the local arrays with the local setup."""
+    return R.leapfrog(f, s_local, time)
 
 
 def make_slab(f_global, row_begin, row_end):

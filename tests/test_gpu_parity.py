@@ -272,3 +272,36 @@ def test_temporal_blocking_interior_only_and_fp32():
         e.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["lens", "waveguide", "mixed", "solver_test"])
+def test_device_painted_coefficients_match_host_bitwise(name):
+    """fdtd_paint_coeffs vs the host path of solver.py:278-279."""
+    from fdtd_em_solver_b200 import solver as S
+    from fdtd_em_solver_b200.engine import Engine
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, SC.spec(name))
+        s._coefficients()
+    n = s.size
+    e = Engine(n, courant=0.1)
+    e.paint_coefficients(s.material.ops, s.dt / s.ds)
+    assert np.array_equal(e.buffers[6].cpu().numpy()[:n, :n], s.eps_coefficient_arr)
+    assert np.array_equal(e.buffers[7].cpu().numpy()[:n, :n], s.mu_coefficient_arr)
+    e.close()
+
+
+def test_solver_with_material_on_device_is_identical():
+    from fdtd_em_solver_b200 import solver as S
+    sc = SC.spec("waveguide")
+    runs = []
+    for on_device in (False, True):
+        with contextlib.redirect_stdout(io.StringIO()):
+            s = SC.drive(S, sc, material_on_device=on_device)
+            s.end_time = 1500.5 * s.dt
+            s.solve(solve_only=True)
+        if on_device:
+            assert not s.material.on_host                    # never materialised on the host
+        runs.append((s.h.copy(), s.ex.copy(), s.ey.copy(), list(s.recorded_energies[0]["energies"])))
+    for a, b in zip(runs[0][:3], runs[1][:3]):
+        assert np.array_equal(a, b)
+    assert runs[0][3] == runs[1][3] and len(runs[0][3]) == 1501

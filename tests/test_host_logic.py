@@ -149,3 +149,25 @@ def test_no_gpu_means_loud_failure_not_a_cpu_fallback():
     with contextlib.redirect_stdout(io.StringIO()):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             s.solve(solve_only=True)
+
+
+def test_recorded_shapes_replay_and_cell_lookup():
+    """MaterialArray(on_device=True): the recorded shapes reproduce the eager host arrays (lazy materialisation and
+    the single-cell lookup used by the energy probes)."""
+    from fdtd_em_solver_b200.solver import MaterialArray
+    def paint(m):
+        m.set_material_rect((0.2, 0.3), (0.9, 0.7), 3, 2)
+        m.set_material_convex((0.1, 0.2), radius=0.9, thickness=0.5, epsilon_rel=5)          # wraps negative indices
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.set_fixed_length_waveguide((0.5, 0), 1.2, 0.1, 0.1, 2.7)
+            m.set_quarter_circle((0.6, 0.4), 0.3, 2.5, mu_rel=2, thickness=0.1)
+        m.set_material_rect((0.8, 0.8), (1.0, 1.0), 4)                                       # far edge: convert -> size
+        m.set_material_rect((5, 40), (200, 300), 1.5, convert=False)                         # clipped by slicing
+    eager, lazy = MaterialArray(57, 1.0, 1.0), MaterialArray(57, 1.0, 1.0, on_device=True)
+    paint(eager); paint(lazy)
+    assert not lazy.on_host and lazy.ops == eager.ops and len(lazy.ops) == 8
+    cells = [(i, j) for i in range(57) for j in range(57)]
+    got = np.array([lazy.cell(i, j) for i, j in cells])
+    assert not lazy.on_host
+    assert np.array_equal(got[:, 0].reshape(57, 57), eager.eps_arr) and np.array_equal(got[:, 1].reshape(57, 57), eager.mu_arr)
+    assert np.array_equal(lazy.eps_arr, eager.eps_arr) and np.array_equal(lazy.mu_arr, eager.mu_arr) and lazy.on_host
