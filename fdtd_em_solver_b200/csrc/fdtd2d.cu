@@ -52,22 +52,28 @@ struct NcclApi {
 
 }  // namespace
 
+struct FrameMaps {                   // per group size K: which tiles the K-step kernel skips and the frame passes cover
+    std::vector<uint8_t> key;       // active-source signature + geometry the maps were built for
+    std::vector<uint8_t> h_skip, h_mask[4];      // h_mask[d]: frame tiles dilated by d rings (d = 0 is the frame itself)
+    unsigned char* d_skip = nullptr; unsigned char* d_mask[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<int2> h_list[4];                 // compact (block column, row tile) launch lists of the frame passes
+    int2* d_list[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
+    int nty = 0, ntx2 = 0, ntx1 = 0;
+    void release() {
+        if (d_skip) cudaFree(d_skip);
+        for (int d = 0; d < 4; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
+    }
+};
+
 struct fdtd_ctx {
     fdtd_config cfg{};
     int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0, host_row0 = 0;
     size_t esize = 8;
-    void* gen[3][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [generation][h,ex,ey]
-    bool has_scratch = false;       // generation 2 bound (needed by temporal blocking)
-    int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1 or 2)
-    std::vector<uint8_t> map_key;   // active-source signature the frame maps were built for
-    std::vector<uint8_t> h_skip, h_maskB, h_maskC;
-    unsigned char* d_skip = nullptr; unsigned char* d_maskB = nullptr; unsigned char* d_maskC = nullptr;
-    std::vector<int2> h_listB, h_listC;          // compact (block column, row tile) launch lists of the frame passes
-    int2* d_listB = nullptr; int2* d_listC = nullptr;
-    size_t d_list_cap = 0;
-    size_t d_skip_cap = 0, d_mask_cap = 0;
-    int nty = 0, ntx2 = 0, ntx1 = 0;
-    int64_t pair_launch_cells = 0;
+    void* gen[4][3] = {};           // [generation][h,ex,ey]: 2 for ping-pong, +1 / +2 scratch for temporal blocking
+    int ngen = 2;                   // generations bound
+    int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1..4)
+    FrameMaps fm[5];                // indexed by group size K (2..4)
     void* epc = nullptr; void* muc = nullptr;
     bool bound = false;
     int cur = 0;
@@ -191,7 +197,7 @@ int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int6
     return 0;
 }
 
-int next_gen(const fdtd_ctx* c, int g) { return c->has_scratch ? (g + 1) % 3 : (g ^ 1); }
+int next_gen(const fdtd_ctx* c, int g) { return (g + 1) % c->ngen; }
 
 template <typename T>
 int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step, int a, int b) {
@@ -348,28 +354,32 @@ int step_impl(fdtd_ctx* c, int64_t step) {
     return 0;
 }
 
-// ---- temporal blocking (2 steps per HBM pass) ----------------------------------------------------------
-// Which two-step tiles must NOT be advanced by step2_stream, and which single-step tiles advance them instead.
+// ---- temporal blocking (K steps per HBM pass) ----------------------------------------------------------
+template <typename T> constexpr int kvec() { return sizeof(T) == 8 ? 2 : 4; }     // columns per lane of stepK_stream
+
+// Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 template <typename T>
-int build_frame_maps(fdtd_ctx* c, int64_t n) {
-    constexpr int V2 = sizeof(T) == 8 ? 2 : 4;
-    const int OUT = 30 * V2, LD = 32 * V2;
+int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
+    FrameMaps& m = c->fm[K];
+    constexpr int V2 = kvec<T>();
+    const int MARGIN = (K + V2 - 1) / V2, OUT = (32 - 2 * MARGIN) * V2, LD = 32 * V2;
     const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
     const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == NR ? 1 : 0);
     const int TR = c->cfg.tile_rows, W1 = 32 * c->cfg.vec;
-    // signature: which pulses are live in step n or n+1, plus the geometry knobs
+    // signature: which pulses are live in any step of the group, plus the geometry knobs
     std::vector<uint8_t> key;
     for (int p = 0; p < c->n_src; ++p) {
         uint8_t live = 0;
-        for (int64_t t = n; t <= n + 1; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
+        for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
         key.push_back(live);
     }
-    key.push_back((uint8_t)TR); key.push_back((uint8_t)c->cfg.vec); key.push_back((uint8_t)c->n_rect); key.push_back((uint8_t)c->n_probe);
-    if (key == c->map_key && c->d_skip) return 0;
+    for (int v : {TR, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
+    if (key == m.key && m.d_skip) return 0;
     const int nty = (int)((hi - lo + TR - 1) / TR);
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
-    c->nty = nty; c->ntx2 = ntx2; c->ntx1 = ntx1;
-    c->h_skip.assign((size_t)nty * ntx2, 0); c->h_maskB.assign((size_t)nty * ntx1, 0); c->h_maskC.assign((size_t)nty * ntx1, 0);
+    m.nty = nty; m.ntx2 = ntx2; m.ntx1 = ntx1;
+    m.h_skip.assign((size_t)nty * ntx2, 0);
+    for (int d = 0; d < 4; ++d) { m.h_mask[d].assign(d < K ? (size_t)nty * ntx1 : 0, 0); m.h_list[d].clear(); }
     struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
     std::vector<Box> mods;
     const int64_t BIG = (int64_t)1 << 40;
@@ -385,143 +395,136 @@ int build_frame_maps(fdtd_ctx* c, int64_t n) {
         for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
             if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
-    int64_t two_step_cells = 0;
     for (int ty = 0; ty < nty; ++ty) {
         const int64_t ta = lo + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hi);
-        const bool rows_ok = ta - 1 >= 1 && tb <= NR - 2 && ta - 2 >= c->cfg.row_begin && tb + 1 <= c->cfg.row_end - 1;
+        // every row a stage touches (ta-K .. tb+K-1) is an OWNED plain interior row of this slab
+        const bool rows_ok = ta - K >= std::max<int64_t>(c->cfg.row_begin, 0) && ta - (K - 1) >= 1 &&
+                             tb + K - 2 <= NR - 2 && tb + K - 1 <= c->cfg.row_end - 1;
         for (int tx = 0; tx < ntx2; ++tx) {
-            const int64_t jw = (int64_t)tx * OUT - V2;
+            const int64_t jw = (int64_t)tx * OUT - (int64_t)MARGIN * V2;
             bool mixed = !rows_ok || jw < 1 || jw + LD - 1 > NC - 2;
             if (!mixed)
-                for (const Box& m : mods)
-                    if (m.r0 <= tb + 2 && m.r1 >= ta - 3 && m.c0 <= jw + LD && m.c1 >= jw - 1) { mixed = true; break; }
-            if (!mixed) { two_step_cells += (tb - ta) * OUT; continue; }
-            c->h_skip[(size_t)ty * ntx2 + tx] = 1;
+                for (const Box& q : mods)
+                    if (q.r0 <= tb + K && q.r1 >= ta - K - 1 && q.c0 <= jw + LD && q.c1 >= jw - 1) { mixed = true; break; }
+            if (!mixed) continue;
+            m.h_skip[(size_t)ty * ntx2 + tx] = 1;
             const int64_t c0 = (int64_t)tx * OUT, c1 = std::min<int64_t>(c0 + OUT - 1, NC);
-            for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) c->h_maskB[(size_t)ty * ntx1 + t1] = 1;
+            for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) m.h_mask[0][(size_t)ty * ntx1 + t1] = 1;
         }
     }
-    for (int ty = 0; ty < nty; ++ty)
-        for (int tx = 0; tx < ntx1; ++tx) {
-            if (!c->h_maskB[(size_t)ty * ntx1 + tx]) continue;
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int y = ty + dy, x = tx + dx;
-                    if (y >= 0 && y < nty && x >= 0 && x < ntx1) c->h_maskC[(size_t)y * ntx1 + x] = 1;
-                }
-        }
-    c->pair_launch_cells = two_step_cells;
-    {
-        const int w = c->cfg.block_warps, nbx = (ntx1 + w - 1) / w;
-        c->h_listB.clear(); c->h_listC.clear();
+    for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one tile
+        for (int ty = 0; ty < nty; ++ty)
+            for (int tx = 0; tx < ntx1; ++tx) {
+                if (!m.h_mask[d - 1][(size_t)ty * ntx1 + tx]) continue;
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int y = ty + dy, x = tx + dx;
+                        if (y >= 0 && y < nty && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
+                    }
+            }
+    const int w = c->cfg.block_warps, nbx = (ntx1 + w - 1) / w;
+    size_t longest = 1;
+    for (int d = 0; d < K; ++d) {
         for (int ty = 0; ty < nty; ++ty)
             for (int bx = 0; bx < nbx; ++bx) {
-                bool anyB = false, anyC = false;
-                for (int t = bx * w; t < std::min(ntx1, (bx + 1) * w); ++t) {
-                    anyB |= c->h_maskB[(size_t)ty * ntx1 + t] != 0;
-                    anyC |= c->h_maskC[(size_t)ty * ntx1 + t] != 0;
-                }
-                if (anyB) c->h_listB.push_back(make_int2(bx, ty));
-                if (anyC) c->h_listC.push_back(make_int2(bx, ty));
+                bool any = false;
+                for (int t = bx * w; t < std::min(ntx1, (bx + 1) * w); ++t) any |= m.h_mask[d][(size_t)ty * ntx1 + t] != 0;
+                if (any) m.h_list[d].push_back(make_int2(bx, ty));
             }
-        const size_t need = std::max<size_t>(1, c->h_listC.size());
-        if (c->d_list_cap < need) {
-            if (c->d_listB) cudaFree(c->d_listB);
-            if (c->d_listC) cudaFree(c->d_listC);
-            CK(cudaMalloc(&c->d_listB, need * sizeof(int2))); CK(cudaMalloc(&c->d_listC, need * sizeof(int2)));
-            c->d_list_cap = need;
-        }
+        longest = std::max(longest, m.h_list[d].size());
     }
-    if (c->d_skip_cap < c->h_skip.size()) {
-        if (c->d_skip) cudaFree(c->d_skip);
-        CK(cudaMalloc(&c->d_skip, c->h_skip.size())); c->d_skip_cap = c->h_skip.size();
-    }
-    if (c->d_mask_cap < c->h_maskB.size()) {
-        if (c->d_maskB) cudaFree(c->d_maskB);
-        if (c->d_maskC) cudaFree(c->d_maskC);
-        CK(cudaMalloc(&c->d_maskB, c->h_maskB.size())); CK(cudaMalloc(&c->d_maskC, c->h_maskC.size()));
-        c->d_mask_cap = c->h_maskB.size();
-    }
-    // the previous pair's launches may still be reading the old maps
+    // the previous group's launches may still be reading the old maps
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->edge_stream));
-    CK(cudaMemcpyAsync(c->d_skip, c->h_skip.data(), c->h_skip.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_maskB, c->h_maskB.data(), c->h_maskB.size(), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_maskC, c->h_maskC.data(), c->h_maskC.size(), cudaMemcpyHostToDevice, c->stream));
-    if (!c->h_listB.empty())
-        CK(cudaMemcpyAsync(c->d_listB, c->h_listB.data(), c->h_listB.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-    if (!c->h_listC.empty())
-        CK(cudaMemcpyAsync(c->d_listC, c->h_listC.data(), c->h_listC.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    if (m.d_skip_cap < m.h_skip.size()) {
+        if (m.d_skip) cudaFree(m.d_skip);
+        CK(cudaMalloc(&m.d_skip, m.h_skip.size())); m.d_skip_cap = m.h_skip.size();
+    }
+    const size_t mask_bytes = (size_t)nty * ntx1;
+    if (m.d_mask_cap < mask_bytes || m.d_list_cap < longest) {
+        for (int d = 0; d < 4; ++d) {
+            if (m.d_mask[d]) cudaFree(m.d_mask[d]);
+            if (m.d_list[d]) cudaFree(m.d_list[d]);
+            CK(cudaMalloc(&m.d_mask[d], mask_bytes)); CK(cudaMalloc(&m.d_list[d], longest * sizeof(int2)));
+        }
+        m.d_mask_cap = mask_bytes; m.d_list_cap = longest;
+    }
+    CK(cudaMemcpyAsync(m.d_skip, m.h_skip.data(), m.h_skip.size(), cudaMemcpyHostToDevice, c->stream));
+    for (int d = 0; d < K; ++d) {
+        CK(cudaMemcpyAsync(m.d_mask[d], m.h_mask[d].data(), mask_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (!m.h_list[d].empty())
+            CK(cudaMemcpyAsync(m.d_list[d], m.h_list[d].data(), m.h_list[d].size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));
-    c->map_key = key;
+    m.key = key;
     return 0;
 }
 
-// Steps n and n+1 in one HBM pass: A -> B.  Frame tiles go A -> C (step n) -> B (step n+1) with masked single steps.
+template <typename T, int K>
+void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
+    constexpr int V2 = kvec<T>();
+    const FrameMaps& m = c->fm[K];
+    const int w = std::min(c->cfg.block_warps, 4);
+    dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)m.nty);
+    const size_t ring_bytes = (size_t)w * FDTD_KRING * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
+    fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
+}
+
+// Steps n .. n+K-1 in one HBM pass: A -> B.  The frame (walls, sources, reflectors, probes, slab interface strips)
+// goes A -> S -> S' -> ... -> B with K masked, compact single-step launches: passes 1..K-1 (frame dilated by K-p rings
+// of tiles) run on the high-priority edge stream CONCURRENTLY with the K-step kernel, the last pass follows both.
+// With slabs the generation each pass wrote has its halo rows exchanged on the comm stream right after the pass.
 template <typename T>
-int pair_impl(fdtd_ctx* c, int64_t n) {
-    constexpr int V2 = sizeof(T) == 8 ? 2 : 4;
-    if (int rc = build_frame_maps<T>(c, n)) return rc;
-    const int A = c->cur, B = (A + 1) % 3, Cg = (A + 2) % 3;
+int group_impl(fdtd_ctx* c, int64_t n, int K) {
+    if (int rc = build_frame_maps<T>(c, n, K)) return rc;
+    const FrameMaps& m = c->fm[K];
+    const int A = c->cur, B = (A + 1) % c->ngen;
+    int scratch[2] = {(A + 2) % c->ngen, (A + 3) % c->ngen};
     const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
-    if (c->n_probe) if (int rc = ensure_probe_capacity(c, 2)) return rc;
-    // pass 1 (frame + one ring of tiles, A -> C, step n) runs on the high-priority edge stream CONCURRENTLY with
-    // pass 2 (everything else, two steps at once, A -> B) on the main stream; pass 3 (frame, C -> B, step n+1)
-    // follows both.  The frame passes are compact launches over the listed tiles only.
-    // With slabs (fdtd_comm_init) the interface strips are part of the frame: generation C's halo rows are exchanged
-    // after pass 1 and generation B's after pass 3, both on the comm stream, hidden behind the two-step kernel.
-    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this pair
+    if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
+    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this group
     CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
-    if (c->comm) CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0));      // halos of generation A have landed
-    {
+    int src = A;
+    for (int p = 1; p <= K; ++p) {
+        const bool last = p == K;
+        const int dst = last ? B : scratch[(p - 1) & 1];
+        const int ring = K - p;                                 // pass p covers the frame dilated by K-p rings
+        cudaStream_t st = last ? c->stream : c->edge_stream;
+        if (c->comm) CK(cudaStreamWaitEvent(st, c->ev_comm, 0));                  // halos of `src` have landed
+        if (last) {
+            StepParams<T> PK;                                   // the K-step kernel: everything but the frame
+            if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
+            PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)lo; PK.row_hi = (int)hi;
+            if (K == 2) launch_stepK<T, 2>(PK, c); else if (K == 3) launch_stepK<T, 3>(PK, c); else launch_stepK<T, 4>(PK, c);
+            c->stats.kernel_launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));                     // passes 1..K-1 done
+        }
         StepParams<T> P;
-        if (int rc = fill_params<T>(c, P, n, A, Cg)) return rc;
-        if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
-        P.tile_mask = c->d_maskC; P.mask_stride = c->ntx1; P.tile_list = c->d_listC;
-        if (int rc = launch_rows<T>(c, P, lo, hi, c->edge_stream, (int)c->h_listC.size())) return rc;
-        CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
-    }
-    if (c->comm) {
-        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-        if (int rc = exchange(c, Cg, c->comm_stream)) return rc;
-        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
-    }
-    {
-        StepParams<T> P;
-        if (int rc = fill_params<T>(c, P, n, A, B)) return rc;
-        P.n_src = 0; P.n_rect = 0; P.n_probe = 0;
-        P.row_lo = (int)lo; P.row_hi = (int)hi;
-        const int w = c->cfg.block_warps;
-        dim3 grid((unsigned)((c->ntx2 + w - 1) / w), (unsigned)c->nty);
-        fdtd::step2_stream<T, V2><<<grid, w * 32, 0, c->stream>>>(P, c->d_skip, c->ntx2);
-        c->stats.kernel_launches++;
-        CK(cudaGetLastError());
-    }
-    CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
-    if (c->comm) CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));           // halos of generation C have landed
-    {
-        StepParams<T> P;
-        if (int rc = fill_params<T>(c, P, n + 1, Cg, B)) return rc;
-        if (c->n_probe) P.probe_out = c->probe_dev + (size_t)(c->probe_count + 1) * c->n_probe * 3;
-        P.tile_mask = c->d_maskB; P.mask_stride = c->ntx1; P.tile_list = c->d_listB;
-        if (int rc = launch_rows<T>(c, P, lo, hi, c->stream, (int)c->h_listB.size())) return rc;
-    }
-    if (c->comm) {
-        CK(cudaEventRecord(c->ev_p3, c->stream));
-        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_p3, 0));
-        if (int rc = exchange(c, B, c->comm_stream)) return rc;
-        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+        if (int rc = fill_params<T>(c, P, n + p - 1, src, dst)) return rc;
+        if (c->n_probe) P.probe_out = c->probe_dev + (size_t)(c->probe_count + p - 1) * c->n_probe * 3;
+        P.tile_mask = m.d_mask[ring]; P.mask_stride = m.ntx1; P.tile_list = m.d_list[ring];
+        if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size())) return rc;
+        if (!last) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+        if (c->comm) {
+            cudaEvent_t done = last ? c->ev_p3 : c->ev_bnd;
+            if (last) CK(cudaEventRecord(c->ev_p3, c->stream));
+            CK(cudaStreamWaitEvent(c->comm_stream, done, 0));
+            if (int rc = exchange(c, dst, c->comm_stream)) return rc;
+            CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+        }
+        src = dst;
     }
     CK(cudaEventRecord(c->ev_int, c->stream));                  // "all owned rows of generation B written"
     c->cur = B;
-    if (c->n_probe) c->probe_count += 2;
-    c->stats.steps += 2;
-    c->stats.cell_updates += 2 * c->owned * c->cfg.cols;
+    if (c->n_probe) c->probe_count += K;
+    c->stats.steps += K;
+    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
     return 0;
 }
 
-int pair_any(fdtd_ctx* c, int64_t n) {
-    return c->cfg.dtype == FDTD_F64 ? pair_impl<double>(c, n) : pair_impl<float>(c, n);
+int group_any(fdtd_ctx* c, int64_t n, int K) {
+    return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
 
 int step_any(fdtd_ctx* c, int64_t step) {
@@ -647,8 +650,7 @@ int fdtd_destroy(fdtd_handle c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->probe_dev) cudaFree(c->probe_dev);
     if (c->stage) cudaFree(c->stage);
-    for (unsigned char* m : {c->d_skip, c->d_maskB, c->d_maskC}) if (m) cudaFree(m);
-    for (int2* m : {c->d_listB, c->d_listC}) if (m) cudaFree(m);
+    for (FrameMaps& m : c->fm) m.release();
     for (int s = 0; s < 2; ++s) {
         if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
         if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
@@ -681,16 +683,17 @@ int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
         if (reinterpret_cast<uintptr_t>(p) % 128) return fail(c, FDTD_ERR_ARG, "device buffers must be 128-byte aligned");
     }
     if (!c->bound) return fail(c, FDTD_ERR_STATE, "bind the two field generations first");
-    if (c->cur == 2) return fail(c, FDTD_ERR_STATE, "scratch generation currently holds the fields");
-    c->gen[2][0] = h2; c->gen[2][1] = ex2; c->gen[2][2] = ey2;
-    c->has_scratch = true;
+    if (c->ngen >= 4) return fail(c, FDTD_ERR_STATE, "at most two scratch generations");
+    c->gen[c->ngen][0] = h2; c->gen[c->ngen][1] = ex2; c->gen[c->ngen][2] = ey2;
+    c->ngen++;
     return 0;
 }
 
 int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     if (!c) return FDTD_ERR_ARG;
-    if (steps_per_pass != 1 && steps_per_pass != 2) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1 or 2");
-    if (steps_per_pass == 2 && !c->has_scratch) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch");
+    if (steps_per_pass < 1 || steps_per_pass > 4) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1..4");
+    const int need = steps_per_pass == 1 ? 2 : (steps_per_pass == 2 ? 3 : 4);
+    if (c->ngen < need) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch (once for 2 steps per pass, twice for 3 or 4)");
     c->temporal = steps_per_pass;
     return 0;
 }
@@ -768,7 +771,7 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
 
 int fdtd_zero_fields(fdtd_handle c) {
     NEED_BOUND();
-    for (int g = 0; g < (c->has_scratch ? 3 : 2); ++g)
+    for (int g = 0; g < c->ngen; ++g)
         for (int f = 0; f < 3; ++f)
             CK(cudaMemsetAsync(c->gen[g][f], 0, (size_t)c->lrows * c->pitch * c->esize, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -816,6 +819,7 @@ int fdtd_get_fields(fdtd_handle c, double* hh, double* ex, double* ey) {
 int fdtd_set_sources(fdtd_handle c, int32_t n, const fdtd_source* src, int64_t table_len,
                      const double* mag, const double* mag_z, const uint8_t* active, const double* last_mag) {
     if (!c) return FDTD_ERR_ARG;
+    for (FrameMaps& m : c->fm) m.key.clear();            // temporal-blocking frame maps depend on the scene
     if (n < 0 || n > 64) return fail(c, FDTD_ERR_ARG, "at most 64 pulses");
     if (n > 0 && (!src || !mag || !mag_z || !active || !last_mag || table_len <= 0))
         return fail(c, FDTD_ERR_ARG, "null source table");
@@ -837,6 +841,7 @@ int fdtd_set_sources(fdtd_handle c, int32_t n, const fdtd_source* src, int64_t t
 
 int fdtd_set_reflectors(fdtd_handle c, int32_t n, const int64_t* rects) {
     if (!c) return FDTD_ERR_ARG;
+    for (FrameMaps& m : c->fm) m.key.clear();
     if (n < 0 || n > FDTD_MAX_RECT) return fail(c, FDTD_ERR_ARG, "at most 24 reflector rectangles");
     if (n > 0 && !rects) return fail(c, FDTD_ERR_ARG, "null rectangle list");
     c->n_rect = n;
@@ -851,6 +856,7 @@ int fdtd_set_reflectors(fdtd_handle c, int32_t n, const int64_t* rects) {
 
 int fdtd_set_probes(fdtd_handle c, int32_t n, const int64_t* ij) {
     if (!c) return FDTD_ERR_ARG;
+    for (FrameMaps& m : c->fm) m.key.clear();
     if (n < 0 || n > FDTD_MAX_PROBE) return fail(c, FDTD_ERR_ARG, "at most 16 probes");
     cudaSetDevice(c->cfg.device);
     if (c->probe_dev) { cudaStreamSynchronize(c->stream); cudaFree(c->probe_dev); c->probe_dev = nullptr; }
@@ -901,13 +907,15 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     int64_t k = 0;
     int rc = 0;
     CK(cudaEventRecord(c->ev_t0, c->stream));
-    const bool pairs = c->temporal == 2 && c->has_scratch && c->cfg.kernel == FDTD_KERNEL_STREAM;
+    const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 4 : (c->ngen == 3 ? 2 : 1)) : 1;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
-        const bool snap_after_first = snaps && (n + 1) % snapshot_every == 0;
-        if (pairs && n + 1 < first_step + n_steps && !snap_after_first &&
-            (c->n_src == 0 || n + 1 < c->table_len)) {
-            if ((rc = pair_any(c, n))) break;
-            ++n;                                         // two steps done
+        // largest group that ends no later than the run, the next snapshot and the source tables
+        int64_t g = std::min<int64_t>(kmax, first_step + n_steps - n);
+        if (snaps) g = std::min<int64_t>(g, snapshot_every - (n % snapshot_every));
+        if (c->n_src > 0) g = std::min<int64_t>(g, c->table_len - n);
+        if (g >= 2) {
+            if ((rc = group_any(c, n, (int)g))) break;
+            n += g - 1;                                  // g steps done
         } else if ((rc = step_any(c, n))) break;
         if (snaps && (n + 1) % snapshot_every == 0) {
             if (k >= max_snapshots) { rc = fail(c, FDTD_ERR_ARG, "snapshot buffer too small"); break; }

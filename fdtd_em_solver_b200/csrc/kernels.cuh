@@ -571,106 +571,156 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
 }
 
 // ---------------------------------------------------------------------------
-// Temporal blocking: TWO leapfrog steps per HBM pass (generation A -> generation B = A + 2 steps).
+// Temporal blocking: K leapfrog steps per HBM pass (generation A -> generation B = A + K steps), K = 2, 3, 4.
 //
-// Only for tiles whose two-step dependency cone touches no wall, source, reflector or probe; the host
-// marks all other tiles in `skip` and advances them with two masked single-step launches through a third
-// generation (fdtd2d.cu: pair_impl).  Per warp: 32 lanes x V columns are LOADED, stage 1 (step n) is
-// computed for all of them, stage 2 (step n+1) trails one row behind in registers, and only lanes 1..30
-// store: lane 0 and lane 31 are sacrificial halo lanes (their neighbour values are garbage), so the tile
-// stride is 30*V columns and no scalar halo loads exist.  Same rounding order as the single-step kernel, so the
-// result is bit-identical to two single steps.  Algorithmic traffic: 8 words per cell per TWO steps.
+// Only for tiles whose K-step dependency cone touches no wall, source, reflector, probe or slab interface; the
+// host marks all other tiles in `skip` and advances them with K masked single-step launches through scratch
+// generations (fdtd2d.cu: group_impl).  Per warp: 32 lanes x V columns are LOADED; stage 1 (step n) is computed for
+// the row just loaded, stage s (step n+s-1) trails s-1 rows behind, fed from register latches that hold the
+// previous stage's last output row and from a register delay line of the coefficient rows; only stage K is stored.
+// The first and last ceil(K/V) lanes are sacrificial halo lanes (their neighbour values are garbage, which moves
+// one column per stage and so cannot reach the storing lanes), so all loads are aligned vectors and no scalar halo
+// loads exist.  All stages run unconditionally: values computed from not-yet-valid latches in the first iterations
+// are never consumed by a stored value (each stage's first needed row is fed by valid rows only).
+// Same rounding order as the single-step kernel => bit-identical to K single steps.
+// Algorithmic traffic: 8 words per cell per K steps.
 // ---------------------------------------------------------------------------
-template <typename T, int V>
-__device__ __forceinline__ void run_tile2(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+#ifndef FDTD_KRING
+#define FDTD_KRING 4                 // rows of the per-warp shared-memory prefetch ring of stepK_stream (0: registers only)
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int V> struct KGeom {
+    static constexpr int MARGIN = (K + V - 1) / V;           // sacrificial lanes on each side
+    static constexpr int OUT = (32 - 2 * MARGIN) * V;        // columns stored per warp
+};
+
+template <typename T, int V, int K>
+__device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
     const unsigned full = 0xffffffffu;
+    constexpr int MARGIN = KGeom<K, V>::MARGIN;
     const int j = jw + lane * V;
     const long long pitch = P.pitch;
     auto at = [&](const T* a, int i) { return a + (long long)(i - P.row_off) * pitch + j; };
-    auto right_of = [&](const T (&x)[V], int v) {            // value in column j+v+1
-        const T nb = __shfl_down_sync(full, x[0], 1);
-        return (v + 1 < V) ? x[v + 1 < V ? v + 1 : 0] : nb;
-    };
 
-    T ex0c[V], hn1p[V], mu_p[V], ep_p[V], ex1p[V], ey1p[V], hn2p[V];
-    {   // prologue: hn1[ta-2] and ex0[ta-1]
+    T ex0c[V];                       // ex of generation A at the stage-1 row
+    T hnp[K][V];                     // hn_s of the previous row, per stage
+    T Lh[K][V], Lex[K][V], Ley[K][V];// latch s (1..K-1): stage s outputs of the row it processed last iteration
+    T Cmu[K][V], Cep[K][V];          // delay line: coefficients of row i-d, d = 1..K-1
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int v = 0; v < V; ++v) hnp[s][v] = Lh[s][v] = Lex[s][v] = Ley[s][v] = Cmu[s][v] = Cep[s][v] = T(0);
+    {   // prologue: hn_1 of row ta-K and ex0 of row ta-K+1
         T h[V], mu[V], exm[V], ey[V];
-        ldvec<T, V>(h, at(P.h, ta - 2)); ldvec<T, V>(mu, at(P.muc, ta - 2)); ldvec<T, V>(exm, at(P.ex, ta - 2));
-        ldvec<T, V>(ex0c, at(P.ex, ta - 1)); ldvec<T, V>(ey, at(P.ey, ta - 2));
+        ldvec<T, V>(h, at(P.h, ta - K)); ldvec<T, V>(mu, at(P.muc, ta - K)); ldvec<T, V>(exm, at(P.ex, ta - K));
+        ldvec<T, V>(ex0c, at(P.ex, ta - K + 1)); ldvec<T, V>(ey, at(P.ey, ta - K));
         const T nb = __shfl_down_sync(full, ey[0], 1);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
-            hn1p[v] = add(h[v], mul(mu[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
-            mu_p[v] = ep_p[v] = ex1p[v] = ey1p[v] = hn2p[v] = T(0);
+            hnp[0][v] = add(h[v], mul(mu[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
         }
     }
     Row<T, V> cur;
+    const int i_first = ta - K + 1, i_last = tb + K - 2;
+#if FDTD_KRING > 0
+    // Rows are prefetched FDTD_KRING-1 deep into a per-warp shared-memory ring with cp.async (LDGSTS): memory-level
+    // parallelism without register cost (with a one-row register prefetch the K=4 body was latency-bound: ncu
+    // long_scoreboard 65 % of stalls, DRAM 60 %).  Every lane copies and later reads back only its own 16 bytes.
+    static_assert(V * sizeof(T) == 16, "the ring moves one 16-byte vector per lane per array");
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    T* ring = reinterpret_cast<T*>(ring_raw) + (size_t)(threadIdx.x >> 5) * (FDTD_KRING * 5 * 32 * V) + lane * V;
+    auto issue = [&](int i) {                                // row i -> slot (i - i_first) mod FDTD_KRING
+        if (i <= i_last) {
+            T* slot = ring + (size_t)((i - i_first) % FDTD_KRING) * (5 * 32 * V);
+            cp_async16(slot + 0 * 32 * V, at(P.h, i)); cp_async16(slot + 1 * 32 * V, at(P.muc, i));
+            cp_async16(slot + 2 * 32 * V, at(P.epc, i)); cp_async16(slot + 3 * 32 * V, at(P.ex, i + 1));
+            cp_async16(slot + 4 * 32 * V, at(P.ey, i));
+        }
+        cp_async_commit();                                   // (an empty group past the end keeps the count uniform)
+    };
+#pragma unroll
+    for (int d = 0; d < FDTD_KRING; ++d) issue(i_first + d);
+#else
     auto load = [&](Row<T, V>& r, int i) {
         ldvec<T, V>(r.h, at(P.h, i)); ldvec<T, V>(r.mu, at(P.muc, i)); ldvec<T, V>(r.ep, at(P.epc, i));
         ldvec<T, V>(r.exn, at(P.ex, i + 1)); ldvec<T, V>(r.ey, at(P.ey, i));
     };
-    load(cur, ta - 1);
-    for (int i = ta - 1; i <= tb; ++i) {                     // stage-1 row i, stage-2 row i-1
-        Row<T, V> nxt;
-        if (i < tb) load(nxt, i + 1);
-        // ---- stage 1: step n on row i
-        T hn1[V], ex1[V], ey1[V];
+    load(cur, i_first);
+#endif
+    for (int i = i_first; i <= i_last; ++i) {                // stage s works on row i-(s-1)
+#if FDTD_KRING > 0
+        cp_async_wait<FDTD_KRING - 1>();                     // the oldest group (row i) has landed
         {
-            const T nb = __shfl_down_sync(full, cur.ey[0], 1);
+            const T* slot = ring + (size_t)((i - i_first) % FDTD_KRING) * (5 * 32 * V);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const T eyr = (v + 1 < V) ? cur.ey[v + 1 < V ? v + 1 : 0] : nb;
-                hn1[v] = add(cur.h[v], mul(cur.mu[v], sub(sub(cur.exn[v], ex0c[v]), sub(eyr, cur.ey[v]))));
+                cur.h[v] = slot[0 * 32 * V + v]; cur.mu[v] = slot[1 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
+                cur.exn[v] = slot[3 * 32 * V + v]; cur.ey[v] = slot[4 * 32 * V + v];
             }
-            const T lf = __shfl_up_sync(full, hn1[V - 1], 1);
+        }
+#else
+        Row<T, V> nxt;
+        if (i < i_last) load(nxt, i + 1);
+#endif
+        // one leapfrog step of one row: fields (h, exc, ey) of that row, ex of the row below (exn), coefficients,
+        // hn of the row above (hp); outputs the new (h, ex, ey) of the row
+        T oh[V], oex[V], oey[V];
+        auto stage = [&](const T (&h)[V], const T (&exc)[V], const T (&exn)[V], const T (&ey)[V], const T (&mu)[V],
+                         const T (&ep)[V], T (&hp)[V]) {
+            const T nb = __shfl_down_sync(full, ey[0], 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const T hl = (v == 0) ? lf : hn1[v > 0 ? v - 1 : 0];
-                ex1[v] = add(ex0c[v], mul(cur.ep[v], sub(hn1[v], hn1p[v])));
-                ey1[v] = sub(cur.ey[v], mul(cur.ep[v], sub(hn1[v], hl)));
+                const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+                oh[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
             }
-        }
-        // ---- stage 2: step n+1 on row r = i-1 (its ex1[r+1] is the ex1 just computed)
-        if (i >= ta) {
-            const int r = i - 1;
-            T hn2[V];
-            const T nb = __shfl_down_sync(full, ey1p[0], 1);
+            const T lf = __shfl_up_sync(full, oh[V - 1], 1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const T eyr = (v + 1 < V) ? ey1p[v + 1 < V ? v + 1 : 0] : nb;
-                hn2[v] = add(hn1p[v], mul(mu_p[v], sub(sub(ex1[v], ex1p[v]), sub(eyr, ey1p[v]))));
+                const T hl = (v == 0) ? lf : oh[v > 0 ? v - 1 : 0];
+                oex[v] = add(exc[v], mul(ep[v], sub(oh[v], hp[v])));
+                oey[v] = sub(ey[v], mul(ep[v], sub(oh[v], hl)));
+                hp[v] = oh[v];
             }
-            if (r >= ta) {
-                const T lf = __shfl_up_sync(full, hn2[V - 1], 1);
-                T ex2[V], ey2[V];
+        };
+        stage(cur.h, ex0c, cur.exn, cur.ey, cur.mu, cur.ep, hnp[0]);                 // stage 1, row i
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const T hl = (v == 0) ? lf : hn2[v > 0 ? v - 1 : 0];
-                    ex2[v] = add(ex1p[v], mul(ep_p[v], sub(hn2[v], hn2p[v])));
-                    ey2[v] = sub(ey1p[v], mul(ep_p[v], sub(hn2[v], hl)));
-                }
-                if (lane >= 1 && lane <= 30) {
-                    const long long o = (long long)(r - P.row_off) * pitch + j;
-                    stvec<T, V>(P.hn + o, hn2); stvec<T, V>(P.exn + o, ex2); stvec<T, V>(P.eyn + o, ey2);
-                }
-            }
+        for (int s = 1; s < K; ++s) {                        // stage s+1, row i-s, fed by latch s and by stage s's fresh ex
+            T ph[V], pex[V], pey[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) hn2p[v] = hn2[v];
+            for (int v = 0; v < V; ++v) { ph[v] = oh[v]; pex[v] = oex[v]; pey[v] = oey[v]; }   // stage s, row i-s+1
+            stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }
+        }
+        const int r = i - (K - 1);                           // row the last stage just produced
+        if (r >= ta && lane >= MARGIN && lane < 32 - MARGIN) {
+            const long long o = (long long)(r - P.row_off) * pitch + j;
+            stvec<T, V>(P.hn + o, oh); stvec<T, V>(P.exn + o, oex); stvec<T, V>(P.eyn + o, oey);
         }
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            ex0c[v] = cur.exn[v]; hn1p[v] = hn1[v]; mu_p[v] = cur.mu[v]; ep_p[v] = cur.ep[v];
-            ex1p[v] = ex1[v]; ey1p[v] = ey1[v];
-        }
+        for (int s = K - 1; s >= 2; --s)
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
+#if FDTD_KRING > 0
+        issue(i + FDTD_KRING);                               // refill the slot just consumed (its values are in registers)
+#else
         cur = nxt;
+#endif
     }
 }
 
-template <typename T, int V>
-__global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step2_stream(const __grid_constant__ StepParams<T> P,
-                                                                   const unsigned char* __restrict__ skip, int skip_stride) {
-    constexpr int OUT = 30 * V;                              // columns stored per warp
+template <typename T, int V, int K>
+__global__ void __launch_bounds__(128, 1) stepK_stream(const __grid_constant__ StepParams<T> P,
+                                                       const unsigned char* __restrict__ skip, int skip_stride) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
     if (tx >= skip_stride) return;
@@ -678,7 +728,7 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step2_stream(const __grid_
     const int ta = P.row_lo + blockIdx.y * P.tile_rows;
     const int tb = min(ta + P.tile_rows, P.row_hi);
     if (ta >= tb) return;
-    run_tile2<T, V>(P, ta, tb, tx * OUT - V, lane);
+    run_tileK<T, V, K>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 }
 
 // ---------------------------------------------------------------------------

@@ -108,13 +108,15 @@ class Engine:
         self.first_bad = None
         self._keep = None
         self.temporal = 1
-        if temporal == 2:
-            self.enable_temporal_blocking()
+        if temporal > 1:
+            self.enable_temporal_blocking(temporal)
 
     def enable_temporal_blocking(self, steps_per_pass=2):
-        """Two leapfrog steps per HBM pass in run(): needs a third generation of h/ex/ey (3 more buffers)."""
+        """K leapfrog steps per HBM pass in run(): needs scratch generations of h/ex/ey (3 more buffers for K=2,
+        6 more for K=3/4)."""
         torch = self.torch
-        if steps_per_pass == 2 and len(self.buffers) == 8:
+        need = {1: 8, 2: 11, 3: 14, 4: 14}[int(steps_per_pass)]
+        while len(self.buffers) < need:
             extra = [torch.zeros((self.lrows, self.pitch), dtype=self.buffers[0].dtype, device=self.device) for _ in range(3)]
             torch.cuda.synchronize(self.device)
             L.check(self.lib, self.handle, self.lib.fdtd_bind_scratch(self.handle, *[C.c_void_p(b.data_ptr()) for b in extra]))

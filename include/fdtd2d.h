@@ -109,11 +109,12 @@ const char* fdtd_last_error(fdtd_handle h);          /* h may be NULL: last erro
 int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
                       void* eps_coef, void* mu_coef);
 
-/* Temporal blocking (BASELINE.json north_star (1)): with a THIRD generation of h/ex/ey bound, fdtd_run advances
- * TWO leapfrog steps per HBM pass wherever the two-step dependency cone touches no wall, source, reflector,
- * probe or slab interface (kernel step2_stream), and advances the remaining frame of tiles with two masked
- * single-step launches through the third generation.  Results are bit-identical to single stepping.
- * With fdtd_comm_init active the slab interface strips belong to the frame and exchange their halo rows every step. */
+/* Temporal blocking (BASELINE.json north_star (1)): with scratch generations of h/ex/ey bound (fdtd_bind_scratch: once
+ * for 2 steps per pass, twice for 3 or 4), fdtd_run advances K leapfrog steps per HBM pass wherever the K-step dependency
+ * cone touches no wall, source, reflector, probe or slab interface (kernel stepK_stream), and advances the remaining
+ * frame of tiles with K masked single-step launches through the scratch generations.  Results are bit-identical to
+ * single stepping.  With fdtd_comm_init active the slab interface strips belong to the frame and exchange halo rows
+ * every step.  Groups never straddle a snapshot. */
 int fdtd_bind_scratch(fdtd_handle h, void* h2, void* ex2, void* ey2);
 int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 
