@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--vec", type=int, default=0)
     ap.add_argument("--warps", type=int, default=1)
-    ap.add_argument("--temporal", type=int, default=2, choices=[1, 2, 3, 4],
+    ap.add_argument("--temporal", type=int, default=2, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="leapfrog steps per HBM pass (>1 = temporal blocking)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -54,15 +54,15 @@ struct NcclApi {
 
 struct FrameMaps {                   // per group size K: which tiles the K-step kernel skips and the frame passes cover
     std::vector<uint8_t> key;       // active-source signature + geometry the maps were built for
-    std::vector<uint8_t> h_skip, h_mask[4];      // h_mask[d]: frame tiles dilated by d rings (d = 0 is the frame itself)
-    unsigned char* d_skip = nullptr; unsigned char* d_mask[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<int2> h_list[4];                 // compact (block column, row tile) launch lists of the frame passes
-    int2* d_list[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<uint8_t> h_skip, h_mask[8];      // h_mask[d]: frame tiles dilated by d rings (d = 0 is the frame itself)
+    unsigned char* d_skip = nullptr; unsigned char* d_mask[8] = {};
+    std::vector<int2> h_list[8];                 // compact (block column, row tile) launch lists of the frame passes
+    int2* d_list[8] = {};
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;
     void release() {
         if (d_skip) cudaFree(d_skip);
-        for (int d = 0; d < 4; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
+        for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
     }
 };
 
@@ -73,7 +73,7 @@ struct fdtd_ctx {
     void* gen[4][3] = {};           // [generation][h,ex,ey]: 2 for ping-pong, +1 / +2 scratch for temporal blocking
     int ngen = 2;                   // generations bound
     int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1..4)
-    FrameMaps fm[5];                // indexed by group size K (2..4)
+    FrameMaps fm[9];                // indexed by group size K (2..8)
     void* epc = nullptr; void* muc = nullptr;
     bool bound = false;
     int cur = 0;
@@ -379,7 +379,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
     m.nty = nty; m.ntx2 = ntx2; m.ntx1 = ntx1;
     m.h_skip.assign((size_t)nty * ntx2, 0);
-    for (int d = 0; d < 4; ++d) { m.h_mask[d].assign(d < K ? (size_t)nty * ntx1 : 0, 0); m.h_list[d].clear(); }
+    for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)nty * ntx1 : 0, 0); m.h_list[d].clear(); }
     struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
     std::vector<Box> mods;
     const int64_t BIG = (int64_t)1 << 40;
@@ -442,7 +442,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     }
     const size_t mask_bytes = (size_t)nty * ntx1;
     if (m.d_mask_cap < mask_bytes || m.d_list_cap < longest) {
-        for (int d = 0; d < 4; ++d) {
+        for (int d = 0; d < K; ++d) {
             if (m.d_mask[d]) cudaFree(m.d_mask[d]);
             if (m.d_list[d]) cudaFree(m.d_list[d]);
             CK(cudaMalloc(&m.d_mask[d], mask_bytes)); CK(cudaMalloc(&m.d_list[d], longest * sizeof(int2)));
@@ -466,7 +466,9 @@ void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
     const FrameMaps& m = c->fm[K];
     const int w = std::min(c->cfg.block_warps, 4);
     dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)m.nty);
-    const size_t ring_bytes = (size_t)w * FDTD_KRING * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
+    const size_t ring_bytes = (size_t)w * fdtd::KRing<K>::ROWS * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
+    if (ring_bytes > 48 * 1024)
+        cudaFuncSetAttribute(fdtd::stepK_stream<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
     fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
 }
 
@@ -495,7 +497,15 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
             StepParams<T> PK;                                   // the K-step kernel: everything but the frame
             if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
             PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)lo; PK.row_hi = (int)hi;
-            if (K == 2) launch_stepK<T, 2>(PK, c); else if (K == 3) launch_stepK<T, 3>(PK, c); else launch_stepK<T, 4>(PK, c);
+            switch (K) {
+                case 2: launch_stepK<T, 2>(PK, c); break;
+                case 3: launch_stepK<T, 3>(PK, c); break;
+                case 4: launch_stepK<T, 4>(PK, c); break;
+                case 5: launch_stepK<T, 5>(PK, c); break;
+                case 6: launch_stepK<T, 6>(PK, c); break;
+                case 7: launch_stepK<T, 7>(PK, c); break;
+                default: launch_stepK<T, 8>(PK, c); break;
+            }
             c->stats.kernel_launches++;
             CK(cudaGetLastError());
             CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));                     // passes 1..K-1 done
@@ -691,9 +701,9 @@ int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
 
 int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     if (!c) return FDTD_ERR_ARG;
-    if (steps_per_pass < 1 || steps_per_pass > 4) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1..4");
+    if (steps_per_pass < 1 || steps_per_pass > 8) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1..8");
     const int need = steps_per_pass == 1 ? 2 : (steps_per_pass == 2 ? 3 : 4);
-    if (c->ngen < need) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch (once for 2 steps per pass, twice for 3 or 4)");
+    if (c->ngen < need) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch (once for 2 steps per pass, twice for 3..8)");
     c->temporal = steps_per_pass;
     return 0;
 }
@@ -907,7 +917,7 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     int64_t k = 0;
     int rc = 0;
     CK(cudaEventRecord(c->ev_t0, c->stream));
-    const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 4 : (c->ngen == 3 ? 2 : 1)) : 1;
+    const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
         // largest group that ends no later than the run, the next snapshot and the source tables
         int64_t g = std::min<int64_t>(kmax, first_step + n_steps - n);

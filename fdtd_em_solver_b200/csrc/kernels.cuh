@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
 }
 
 // ---------------------------------------------------------------------------
-// Temporal blocking: K leapfrog steps per HBM pass (generation A -> generation B = A + K steps), K = 2, 3, 4.
+// Temporal blocking: K leapfrog steps per HBM pass (generation A -> generation B = A + K steps), K = 2 .. 8.
 //
 // Only for tiles whose K-step dependency cone touches no wall, source, reflector, probe or slab interface; the
 // host marks all other tiles in `skip` and advances them with K masked single-step launches through scratch
@@ -585,9 +585,9 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
 // Same rounding order as the single-step kernel => bit-identical to K single steps.
 // Algorithmic traffic: 8 words per cell per K steps.
 // ---------------------------------------------------------------------------
-#ifndef FDTD_KRING
-#define FDTD_KRING 4                 // rows of the per-warp shared-memory prefetch ring of stepK_stream (0: registers only)
-#endif
+// rows of the per-warp shared-memory prefetch ring of stepK_stream (0: one-row register prefetch; measured best for
+// K = 2, while K >= 3 needs the deeper ring: K = 4 went from 243 to 315 Gcell/s, profiles/sweep_r1l_ring.jsonl)
+template <int K> struct KRing { static constexpr int ROWS = (K <= 2) ? 0 : 4; };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -600,7 +600,7 @@ template <int K, int V> struct KGeom {
     static constexpr int OUT = (32 - 2 * MARGIN) * V;        // columns stored per warp
 };
 
-template <typename T, int V, int K>
+template <typename T, int V, int K, int RING>
 __device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
     const unsigned full = 0xffffffffu;
     constexpr int MARGIN = KGeom<K, V>::MARGIN;
@@ -629,46 +629,45 @@ __device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb
     }
     Row<T, V> cur;
     const int i_first = ta - K + 1, i_last = tb + K - 2;
-#if FDTD_KRING > 0
-    // Rows are prefetched FDTD_KRING-1 deep into a per-warp shared-memory ring with cp.async (LDGSTS): memory-level
+    // Rows are prefetched RING-1 deep into a per-warp shared-memory ring with cp.async (LDGSTS): memory-level
     // parallelism without register cost (with a one-row register prefetch the K=4 body was latency-bound: ncu
     // long_scoreboard 65 % of stalls, DRAM 60 %).  Every lane copies and later reads back only its own 16 bytes.
     static_assert(V * sizeof(T) == 16, "the ring moves one 16-byte vector per lane per array");
+    constexpr int RR = RING > 0 ? RING : 1;
     extern __shared__ __align__(16) unsigned char ring_raw[];
-    T* ring = reinterpret_cast<T*>(ring_raw) + (size_t)(threadIdx.x >> 5) * (FDTD_KRING * 5 * 32 * V) + lane * V;
-    auto issue = [&](int i) {                                // row i -> slot (i - i_first) mod FDTD_KRING
+    T* ring = reinterpret_cast<T*>(ring_raw) + (size_t)(threadIdx.x >> 5) * (RR * 5 * 32 * V) + lane * V;
+    auto issue = [&](int i) {                                // row i -> slot (i - i_first) mod RING
         if (i <= i_last) {
-            T* slot = ring + (size_t)((i - i_first) % FDTD_KRING) * (5 * 32 * V);
+            T* slot = ring + (size_t)((i - i_first) % RR) * (5 * 32 * V);
             cp_async16(slot + 0 * 32 * V, at(P.h, i)); cp_async16(slot + 1 * 32 * V, at(P.muc, i));
             cp_async16(slot + 2 * 32 * V, at(P.epc, i)); cp_async16(slot + 3 * 32 * V, at(P.ex, i + 1));
             cp_async16(slot + 4 * 32 * V, at(P.ey, i));
         }
         cp_async_commit();                                   // (an empty group past the end keeps the count uniform)
     };
-#pragma unroll
-    for (int d = 0; d < FDTD_KRING; ++d) issue(i_first + d);
-#else
     auto load = [&](Row<T, V>& r, int i) {
         ldvec<T, V>(r.h, at(P.h, i)); ldvec<T, V>(r.mu, at(P.muc, i)); ldvec<T, V>(r.ep, at(P.epc, i));
         ldvec<T, V>(r.exn, at(P.ex, i + 1)); ldvec<T, V>(r.ey, at(P.ey, i));
     };
-    load(cur, i_first);
-#endif
+    if constexpr (RING > 0) {
+#pragma unroll
+        for (int d = 0; d < RING; ++d) issue(i_first + d);
+    } else {
+        load(cur, i_first);
+    }
     for (int i = i_first; i <= i_last; ++i) {                // stage s works on row i-(s-1)
-#if FDTD_KRING > 0
-        cp_async_wait<FDTD_KRING - 1>();                     // the oldest group (row i) has landed
-        {
-            const T* slot = ring + (size_t)((i - i_first) % FDTD_KRING) * (5 * 32 * V);
+        Row<T, V> nxt;
+        if constexpr (RING > 0) {
+            cp_async_wait<(RING > 0 ? RING - 1 : 0)>();      // the oldest group (row i) has landed
+            const T* slot = ring + (size_t)((i - i_first) % RR) * (5 * 32 * V);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 cur.h[v] = slot[0 * 32 * V + v]; cur.mu[v] = slot[1 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
                 cur.exn[v] = slot[3 * 32 * V + v]; cur.ey[v] = slot[4 * 32 * V + v];
             }
+        } else {
+            if (i < i_last) load(nxt, i + 1);
         }
-#else
-        Row<T, V> nxt;
-        if (i < i_last) load(nxt, i + 1);
-#endif
         // one leapfrog step of one row: fields (h, exc, ey) of that row, ex of the row below (exn), coefficients,
         // hn of the row above (hp); outputs the new (h, ex, ey) of the row
         T oh[V], oex[V], oey[V];
@@ -710,11 +709,8 @@ __device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb
             for (int v = 0; v < V; ++v) { Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
 #pragma unroll
         for (int v = 0; v < V; ++v) { Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
-#if FDTD_KRING > 0
-        issue(i + FDTD_KRING);                               // refill the slot just consumed (its values are in registers)
-#else
-        cur = nxt;
-#endif
+        if constexpr (RING > 0) issue(i + RING);             // refill the slot just consumed (its values are in registers)
+        else cur = nxt;
     }
 }
 
@@ -728,7 +724,7 @@ __global__ void __launch_bounds__(128, 1) stepK_stream(const __grid_constant__ S
     const int ta = P.row_lo + blockIdx.y * P.tile_rows;
     const int tb = min(ta + P.tile_rows, P.row_hi);
     if (ta >= tb) return;
-    run_tileK<T, V, K>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+    run_tileK<T, V, K, KRing<K>::ROWS>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 }
 
 // ---------------------------------------------------------------------------

@@ -113,9 +113,9 @@ class Engine:
 
     def enable_temporal_blocking(self, steps_per_pass=2):
         """K leapfrog steps per HBM pass in run(): needs scratch generations of h/ex/ey (3 more buffers for K=2,
-        6 more for K=3/4)."""
+        6 more for K=3..8)."""
         torch = self.torch
-        need = {1: 8, 2: 11, 3: 14, 4: 14}[int(steps_per_pass)]
+        need = 8 if steps_per_pass <= 1 else (11 if steps_per_pass == 2 else 14)
         while len(self.buffers) < need:
             extra = [torch.zeros((self.lrows, self.pitch), dtype=self.buffers[0].dtype, device=self.device) for _ in range(3)]
             torch.cuda.synchronize(self.device)

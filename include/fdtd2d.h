@@ -110,7 +110,7 @@ int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, v
                       void* eps_coef, void* mu_coef);
 
 /* Temporal blocking (BASELINE.json north_star (1)): with scratch generations of h/ex/ey bound (fdtd_bind_scratch: once
- * for 2 steps per pass, twice for 3 or 4), fdtd_run advances K leapfrog steps per HBM pass wherever the K-step dependency
+ * for 2 steps per pass, twice for 3..8), fdtd_run advances K leapfrog steps per HBM pass wherever the K-step dependency
  * cone touches no wall, source, reflector, probe or slab interface (kernel stepK_stream), and advances the remaining
  * frame of tiles with K masked single-step launches through the scratch generations.  Results are bit-identical to
  * single stepping.  With fdtd_comm_init active the slab interface strips belong to the frame and exchange halo rows
