@@ -147,8 +147,8 @@ def workload_config(args, n_gpus):
                   % (ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
             "parallelism": "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus if n_gpus > 1 else "1 GPU",
             "kernel": "%s vec=%d tile_rows=%d warps=%d" % (
-                "step2_stream (2 steps per HBM pass) + masked step_stream frame passes" if args.temporal == 2
-                else "step_stream", args.vec, args.tile_rows, args.warps),
+                "stepK_stream (%d steps per HBM pass) + masked step_stream frame passes" % args.temporal
+                if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
             "temporal_blocking": args.temporal}
 
 
@@ -159,10 +159,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tile-rows", type=int, default=8)
+    ap.add_argument("--tile-rows", type=int, default=0, help="rows per warp tile (0 = library default for the chosen --temporal)")
     ap.add_argument("--vec", type=int, default=0)
-    ap.add_argument("--warps", type=int, default=1)
-    ap.add_argument("--temporal", type=int, default=2, choices=[1, 2, 3, 4, 5, 6, 7, 8],
+    ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = library default)")
+    ap.add_argument("--temporal", type=int, default=6, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="leapfrog steps per HBM pass (>1 = temporal blocking)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -215,6 +215,10 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.tile_rows == 0 or args.warps == 0:
+        args.tile_rows = args.tile_rows or {1: 8, 2: 8, 3: 12, 4: 16, 5: 32, 6: 48, 7: 48, 8: 56}[args.temporal]
+        args.warps = args.warps or (4 if args.temporal == 1 else (2 if args.temporal == 4 else 1))
 
     # ---- device-resident timing ("value") -------------------------------------------------
     step = 0
@@ -300,21 +304,22 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ROWS_PER_GPU * COLS * bpc * args.temporal,
-                     "kernel": ("fdtd::step2_stream<%s,%d>: one launch advances TWO steps (algorithmic bytes are counted per "
+                     "kernel": ("fdtd::stepK_stream<%s,%d,%d>: one launch advances %d steps (algorithmic bytes are counted per "
                                 "step, so frac > 1 is the temporal-blocking gain; DRAM-level traffic is in `traffic`)"
-                                % ("double" if args.dtype == "f64" else "float", 2 if args.dtype == "f64" else 4))
-                     if args.temporal == 2 else
+                                % ("double" if args.dtype == "f64" else "float", 2 if args.dtype == "f64" else 4,
+                                   args.temporal, args.temporal))
+                     if args.temporal > 1 else
                      "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
                          "double" if args.dtype == "f64" else "float", args.vec,
                          "; 3 launches with halo overlap" if n_gpus > 1 else ""),
-                     "launch_ms": ms / args.steps * (2 if args.temporal == 2 else 1),
+                     "launch_ms": ms / args.steps * args.temporal,
                      "steps_per_launch": args.temporal},
         "wall_s_timed_region": wall,
     }
     if n_gpus > 1:
         line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s.json" % (args.dtype, "_temporal2" if args.temporal == 2 else ""))
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s.json" % (args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else ""))
     if os.path.isfile(traffic_file):
         try:
             line["roofline"]["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,7 +60,8 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     std::vector<int2> h_list[8];                 // compact (block column, row tile) launch lists of the frame passes
     int2* d_list[8] = {};
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
-    int nty = 0, ntx2 = 0, ntx1 = 0;
+    int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
+    int frame_tile_rows = 0, frame_vec = 0, frame_nty = 0;   // the frame passes use smaller tiles than the K-step kernel
     void release() {
         if (d_skip) cudaFree(d_skip);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
@@ -72,7 +74,8 @@ struct fdtd_ctx {
     size_t esize = 8;
     void* gen[4][3] = {};           // [generation][h,ex,ey]: 2 for ping-pong, +1 / +2 scratch for temporal blocking
     int ngen = 2;                   // generations bound
-    int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1..4)
+    int temporal = 1;               // leapfrog steps per HBM pass in fdtd_run (1..8)
+    bool auto_tile_rows = false, auto_warps = false;   // launch geometry left to the library (follows `temporal`)
     FrameMaps fm[9];                // indexed by group size K (2..8)
     void* epc = nullptr; void* muc = nullptr;
     bool bound = false;
@@ -245,7 +248,8 @@ void launch_stream(const StepParams<T>& P, int WARPS, cudaStream_t s, int n_list
 }
 
 template <typename T>
-int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, cudaStream_t s, int n_list = 0) {
+int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, cudaStream_t s, int n_list = 0,
+                int vec_override = 0) {
     if (row_hi <= row_lo) return 0;
     if (P.tile_list && n_list == 0) return 0;
     P.row_lo = (int)row_lo; P.row_hi = (int)row_hi;
@@ -253,7 +257,7 @@ int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, c
         dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)(row_hi - row_lo));
         fdtd::step_exact<T><<<grid, 256, 0, s>>>(P);
     } else {
-        const int v = c->cfg.vec, w = c->cfg.block_warps;
+        const int v = vec_override ? vec_override : c->cfg.vec, w = c->cfg.block_warps;
         constexpr int VA = sizeof(T) == 8 ? 2 : 4, VB = 2 * VA;
         if (w < 1 || w > 8) return fail(c, FDTD_ERR_ARG, "block_warps must be 1..8");
         if (v == VA) launch_stream<T, VA>(P, w, s, n_list);
@@ -365,7 +369,11 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     const int MARGIN = (K + V2 - 1) / V2, OUT = (32 - 2 * MARGIN) * V2, LD = 32 * V2;
     const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
     const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == NR ? 1 : 0);
-    const int TR = c->cfg.tile_rows, W1 = 32 * c->cfg.vec;
+    const int TR = c->cfg.tile_rows;                               // rows per K-step tile
+    // The frame passes run latency-bound "mixed" tiles, so they get the narrowest lanes and half-height tiles:
+    // more, shorter CTAs and thinner dilation rings (profiles: 0.33 ms -> see sweep_r1n) than the K-step geometry.
+    const int VF = kvec<T>(), W1 = 32 * VF;
+    const int TRF = (TR % 2 == 0 && TR >= 8) ? TR / 2 : TR;
     // signature: which pulses are live in any step of the group, plus the geometry knobs
     std::vector<uint8_t> key;
     for (int p = 0; p < c->n_src; ++p) {
@@ -375,11 +383,11 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     }
     for (int v : {TR, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
     if (key == m.key && m.d_skip) return 0;
-    const int nty = (int)((hi - lo + TR - 1) / TR);
+    const int nty = (int)((hi - lo + TR - 1) / TR), ntyF = (int)((hi - lo + TRF - 1) / TRF);
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
-    m.nty = nty; m.ntx2 = ntx2; m.ntx1 = ntx1;
+    m.nty = nty; m.ntx2 = ntx2; m.ntx1 = ntx1; m.frame_tile_rows = TRF; m.frame_vec = VF; m.frame_nty = ntyF;
     m.h_skip.assign((size_t)nty * ntx2, 0);
-    for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)nty * ntx1 : 0, 0); m.h_list[d].clear(); }
+    for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)ntyF * ntx1 : 0, 0); m.h_list[d].clear(); }
     struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
     std::vector<Box> mods;
     const int64_t BIG = (int64_t)1 << 40;
@@ -409,23 +417,24 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
             if (!mixed) continue;
             m.h_skip[(size_t)ty * ntx2 + tx] = 1;
             const int64_t c0 = (int64_t)tx * OUT, c1 = std::min<int64_t>(c0 + OUT - 1, NC);
-            for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) m.h_mask[0][(size_t)ty * ntx1 + t1] = 1;
+            for (int64_t fy = (ta - lo) / TRF; fy <= (tb - 1 - lo) / TRF && fy < ntyF; ++fy)
+                for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) m.h_mask[0][(size_t)fy * ntx1 + t1] = 1;
         }
     }
-    for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one tile
-        for (int ty = 0; ty < nty; ++ty)
+    for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one frame tile
+        for (int ty = 0; ty < ntyF; ++ty)
             for (int tx = 0; tx < ntx1; ++tx) {
                 if (!m.h_mask[d - 1][(size_t)ty * ntx1 + tx]) continue;
                 for (int dy = -1; dy <= 1; ++dy)
                     for (int dx = -1; dx <= 1; ++dx) {
                         const int y = ty + dy, x = tx + dx;
-                        if (y >= 0 && y < nty && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
+                        if (y >= 0 && y < ntyF && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
                     }
             }
     const int w = c->cfg.block_warps, nbx = (ntx1 + w - 1) / w;
     size_t longest = 1;
     for (int d = 0; d < K; ++d) {
-        for (int ty = 0; ty < nty; ++ty)
+        for (int ty = 0; ty < ntyF; ++ty)
             for (int bx = 0; bx < nbx; ++bx) {
                 bool any = false;
                 for (int t = bx * w; t < std::min(ntx1, (bx + 1) * w); ++t) any |= m.h_mask[d][(size_t)ty * ntx1 + t] != 0;
@@ -440,7 +449,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         if (m.d_skip) cudaFree(m.d_skip);
         CK(cudaMalloc(&m.d_skip, m.h_skip.size())); m.d_skip_cap = m.h_skip.size();
     }
-    const size_t mask_bytes = (size_t)nty * ntx1;
+    const size_t mask_bytes = (size_t)ntyF * ntx1;
     if (m.d_mask_cap < mask_bytes || m.d_list_cap < longest) {
         for (int d = 0; d < K; ++d) {
             if (m.d_mask[d]) cudaFree(m.d_mask[d]);
@@ -514,7 +523,10 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         if (int rc = fill_params<T>(c, P, n + p - 1, src, dst)) return rc;
         if (c->n_probe) P.probe_out = c->probe_dev + (size_t)(c->probe_count + p - 1) * c->n_probe * 3;
         P.tile_mask = m.d_mask[ring]; P.mask_stride = m.ntx1; P.tile_list = m.d_list[ring];
-        if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size())) return rc;
+        P.tile_rows = m.frame_tile_rows;
+        static const int dbg_skip = getenv("FDTD_DEBUG_SKIP_FRAME") ? atoi(getenv("FDTD_DEBUG_SKIP_FRAME")) : 0;   // timing experiments only
+        if (!((dbg_skip & 1) && !last) && !((dbg_skip & 2) && last))
+        if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size(), m.frame_vec)) return rc;
         if (!last) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
         if (c->comm) {
             cudaEvent_t done = last ? c->ev_p3 : c->ev_bnd;
@@ -619,6 +631,8 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
         const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 7) / 8);
         const bool small = wide_tiles < 2 * 148;
         if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 4;     // 4 columns per lane: 256-bit (f64) / 128-bit (f32) accesses
+        c->auto_warps = c->cfg.block_warps <= 0 && !small;
+        c->auto_tile_rows = c->cfg.tile_rows <= 0 && !small;
         if (c->cfg.block_warps <= 0) c->cfg.block_warps = small ? 1 : 4;
         if (c->cfg.tile_rows <= 0) {
             c->cfg.tile_rows = 8;
@@ -705,6 +719,12 @@ int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     const int need = steps_per_pass == 1 ? 2 : (steps_per_pass == 2 ? 3 : 4);
     if (c->ngen < need) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch (once for 2 steps per pass, twice for 3..8)");
     c->temporal = steps_per_pass;
+    // measured on the 8192 x 65536 slab (profiles/sweep_r1*.jsonl): the K-step kernel wants taller tiles as K grows
+    // (its prologue is 2K-1 rows) and one warp per CTA
+    static const int rows_for_k[9] = {8, 8, 8, 12, 16, 32, 48, 48, 56};
+    if (c->auto_tile_rows) c->cfg.tile_rows = rows_for_k[steps_per_pass];
+    if (c->auto_warps) c->cfg.block_warps = steps_per_pass == 1 ? 4 : (steps_per_pass == 4 ? 2 : 1);
+    for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
 
@@ -916,6 +936,22 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
     int64_t k = 0;
     int rc = 0;
+    const int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
+    if (kmax_pre >= 2) {
+        // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
+        bool seen[9] = {};
+        for (int64_t n = first_step; n < first_step + n_steps;) {
+            int64_t g = std::min<int64_t>(kmax_pre, first_step + n_steps - n);
+            if (snaps) g = std::min<int64_t>(g, snapshot_every - (n % snapshot_every));
+            if (c->n_src > 0) g = std::min<int64_t>(g, c->table_len - n);
+            if (g >= 2 && !seen[g]) {
+                seen[g] = true;
+                const int rc0 = c->cfg.dtype == FDTD_F64 ? build_frame_maps<double>(c, n, (int)g) : build_frame_maps<float>(c, n, (int)g);
+                if (rc0) return rc0;
+            }
+            n += std::max<int64_t>(g, 1);
+        }
+    }
     CK(cudaEventRecord(c->ev_t0, c->stream));
     const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
@@ -957,9 +993,10 @@ int fdtd_set_tuning(fdtd_handle c, int32_t tile_rows, int32_t vec, int32_t block
     const int va = c->cfg.dtype == FDTD_F64 ? 2 : 4;
     if (vec && vec != va && vec != 2 * va) return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
     if (block_warps < 0 || block_warps > 8 || tile_rows < 0) return fail(c, FDTD_ERR_ARG, "bad tuning");
-    if (tile_rows) c->cfg.tile_rows = tile_rows;
+    if (tile_rows) { c->cfg.tile_rows = tile_rows; c->auto_tile_rows = false; }
     if (vec) c->cfg.vec = vec;
-    if (block_warps) c->cfg.block_warps = block_warps;
+    if (block_warps) { c->cfg.block_warps = block_warps; c->auto_warps = false; }
+    for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
 

@@ -223,7 +223,7 @@ def test_cuda_against_reference_golden_vectors():
         e.close()
 
 
-@pytest.mark.parametrize("temporal", [2, 3, 4])
+@pytest.mark.parametrize("temporal", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("shape,tile_rows,warps", [((200, 900), 8, 4), ((131, 517), 4, 2), ((64, 300), 16, 1)])
 def test_temporal_blocking_k_steps_per_pass_bitwise(shape, tile_rows, warps, temporal):
     """fdtd_run with K steps per HBM pass (stepK_stream + masked frame passes) == oracle, every snapshot/probe."""
@@ -254,8 +254,8 @@ def test_temporal_blocking_k_steps_per_pass_bitwise(shape, tile_rows, warps, tem
 def test_temporal_blocking_interior_only_and_fp32():
     """No sources/reflectors: almost every tile goes through the two-step kernel.  fp32: identical bits to single steps."""
     from fdtd_em_solver_b200.engine import Engine
-    for temporal in (2, 3, 4):
-        f, setup, times = SC.random_case(300, 2000, 9, n_steps=13, with_sources=False, with_rects=False)
+    for temporal in (2, 3, 4, 5, 7, 8):
+        f, setup, times = SC.random_case(300, 2000, 9, n_steps=19, with_sources=False, with_rects=False)
         e = _engine_for(f, setup, times, kernel="stream", tile_rows=8, temporal=temporal)
         R.run(f, setup, times)
         e.run(0, len(times))
@@ -263,7 +263,7 @@ def test_temporal_blocking_interior_only_and_fp32():
         e.close()
     f, setup, times = SC.random_case(150, 1200, 10, n_steps=10)
     outs = []
-    for temporal in (1, 2, 4):
+    for temporal in (1, 2, 4, 6):
         rows, cols = f.h.shape
         S = setup.courant
         e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, dtype="float32",

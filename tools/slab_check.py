@@ -19,7 +19,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
                                 (97, 300, 13, dict(tile_rows=4, temporal=2)), (1500, 4100, 25, dict(temporal=2)),
                                 (2000, 9000, 16, dict(temporal=2, block_warps=2)),
-                                (1500, 4100, 26, dict(temporal=4)), (2000, 9000, 19, dict(temporal=3, block_warps=2))]:
+                                (1500, 4100, 26, dict(temporal=4)), (2000, 9000, 19, dict(temporal=3, block_warps=2)),
+                                (2000, 9000, 27, dict(temporal=6, tile_rows=16)), (1500, 4100, 33, dict(temporal=8))]:
     f, setup, times = SC.random_case(rows, cols, 3, walls=(False, False, False, True), n_steps=n_steps)
     b, e_ = SL.split_rows(rows, world)[rank]
     S = setup.courant
