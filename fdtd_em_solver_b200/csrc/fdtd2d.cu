@@ -373,7 +373,9 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     // The frame passes run latency-bound "mixed" tiles, so they get the narrowest lanes and half-height tiles:
     // more, shorter CTAs and thinner dilation rings (profiles: 0.33 ms -> see sweep_r1n) than the K-step geometry.
     const int VF = kvec<T>(), W1 = 32 * VF;
-    const int TRF = (TR % 2 == 0 && TR >= 8) ? TR / 2 : TR;
+    int TRF = TR;                                                  // largest divisor of TR not above 8: thin dilation rings
+    for (int d = 8; d >= 2; --d) if (TR % d == 0) { TRF = d; break; }
+    if (TR <= 8) TRF = (TR % 2 == 0 && TR >= 8) ? TR / 2 : TR;
     // signature: which pulses are live in any step of the group, plus the geometry knobs
     std::vector<uint8_t> key;
     for (int p = 0; p < c->n_src; ++p) {
@@ -524,8 +526,6 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         if (c->n_probe) P.probe_out = c->probe_dev + (size_t)(c->probe_count + p - 1) * c->n_probe * 3;
         P.tile_mask = m.d_mask[ring]; P.mask_stride = m.ntx1; P.tile_list = m.d_list[ring];
         P.tile_rows = m.frame_tile_rows;
-        static const int dbg_skip = getenv("FDTD_DEBUG_SKIP_FRAME") ? atoi(getenv("FDTD_DEBUG_SKIP_FRAME")) : 0;   // timing experiments only
-        if (!((dbg_skip & 1) && !last) && !((dbg_skip & 2) && last))
         if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size(), m.frame_vec)) return rc;
         if (!last) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
         if (c->comm) {
