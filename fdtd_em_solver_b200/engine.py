@@ -182,6 +182,15 @@ class Engine:
         L.check(self.lib, self.handle, self.lib.fdtd_get_fields(self.handle, _ptr(h), _ptr(ex), _ptr(ey)))
         return h, ex, ey
 
+    def generation_buffers(self):
+        """The torch tensors that currently hold (h, ex, ey): generations 0/1 are buffers[0..5] interleaved as
+        h0,h1,ex0,ex1,ey0,ey1; scratch generations 2 and 3 follow the coefficient planes as h,ex,ey triples."""
+        g = int(self.lib.fdtd_current_generation(self.handle))
+        if g < 2:
+            return self.buffers[0 + g], self.buffers[2 + g], self.buffers[4 + g]
+        base = 8 + 3 * (g - 2)
+        return self.buffers[base], self.buffers[base + 1], self.buffers[base + 2]
+
     # ---- time stepping -----------------------------------------------------------------------
     def step(self, n):
         if self.first_bad is not None and n >= self.first_bad:

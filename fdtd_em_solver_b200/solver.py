@@ -9,7 +9,10 @@ What moved to the device: Solver.update (:169-257) and the run loops of
 Solver.solve (:288-292, :319-337) -- see engine.py / csrc/.
 
 Extra, optional constructor keywords (defaults keep reference scripts
-unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact".
+unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact",
+material_on_device=False (paint eps/mu on the GPU from the recorded shapes),
+temporal_block=1 (leapfrog steps per HBM pass in solve(); 2..8 = temporal
+blocking, worthwhile for grids far larger than L2, bit-identical results).
 """
 import json
 import math
@@ -40,7 +43,7 @@ class Solver:
     """reference solver.py:14-349."""
 
     def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
-                 dtype="float64", device=0, kernel="stream", material_on_device=False):
+                 dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=1):
         self.points_per_wavelength = points_per_wavelength
         self.stability = stability
         self.n_max = math.sqrt(eps_r_max * mu_r_max)
@@ -80,6 +83,7 @@ class Solver:
         # device side
         self._dtype, self._device, self._kernel = dtype, device, kernel
         self._material_on_device = material_on_device
+        self._temporal_block = int(temporal_block)      # leapfrog steps per HBM pass in the run loops (1..8)
         self._engine = None
         self._engine_key = None
         self._host = None           # (h, ex, ey) host copies valid for the current step, or None
@@ -188,14 +192,16 @@ class Solver:
     def _sync_engine(self, times):
         """(Re)build the device state from the host-side description when it changed."""
         courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
-        key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant)
+        key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant,
+               self._temporal_block)
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 if self._pending is None:
                     self._pending = self._fetch()
                 self._engine.close()
             self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
-                                  device=self._device, reflect=self.boundaries, kernel=self._kernel)
+                                  device=self._device, reflect=self.boundaries, kernel=self._kernel,
+                                  temporal=self._temporal_block)
             self._engine_key = key
             self._static_key = None
             self._probe_seen = 0
@@ -397,8 +403,25 @@ class MaterialArray:
             self.ops = ops
         return self
 
-    eps_arr = property(lambda self: self._host()._eps, lambda self, v: (self._host(), setattr(self, "_eps", v), setattr(self, "ops_complete", False)) and None)
-    mu_arr = property(lambda self: self._host()._mu, lambda self, v: (self._host(), setattr(self, "_mu", v), setattr(self, "ops_complete", False)) and None)
+    @property
+    def eps_arr(self):
+        return self._host()._eps
+
+    @eps_arr.setter
+    def eps_arr(self, value):
+        self._host()
+        self._eps = value
+        self.ops_complete = False           # arrays edited by hand: the recorded shapes no longer describe them
+
+    @property
+    def mu_arr(self):
+        return self._host()._mu
+
+    @mu_arr.setter
+    def mu_arr(self, value):
+        self._host()
+        self._mu = value
+        self.ops_complete = False
 
     @property
     def on_host(self):

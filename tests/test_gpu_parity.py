@@ -309,3 +309,20 @@ def test_solver_with_material_on_device_is_identical():
     for a, b in zip(runs[0][:3], runs[1][:3]):
         assert np.array_equal(a, b)
     assert runs[0][3] == runs[1][3] and len(runs[0][3]) == 1501
+
+
+def test_solver_api_with_temporal_blocking_and_snapshots(tmp_path):
+    """Solver(..., temporal_block=4): the drop-in API over the K-step path, snapshot cadence 5 (groups of 4 + 1)."""
+    from fdtd_em_solver_b200 import solver as S
+    sc = SC.spec("tutorial")
+    f, setup, times, info = SC.restate(sc)
+    times = times[:403]
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, sc, temporal_block=4)
+        s.end_time = float(times[-1]) + 0.5 * s.dt
+        s.save(str(tmp_path / "t"))
+        s.solve(realtime=False, step_frequency=5)
+    want = np.array(R.run_saving(f, setup, times, 5))
+    got = np.load(str(tmp_path / "t.npy"))
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(s.h, f.h) and np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)

@@ -97,14 +97,12 @@ def _copy_halos(engines):
     """What fdtd_halo_exchange does over NCCL, done here with device-to-device row copies."""
     world = len(engines)
     for r, e in enumerate(engines):
-        g = e.lib.fdtd_current_generation(e.handle)
-        bufs = {"h": e.buffers[0 + g], "ex": e.buffers[2 + g], "ey": e.buffers[4 + g]}
+        bufs = dict(zip(("h", "ex", "ey"), e.generation_buffers()))
         plan = SL.plan_for(r, world, e.rows, e.cols)
         for m in plan.sends():
             peer = engines[m.peer]
             pp = SL.plan_for(m.peer, world, e.rows, e.cols)
-            pg = peer.lib.fdtd_current_generation(peer.handle)
-            pb = {"h": peer.buffers[0 + pg], "ex": peer.buffers[2 + pg], "ey": peer.buffers[4 + pg]}
+            pb = dict(zip(("h", "ex", "ey"), peer.generation_buffers()))
             pb[m.field][m.row - pp.row_off, :m.count].copy_(bufs[m.field][m.row - plan.row_off, :m.count])
     import torch
     torch.cuda.synchronize()
