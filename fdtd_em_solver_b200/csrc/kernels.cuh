@@ -557,6 +557,11 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
     while (r < tb) {
         int e = min(r + FDTD_CHUNK, tb);
         if (tile_is_mixed(P, r, e, jw, jw + W)) {
+            while (e < tb) {                                 // merge consecutive mixed chunks too: one prologue per run
+                const int e2 = min(e + FDTD_CHUNK, tb);
+                if (!tile_is_mixed(P, e, e2, jw, jw + W)) break;
+                e = e2;
+            }
             run_tile_mixed<T, V>(P, r, e, jw, lane);
         } else {
             while (e < tb) {
@@ -714,8 +719,11 @@ __device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb
     }
 }
 
+// K <= 6 fits 168 registers without spills => 12 warps per SM instead of 8 (K = 6: 395 -> 420 Gcell/s); K = 7, 8 would spill
+template <int K> struct KBounds { static constexpr int MIN_BLOCKS = (K <= 6) ? 3 : 1; };
+
 template <typename T, int V, int K>
-__global__ void __launch_bounds__(128, 1) stepK_stream(const __grid_constant__ StepParams<T> P,
+__global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_stream(const __grid_constant__ StepParams<T> P,
                                                        const unsigned char* __restrict__ skip, int skip_stride) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
