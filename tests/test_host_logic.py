@@ -171,3 +171,34 @@ def test_recorded_shapes_replay_and_cell_lookup():
     assert not lazy.on_host
     assert np.array_equal(got[:, 0].reshape(57, 57), eager.eps_arr) and np.array_equal(got[:, 1].reshape(57, 57), eager.mu_arr)
     assert np.array_equal(lazy.eps_arr, eager.eps_arr) and np.array_equal(lazy.mu_arr, eager.mu_arr) and lazy.on_host
+
+
+def test_c_abi_argument_validation_needs_no_gpu():
+    """Geometry checks of fdtd_create happen before any device is touched: error codes + messages (include/fdtd2d.h)."""
+    from fdtd_em_solver_b200 import _lib as L
+    lib = L.load()
+
+    def create(**kw):
+        cfg = L.Config()
+        cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = 64, 64, 0, 64
+        cfg.kernel = L.KERNEL_STREAM
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        h = ctypes.c_void_p()
+        rc = lib.fdtd_create(ctypes.byref(cfg), ctypes.byref(h))
+        msg = lib.fdtd_last_error(None).decode()
+        if rc == 0:
+            lib.fdtd_destroy(h)
+        return rc, msg
+
+    assert create(rows=2)[0] == -1 and "at least 3x3" in create(rows=2)[1]
+    assert create(cols=1)[0] == -1
+    assert create(row_begin=10, row_end=5)[0] == -1 and "slab" in create(row_begin=10, row_end=5)[1]
+    assert create(row_begin=0, row_end=1)[0] == -1 and "at least 2 rows" in create(row_begin=0, row_end=1)[1]
+    assert create(row_end=65)[0] == -1
+    assert create(dtype=7)[0] == -1 and "dtype" in create(dtype=7)[1]
+    assert create(kernel=9)[0] == -1
+    assert lib.fdtd_create(None, None) == -1
+    # NULL handles are rejected, never dereferenced
+    assert lib.fdtd_step(None, 0) == -1 and lib.fdtd_sync(None) == -1 and lib.fdtd_destroy(None) == 0
+    assert lib.fdtd_set_temporal_blocking(None, 2) == -1 and lib.fdtd_current_generation(None) == -1
