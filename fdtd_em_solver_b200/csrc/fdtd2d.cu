@@ -62,6 +62,7 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
     int frame_tile_rows = 0, frame_vec = 0, frame_nty = 0;   // the frame passes use smaller tiles than the K-step kernel
+    int64_t k_row_lo = 0, k_row_hi = 0;                      // rows the K-step tiles own
     void release() {
         if (d_skip) cudaFree(d_skip);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
@@ -385,11 +386,18 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     }
     for (int v : {TR, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
     if (key == m.key && m.d_skip) return 0;
-    const int nty = (int)((hi - lo + TR - 1) / TR), ntyF = (int)((hi - lo + TRF - 1) / TRF);
+    // K-step tiles own rows [loK, hiK): they start K rows (rounded up to a frame tile) below the slab top and stop K
+    // rows above its bottom, so that only a thin band of rows at the top/bottom (or at a slab interface) is frame.
+    const int64_t loK = lo + ((K + TRF - 1) / TRF) * (int64_t)TRF;
+    int64_t hiK = std::min<int64_t>(c->cfg.row_end, NR) - K;       // tb+K-1 <= row_end-1 and tb+K-2 <= NR-2
+    hiK = hiK > lo ? lo + ((hiK - lo) / TRF) * TRF : lo;
+    const int nty = hiK > loK ? (int)((hiK - loK + TR - 1) / TR) : 0, ntyF = (int)((hi - lo + TRF - 1) / TRF);
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
     m.nty = nty; m.ntx2 = ntx2; m.ntx1 = ntx1; m.frame_tile_rows = TRF; m.frame_vec = VF; m.frame_nty = ntyF;
-    m.h_skip.assign((size_t)nty * ntx2, 0);
-    for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)ntyF * ntx1 : 0, 0); m.h_list[d].clear(); }
+    m.k_row_lo = loK; m.k_row_hi = hiK;
+    m.h_skip.assign((size_t)std::max(nty, 1) * ntx2, 0);
+    // frame tiles: everything that is not completely covered by K-step tiles the K-step kernel really advances
+    for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)ntyF * ntx1 : 0, d == 0 ? 1 : 0); m.h_list[d].clear(); }
     struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
     std::vector<Box> mods;
     const int64_t BIG = (int64_t)1 << 40;
@@ -405,9 +413,10 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
             if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
+    std::vector<uint8_t> plain(ntx2);
     for (int ty = 0; ty < nty; ++ty) {
-        const int64_t ta = lo + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hi);
-        // every row a stage touches (ta-K .. tb+K-1) is an OWNED plain interior row of this slab
+        const int64_t ta = loK + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hiK);
+        // every row a stage touches (ta-K .. tb+K-1) is an OWNED plain interior row of this slab (by construction)
         const bool rows_ok = ta - K >= std::max<int64_t>(c->cfg.row_begin, 0) && ta - (K - 1) >= 1 &&
                              tb + K - 2 <= NR - 2 && tb + K - 1 <= c->cfg.row_end - 1;
         for (int tx = 0; tx < ntx2; ++tx) {
@@ -416,12 +425,16 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
             if (!mixed)
                 for (const Box& q : mods)
                     if (q.r0 <= tb + K && q.r1 >= ta - K - 1 && q.c0 <= jw + LD && q.c1 >= jw - 1) { mixed = true; break; }
-            if (!mixed) continue;
-            m.h_skip[(size_t)ty * ntx2 + tx] = 1;
-            const int64_t c0 = (int64_t)tx * OUT, c1 = std::min<int64_t>(c0 + OUT - 1, NC);
-            for (int64_t fy = (ta - lo) / TRF; fy <= (tb - 1 - lo) / TRF && fy < ntyF; ++fy)
-                for (int64_t t1 = c0 / W1; t1 <= c1 / W1 && t1 < ntx1; ++t1) m.h_mask[0][(size_t)fy * ntx1 + t1] = 1;
+            m.h_skip[(size_t)ty * ntx2 + tx] = mixed;
+            plain[tx] = !mixed;
         }
+        for (int64_t fy = (ta - lo) / TRF; fy < (tb - lo) / TRF && fy < ntyF; ++fy)       // ta, tb are frame-tile aligned
+            for (int t1 = 0; t1 < ntx1; ++t1) {
+                const int64_t c0 = (int64_t)t1 * W1, c1 = std::min<int64_t>(c0 + W1 - 1, NC);
+                bool covered = true;
+                for (int64_t tx = c0 / OUT; tx <= c1 / OUT && covered; ++tx) covered = tx < ntx2 && plain[tx];
+                if (covered) m.h_mask[0][(size_t)fy * ntx1 + t1] = 0;
+            }
     }
     for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one frame tile
         for (int ty = 0; ty < ntyF; ++ty)
@@ -507,8 +520,8 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         if (last) {
             StepParams<T> PK;                                   // the K-step kernel: everything but the frame
             if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
-            PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)lo; PK.row_hi = (int)hi;
-            switch (K) {
+            PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
+            if (m.nty > 0) switch (K) {
                 case 2: launch_stepK<T, 2>(PK, c); break;
                 case 3: launch_stepK<T, 3>(PK, c); break;
                 case 4: launch_stepK<T, 4>(PK, c); break;
@@ -517,7 +530,7 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
                 case 7: launch_stepK<T, 7>(PK, c); break;
                 default: launch_stepK<T, 8>(PK, c); break;
             }
-            c->stats.kernel_launches++;
+            if (m.nty > 0) c->stats.kernel_launches++;
             CK(cudaGetLastError());
             CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));                     // passes 1..K-1 done
         }
