@@ -245,7 +245,7 @@ def main():
     if not args.no_e2e:
         owned = ROWS_PER_GPU
         tdt = torch.float64
-        lo, hi = (1 if rank > 0 else 0), (1 if rank > 0 else 0) + owned
+        lo = 1 if rank > 0 else 0                        # halo row above the slab travels with the coefficient planes
         # host-resident inputs of this slab: the two coefficient planes, pinned, float64 (what
         # Solver.solve hands over, solver.py:278-279); built once outside the timed region
         eps_slab = torch.empty((owned + 1, COLS), dtype=tdt, pin_memory=True)

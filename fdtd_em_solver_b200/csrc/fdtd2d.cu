@@ -497,8 +497,8 @@ void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
 }
 
 // Steps n .. n+K-1 in one HBM pass: A -> B.  The frame (walls, sources, reflectors, probes, slab interface strips)
-// goes A -> S -> S' -> ... -> B with K masked, compact single-step launches: passes 1..K-1 (frame dilated by K-p rings
-// of tiles) run on the high-priority edge stream CONCURRENTLY with the K-step kernel, the last pass follows both.
+// goes A -> S -> S' -> ... -> B with K masked, compact single-step launches: passes 1..K-1 (frame dilated by a ring
+// of tiles wide enough for the K-p cells of validity still needed) run on the high-priority edge stream CONCURRENTLY with the K-step kernel, the last pass follows both.
 // With slabs the generation each pass wrote has its halo rows exchanged on the comm stream right after the pass.
 template <typename T>
 int group_impl(fdtd_ctx* c, int64_t n, int K) {
@@ -514,7 +514,10 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
     for (int p = 1; p <= K; ++p) {
         const bool last = p == K;
         const int dst = last ? B : scratch[(p - 1) & 1];
-        const int ring = K - p;                                 // pass p covers the frame dilated by K-p rings
+        // Pass p must be exact on the frame dilated by K-p CELLS (one cell of validity is lost per step); it runs on
+        // the frame dilated by ceil((K-p)/frame_tile_rows) TILES.  Values it computes further out from stale inputs
+        // are never read by a value that is kept.
+        const int ring = (K - p + m.frame_tile_rows - 1) / m.frame_tile_rows;
         cudaStream_t st = last ? c->stream : c->edge_stream;
         if (c->comm) CK(cudaStreamWaitEvent(st, c->ev_comm, 0));                  // halos of `src` have landed
         if (last) {

@@ -1,26 +1,24 @@
 // Device code of libfdtd2d.so: the fused 2D Yee leapfrog step for sm_100a.
 //
-// Two kernels compute the SAME function (one call of the reference's
-// Solver.update, /root/reference/solver.py:169-257), from generation A of the
-// fields into generation B (ping-pong):
+// Three kernels compute the SAME function (calls of the reference's Solver.update,
+// /root/reference/solver.py:169-257), from generation A of the fields into generation B (ping-pong):
 //
-//   step_exact   one thread per cell; every output value is the closed form of
-//                the reference's statement sequence, written
-//                as the recursive functions of struct Exact.  Slow (it re-reads
-//                its stencil from L1/L2) but obviously right: the in-repo GPU
-//                reference, and the per-cell fix-up used by step_stream.
-//   step_stream  production path.  Each warp owns a (tile_rows x 32*V) tile and
-//                marches down its rows with ex[i,:] and hn[i-1,:] carried in
-//                registers, hn[i,j-1] by warp shuffle and a one-column halo
-//                recomputed by lane 0.  Each field/coefficient word is read once
-//                with 128-bit loads; H and E updates are fused.  Tiles that
-//                touch a wall, a source line, a reflector or a probe ("mixed"
-//                tiles) run the same loop with guarded loads and overwrite their
-//                special cells with Exact -- walls, sources and reflectors are
-//                tile predicates of the one launch, not extra launches.
+//   step_exact    one thread per cell; every output value is the closed form of the reference's statement
+//                 sequence, written as the functions of struct Exact.  Slow (it re-reads its
+//                 stencil from L1/L2) but obviously right: the in-repo GPU reference, and the fallback for the few
+//                 corner cells of step_stream.
+//   step_stream   ONE step.  Each warp owns a (tile_rows x 32*V) tile and marches down its rows with ex[i,:] and
+//                 hn[i-1,:] carried in registers, hn[i,j-1] by warp shuffle and a one-column halo recomputed by
+//                 lane 0.  Each field/coefficient word is read once with 128/256-bit loads; H and E updates are
+//                 fused.  Tiles that touch a wall, a source line, a reflector or a probe ("mixed" tiles) run the
+//                 same loop with guarded loads and exact per-cell helpers on register operands -- walls, sources
+//                 and reflectors are tile predicates of the one launch, not extra launches.
+//   stepK_stream  K = 2..8 steps per pass over HBM (temporal blocking): the same march as a K-stage register
+//                 pipeline with sacrificial halo lanes and a cp.async shared-memory prefetch ring; plain interior
+//                 tiles only, the host advances the rest ("frame") with masked step_stream launches.
 //
-// Arithmetic: explicit round-to-nearest intrinsics, never contracted to FMA
-// (numpy rounds after every ufunc); the association order is the reference's.
+// Arithmetic: explicit round-to-nearest intrinsics, never contracted to FMA (numpy rounds after every ufunc);
+// the association order is the reference's, so fp64 results are bit-identical to the reference.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
