@@ -328,6 +328,7 @@ int step_impl(fdtd_ctx* c, int64_t step) {
     }
     const int64_t lo = c->cfg.row_begin;
     const int64_t hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);   // last slab also owns ex[rows]
+    if (c->auto_tile_rows) P.tile_rows = 8;        // cfg.tile_rows follows the K-step kernel; a lone single step wants short tiles
     if (!c->comm) {
         if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
     } else {
@@ -336,7 +337,7 @@ int step_impl(fdtd_ctx* c, int64_t step) {
         //   edge(n)     after interior(n-1) [it overwrites A strip rows interior(n-1) still reads] and comm(n-1)
         //   comm(n)     after edge(n)
         //   interior(n) after edge(n-1) [it reads generation A strip rows that edge(n-1) wrote]; same stream as interior(n-1)
-        const int64_t tr = c->cfg.tile_rows;
+        const int64_t tr = P.tile_rows;
         const bool has_up = c->rank > 0, has_down = c->rank + 1 < c->nranks;
         int64_t a = has_up ? std::min(lo + tr, hi) : lo;
         int64_t b = has_down ? std::max(a, c->cfg.row_end - tr) : hi;
@@ -498,7 +499,8 @@ void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
 
 // Steps n .. n+K-1 in one HBM pass: A -> B.  The frame (walls, sources, reflectors, probes, slab interface strips)
 // goes A -> S -> S' -> ... -> B with K masked, compact single-step launches: passes 1..K-1 (frame dilated by a ring
-// of tiles wide enough for the K-p cells of validity still needed) run on the high-priority edge stream CONCURRENTLY with the K-step kernel, the last pass follows both.
+// of tiles wide enough for the K-p cells of validity still needed) run on the high-priority edge stream
+// CONCURRENTLY with the K-step kernel, the last pass follows both.
 // With slabs the generation each pass wrote has its halo rows exchanged on the comm stream right after the pass.
 template <typename T>
 int group_impl(fdtd_ctx* c, int64_t n, int K) {
