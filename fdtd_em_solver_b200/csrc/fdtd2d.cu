@@ -100,6 +100,8 @@ struct fdtd_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_bnd = nullptr, ev_comm = nullptr, ev_int = nullptr, ev_p3 = nullptr;
     cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     double* snap_dev[2] = {nullptr, nullptr};
+    double* snap_pin[2] = {nullptr, nullptr};        // pinned host ring: snapshots reach pageable user memory through it
+    struct SnapCopy { double* dst; const double* src; size_t bytes; } snap_job[2] = {};
     void* stage = nullptr; size_t stage_bytes = 0;
 
     ncclComm_t comm = nullptr;
@@ -593,7 +595,15 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_packed[slot], c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[slot], 0));
-    CK(cudaMemcpyAsync(host_dst, c->snap_dev[slot], (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    // device slot -> pinned host slot (async DMA) -> the caller's array (plain memcpy run by the driver's callback
+    // thread, in stream order).  The caller's array can stay pageable: pinning a whole snapshot stack costs ~1 ms per MB
+    // (0.3 s for the tutorial's 331 MB, seconds for doubleslit's 5.2 GB), more than the run itself.
+    CK(cudaMemcpyAsync(c->snap_pin[slot], c->snap_dev[slot], (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    c->snap_job[slot] = {host_dst, c->snap_pin[slot], (size_t)rows * cols * 8};      // slot reuse waits for ev_free below
+    CK(cudaLaunchHostFunc(c->copy_stream, [](void* p) {
+        auto* j = static_cast<fdtd_ctx::SnapCopy*>(p);
+        std::memcpy(j->dst, j->src, j->bytes);
+    }, &c->snap_job[slot]));
     CK(cudaEventRecord(c->ev_free[slot], c->copy_stream));
     return 0;
 }
@@ -695,6 +705,7 @@ int fdtd_destroy(fdtd_handle c) {
     for (FrameMaps& m : c->fm) m.release();
     for (int s = 0; s < 2; ++s) {
         if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
+        if (c->snap_pin[s]) cudaFreeHost(c->snap_pin[s]);
         if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
         if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
     }
@@ -949,7 +960,10 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     const bool snaps = snapshot_every > 0 && snapshots_host != nullptr;
     if (snaps) {
         for (int s = 0; s < 2; ++s)
-            if (!c->snap_dev[s]) CK(cudaMalloc(&c->snap_dev[s], (size_t)c->owned * c->cfg.cols * 8));
+            if (!c->snap_dev[s]) {
+                CK(cudaMalloc(&c->snap_dev[s], (size_t)c->owned * c->cfg.cols * 8));
+                CK(cudaHostAlloc(&c->snap_pin[s], (size_t)c->owned * c->cfg.cols * 8, cudaHostAllocDefault));
+            }
     }
     if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
     int64_t k = 0;

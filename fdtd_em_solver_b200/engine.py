@@ -197,34 +197,28 @@ class Engine:
             raise IndexError("index %d is out of bounds for the pulse magnitude table" % n)
         L.check(self.lib, self.handle, self.lib.fdtd_step(self.handle, int(n)))
 
-    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None, pinned=True):
-        """Steps [first_step, first_step+n_steps); returns the float64 snapshot stack (or None)."""
+    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None):
+        """Steps [first_step, first_step+n_steps); returns the float64 snapshot stack (or None).  The stack is an
+        ordinary numpy array: the library stages each snapshot through its own small pinned ring."""
         first_step, n_steps = int(first_step), int(n_steps)
         total_calls = first_step + n_steps if total_calls is None else int(total_calls)
         bad = None
         if self.first_bad is not None and first_step + n_steps > self.first_bad:
             bad = self.first_bad
             n_steps = max(0, bad - first_step)
-        snaps, n_snaps, host = None, 0, None
+        snaps, n_snaps = None, 0
         if snapshot_every:
             k = int(snapshot_every)
             n_snaps = (first_step + n_steps) // k - first_step // k
             if n_snaps:
-                t = self.torch.empty((n_snaps, self.owned, self.cols), dtype=self.torch.float64,
-                                     pin_memory=bool(pinned))
-                host = t
-                snaps = t.numpy()
+                snaps = np.empty((n_snaps, self.owned, self.cols), dtype=np.float64)
         got = C.c_int64(0)
         L.check(self.lib, self.handle, self.lib.fdtd_run(
             self.handle, first_step, n_steps, int(snapshot_every), _ptr(snaps) if snaps is not None else None,
             n_snaps, total_calls, C.byref(got)))
-        self._last_host = host
         if bad is not None:
             raise IndexError("index %d is out of bounds for the pulse magnitude table" % bad)
         return snaps
-
-    def set_tuning(self, tile_rows=0, vec=0, block_warps=0):
-        L.check(self.lib, self.handle, self.lib.fdtd_set_tuning(self.handle, int(tile_rows), int(vec), int(block_warps)))
 
     def sync(self):
         L.check(self.lib, self.handle, self.lib.fdtd_sync(self.handle))

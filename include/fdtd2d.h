@@ -165,7 +165,8 @@ int fdtd_step(fdtd_handle h, int64_t step);
  * written as float64 to snapshots_host[k] (owned_rows x cols each, dense), k counting from 0, with the
  * reference's list-aliasing rule applied (solver.py:337 vs :180: point-source cells hold the NEXT call's
  * magnitude when that call exists, i.e. step+1 < total_calls, and the pulse is active then).
- * Returns after all device work and copies completed. */
+ * snapshots_host may be ordinary pageable memory: each snapshot goes device -> a pinned ring owned by the library
+ * (async DMA on a side stream) -> snapshots_host (memcpy in stream order).  Returns after everything completed. */
 int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
              double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots);
 

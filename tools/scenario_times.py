@@ -7,6 +7,11 @@ import numpy as np
 from oracle import restated as R, scenarios as SC
 from fdtd_em_solver_b200 import solver as S
 
+import torch
+torch.zeros(1, device="cuda"); torch.cuda.synchronize()          # CUDA context creation is not part of any config's time
+from fdtd_em_solver_b200 import _lib
+_lib.load()
+
 for name in ("tutorial", "lens", "waveguide", "doubleslit"):
     sc = SC.spec(name)
     f, setup, times, info = SC.restate(sc)

@@ -23,8 +23,5 @@ for n in range(n_steps):
     e.lib.fdtd_step(e.handle, 50 + n_steps + n)
 t1 = time.perf_counter(); e.sync(); t2 = time.perf_counter()
 print(json.dumps(dict(enqueue_us_per_step=1e6 * (t1 - t0) / n_steps, total_us_per_step=1e6 * (t2 - t0) / n_steps)))
-import torch
-t0 = time.perf_counter(); x = torch.empty((636, 255, 255), dtype=torch.float64, pin_memory=True); t1 = time.perf_counter()
-print(json.dumps(dict(pinned_alloc_331MB_s=t1 - t0)))
 t0 = time.perf_counter(); snaps = e.run(50 + 2 * n_steps, 500, snapshot_every=5, total_calls=10 ** 6); t1 = time.perf_counter()
 print(json.dumps(dict(run500_with_100_snapshots_s=t1 - t0)))
