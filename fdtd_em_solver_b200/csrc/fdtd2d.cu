@@ -101,7 +101,7 @@ struct fdtd_ctx {
     cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     double* snap_dev[2] = {nullptr, nullptr};
     double* snap_pin[2] = {nullptr, nullptr};        // pinned host ring: snapshots reach pageable user memory through it
-    struct SnapCopy { double* dst; const double* src; size_t bytes; } snap_job[2] = {};
+    struct SnapCopy { double* dst; const double* src; size_t bytes; };
     void* stage = nullptr; size_t stage_bytes = 0;
 
     ncclComm_t comm = nullptr;
@@ -599,11 +599,14 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     // thread, in stream order).  The caller's array can stay pageable: pinning a whole snapshot stack costs ~1 ms per MB
     // (0.3 s for the tutorial's 331 MB, seconds for doubleslit's 5.2 GB), more than the run itself.
     CK(cudaMemcpyAsync(c->snap_pin[slot], c->snap_dev[slot], (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-    c->snap_job[slot] = {host_dst, c->snap_pin[slot], (size_t)rows * cols * 8};      // slot reuse waits for ev_free below
-    CK(cudaLaunchHostFunc(c->copy_stream, [](void* p) {
+    // one heap job per snapshot: the host enqueues far ahead of the callbacks, so a per-slot job would be overwritten
+    auto* job = new fdtd_ctx::SnapCopy{host_dst, c->snap_pin[slot], (size_t)rows * cols * 8};
+    cudaError_t he = cudaLaunchHostFunc(c->copy_stream, [](void* p) {
         auto* j = static_cast<fdtd_ctx::SnapCopy*>(p);
         std::memcpy(j->dst, j->src, j->bytes);
-    }, &c->snap_job[slot]));
+        delete j;
+    }, job);
+    if (he != cudaSuccess) { delete job; return fail(c, FDTD_ERR_CUDA, std::string("cudaLaunchHostFunc: ") + cudaGetErrorString(he)); }
     CK(cudaEventRecord(c->ev_free[slot], c->copy_stream));
     return 0;
 }
