@@ -45,6 +45,13 @@ class Shape(C.Structure):
 SHAPE_RECT, SHAPE_QUARTER, SHAPE_CONVEX = 0, 1, 2
 
 
+class FramePlan(C.Structure):
+    _fields_ = [("k_tile_rows", C.c_int32), ("k_tile_cols", C.c_int32), ("k_load_cols", C.c_int32),
+                ("k_margin_cols", C.c_int32), ("k_tiles_y", C.c_int32), ("k_tiles_x", C.c_int32),
+                ("k_row_lo", C.c_int64), ("k_row_hi", C.c_int64), ("frame_tile_rows", C.c_int32),
+                ("frame_tile_cols", C.c_int32), ("frame_tiles_y", C.c_int32), ("frame_tiles_x", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("cell_updates", C.c_int64), ("kernel_launches", C.c_int64),
                 ("halo_bytes_sent", C.c_int64), ("last_run_ms", C.c_double)]
@@ -60,6 +67,7 @@ SIGNATURES = {
     "fdtd_destroy": (C.c_int, [_P]),
     "fdtd_last_error": (C.c_char_p, [_P]),
     "fdtd_bind_buffers": (C.c_int, [_P] * 9),
+    "fdtd_plan_frame": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P]),
     "fdtd_bind_scratch": (C.c_int, [_P, _P, _P, _P]),
     "fdtd_set_temporal_blocking": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),

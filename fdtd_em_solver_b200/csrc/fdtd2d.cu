@@ -366,33 +366,26 @@ int step_impl(fdtd_ctx* c, int64_t step) {
 template <typename T> constexpr int kvec() { return sizeof(T) == 8 ? 2 : 4; }     // columns per lane of stepK_stream
 
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
-template <typename T>
-int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
-    FrameMaps& m = c->fm[K];
-    constexpr int V2 = kvec<T>();
+// Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
+struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
+struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; };
+
+void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
+    const int K = g.K, V2 = g.V2;
     const int MARGIN = (K + V2 - 1) / V2, OUT = (32 - 2 * MARGIN) * V2, LD = 32 * V2;
-    const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
-    const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == NR ? 1 : 0);
-    const int TR = c->cfg.tile_rows;                               // rows per K-step tile
-    // The frame passes run latency-bound "mixed" tiles, so they get the narrowest lanes and half-height tiles:
-    // more, shorter CTAs and thinner dilation rings (profiles: 0.33 ms -> see sweep_r1n) than the K-step geometry.
-    const int VF = kvec<T>(), W1 = 32 * VF;
-    int TRF = TR;                                                  // largest divisor of TR not above 8: thin dilation rings
+    const int64_t NR = g.rows, NC = g.cols;
+    const int64_t lo = g.row_begin, hi = g.row_end + (g.row_end == NR ? 1 : 0);
+    const int TR = g.tile_rows;                                    // rows per K-step tile
+    // The frame passes run latency-bound "mixed" tiles, so they get the narrowest lanes and short tiles: more, shorter
+    // CTAs and a thin dilation ring (profiles/sweep_r1n..p) instead of the K-step geometry.
+    const int VF = V2, W1 = 32 * VF;
+    int TRF = TR;                                                  // largest divisor of TR not above 8
     for (int d = 8; d >= 2; --d) if (TR % d == 0) { TRF = d; break; }
     if (TR <= 8) TRF = (TR % 2 == 0 && TR >= 8) ? TR / 2 : TR;
-    // signature: which pulses are live in any step of the group, plus the geometry knobs
-    std::vector<uint8_t> key;
-    for (int p = 0; p < c->n_src; ++p) {
-        uint8_t live = 0;
-        for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
-        key.push_back(live);
-    }
-    for (int v : {TR, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
-    if (key == m.key && m.d_skip) return 0;
     // K-step tiles own rows [loK, hiK): they start K rows (rounded up to a frame tile) below the slab top and stop K
     // rows above its bottom, so that only a thin band of rows at the top/bottom (or at a slab interface) is frame.
     const int64_t loK = lo + ((K + TRF - 1) / TRF) * (int64_t)TRF;
-    int64_t hiK = std::min<int64_t>(c->cfg.row_end, NR) - K;       // tb+K-1 <= row_end-1 and tb+K-2 <= NR-2
+    int64_t hiK = std::min<int64_t>(g.row_end, NR) - K;            // tb+K-1 <= row_end-1 and tb+K-2 <= NR-2
     hiK = hiK > lo ? lo + ((hiK - lo) / TRF) * TRF : lo;
     const int nty = hiK > loK ? (int)((hiK - loK + TR - 1) / TR) : 0, ntyF = (int)((hi - lo + TRF - 1) / TRF);
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
@@ -401,32 +394,17 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     m.h_skip.assign((size_t)std::max(nty, 1) * ntx2, 0);
     // frame tiles: everything that is not completely covered by K-step tiles the K-step kernel really advances
     for (int d = 0; d < 8; ++d) { m.h_mask[d].assign(d < K ? (size_t)ntyF * ntx1 : 0, d == 0 ? 1 : 0); m.h_list[d].clear(); }
-    struct Box { int64_t r0, r1, c0, c1; };                       // inclusive
-    std::vector<Box> mods;
-    const int64_t BIG = (int64_t)1 << 40;
-    for (int p = 0; p < c->n_src; ++p) {
-        if (!key[p]) continue;
-        const fdtd_source& q = c->src[p];
-        if (q.kind == FDTD_SRC_POINT) mods.push_back({q.row, q.row, q.col, q.col});
-        else if (q.kind == FDTD_SRC_RIGHT || q.kind == FDTD_SRC_LEFT) mods.push_back({-BIG, BIG, q.col, q.col});
-        else if (q.kind == FDTD_SRC_UP) mods.push_back({q.row + 1, q.row + 1, -BIG, BIG});
-        else mods.push_back({q.row, q.row, -BIG, BIG});
-    }
-    for (int r = 0; r < c->n_rect; ++r)
-        for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
-            if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
-    for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
     std::vector<uint8_t> plain(ntx2);
     for (int ty = 0; ty < nty; ++ty) {
         const int64_t ta = loK + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hiK);
         // every row a stage touches (ta-K .. tb+K-1) is an OWNED plain interior row of this slab (by construction)
-        const bool rows_ok = ta - K >= std::max<int64_t>(c->cfg.row_begin, 0) && ta - (K - 1) >= 1 &&
-                             tb + K - 2 <= NR - 2 && tb + K - 1 <= c->cfg.row_end - 1;
+        const bool rows_ok = ta - K >= std::max<int64_t>(g.row_begin, 0) && ta - (K - 1) >= 1 &&
+                             tb + K - 2 <= NR - 2 && tb + K - 1 <= g.row_end - 1;
         for (int tx = 0; tx < ntx2; ++tx) {
             const int64_t jw = (int64_t)tx * OUT - (int64_t)MARGIN * V2;
             bool mixed = !rows_ok || jw < 1 || jw + LD - 1 > NC - 2;
             if (!mixed)
-                for (const Box& q : mods)
+                for (const FrameBox& q : mods)
                     if (q.r0 <= tb + K && q.r1 >= ta - K - 1 && q.c0 <= jw + LD && q.c1 >= jw - 1) { mixed = true; break; }
             m.h_skip[(size_t)ty * ntx2 + tx] = mixed;
             plain[tx] = !mixed;
@@ -449,17 +427,47 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
                         if (y >= 0 && y < ntyF && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
                     }
             }
-    const int w = c->cfg.block_warps, nbx = (ntx1 + w - 1) / w;
-    size_t longest = 1;
-    for (int d = 0; d < K; ++d) {
+    const int w = g.block_warps, nbx = (ntx1 + w - 1) / w;
+    for (int d = 0; d < K; ++d)
         for (int ty = 0; ty < ntyF; ++ty)
             for (int bx = 0; bx < nbx; ++bx) {
                 bool any = false;
                 for (int t = bx * w; t < std::min(ntx1, (bx + 1) * w); ++t) any |= m.h_mask[d][(size_t)ty * ntx1 + t] != 0;
                 if (any) m.h_list[d].push_back(make_int2(bx, ty));
             }
-        longest = std::max(longest, m.h_list[d].size());
+}
+
+template <typename T>
+int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
+    FrameMaps& m = c->fm[K];
+    // signature: which pulses are live in any step of the group, plus the geometry knobs
+    std::vector<uint8_t> key;
+    for (int p = 0; p < c->n_src; ++p) {
+        uint8_t live = 0;
+        for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
+        key.push_back(live);
     }
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
+    if (key == m.key && m.d_skip) return 0;
+    std::vector<FrameBox> mods;
+    const int64_t BIG = (int64_t)1 << 40;
+    for (int p = 0; p < c->n_src; ++p) {
+        if (!key[p]) continue;
+        const fdtd_source& q = c->src[p];
+        if (q.kind == FDTD_SRC_POINT) mods.push_back({q.row, q.row, q.col, q.col});
+        else if (q.kind == FDTD_SRC_RIGHT || q.kind == FDTD_SRC_LEFT) mods.push_back({-BIG, BIG, q.col, q.col});
+        else if (q.kind == FDTD_SRC_UP) mods.push_back({q.row + 1, q.row + 1, -BIG, BIG});
+        else mods.push_back({q.row, q.row, -BIG, BIG});
+    }
+    for (int r = 0; r < c->n_rect; ++r)
+        for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
+            if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
+    for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
+    plan_frame(FrameGeom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
+                         c->cfg.block_warps, K, kvec<T>()}, mods, m);
+    const int ntyF = m.frame_nty, ntx1 = m.ntx1;
+    size_t longest = 1;
+    for (int d = 0; d < K; ++d) longest = std::max(longest, m.h_list[d].size());
     // the previous group's launches may still be reading the old maps
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->edge_stream));
@@ -729,6 +737,32 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
     c->gen[0][0] = h0; c->gen[1][0] = h1; c->gen[0][1] = ex0; c->gen[1][1] = ex1; c->gen[0][2] = ey0; c->gen[1][2] = ey1;
     c->epc = eps_coef; c->muc = mu_coef;
     c->bound = true; c->cur = 0;
+    return 0;
+}
+
+int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                    fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks) {
+    fdtd_ctx* c = nullptr;
+    if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes))
+        return fail(c, FDTD_ERR_ARG, "bad argument");
+    if (cfg->rows < 3 || cfg->cols < 3 || cfg->tile_rows <= 0 || cfg->block_warps <= 0 || cfg->row_begin < 0 ||
+        cfg->row_end > cfg->rows || cfg->row_end <= cfg->row_begin)
+        return fail(c, FDTD_ERR_ARG, "bad geometry");
+    std::vector<FrameBox> mods;
+    for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
+    const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+    FrameMaps m;
+    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2}, mods, m);
+    const int margin = (K + V2 - 1) / V2;
+    plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
+    plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
+    plan->k_row_lo = m.k_row_lo; plan->k_row_hi = m.k_row_hi;
+    plan->frame_tile_rows = m.frame_tile_rows; plan->frame_tile_cols = 32 * m.frame_vec;
+    plan->frame_tiles_y = m.frame_nty; plan->frame_tiles_x = m.ntx1;
+    if (skip && m.nty > 0) std::memcpy(skip, m.h_skip.data(), (size_t)m.nty * m.ntx2);
+    if (masks)
+        for (int d = 0; d < K; ++d)
+            std::memcpy(masks + (size_t)d * m.frame_nty * m.ntx1, m.h_mask[d].data(), (size_t)m.frame_nty * m.ntx1);
     return 0;
 }
 

@@ -118,6 +118,20 @@ int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, v
 int fdtd_bind_scratch(fdtd_handle h, void* h2, void* ex2, void* ey2);
 int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 
+/* The frame plan of temporal blocking as pure host logic (no CUDA call, works without a GPU; used by the tests).
+ * cfg: rows, cols, row_begin, row_end, dtype, tile_rows (> 0) and block_warps (> 0) are read.  boxes: n_boxes x
+ * {r0, r1, c0, c1} INCLUSIVE cell boxes that the K-step kernel must stay away from (sources, reflectors, probes).
+ * plan receives the geometry; skip (k_tiles_y x k_tiles_x bytes, 1 = tile left to the frame passes) and masks
+ * (steps_per_pass x frame_tiles_y x frame_tiles_x bytes, masks[d] = frame dilated by d rings of tiles) may be NULL. */
+typedef struct fdtd_frame_plan {
+    int32_t k_tile_rows, k_tile_cols, k_load_cols, k_margin_cols;   /* stepK_stream tile: rows, stored / loaded columns, halo */
+    int32_t k_tiles_y, k_tiles_x;
+    int64_t k_row_lo, k_row_hi;                                     /* rows owned by K-step tiles: [k_row_lo, k_row_hi)    */
+    int32_t frame_tile_rows, frame_tile_cols, frame_tiles_y, frame_tiles_x;
+} fdtd_frame_plan;
+int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                    fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks);
+
 /* Host arrays handed to fdtd_upload_coeffs / fdtd_set_fields / fdtd_get_fields normally start at global
  * row 0.  A rank that keeps only its slab on the host declares the global row its host arrays start at. */
 int fdtd_set_host_row_origin(fdtd_handle h, int64_t first_global_row);
