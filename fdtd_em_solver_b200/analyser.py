@@ -1,22 +1,55 @@
-"""Drop-in `analyser` module (reference analyser.py:7-159): consumers of the
-`.npy` snapshot stack + `.txt` JSON constants that Solver.save/solve write.
-Host-side numpy only -- out of the accelerated path; kept so
-that reference scripts run unchanged against this package.
+"""Drop-in `analyser` module: the consumers of what `Solver.save()` + `Solver.solve()` leave on disk
+(`<name>.npy` = float64 snapshot stack, `<name>.txt` = JSON run constants).
+
+Same public surface and behaviour as the reference's analyser.py (FileLoader: analyser.py:7-84, DataCollector:
+:87-159) so that reference scripts run unchanged, but organised around three module-level helpers.  Host-side numpy
+only: this is outside the accelerated path; matplotlib is imported lazily because it is optional
+on a GPU box.
 """
 import json
 
 import numpy as np
 
-_KEYS = ('dt', 'ds', 'length_x', 'length_y', 'stability', 'omega_max', 'end_time', 'step_frequency')
+# the scalar run constants both classes mirror as attributes (written by Solver.save_to_json)
+RUN_KEYS = ("dt", "ds", "length_x", "length_y", "stability", "omega_max", "end_time", "step_frequency")
+FFT_POINTS = 2 ** 14
 
 
-def _pyplot():
-    import matplotlib.pyplot as plt
-    return plt
+def _mpl():
+    import matplotlib.pyplot as pyplot
+    import matplotlib.animation as animation
+    return pyplot, animation
+
+
+def _adopt(obj, constants):
+    """Mirror the scalar run constants of a `.txt` file as attributes of `obj`."""
+    for key in RUN_KEYS:
+        setattr(obj, key, constants[key])
+
+
+def _cell(value, ds):
+    """SI coordinate -> grid index the way the analysers do it (NOT Solver.convert: can differ by one cell)."""
+    return int(value / ds)
+
+
+def _draw_field(plt, frame, limit, extent):
+    image = plt.imshow(frame, vmax=limit, vmin=-limit, extent=extent, cmap='seismic')
+    plt.colorbar(image)
+    plt.ylabel("Y (m)")
+    plt.xlabel("X (m)")
+    return image
+
+
+def _power_spectrum(samples, spacing, omega_max):
+    """|FFT|^2 of the zero-padded series on 0 < omega < omega_max, omega in rad/s."""
+    padded = np.zeros(FFT_POINTS)
+    padded[:len(samples)] = samples
+    omega = 2 * np.pi * np.fft.fftfreq(FFT_POINTS, d=spacing)
+    band = (omega > 0) & (omega < omega_max)
+    return omega[band], np.absolute(np.fft.fft(padded)[band]) ** 2
 
 
 class FileLoader:
-    """reference analyser.py:7-84."""
 
     def __init__(self, file_name):
         self.file_name = file_name
@@ -29,92 +62,85 @@ class FileLoader:
         print("Loading npy file...")
         self.h_matrix = np.load(self.file_name + ".npy")
         try:
-            with open(self.file_name + ".txt") as json_file:
-                print("Loading txt file...")
-                self.constants = json.load(json_file)
+            handle = open(self.file_name + ".txt")
         except FileNotFoundError:
             print("Simulation constants txt file could not be found")
             return
+        with handle:
+            print("Loading txt file...")
+            self.constants = json.load(handle)
         self.unpack_constants_from_json()
 
     def unpack_constants_from_json(self):
-        for key in _KEYS:
-            setattr(self, key, self.constants[key])
+        _adopt(self, self.constants)
         self.material = np.array(self.constants['material'])
         self.size = len(self.material)
         self.pulses = self.constants['pulses']
 
+    def _extent(self):
+        return [0, self.length_x, self.length_y, 0]
+
     def play(self, interval=1, colourdepth=0.8, jupyter=False):
-        plt = _pyplot()
-        import matplotlib.animation as animation
-        scale = (1 - colourdepth) * np.max(self.h_matrix)
-        fig, ax = plt.subplots()
-        image = ax.imshow(self.h_matrix[0], vmax=scale, vmin=-scale, extent=[0, self.length_x, self.length_y, 0],
-                          cmap='seismic')
+        plt, animation = _mpl()
+        fig = plt.figure()
+        limit = (1 - colourdepth) * np.max(self.h_matrix)
+        image = _draw_field(plt, self.h_matrix[0], limit, self._extent())
 
-        def animate(i):
-            image.set_array(self.h_matrix[i])
-            fig.suptitle("Time step: {}".format(i * self.step_frequency))
+        def show(k):
+            image.set_array(self.h_matrix[k])
+            fig.suptitle("Time step: {}".format(k * self.step_frequency))
 
-        plt.colorbar(image)
-        plt.ylabel("Y (m)")
-        plt.xlabel("X (m)")
-        ani = animation.FuncAnimation(fig, animate, frames=len(self.h_matrix), interval=interval, repeat=False)
+        movie = animation.FuncAnimation(fig, show, frames=len(self.h_matrix), interval=interval, repeat=False)
         if jupyter:
-            return ani
+            return movie
         plt.show()
 
     def plot_matrix_at_time(self, time):
-        plt = _pyplot()
+        plt, _ = _mpl()
         plt.figure()
-        frame = int(time / (self.dt * self.step_frequency))
-        top = np.max(self.h_matrix)
-        im = plt.imshow(self.h_matrix[frame], vmax=top, vmin=-top, extent=[0, self.length_x, self.length_y, 0],
-                        cmap='seismic')
-        plt.colorbar(im)
+        frame = self.h_matrix[int(time / (self.dt * self.step_frequency))]
+        _draw_field(plt, frame, np.max(self.h_matrix), self._extent())
         plt.suptitle("Time: " + str(time))
-        plt.ylabel("Y (m)")
-        plt.xlabel("X (m)")
         plt.show()
 
     def get_matrix(self):
         return self.h_matrix
 
     def convert(self, value):
-        return int(value / self.ds)
+        return _cell(value, self.ds)
 
     def create_data_collector(self, location):
         return DataCollector(self.h_matrix, location, self.constants)
 
 
 class DataCollector:
-    """reference analyser.py:87-159: one probe cell's time series and its power spectrum."""
+    """The time series of one probe cell of a snapshot stack, and its power spectrum."""
 
     def __init__(self, matrix, location, constants):
-        self.matrix = matrix
-        self.location = location
-        self.constants = constants
+        self.matrix, self.location, self.constants = matrix, location, constants
         self.data = []
-        self.fft_amplitude = None
-        self.fft_frequencies = None
+        self.fft_amplitude = self.fft_frequencies = None
         self.unpack_constants()
         self.collect_all()
 
     def unpack_constants(self):
-        for key in _KEYS:
-            setattr(self, key, self.constants[key])
-        self.i_pos = self.convert(self.location[0])
-        self.j_pos = self.convert(self.location[1])
+        _adopt(self, self.constants)
+        self.i_pos, self.j_pos = (self.convert(v) for v in self.location[:2])
+        # one sample per SAVED snapshot, i.e. every step_frequency-th step
         self.time_vector = np.arange(0, len(self.matrix)) * self.dt * self.step_frequency
 
     def convert(self, value):
-        return int(value / self.ds)
+        return _cell(value, self.ds)
 
     def collect_all(self):
         self.data = self.matrix[:, self.i_pos, self.j_pos]
 
+    def fft(self):
+        self.fft_frequencies, self.fft_amplitude = _power_spectrum(self.data, self.dt * self.step_frequency,
+                                                                   self.omega_max)
+
     def plot_time(self, show=True):
-        plt = _pyplot()
+        plt, _ = _mpl()
         plt.suptitle("Detected pulse")
         plt.xlabel("Time (seconds)")
         plt.ylabel("Magnitude")
@@ -122,20 +148,12 @@ class DataCollector:
         if show:
             plt.show()
 
-    def fft(self):
-        """Zero-padded 2**14-point spectrum; sample spacing is dt*step_frequency (analyser.py:134-145)."""
-        padded = np.concatenate((self.data, np.zeros(2 ** 14 - len(self.data))))
-        freqs = 2 * np.pi * np.fft.fftfreq(len(padded), d=self.dt * self.step_frequency)
-        keep = np.logical_and(freqs > 0, freqs < self.omega_max)
-        self.fft_amplitude = np.absolute(np.fft.fft(padded)[keep]) ** 2
-        self.fft_frequencies = freqs[keep]
-
     def plot_frequency(self, show=True, title=None):
-        plt = _pyplot()
+        plt, _ = _mpl()
         if self.fft_amplitude is None:
             self.fft()
         if title is not None:
-            plt.suptitle = title
+            plt.suptitle = title          # (sic) the reference assigns instead of calling; kept for identical behaviour
         plt.xlabel("Frequency (rad/s)")
         plt.ylabel("Amplitude")
         plt.plot(self.fft_frequencies, self.fft_amplitude)

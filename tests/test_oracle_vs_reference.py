@@ -108,3 +108,26 @@ def test_random_index_level_cases(ref, seed, shape):
         s.update(t)
         R.leapfrog(f, setup, t)
         assert np.array_equal(f.h, s.h) and np.array_equal(f.ex, s.ex) and np.array_equal(f.ey, s.ey), f.step
+
+
+def test_product_analyser_matches_reference_analyser(tmp_path):
+    """FileLoader / DataCollector of the package against the reference's analyser.py on the same files."""
+    import json
+    from fdtd_em_solver_b200 import analyser as A
+    ref_an = ref_import.load()[1]
+    rng = np.random.default_rng(0)
+    stack = rng.standard_normal((300, 20, 20))
+    const = dict(dt=4e-12, ds=0.0125, length_x=0.25, length_y=0.25, stability=0.1, omega_max=9e9, end_time=1e-8,
+                 step_frequency=5, material=np.ones((20, 20)).tolist(), pulses=[{"type": "gd"}])
+    np.save(str(tmp_path / "run"), stack)
+    json.dump(const, open(str(tmp_path / "run.txt"), "w"))
+    mine, theirs = _quiet(A.FileLoader, str(tmp_path / "run")), _quiet(ref_an.FileLoader, str(tmp_path / "run"))
+    for attr in ("dt", "ds", "length_x", "length_y", "stability", "omega_max", "end_time", "step_frequency", "size", "pulses"):
+        assert getattr(mine, attr) == getattr(theirs, attr)
+    assert np.array_equal(mine.get_matrix(), theirs.get_matrix()) and np.array_equal(mine.material, theirs.material)
+    assert mine.convert(0.13) == theirs.convert(0.13)
+    a, b = mine.create_data_collector((0.1, 0.2)), theirs.create_data_collector((0.1, 0.2))
+    a.fft(); b.fft()
+    assert (a.i_pos, a.j_pos) == (b.i_pos, b.j_pos)
+    assert np.array_equal(a.data, b.data) and np.array_equal(a.time_vector, b.time_vector)
+    assert np.array_equal(a.fft_amplitude, b.fft_amplitude) and np.array_equal(a.fft_frequencies, b.fft_frequencies)
