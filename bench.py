@@ -217,7 +217,7 @@ def main():
         return float(t.item())
 
     if args.tile_rows == 0 or args.warps == 0:
-        args.tile_rows = args.tile_rows or {1: 8, 2: 8, 3: 12, 4: 16, 5: 32, 6: 48, 7: 48, 8: 56}[args.temporal]
+        args.tile_rows = args.tile_rows or {1: 6, 2: 8, 3: 12, 4: 16, 5: 32, 6: 48, 7: 48, 8: 56}[args.temporal]
         args.warps = args.warps or (4 if args.temporal == 1 else (2 if args.temporal == 4 else 1))
 
     # ---- device-resident timing ("value") -------------------------------------------------

@@ -330,7 +330,7 @@ int step_impl(fdtd_ctx* c, int64_t step) {
     }
     const int64_t lo = c->cfg.row_begin;
     const int64_t hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);   // last slab also owns ex[rows]
-    if (c->auto_tile_rows) P.tile_rows = 8;        // cfg.tile_rows follows the K-step kernel; a lone single step wants short tiles
+    if (c->auto_tile_rows) P.tile_rows = 6;        // cfg.tile_rows follows the K-step kernel; a lone single step wants short tiles
     if (!c->comm) {
         if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
     } else {
@@ -663,18 +663,18 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->lrows = fdtd_local_rows(cfg);
     {
         // Launch geometry defaults (tools/sweep.py on the 8192 x 65536 slab): 256-bit lanes, 4 warps per CTA and
-        // SHORT tiles -- 8 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
+        // SHORT tiles -- 6 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
         // Small grids (the script configs, N = 139..442) get narrow single-warp tiles so that the launch
         // still spreads over the 148 SMs.
         const int va = cfg->dtype == FDTD_F64 ? 2 : 4;
-        const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 7) / 8);
+        const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 5) / 6);
         const bool small = wide_tiles < 2 * 148;
         if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 4;     // 4 columns per lane: 256-bit (f64) / 128-bit (f32) accesses
         c->auto_warps = c->cfg.block_warps <= 0 && !small;
         c->auto_tile_rows = c->cfg.tile_rows <= 0 && !small;
         if (c->cfg.block_warps <= 0) c->cfg.block_warps = small ? 1 : 4;
         if (c->cfg.tile_rows <= 0) {
-            c->cfg.tile_rows = 8;
+            c->cfg.tile_rows = 6;
             if (small) {
                 const int64_t col_tiles = (cfg->cols + 1 + 32 * va - 1) / (32 * va);
                 const int64_t want_row_tiles = std::max<int64_t>(1, 592 / col_tiles);
@@ -787,7 +787,7 @@ int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     c->temporal = steps_per_pass;
     // measured on the 8192 x 65536 slab (profiles/sweep_r1*.jsonl): the K-step kernel wants taller tiles as K grows
     // (its prologue is 2K-1 rows) and one warp per CTA
-    static const int rows_for_k[9] = {8, 8, 8, 12, 16, 32, 48, 48, 56};
+    static const int rows_for_k[9] = {6, 6, 8, 12, 16, 32, 48, 48, 56};
     if (c->auto_tile_rows) c->cfg.tile_rows = rows_for_k[steps_per_pass];
     if (c->auto_warps) c->cfg.block_warps = steps_per_pass == 1 ? 4 : (steps_per_pass == 4 ? 2 : 1);
     for (FrameMaps& m : c->fm) m.key.clear();
