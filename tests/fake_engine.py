@@ -1,0 +1,88 @@
+"""TEST DOUBLE -- an `Engine` look-alike that steps with the numpy oracle, so that the host logic of the drop-in
+`Solver` (engine life-cycle, snapshot/probe plumbing, update() paths, error behaviour) can be exercised on a box
+without a GPU.  Lives in tests/ and is only ever monkeypatched in by tests; the product has no such path."""
+import numpy as np
+
+from oracle import restated as R
+from fdtd_em_solver_b200.engine import build_source_tables
+
+
+class FakeEngine:
+    created = 0
+
+    def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
+                 reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
+                 tile_rows=0, vec=0, block_warps=0, temporal=1):
+        FakeEngine.created += 1
+        cols = rows if cols is None else cols
+        assert one_minus_courant is None or one_minus_courant == (1 - courant)
+        self.rows, self.cols = rows, cols
+        self.f = R.Fields.zeros(rows, cols)
+        self.setup = R.Setup(eps_coef=None, mu_coef=None, courant=courant, reflect_walls=tuple(bool(b) for b in reflect))
+        self.first_bad = None
+        self.n_steps = 0
+        self.cells = []
+        self.records = []
+        self.times = None
+        self.closed = False
+
+    def upload_coefficients(self, eps_coef, mu_coef):
+        self.setup.eps_coef, self.setup.mu_coef = np.array(eps_coef), np.array(mu_coef)
+
+    def paint_coefficients(self, shapes, dt_over_ds):
+        raise AssertionError("device painting is not part of the CPU double")
+
+    def set_sources(self, pulses, times):
+        _, _, _, _, _, self.first_bad = build_source_tables(pulses, times)       # the product's own table logic
+        self.times = np.asarray(times, dtype=np.float64)
+        self.setup.pulses = [R.PulseSpec(p.get_type(), p.get_direction(), p.get_row(), p.get_col(), p.get_start_time(),
+                                         p.get_end_time(), p._magnitude_vector) for p in pulses]
+
+    def set_reflectors(self, rects):
+        self.setup.reflectors = [list(map(int, r)) for r in rects]
+
+    def set_probes(self, cells):
+        self.cells = [tuple(map(int, c)) for c in cells]
+        self.records = []
+
+    def set_fields(self, h=None, ex=None, ey=None):
+        z = R.Fields.zeros(self.rows, self.cols)
+        self.f.h = np.array(h) if h is not None else z.h
+        self.f.ex = np.array(ex) if ex is not None else z.ex
+        self.f.ey = np.array(ey) if ey is not None else z.ey
+
+    def get_fields(self, which="hxy", out=None):
+        return self.f.h.copy(), self.f.ex.copy(), self.f.ey.copy()
+
+    def _one(self, n):
+        if self.first_bad is not None and n >= self.first_bad:
+            raise IndexError("index %d is out of bounds for the pulse magnitude table" % n)
+        self.f.step = n
+        R.leapfrog(self.f, self.setup, self.times[n])
+        self.n_steps += 1
+        if self.cells:
+            self.records.append([(self.f.h[i][j], self.f.ex[i][j], self.f.ey[i][j]) for i, j in self.cells])
+
+    def step(self, n):
+        self._one(int(n))
+
+    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None):
+        saved = []
+        for n in range(int(first_step), int(first_step) + int(n_steps)):
+            self._one(n)                                   # the next call's source write mutates saved[-1]: App. A-Q8
+            if snapshot_every and (n + 1) % snapshot_every == 0:
+                saved.append(self.f.h)
+        return np.array(saved) if saved else None
+
+    def probes(self):
+        return np.array(self.records, dtype=np.float64).reshape(len(self.records), len(self.cells), 3)
+
+    def stats(self):
+        return dict(steps=self.n_steps, cell_updates=self.n_steps * self.rows * self.cols, kernel_launches=0,
+                    halo_bytes_sent=0, last_run_ms=0.0)
+
+    def sync(self):
+        pass
+
+    def close(self):
+        self.closed = True

@@ -1,0 +1,114 @@
+"""CPU: the drop-in Solver's host logic end to end, with the device engine replaced by the oracle-backed test double
+(tests/fake_engine.py).  What is checked here is solver.py itself: engine life-cycle, run loops, snapshot and probe
+plumbing, update() on and off the time axis, reset / re-solve, and the reference's error behaviour."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import restated as R, scenarios as SC
+from fake_engine import FakeEngine
+
+
+@pytest.fixture
+def S(monkeypatch):
+    from fdtd_em_solver_b200 import solver
+    monkeypatch.setattr(solver, "Engine", FakeEngine)
+    return solver
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.mark.parametrize("name,n_calls", [("tutorial", 600), ("waveguide", 900), ("mixed", 700), ("lens", 400)])
+def test_save_path_snapshots_probes_and_files(S, name, n_calls, tmp_path):
+    sc = SC.spec(name)
+    f, setup, times, info = SC.restate(sc)
+    times = times[:n_calls]
+    s = _quiet(SC.drive, S, sc)
+    s.end_time = float(times[-1]) + 0.5 * s.dt
+    s.save(str(tmp_path / name))
+    _quiet(s.solve, realtime=False, step_frequency=sc["step_frequency"])
+    want = np.array(R.run_saving(f, setup, times, sc["step_frequency"]))
+    got = np.load(str(tmp_path / name) + ".npy")
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert len(s.h_list) == len(want) and np.array_equal(s.h_list[-1], want[-1])
+    assert np.array_equal(s.h, f.h) and np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)
+    assert s.step == len(times) and len(s.time_vector) == len(times)
+    for d, (i, j, series) in zip(s.recorded_energies, f.probes):
+        assert d["energies"] == series
+    import json
+    meta = json.load(open(str(tmp_path / name) + ".txt"))
+    assert meta["dt"] == s.dt and meta["step_frequency"] == sc["step_frequency"] and len(meta["material"]) == s.size
+
+
+def test_update_on_and_off_the_time_axis(S):
+    sc = SC.spec("waveguide")
+    f, setup, times, info = SC.restate(sc)
+    s = _quiet(SC.drive, S, sc)
+    for t in times[:40]:                                    # on-axis: exactly the loop of solver.py:289-291
+        R.leapfrog(f, setup, t)
+        assert np.array_equal(s.update(t), f.h)
+    for k in range(5):                                      # off-axis: the caller's time gates the pulses, step indexes the tables
+        t = float(times[40 + k]) * 1.0003 + 1e-14
+        R.leapfrog(f, setup, t)
+        assert np.array_equal(s.update(t), f.h)
+    assert np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)
+    assert s.recorded_energies[0]["energies"] == f.probes[0][2] and s.step == 45
+
+
+def test_reset_keeps_history_and_rezeroes_fields(S):
+    sc = SC.spec("waveguide")
+    s = _quiet(SC.drive, S, sc)
+    s.end_time = 300.5 * s.dt
+    _quiet(s.solve, solve_only=True)
+    first = s.h.copy()
+    assert s.step == 301 and first.any() and len(s.recorded_energies[0]["energies"]) == 301
+    s.reset()                                               # solver.py:347-349: step and fields only
+    assert s.step == 0 and not s.h.any() and len(s.recorded_energies[0]["energies"]) == 301
+    created = FakeEngine.created
+    _quiet(s.solve, solve_only=True)
+    assert np.array_equal(s.h, first) and len(s.recorded_energies[0]["energies"]) == 602
+    assert FakeEngine.created == created                    # same geometry: the engine is reused, fields re-uploaded
+
+
+def test_engine_is_rebuilt_when_the_scene_geometry_changes(S):
+    s = _quiet(S.Solver, 10, 0.1, 1, 1, 1.0, 2e-9)
+    _quiet(s.add_gaussian_pulse, 1e9, (0.5, 0.5))
+    s.create_material()
+    _quiet(s.solve, solve_only=True)
+    n0, created = s.size, FakeEngine.created
+    s.set_reflect_boundaries(up=True, down=False, left=False, right=False)   # walls are part of the engine key
+    s.reset()
+    _quiet(s.solve, solve_only=True)
+    assert FakeEngine.created == created + 1 and s.size == n0
+
+
+def test_stale_pulse_index_error_and_partial_progress(S):
+    s = _quiet(S.Solver, 10, 0.1, 1, 1, 1.0, 4e-9)
+    _quiet(s.add_gaussian_pulse, 2e9, (0.3, 0.3))
+    n_short = len(s.pulses[0]._magnitude_vector)
+    _quiet(s.add_oscillating_pulse, 3e9, (0.5, 0.5), 8e9)    # re-meshes: the first pulse keeps its short table
+    s.create_material()
+    with pytest.raises(IndexError):
+        _quiet(s.solve, solve_only=True)
+    assert s.step == n_short
+
+
+def test_second_solve_without_reset_replays_the_reference_literally(S):
+    """solve() twice: times restart at 0 while self.step keeps counting (solver.py:284-291)."""
+    sc = SC.spec("tutorial")
+    s = _quiet(SC.drive, S, sc)
+    s.end_time = 120.5 * s.dt
+    f, setup, times, _ = SC.restate(sc)
+    times = times[:121]
+    _quiet(s.solve, solve_only=True)
+    R.run(f, setup, times)
+    assert np.array_equal(s.h, f.h)
+    _quiet(s.solve, solve_only=True)
+    for t in times:                                         # the oracle with the same quirk: step continues, time restarts
+        R.leapfrog(f, setup, t)
+    assert s.step == f.step == 242 and np.array_equal(s.h, f.h)
