@@ -357,3 +357,14 @@ def test_full_size_slab_temporal_blocking_equals_single_stepping():
     assert float(fa[0].abs().max()) > 0 and float(fa[2].abs().max()) > 0
     assert b.stats()["kernel_launches"] < a.stats()["kernel_launches"] * 2
     a.close(); b.close()
+
+
+def test_4096_grid_all_features_vs_oracle():
+    """SURVEY.md 8(d) 'parity at scale': the largest grid the numpy oracle still steps in seconds (4096 x 4096,
+    heterogeneous eps/mu, every pulse kind, reflectors, mixed walls), default launch geometry, K = 6 -- bitwise."""
+    f, setup, times = SC.random_case(4096, 4096, 33, walls=(False, True, False, False), n_steps=14)
+    e = _engine_for(f, setup, times, kernel="stream", temporal=6)
+    R.run(f, setup, times)
+    e.run(0, len(times))
+    _same(e, f, "4096^2, K=6")
+    e.close()
