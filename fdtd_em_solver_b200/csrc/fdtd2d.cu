@@ -447,7 +447,9 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
         key.push_back(live);
     }
-    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) key.push_back((uint8_t)v);
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) {
+        key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
+    }
     if (key == m.key && m.d_skip) return 0;
     std::vector<FrameBox> mods;
     const int64_t BIG = (int64_t)1 << 40;
