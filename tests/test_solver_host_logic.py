@@ -112,3 +112,47 @@ def test_second_solve_without_reset_replays_the_reference_literally(S):
     for t in times:                                         # the oracle with the same quirk: step continues, time restarts
         R.leapfrog(f, setup, t)
     assert s.step == f.step == 242 and np.array_equal(s.h, f.h)
+
+
+def test_realtime_path_updates_once_per_frame(S, monkeypatch):
+    """solve() without save(): plot_and_show drives one update() per animation frame (solver.py:309-329).  matplotlib
+    is replaced by a stand-in whose FuncAnimation simply plays every frame."""
+    import sys
+    import types
+    shown = []
+
+    class Image:
+        def set_array(self, a):
+            shown.append(np.array(a))
+
+    class Axes:
+        def imshow(self, *a, **k): return Image()
+        def set_aspect(self, *a, **k): pass
+        xaxis = types.SimpleNamespace(set_ticks_position=lambda *a: None, set_label_position=lambda *a: None)
+
+    class Figure:
+        def colorbar(self, *a, **k): pass
+        def suptitle(self, *a, **k): pass
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.subplots = lambda *a, **k: (Figure(), Axes())
+    plt.show = lambda *a, **k: None
+    anim = types.ModuleType("matplotlib.animation")
+
+    def FuncAnimation(fig, func, frames, **k):
+        for frame in frames:
+            func(frame)
+    anim.FuncAnimation = FuncAnimation
+    top = types.ModuleType("matplotlib")
+    top.pyplot, top.animation = plt, anim
+    for name, mod in (("matplotlib", top), ("matplotlib.pyplot", plt), ("matplotlib.animation", anim)):
+        monkeypatch.setitem(sys.modules, name, mod)
+
+    sc = SC.spec("lens")
+    f, setup, times, _ = SC.restate(sc)
+    s = _quiet(SC.drive, S, sc)
+    s.end_time = 60.5 * s.dt
+    _quiet(s.solve)                                          # realtime=True and no save file -> plot_and_show
+    for t in times[:61]:
+        R.leapfrog(f, setup, t)
+    assert len(shown) == 61 and s.step == 61 and np.array_equal(shown[-1], f.h)
