@@ -119,6 +119,36 @@ def cpu_baseline(steps_budget_s=15.0):
     return rows * cols * n / dt / 1e9, n, dt
 
 
+def cpu_baseline_c(budget_s=5.0):
+    """Informational: the same sample through the C restatement (oracle/restated.c, bit-identical to the numpy one) with
+    every host thread OpenMP gives it -- what a compiled multi-core CPU port of the reference step would reach.
+    Returns None when gcc is absent or anything goes wrong: it must never cost the bench line."""
+    try:
+        from oracle import c_oracle as CO, restated as R
+        from fdtd_em_solver_b200 import synthetic as SY
+        if not CO.available():
+            return None
+        CO.lib()
+        rows, cols = CPU_SAMPLE
+        epc, muc = R.synthetic_coefficients(rows, cols, SY.DT, SY.DS, seed=0, total_cols=COLS)
+        n_calls = 2048
+        pulses = [R.PulseSpec("table", p.direction, p.row, p.col, p.start, p.end, p.table)
+                  for p in SY.pulses(rows, cols, n_calls)]
+        setup = R.Setup(eps_coef=epc, mu_coef=muc, courant=(SY.C0 * SY.DT / SY.DS), pulses=pulses)
+        f = R.Fields.zeros(rows, cols)
+        t = SY.times(n_calls)
+        CO.leapfrog(f, setup, t[0])
+        n, t0 = 0, time.perf_counter()
+        while n < n_calls - 1 and (n < 3 or time.perf_counter() - t0 < budget_s):
+            CO.leapfrog(f, setup, t[n + 1])
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": rows * cols * n / dt / 1e9, "unit": "Gcell-updates/s", "cores": os.cpu_count(),
+                "sample": "%dx%d, %d steps in %.1f s, gcc -O2 + OpenMP" % (rows, cols, n, dt)}
+    except Exception:
+        return None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -130,7 +160,7 @@ def run_reference(args, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count(),
+                         "host_cores": os.cpu_count(), "threaded_c_port": cpu_baseline_c(),
                          "note": "numpy elementwise ufuncs are single-threaded; oracle/restated.py is bit-identical "
                                  "to reference solver.py:169-257 (tests/test_oracle_vs_reference.py)"},
         "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -330,7 +360,8 @@ def main():
         v, n, dt = cpu_baseline()
         line["cpu_baseline"] = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": "port",
                                 "sample": "%dx%d sub-grid of the C5 recipe, %d numpy steps in %.1f s (host has %d cores; "
-                                          "numpy ufuncs use 1)" % (CPU_SAMPLE + (n, dt, os.cpu_count()))}
+                                          "numpy ufuncs use 1)" % (CPU_SAMPLE + (n, dt, os.cpu_count())),
+                                "threaded_c_port": cpu_baseline_c()}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
