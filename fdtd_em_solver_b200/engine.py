@@ -197,9 +197,11 @@ class Engine:
             raise IndexError("index %d is out of bounds for the pulse magnitude table" % n)
         L.check(self.lib, self.handle, self.lib.fdtd_step(self.handle, int(n)))
 
-    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None):
+    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None, alloc=None):
         """Steps [first_step, first_step+n_steps); returns the float64 snapshot stack (or None).  The stack is an
-        ordinary numpy array: the library stages each snapshot through its own small pinned ring."""
+        ordinary numpy array: the library stages each snapshot through its own small pinned ring.  `alloc(shape)`
+        may supply the stack instead of np.empty (e.g. a np.lib.format.open_memmap, so a long run streams straight
+        into its .npy file); it must return a writeable C-contiguous float64 array of that shape."""
         first_step, n_steps = int(first_step), int(n_steps)
         total_calls = first_step + n_steps if total_calls is None else int(total_calls)
         bad = None
@@ -211,7 +213,11 @@ class Engine:
             k = int(snapshot_every)
             n_snaps = (first_step + n_steps) // k - first_step // k
             if n_snaps:
-                snaps = np.empty((n_snaps, self.owned, self.cols), dtype=np.float64)
+                shape = (n_snaps, self.owned, self.cols)
+                snaps = np.empty(shape, dtype=np.float64) if alloc is None else alloc(shape)
+                if (snaps.shape != shape or snaps.dtype != np.float64 or not snaps.flags.c_contiguous
+                        or not snaps.flags.writeable):
+                    raise ValueError("alloc() must return a writeable C-contiguous float64 array of shape %r" % (shape,))
         got = C.c_int64(0)
         L.check(self.lib, self.handle, self.lib.fdtd_run(
             self.handle, first_step, n_steps, int(snapshot_every), _ptr(snaps) if snaps is not None else None,

@@ -27,6 +27,9 @@ MU = 1.26 * (10 ** (-6))
 EPSILON = 8.85 * (10 ** (-12))
 
 VERBOSE = True
+# plot_and_save streams the snapshot stack straight into <name>.npy (np.lib.format.open_memmap) once it is at least
+# this big, instead of holding it in RAM and np.save-ing it afterwards (doubleslit: 6387 x 319^2 x 8 B = 5.2 GB)
+STREAM_SNAPSHOT_BYTES = 1 << 30
 
 
 def _say(*a):
@@ -238,6 +241,20 @@ class Solver:
                 d["energies"].append(0.5 * ((eps_ij * (exv ** 2 + eyv ** 2) + mu_ij * hv ** 2)))
         self._probe_seen = len(raw)
 
+    def _npy_path(self):
+        name = self.save_file_name
+        return name if name.endswith(".npy") else name + ".npy"          # np.save's rule
+
+    def _snapshot_alloc(self, shape):
+        """Where the snapshot stack of a run lives: RAM, or the .npy file itself for big stacks."""
+        nbytes = 8 * int(np.prod(shape))
+        if self.save_file and not self.h_list and nbytes >= STREAM_SNAPSHOT_BYTES:
+            self._streamed = self._npy_path()
+            return np.lib.format.open_memmap(self._streamed, mode="w+", dtype=np.float64, shape=tuple(shape))
+        return np.empty(shape, dtype=np.float64)
+
+    _streamed = None
+
     def _run_device(self, times, snapshot_every=0):
         """The loops of solver.py:288-292 / :331-337 for calls self.step .. len(times)-1."""
         self._sync_engine(times)
@@ -245,7 +262,8 @@ class Solver:
         n = len(times) - first
         self._host = None
         try:
-            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times))
+            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
+                                     alloc=self._snapshot_alloc if snapshot_every else None)
         finally:
             done = self._engine.stats()["steps"]
             self.step = first + (done - self._steps_seen)
@@ -302,7 +320,9 @@ class Solver:
                 raise Exception("Must create a save file name for non-realtime simulation")
             self.plot_and_save(step_frequency=step_frequency)
             _say("Saving to npy file...")
-            np.save(self.save_file_name, self._stack if self._stack is not None else self.h_list)
+            if self._streamed is None:
+                np.save(self.save_file_name, self._stack if self._stack is not None else self.h_list)
+            self._streamed = None             # (a streamed stack already IS the file; the page cache keeps it coherent)
             _say("Saving to txt file...")
             self.save_to_json()
             _say("Complete!")
@@ -326,8 +346,17 @@ class Solver:
 
     def plot_and_save(self, step_frequency):
         """reference solver.py:331-337: headless loop + snapshot capture every `step_frequency` calls."""
-        stack = self._loop(step_frequency if self.save_file else 0)
         fresh = not self.h_list
+        self._streamed = None
+        try:
+            stack = self._loop(step_frequency if self.save_file else 0)
+        except BaseException:
+            if self._streamed is not None:         # the reference writes no file when the loop raises
+                import os
+                path, self._streamed = self._streamed, None
+                if os.path.exists(path):
+                    os.remove(path)
+            raise
         if stack is not None:
             self.h_list.extend(stack[k] for k in range(len(stack)))
         self._stack = stack if fresh else None

@@ -66,13 +66,22 @@ class FakeEngine:
     def step(self, n):
         self._one(int(n))
 
-    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None):
-        saved = []
+    def run(self, first_step, n_steps, snapshot_every=0, total_calls=None, alloc=None):
+        saved, out = [], None
+        if alloc is not None and snapshot_every:           # like the real engine: the stack exists before the run starts
+            k, a, b = int(snapshot_every), int(first_step), int(first_step) + int(n_steps)
+            if b // k - a // k:
+                out = alloc((b // k - a // k, self.rows, self.cols))
         for n in range(int(first_step), int(first_step) + int(n_steps)):
             self._one(n)                                   # the next call's source write mutates saved[-1]: App. A-Q8
             if snapshot_every and (n + 1) % snapshot_every == 0:
                 saved.append(self.f.h)
-        return np.array(saved) if saved else None
+        if not saved:
+            return None
+        if out is None:
+            return np.array(saved)
+        out[...] = saved
+        return out
 
     def probes(self):
         return np.array(self.records, dtype=np.float64).reshape(len(self.records), len(self.cells), 3)

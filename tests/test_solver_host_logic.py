@@ -156,3 +156,37 @@ def test_realtime_path_updates_once_per_frame(S, monkeypatch):
     for t in times[:61]:
         R.leapfrog(f, setup, t)
     assert len(shown) == 61 and s.step == 61 and np.array_equal(shown[-1], f.h)
+
+
+def test_big_snapshot_stacks_stream_into_the_npy_file(S, monkeypatch, tmp_path):
+    """above STREAM_SNAPSHOT_BYTES the stack is an open_memmap of <name>.npy, never a RAM copy +
+    np.save; the file, h_list and what FileLoader sees are the same as on the in-RAM route."""
+    from fdtd_em_solver_b200 import analyser
+    sc = SC.spec("tutorial")
+    out = {}
+    for mode, limit in (("ram", 1 << 40), ("stream", 1)):
+        monkeypatch.setattr(S, "STREAM_SNAPSHOT_BYTES", limit)
+        s = _quiet(SC.drive, S, sc)
+        s.end_time = 300.5 * s.dt
+        s.save(str(tmp_path / mode))
+        _quiet(s.solve, realtime=False, step_frequency=5)
+        assert isinstance(s._stack, np.memmap) == (mode == "stream") and s._streamed is None
+        out[mode] = (np.load(str(tmp_path / mode) + ".npy"), np.array(s.h_list))
+    assert out["ram"][0].shape == (60, 255, 255)
+    assert np.array_equal(out["ram"][0], out["stream"][0]) and np.array_equal(out["ram"][1], out["stream"][1])
+    loaded = _quiet(analyser.FileLoader, str(tmp_path / "stream"))
+    assert np.array_equal(loaded.get_matrix(), out["ram"][0]) and loaded.size == 255
+
+
+def test_streamed_file_is_removed_when_the_loop_raises(S, monkeypatch, tmp_path):
+    """The reference reaches np.save only after a complete loop (solver.py:297-303): a stale pulse leaves no file."""
+    import os
+    monkeypatch.setattr(S, "STREAM_SNAPSHOT_BYTES", 1)
+    s = _quiet(S.Solver, 10, 0.1, 1, 1, 1.0, 4e-9)
+    _quiet(s.add_gaussian_pulse, 2e9, (0.3, 0.3))
+    _quiet(s.add_oscillating_pulse, 3e9, (0.5, 0.5), 8e9)
+    s.create_material()
+    s.save(str(tmp_path / "broken"))
+    with pytest.raises(IndexError):
+        _quiet(s.solve, realtime=False)
+    assert not os.path.exists(str(tmp_path / "broken") + ".npy") and s._streamed is None
