@@ -234,11 +234,13 @@ class Solver:
             return
         raw = self._engine.probes()
         cells = [self.material.cell(d["i"], d["j"]) for d in self.recorded_energies]
-        for rec in raw[self._probe_seen:]:
-            for k, d in enumerate(self.recorded_energies):
-                eps_ij, mu_ij = cells[k]
-                hv, exv, eyv = (np.float64(v) for v in rec[k])
-                d["energies"].append(0.5 * ((eps_ij * (exv ** 2 + eyv ** 2) + mu_ij * hv ** 2)))
+        # scalar arithmetic on purpose: np.float64 ** 2 is libm pow(), which is NOT always the correctly rounded x*x
+        # that a vectorised `array ** 2` computes -- the reference's energies are the scalar kind (solver.py:251-255)
+        for k, d in enumerate(self.recorded_energies):
+            eps_ij, mu_ij = cells[k]
+            out = d["energies"]
+            for hv, exv, eyv in raw[self._probe_seen:, k]:           # iterating float64 rows yields np.float64 scalars
+                out.append(0.5 * ((eps_ij * (exv ** 2 + eyv ** 2) + mu_ij * hv ** 2)))
         self._probe_seen = len(raw)
 
     def _npy_path(self):
