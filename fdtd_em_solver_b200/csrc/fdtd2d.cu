@@ -5,6 +5,7 @@
 // that computes needs a CUDA device.
 #include "fdtd2d.h"
 #include "kernels.cuh"
+#include "resident.cuh"
 
 #include <dlfcn.h>
 
@@ -106,6 +107,13 @@ struct fdtd_ctx {
 
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+
+    // resident mode (step_resident: many steps per cooperative launch, for grids that live in L2)
+    int resident = 0;
+    int64_t resident_max_cells = 512 * 512;      // (rows+1)*(cols+1) up to which fdtd_run uses it
+    void* rs_count = nullptr; void* rs_last = nullptr; void* rs_src = nullptr;   // per-call pulse records on the device
+    bool rs_valid = false;
+    int rs_stride = 0, res_blocks_max = 0;
 
     fdtd_stats stats{};
     std::string err;
@@ -575,6 +583,99 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
     return 0;
 }
 
+// ---- resident mode: many steps per cooperative launch (resident.cuh) ------------------------------------
+bool resident_eligible(const fdtd_ctx* c) {
+    if (!c->resident || c->comm || c->cfg.kernel != FDTD_KERNEL_STREAM) return false;
+    if (c->cfg.row_begin != 0 || c->cfg.row_end != c->cfg.rows) return false;            // whole grid on this GPU
+    if ((c->cfg.rows + 1) * (c->cfg.cols + 1) > c->resident_max_cells) return false;
+    if (c->n_src > FDTD_MAX_SRC) return false;
+    for (int p = 0; p < c->n_src; ++p)
+        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
+    return true;
+}
+
+void resident_free_tables(fdtd_ctx* c) {
+    for (void** p : {&c->rs_count, &c->rs_last, &c->rs_src}) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->rs_valid = false; c->rs_stride = 0;
+}
+
+// Per-call records of the ACTIVE pulses in list order (what fill_params builds for one call), for every call of the
+// tables, uploaded once per fdtd_set_sources.
+template <typename T>
+int resident_tables(fdtd_ctx* c) {
+    if (c->rs_valid) return 0;
+    CK(cudaStreamSynchronize(c->stream));                        // an earlier launch may still read the old records
+    resident_free_tables(c);
+    if (c->n_src > 0) {
+        const int64_t L = c->table_len;
+        const int stride = c->n_src;
+        std::vector<int> count((size_t)L, 0);
+        std::vector<T> last((size_t)L, T(0));
+        std::vector<fdtd::SrcStep<T>> src((size_t)L * stride);
+        std::memset(src.data(), 0, src.size() * sizeof(fdtd::SrcStep<T>));
+        for (int64_t n = 0; n < L; ++n) {
+            int k = 0;
+            for (int p = 0; p < c->n_src; ++p) {
+                if (!c->active[(size_t)p * L + n]) continue;
+                fdtd::SrcStep<T>& q = src[(size_t)n * stride + k++];
+                q.kind = c->src[p].kind; q.row = (int)c->src[p].row; q.col = (int)c->src[p].col; q.pad = 0;
+                q.mag = (T)c->mag[(size_t)p * L + n];
+                q.magz = (T)c->magz[(size_t)p * L + n];
+            }
+            count[(size_t)n] = k;
+            last[(size_t)n] = (T)c->last[(size_t)n];
+        }
+        CK(cudaMalloc(&c->rs_count, count.size() * sizeof(int)));
+        CK(cudaMalloc(&c->rs_last, last.size() * sizeof(T)));
+        CK(cudaMalloc(&c->rs_src, src.size() * sizeof(fdtd::SrcStep<T>)));
+        CK(cudaMemcpy(c->rs_count, count.data(), count.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->rs_last, last.data(), last.size() * sizeof(T), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->rs_src, src.data(), src.size() * sizeof(fdtd::SrcStep<T>), cudaMemcpyHostToDevice));
+        c->rs_stride = stride;
+    }
+    c->rs_valid = true;
+    return 0;
+}
+
+// calls n .. n+g-1 in ONE cooperative launch
+template <typename T>
+int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
+    using G = fdtd::ResGeom;
+    if (int rc = resident_tables<T>(c)) return rc;
+    const int A = c->cur, B = next_gen(c, A);
+    StepParams<T> P;
+    if (int rc = fill_params<T>(c, P, n, A, B)) return rc;
+    P.n_src = 0; P.last_mag = T(0);                              // the kernel loads each call's record itself
+    P.row_lo = 0; P.row_hi = (int)c->cfg.rows + 1;
+    if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    if (!c->res_blocks_max) {
+        int coop = 0, sms = 0, per_sm = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdtd::step_resident<T>, fdtd::RES_THREADS, 0));
+        if (!coop || per_sm < 1) return fail(c, FDTD_ERR_CUDA, "cooperative launch unavailable for step_resident");
+        c->res_blocks_max = per_sm * sms;
+    }
+    const int tiles = fdtd::resident_tiles_x<G>(P.NC) * fdtd::resident_tiles_y<G>(P.NR);
+    const int blocks = std::min(tiles, c->res_blocks_max);       // all CTAs co-resident; they stride over the tiles
+    T* h1 = (T*)c->gen[B][0]; T* ex1 = (T*)c->gen[B][1]; T* ey1 = (T*)c->gen[B][2];
+    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+    long long first = n;
+    int ns = (int)g;
+    void* args[] = {&P, &h1, &ex1, &ey1, &R, &first, &ns};
+    CK(cudaLaunchCooperativeKernel((void*)fdtd::step_resident<T>, dim3((unsigned)blocks), dim3(fdtd::RES_THREADS), args, 0, c->stream));
+    c->stats.kernel_launches++;
+    c->cur = (g & 1) ? B : A;
+    if (c->n_probe) c->probe_count += g;
+    c->stats.steps += g;
+    c->stats.cell_updates += g * c->owned * c->cfg.cols;
+    return 0;
+}
+
+int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
+    return c->cfg.dtype == FDTD_F64 ? resident_run<double>(c, n, g) : resident_run<float>(c, n, g);
+}
+
 int group_any(fdtd_ctx* c, int64_t n, int K) {
     return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
@@ -715,6 +816,7 @@ int fdtd_destroy(fdtd_handle c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->probe_dev) cudaFree(c->probe_dev);
     if (c->stage) cudaFree(c->stage);
+    resident_free_tables(c);
     for (FrameMaps& m : c->fm) m.release();
     for (int s = 0; s < 2; ++s) {
         if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
@@ -795,6 +897,16 @@ int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
+
+int fdtd_set_resident(fdtd_handle c, int32_t enable, int64_t max_cells) {
+    if (!c) return FDTD_ERR_ARG;
+    if (max_cells < 0) return fail(c, FDTD_ERR_ARG, "max_cells must be >= 0 (0 keeps the default)");
+    c->resident = enable ? 1 : 0;
+    if (max_cells > 0) c->resident_max_cells = max_cells;
+    return 0;
+}
+
+int fdtd_resident_active(fdtd_handle c) { return c ? (resident_eligible(c) ? 1 : 0) : FDTD_ERR_ARG; }
 
 #define NEED_BOUND() do { if (!c) return FDTD_ERR_ARG; if (!c->bound) return fail(c, FDTD_ERR_STATE, "buffers not bound"); \
     CK(cudaSetDevice(c->cfg.device)); } while (0)
@@ -918,6 +1030,7 @@ int fdtd_set_sources(fdtd_handle c, int32_t n, const fdtd_source* src, int64_t t
                      const double* mag, const double* mag_z, const uint8_t* active, const double* last_mag) {
     if (!c) return FDTD_ERR_ARG;
     for (FrameMaps& m : c->fm) m.key.clear();            // temporal-blocking frame maps depend on the scene
+    c->rs_valid = false;                                  // so do the resident kernel's per-call pulse records
     if (n < 0 || n > 64) return fail(c, FDTD_ERR_ARG, "at most 64 pulses");
     if (n > 0 && (!src || !mag || !mag_z || !active || !last_mag || table_len <= 0))
         return fail(c, FDTD_ERR_ARG, "null source table");
@@ -1007,8 +1120,9 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
     int64_t k = 0;
     int rc = 0;
+    const bool resident = resident_eligible(c);
     const int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
-    if (kmax_pre >= 2) {
+    if (kmax_pre >= 2 && !resident) {
         // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
         bool seen[9] = {};
         for (int64_t n = first_step; n < first_step + n_steps;) {
@@ -1030,7 +1144,16 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
         int64_t g = std::min<int64_t>(kmax, first_step + n_steps - n);
         if (snaps) g = std::min<int64_t>(g, snapshot_every - (n % snapshot_every));
         if (c->n_src > 0) g = std::min<int64_t>(g, c->table_len - n);
-        if (g >= 2) {
+        if (resident) {
+            // every call up to the next snapshot (or the end of the run / of the pulse tables) in one cooperative launch
+            int64_t r = std::min<int64_t>(first_step + n_steps - n, 1 << 20);
+            if (snaps) r = std::min<int64_t>(r, snapshot_every - (n % snapshot_every));
+            if (c->n_src > 0) r = std::min<int64_t>(r, c->table_len - n);
+            if (r >= 1) {
+                if ((rc = resident_any(c, n, r))) break;
+                n += r - 1;
+            } else if ((rc = step_any(c, n))) break;     // past the pulse tables: reports the range error
+        } else if (g >= 2) {
             if ((rc = group_any(c, n, (int)g))) break;
             n += g - 1;                                  // g steps done
         } else if ((rc = step_any(c, n))) break;

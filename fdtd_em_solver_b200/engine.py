@@ -7,6 +7,7 @@ CUDA library.  There is deliberately no CPU implementation here.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -17,6 +18,16 @@ C0 = 2.99 * (10 ** 8)
 MU = 1.26 * (10 ** (-6))
 EPSILON = 8.85 * (10 ** (-12))
 IMPEDANCE = math.sqrt(MU / EPSILON)
+
+
+# Resident mode (many update() calls per cooperative launch, for grids that live in L2): what Engine(resident=None)
+# means.  FDTD_RESIDENT=0/1 overrides it for experiments.
+RESIDENT_DEFAULT = False
+
+
+def _resident_default():
+    v = os.environ.get("FDTD_RESIDENT")
+    return RESIDENT_DEFAULT if v is None or v == "" else v not in ("0", "false", "no")
 
 
 def _ptr(a):
@@ -68,7 +79,7 @@ def build_source_tables(pulses, times):
 class Engine:
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0, temporal=1):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
@@ -110,6 +121,18 @@ class Engine:
         self.temporal = 1
         if temporal > 1:
             self.enable_temporal_blocking(temporal)
+        self.set_resident(_resident_default() if resident is None else resident)
+
+    def set_resident(self, on=True, max_cells=0):
+        """run() advances all calls up to the next snapshot in ONE cooperative launch (kernel step_resident) when the
+        whole grid is on this GPU and (rows+1)*(cols+1) <= max_cells (0 = the library default, 512*512); larger grids
+        and slabs keep the per-call / temporal-blocking path.  Same bits either way."""
+        L.check(self.lib, self.handle, self.lib.fdtd_set_resident(self.handle, 1 if on else 0, int(max_cells)))
+        self.resident = bool(on)
+
+    def resident_active(self):
+        """Would run() use the resident kernel for the scene as it is now?"""
+        return bool(self.lib.fdtd_resident_active(self.handle))
 
     def enable_temporal_blocking(self, steps_per_pass=2):
         """K leapfrog steps per HBM pass in run(): needs scratch generations of h/ex/ey (3 more buffers for K=2,

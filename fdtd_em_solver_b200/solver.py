@@ -12,7 +12,10 @@ Extra, optional constructor keywords (defaults keep reference scripts
 unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact",
 material_on_device=False (paint eps/mu on the GPU from the recorded shapes),
 temporal_block=1 (leapfrog steps per HBM pass in solve(); 2..8 = temporal
-blocking, worthwhile for grids far larger than L2, bit-identical results).
+blocking, worthwhile for grids far larger than L2, bit-identical results),
+resident=None (True/False: all calls between two snapshots in ONE cooperative
+launch for grids that live in L2, i.e. every script of the reference; None =
+engine.RESIDENT_DEFAULT / $FDTD_RESIDENT; bit-identical results).
 """
 import json
 import math
@@ -46,7 +49,8 @@ class Solver:
     """reference solver.py:14-349."""
 
     def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
-                 dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=1):
+                 dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=1,
+                 resident=None):
         self.points_per_wavelength = points_per_wavelength
         self.stability = stability
         self.n_max = math.sqrt(eps_r_max * mu_r_max)
@@ -87,6 +91,7 @@ class Solver:
         self._dtype, self._device, self._kernel = dtype, device, kernel
         self._material_on_device = material_on_device
         self._temporal_block = int(temporal_block)      # leapfrog steps per HBM pass in the run loops (1..8)
+        self._resident = resident                       # None = the engine's default
         self._engine = None
         self._engine_key = None
         self._host = None           # (h, ex, ey) host copies valid for the current step, or None
@@ -196,7 +201,7 @@ class Solver:
         """(Re)build the device state from the host-side description when it changed."""
         courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
         key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant,
-               self._temporal_block)
+               self._temporal_block, self._resident)
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 if self._pending is None:
@@ -204,7 +209,7 @@ class Solver:
                 self._engine.close()
             self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
                                   device=self._device, reflect=self.boundaries, kernel=self._kernel,
-                                  temporal=self._temporal_block)
+                                  temporal=self._temporal_block, resident=self._resident)
             self._engine_key = key
             self._static_key = None
             self._probe_seen = 0

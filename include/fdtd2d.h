@@ -118,6 +118,16 @@ int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, v
 int fdtd_bind_scratch(fdtd_handle h, void* h2, void* ex2, void* ey2);
 int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 
+/* Resident mode for grids that live in L2 (the reference's own scenario scripts, N = 139..442; solver.py:288-292 and
+ * :331-337 drive thousands of update() calls on them): with enable != 0, fdtd_run advances ALL calls up to the next
+ * snapshot in ONE cooperative launch of step_resident (fields ping-pong in L2, per-call pulse records read from a
+ * device table, grid-wide barrier between calls) instead of one launch per call.  Used when the context owns the
+ * whole grid, (rows+1)*(cols+1) <= max_cells (0 keeps the default 512*512), no halo transport is active and no TF/SF
+ * "right" line sits at column 0; otherwise fdtd_run silently keeps the per-call path.  Results are bit-identical
+ * either way.  fdtd_resident_active reports whether fdtd_run would use it for the current scene (1/0). */
+int fdtd_set_resident(fdtd_handle h, int32_t enable, int64_t max_cells);
+int fdtd_resident_active(fdtd_handle h);
+
 /* The frame plan of temporal blocking as pure host logic (no CUDA call, works without a GPU; used by the tests).
  * cfg: rows, cols, row_begin, row_end, dtype, tile_rows (> 0) and block_warps (> 0) are read.  boxes: n_boxes x
  * {r0, r1, c0, c1} INCLUSIVE cell boxes that the K-step kernel must stay away from (sources, reflectors, probes).

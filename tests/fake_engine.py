@@ -12,7 +12,7 @@ class FakeEngine:
 
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0, temporal=1):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None):
         FakeEngine.created += 1
         cols = rows if cols is None else cols
         assert one_minus_courant is None or one_minus_courant == (1 - courant)

@@ -1,0 +1,184 @@
+"""GPU parity of resident mode (kernel step_resident, fdtd_em_solver_b200/csrc/resident.cuh): fdtd_run advancing all
+calls between two snapshots in ONE cooperative launch.  Everything is bit-exact against the oracle / the per-call path
+(fp64 bar of BASELINE.json: 1e-12 relative L2; what is asserted here is equality).
+
+The window algorithm itself is pinned on the CPU by tests/test_resident_emulation.py; these tests add what only a GPU
+can show: the cooperative launch, grid.sync between calls, the generation ping-pong and the device pulse records.
+"""
+import contextlib
+import io
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restated as R, scenarios as SC
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FDTD_TEST_RESIDENT", "0") == "0",
+                                 reason="resident mode awaits its first GPU run: set FDTD_TEST_RESIDENT=1")]
+
+WALLS = list(itertools.product([False, True], repeat=4))
+
+
+def _engine_for(f, setup, times, **kw):
+    from fdtd_em_solver_b200.engine import Engine
+    rows, cols = f.h.shape
+    S = setup.courant
+    e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, **kw)
+    e.upload_coefficients(setup.eps_coef, setup.mu_coef)
+    e.set_sources(setup.pulses, times)
+    e.set_reflectors(setup.reflectors)
+    e.set_fields(f.h, f.ex, f.ey)
+    return e
+
+
+def _same(e, f, where=""):
+    h, ex, ey = e.get_fields()
+    for name, a, b in (("h", h, f.h), ("ex", ex, f.ex), ("ey", ey, f.ey)):
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError("%s differs %s: %d cells, first %s: got %r want %r" % (
+                name, where, len(bad), bad[0], a[tuple(bad[0])], b[tuple(bad[0])]))
+
+
+def _has_wrapping_line(setup):
+    return any(p.direction == "right" and p.col == 0 for p in setup.pulses)
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (4, 7), (9, 5), (33, 33), (40, 70), (67, 131), (139, 139), (300, 200)])
+def test_random_cases_run_loop_bitwise(shape):
+    """All pulse kinds, reflectors, probes, every snapshot cadence; seeds 0 and 3 carry a TF/SF line at column 0, which
+    must silently stay on the per-call path."""
+    rows, cols = shape
+    for seed, k in ((0, 0), (1, 1), (2, 3), (3, 5), (4, 4), (5, 0)):
+        walls = WALLS[(seed * 5 + rows + cols) % 16]
+        f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=13)
+        cells = [(0, 0), (rows // 2, cols // 2), (rows - 1, cols - 1)]
+        f.raw_probes = [(i, j, []) for i, j in cells]
+        e = _engine_for(f, setup, times, resident=True)
+        e.set_probes(cells)
+        assert e.resident_active() == (not _has_wrapping_line(setup))
+        launches0 = e.stats()["kernel_launches"]
+        if k:
+            want = np.array(R.run_saving(f, setup, times, k))
+            got = e.run(0, len(times), snapshot_every=k, total_calls=len(times))
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, seed, k)
+            if e.resident_active():                  # one launch per snapshot interval (+ the tail) + one pack per snapshot
+                n_groups = -(-len(times) // k)
+                assert e.stats()["kernel_launches"] - launches0 == n_groups + len(times) // k
+        else:
+            R.run(f, setup, times)
+            e.run(0, len(times))
+            if e.resident_active():
+                assert e.stats()["kernel_launches"] - launches0 == 1
+        _same(e, f, "shape %s seed %d" % (shape, seed))
+        raw = e.probes()
+        for c, (i, j, series) in enumerate(f.raw_probes):
+            assert np.array_equal(raw[:, c, :], np.array(series)), (shape, seed, c)
+        e.close()
+
+
+@pytest.mark.parametrize("walls", WALLS)
+def test_all_wall_combinations(walls):
+    for shape in [(6, 6), (17, 12), (20, 150)]:
+        f, setup, times = SC.random_case(shape[0], shape[1], 11, walls=walls, n_steps=7)
+        e = _engine_for(f, setup, times, resident=True)
+        assert e.resident_active()
+        R.run(f, setup, times)
+        e.run(0, len(times))
+        _same(e, f, "walls %s shape %s" % (walls, shape))
+        e.close()
+
+
+def test_chained_runs_and_single_steps_share_the_generations():
+    """Odd and even launch lengths (the result lands in either generation), fdtd_step in between."""
+    f, setup, times = SC.random_case(50, 90, 7, walls=(False, True, False, False), n_steps=30)
+    e = _engine_for(f, setup, times, resident=True)
+    n = 0
+    for length in (7, 1, 6, 2):
+        e.run(n, length)
+        for t in times[n:n + length]:
+            R.leapfrog(f, setup, t)
+        n += length
+        _same(e, f, "after call %d" % n)
+        e.step(n)
+        R.leapfrog(f, setup, times[n])
+        n += 1
+        _same(e, f, "after single call %d" % n)
+    e.close()
+
+
+def test_more_tiles_than_co_resident_blocks():
+    """700 x 1100 cells = 1584 tiles of 8 x 64: more than the blocks one cooperative launch can hold, so every block
+    strides over several tiles per call."""
+    f, setup, times = SC.random_case(700, 1100, 5, walls=(False, True, False, False), n_steps=9)
+    e = _engine_for(f, setup, times)
+    e.set_resident(True, max_cells=1 << 22)
+    assert e.resident_active()
+    R.run(f, setup, times)
+    e.run(0, len(times))
+    _same(e, f, "strided tiles")
+    assert e.stats()["kernel_launches"] == 1
+    e.close()
+
+
+def test_reference_golden_vectors_in_resident_mode():
+    """The fixtures the real reference produced (tests/golden/), full length, snapshot stacks included."""
+    from golden_util import load, setup_of, sha
+    from fdtd_em_solver_b200.engine import Engine
+    for name in ("tutorial", "lens", "waveguide", "waveguide_mixed_walls", "mixed", "doubleslit"):
+        g = load(name)
+        s = setup_of(g)
+        n = int(g["size"])
+        e = Engine(n, courant=s.courant, one_minus_courant=(1 - s.courant), reflect=s.reflect_walls, resident=True)
+        e.upload_coefficients(g["eps_coef"], g["mu_coef"])
+        e.set_sources(s.pulses, g["times"])
+        e.set_reflectors(s.reflectors)
+        assert e.resident_active()
+        stack = e.run(0, len(g["times"]), snapshot_every=int(g["step_frequency"]), total_calls=len(g["times"]))
+        h, ex, ey = e.get_fields()
+        assert np.array_equal(h, g["final_h"]) and sha(ex) == str(g["sha_ex"]) and sha(ey) == str(g["sha_ey"]), name
+        assert len(stack) == int(g["n_snapshots"]) and sha(stack) == str(g["sha_stack"]), name
+        e.close()
+
+
+@pytest.mark.parametrize("name,n_calls", [("tutorial", None), ("waveguide", None), ("mixed", None)])
+def test_scenarios_through_the_python_api(name, n_calls, tmp_path):
+    """Solver(..., resident=True): snapshot stack, final fields and the energy probe series vs the oracle, bitwise."""
+    from fdtd_em_solver_b200 import solver as S
+    sc = SC.spec(name)
+    f, setup, times, info = SC.restate(sc)
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = SC.drive(S, sc, resident=True)
+        s.save(str(tmp_path / name))
+        s.solve(realtime=False, step_frequency=sc["step_frequency"])
+    assert s._engine.resident_active()
+    want = np.array(R.run_saving(f, setup, times, sc["step_frequency"]))
+    got = np.load(str(tmp_path / name) + ".npy")
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(s.h, f.h) and np.array_equal(s.ex, f.ex) and np.array_equal(s.ey, f.ey)
+    assert s.step == f.step == len(times)
+    for d, (i, j, series) in zip(s.recorded_energies, f.probes):
+        assert (d["i"], d["j"]) == (i, j) and d["energies"] == series
+
+
+def test_fp32_resident_equals_per_call_path():
+    from fdtd_em_solver_b200.engine import Engine
+    f, setup, times = SC.random_case(150, 260, 10, n_steps=12)
+    outs = []
+    for resident in (False, True):
+        rows, cols = f.h.shape
+        S = setup.courant
+        e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, dtype="float32",
+                   resident=resident)
+        e.upload_coefficients(setup.eps_coef, setup.mu_coef); e.set_sources(setup.pulses, times)
+        e.set_reflectors(setup.reflectors); e.set_fields(f.h, f.ex, f.ey)
+        assert e.resident_active() == resident
+        stack = e.run(0, len(times), snapshot_every=4, total_calls=len(times))
+        outs.append(e.get_fields() + (stack,))
+        e.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert np.abs(outs[0][0]).max() > 0
