@@ -115,6 +115,8 @@ struct fdtd_ctx {
     bool rs_valid = false;
     int rs_stride = 0, res_blocks_max = 0;
 
+    bool overlap_last = false;       // temporal blocking: last frame pass on the edge stream (FDTD_OVERLAP_LAST=1; experiment)
+
     fdtd_stats stats{};
     std::string err;
 };
@@ -540,7 +542,11 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         // the frame dilated by ceil((K-p)/frame_tile_rows) TILES.  Values it computes further out from stale inputs
         // are never read by a value that is kept.
         const int ring = (K - p + m.frame_tile_rows - 1) / m.frame_tile_rows;
-        cudaStream_t st = last ? c->stream : c->edge_stream;
+        // The last pass writes only frame tiles of B (from a scratch generation) and the K-step kernel only non-frame
+        // tiles of B (from A): they are independent, so with overlap_last the whole chain of passes stays on the edge
+        // stream and hides behind the K-step kernel; otherwise the last pass follows the K-step kernel on the main stream.
+        const bool on_edge = !last || c->overlap_last;
+        cudaStream_t st = on_edge ? c->edge_stream : c->stream;
         if (c->comm) CK(cudaStreamWaitEvent(st, c->ev_comm, 0));                  // halos of `src` have landed
         if (last) {
             StepParams<T> PK;                                   // the K-step kernel: everything but the frame
@@ -557,7 +563,7 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
             }
             if (m.nty > 0) c->stats.kernel_launches++;
             CK(cudaGetLastError());
-            CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));                     // passes 1..K-1 done
+            if (!on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // passes 1..K-1 done
         }
         StepParams<T> P;
         if (int rc = fill_params<T>(c, P, n + p - 1, src, dst)) return rc;
@@ -565,10 +571,11 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         P.tile_mask = m.d_mask[ring]; P.mask_stride = m.ntx1; P.tile_list = m.d_list[ring];
         P.tile_rows = m.frame_tile_rows;
         if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size(), m.frame_vec)) return rc;
-        if (!last) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+        if (on_edge) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+        if (last && on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));    // main-stream order = "all of B written"
         if (c->comm) {
-            cudaEvent_t done = last ? c->ev_p3 : c->ev_bnd;
-            if (last) CK(cudaEventRecord(c->ev_p3, c->stream));
+            cudaEvent_t done = on_edge ? c->ev_bnd : c->ev_p3;
+            if (!on_edge) CK(cudaEventRecord(c->ev_p3, c->stream));
             CK(cudaStreamWaitEvent(c->comm_stream, done, 0));
             if (int rc = exchange(c, dst, c->comm_stream)) return rc;
             CK(cudaEventRecord(c->ev_comm, c->comm_stream));
@@ -764,6 +771,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->row_off = cfg->row_begin - c->halo_top;
     c->owned = cfg->row_end - cfg->row_begin;
     c->lrows = fdtd_local_rows(cfg);
+    if (const char* v = std::getenv("FDTD_OVERLAP_LAST")) c->overlap_last = v[0] && v[0] != '0';
     {
         // Launch geometry defaults (tools/sweep.py on the 8192 x 65536 slab): 256-bit lanes, 4 warps per CTA and
         // SHORT tiles -- 6 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
@@ -1101,6 +1109,10 @@ int fdtd_probe_clear(fdtd_handle c) {
 
 int fdtd_step(fdtd_handle c, int64_t step) {
     NEED_BOUND();
+    if (resident_eligible(c)) {                          // a one-call launch of step_resident: no slow corner CTA
+        if (int rc = ensure_probe_capacity(c, 1)) return rc;
+        return resident_any(c, step, 1);
+    }
     return step_any(c, step);
 }
 

@@ -112,6 +112,32 @@ struct ResSources {
     int stride;
 };
 
+// what phase 0 brings into the window for one cell: the OLD values, zeros outside the arrays, h already carrying the
+// hard point-source writes of solver.py:178-180 (later pulses win)
+template <typename T> struct ResCell { T h, mu, ep, ex, ey; };
+
+template <typename T>
+FDTD_HD ResCell<T> resident_fetch(const StepParams<T>& P, int i, int j) {
+    const bool in_h = i >= 0 && i < P.NR && j >= 0 && j < P.NC;
+    const bool in_ex = i >= 0 && i <= P.NR && j >= 0 && j < P.NC;
+    const bool in_ey = i >= 0 && i < P.NR && j >= 0 && j <= P.NC;
+    const long long o = (long long)i * P.pitch + j;
+    ResCell<T> v;
+    v.h = v.mu = v.ep = v.ex = v.ey = T(0);
+    if (in_h) { v.h = r_ld_field(P.h + o); v.mu = r_ld_const(P.muc + o); v.ep = r_ld_const(P.epc + o); }
+    if (in_ex) v.ex = r_ld_field(P.ex + o);
+    if (in_ey) v.ey = r_ld_field(P.ey + o);
+    if (in_h)
+        for (int s = 0; s < P.n_src; ++s)
+            if (P.src[s].kind == 0 && P.src[s].row == i && P.src[s].col == j) v.h = P.src[s].mag;
+    return v;
+}
+
+template <typename T>
+FDTD_HD void resident_put(const ResWindow<T>& W, int l, const ResCell<T>& v) {
+    W.h[l] = v.h; W.mu[l] = v.mu; W.ep[l] = v.ep; W.ex[l] = v.ex; W.ey[l] = v.ey;
+}
+
 template <typename T, typename G, int PHASE>
 FDTD_HD void resident_cell(const StepParams<T>& P, const ResWindow<T>& W, int ta, int tb, int ja, int jb, int li, int lj) {
     constexpr int WR = G::WR, WC = G::WC;
@@ -124,16 +150,7 @@ FDTD_HD void resident_cell(const StepParams<T>& P, const ResWindow<T>& W, int ta
     const bool has_dn = li + 1 < WR, has_up = li >= 1, has_rt = lj + 1 < WC, has_lf = lj >= 1;
 
     if constexpr (PHASE == 0) {
-        const long long o = (long long)i * P.pitch + j;
-        T h = T(0), mu = T(0), ep = T(0), ex = T(0), ey = T(0);
-        if (in_h) {
-            h = r_ld_field(P.h + o); mu = r_ld_const(P.muc + o); ep = r_ld_const(P.epc + o);
-            for (int s = 0; s < P.n_src; ++s)                               // solver.py:178-180, later pulses win
-                if (P.src[s].kind == 0 && P.src[s].row == i && P.src[s].col == j) h = P.src[s].mag;
-        }
-        if (in_ex) ex = r_ld_field(P.ex + o);
-        if (in_ey) ey = r_ld_field(P.ey + o);
-        W.h[l] = h; W.mu[l] = mu; W.ep[l] = ep; W.ex[l] = ex; W.ey[l] = ey;
+        resident_put<T>(W, l, resident_fetch<T>(P, i, j));
     } else if constexpr (PHASE == 1) {
         T v = T(0);
         if (in_h && has_dn && has_rt) {
@@ -227,8 +244,25 @@ using ResGeom = ResTile<8, 64>;
 
 template <typename T, typename G, int PHASE>
 __device__ __forceinline__ void resident_phase(const StepParams<T>& P, const ResWindow<T>& W, int ta, int tb, int ja, int jb) {
-    for (int idx = threadIdx.x; idx < G::CELLS; idx += RES_THREADS)
-        resident_cell<T, G, PHASE>(P, W, ta, tb, ja, jb, idx / G::WC, idx % G::WC);
+    if constexpr (PHASE == 0) {
+        // all of a thread's loads are issued before the first shared-memory store: one L2 round trip per tile, not one
+        // per cell (the stores go through generic pointers, so the compiler would not hoist the loads itself)
+        constexpr int IT = (G::CELLS + RES_THREADS - 1) / RES_THREADS;
+        ResCell<T> v[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const int idx = threadIdx.x + k * RES_THREADS;
+            if (idx < G::CELLS) v[k] = resident_fetch<T>(P, W.wa + idx / G::WC, W.ca + idx % G::WC);
+        }
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const int idx = threadIdx.x + k * RES_THREADS;
+            if (idx < G::CELLS) resident_put<T>(W, idx, v[k]);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < G::CELLS; idx += RES_THREADS)
+            resident_cell<T, G, PHASE>(P, W, ta, tb, ja, jb, idx / G::WC, idx % G::WC);
+    }
 }
 
 // gen0 / gen1: the two generations of (h, ex, ey); call first_step + s reads generation (s & 1 ? gen1 : gen0).
@@ -250,12 +284,19 @@ __global__ void __launch_bounds__(RES_THREADS) step_resident(const __grid_consta
     W.h = sh; W.hn = shn; W.ex = sex; W.ey = sey; W.mu = smu; W.ep = sep;
     for (int s = 0; s < n_steps; ++s) {
         __syncthreads();                                         // everyone is done with the previous step's P
-        if (threadIdx.x == 0) {
-            const bool odd = s & 1;
-            P.h = odd ? g1[0] : g0[0]; P.ex = odd ? g1[1] : g0[1]; P.ey = odd ? g1[2] : g0[2];
-            P.hn = odd ? g0[0] : g1[0]; P.exn = odd ? g0[1] : g1[1]; P.eyn = odd ? g0[2] : g1[2];
-            P.probe_out = P0.probe_out ? P0.probe_out + (size_t)s * P0.n_probe * 3 : nullptr;
-            resident_load_sources<T>(P, R, first_step + s);
+        {   // this call's view of the scene: generations swapped, the call's pulse record (= resident_load_sources,
+            // spread over threads so that it costs one memory round trip)
+            const long long n = first_step + s;
+            const int t = threadIdx.x;
+            if (t == 0) {
+                const bool odd = s & 1;
+                P.h = odd ? g1[0] : g0[0]; P.ex = odd ? g1[1] : g0[1]; P.ey = odd ? g1[2] : g0[2];
+                P.hn = odd ? g0[0] : g1[0]; P.exn = odd ? g0[1] : g1[1]; P.eyn = odd ? g0[2] : g1[2];
+                P.probe_out = P0.probe_out ? P0.probe_out + (size_t)s * P0.n_probe * 3 : nullptr;
+            }
+            if (t < R.stride && t < FDTD_MAX_SRC) P.src[t] = R.src[n * R.stride + t];      // entries past count are unused
+            if (t == 32) P.n_src = R.count ? R.count[n] : 0;
+            if (t == 33) P.last_mag = R.count ? R.last[n] : T(0);
         }
         __syncthreads();
         for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {

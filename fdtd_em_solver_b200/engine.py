@@ -121,10 +121,14 @@ class Engine:
         self.temporal = 1
         if temporal > 1:
             self.enable_temporal_blocking(temporal)
-        self.set_resident(_resident_default() if resident is None else resident)
+        if resident is None:                # default: only when the caller left the launch strategy to the library
+            resident = (_resident_default() and temporal <= 1 and kernel == "stream"
+                        and not (tile_rows or vec or block_warps))
+        self.set_resident(resident)
 
     def set_resident(self, on=True, max_cells=0):
-        """run() advances all calls up to the next snapshot in ONE cooperative launch (kernel step_resident) when the
+        """run() advances all calls up to the next snapshot in ONE cooperative launch (kernel step_resident; step() = a
+        launch of one call) when the
         whole grid is on this GPU and (rows+1)*(cols+1) <= max_cells (0 = the library default, 512*512); larger grids
         and slabs keep the per-call / temporal-blocking path.  Same bits either way."""
         L.check(self.lib, self.handle, self.lib.fdtd_set_resident(self.handle, 1 if on else 0, int(max_cells)))

@@ -121,9 +121,10 @@ int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 /* Resident mode for grids that live in L2 (the reference's own scenario scripts, N = 139..442; solver.py:288-292 and
  * :331-337 drive thousands of update() calls on them): with enable != 0, fdtd_run advances ALL calls up to the next
  * snapshot in ONE cooperative launch of step_resident (fields ping-pong in L2, per-call pulse records read from a
- * device table, grid-wide barrier between calls) instead of one launch per call.  Used when the context owns the
+ * device table, grid-wide barrier between calls) instead of one launch per call, and fdtd_step launches the same
+ * kernel for its one call.  Used when the context owns the
  * whole grid, (rows+1)*(cols+1) <= max_cells (0 keeps the default 512*512), no halo transport is active and no TF/SF
- * "right" line sits at column 0; otherwise fdtd_run silently keeps the per-call path.  Results are bit-identical
+ * "right" line sits at column 0; otherwise fdtd_run / fdtd_step silently keep the per-call path.  Results are bit-identical
  * either way.  fdtd_resident_active reports whether fdtd_run would use it for the current scene (1/0). */
 int fdtd_set_resident(fdtd_handle h, int32_t enable, int64_t max_cells);
 int fdtd_resident_active(fdtd_handle h);

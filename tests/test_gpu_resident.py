@@ -93,21 +93,40 @@ def test_all_wall_combinations(walls):
 
 
 def test_chained_runs_and_single_steps_share_the_generations():
-    """Odd and even launch lengths (the result lands in either generation), fdtd_step in between."""
+    """Odd and even launch lengths (the result lands in either generation), fdtd_step in between (itself a one-call
+    launch of step_resident, or the per-call kernel when resident mode is switched off in between)."""
     f, setup, times = SC.random_case(50, 90, 7, walls=(False, True, False, False), n_steps=30)
     e = _engine_for(f, setup, times, resident=True)
     n = 0
-    for length in (7, 1, 6, 2):
+    for length, resident_step in ((7, True), (1, False), (6, True), (2, False)):
         e.run(n, length)
         for t in times[n:n + length]:
             R.leapfrog(f, setup, t)
         n += length
         _same(e, f, "after call %d" % n)
+        e.set_resident(resident_step)
         e.step(n)
+        e.set_resident(True)
         R.leapfrog(f, setup, times[n])
         n += 1
         _same(e, f, "after single call %d" % n)
     e.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (9, 5), (40, 70), (67, 131)])
+def test_single_calls_every_step_bitwise(shape):
+    """fdtd_step in resident mode (Solver.update, the realtime path): h, ex, ey after every call."""
+    rows, cols = shape
+    for seed in (1, 2, 4):
+        walls = WALLS[(seed * 5 + rows + cols) % 16]
+        f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=10)
+        e = _engine_for(f, setup, times, resident=True)
+        assert e.resident_active()
+        for n, t in enumerate(times):
+            R.leapfrog(f, setup, t)
+            e.step(n)
+            _same(e, f, "shape %s seed %d step %d" % (shape, seed, n))
+        e.close()
 
 
 def test_more_tiles_than_co_resident_blocks():
