@@ -115,8 +115,6 @@ struct fdtd_ctx {
     bool rs_valid = false;
     int rs_stride = 0, res_blocks_max = 0;
 
-    bool overlap_last = false;       // temporal blocking: last frame pass on the edge stream (FDTD_OVERLAP_LAST=1; experiment)
-
     fdtd_stats stats{};
     std::string err;
 };
@@ -542,10 +540,11 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         // the frame dilated by ceil((K-p)/frame_tile_rows) TILES.  Values it computes further out from stale inputs
         // are never read by a value that is kept.
         const int ring = (K - p + m.frame_tile_rows - 1) / m.frame_tile_rows;
-        // The last pass writes only frame tiles of B (from a scratch generation) and the K-step kernel only non-frame
-        // tiles of B (from A): they are independent, so with overlap_last the whole chain of passes stays on the edge
-        // stream and hides behind the K-step kernel; otherwise the last pass follows the K-step kernel on the main stream.
-        const bool on_edge = !last || c->overlap_last;
+        // The last pass is independent of the K-step kernel too (it writes frame tiles of B from a scratch generation),
+        // but queuing it on the edge stream next to the kernel measured SLOWER (433.8 vs 450.0 Gcell/s on the C5 slab,
+        // profiles/r1_overlap_last_pass.json: its latency-bound CTAs take SM slots from the kernel for longer than the
+        // tail they save), so it follows the kernel on the main stream.
+        const bool on_edge = !last;
         cudaStream_t st = on_edge ? c->edge_stream : c->stream;
         if (c->comm) CK(cudaStreamWaitEvent(st, c->ev_comm, 0));                  // halos of `src` have landed
         if (last) {
@@ -572,7 +571,6 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
         P.tile_rows = m.frame_tile_rows;
         if (int rc = launch_rows<T>(c, P, lo, hi, st, (int)m.h_list[ring].size(), m.frame_vec)) return rc;
         if (on_edge) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
-        if (last && on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));    // main-stream order = "all of B written"
         if (c->comm) {
             cudaEvent_t done = on_edge ? c->ev_bnd : c->ev_p3;
             if (!on_edge) CK(cudaEventRecord(c->ev_p3, c->stream));
@@ -771,7 +769,6 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->row_off = cfg->row_begin - c->halo_top;
     c->owned = cfg->row_end - cfg->row_begin;
     c->lrows = fdtd_local_rows(cfg);
-    if (const char* v = std::getenv("FDTD_OVERLAP_LAST")) c->overlap_last = v[0] && v[0] != '0';
     {
         // Launch geometry defaults (tools/sweep.py on the 8192 x 65536 slab): 256-bit lanes, 4 warps per CTA and
         // SHORT tiles -- 6 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.

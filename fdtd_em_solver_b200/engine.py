@@ -21,8 +21,9 @@ IMPEDANCE = math.sqrt(MU / EPSILON)
 
 
 # Resident mode (many update() calls per cooperative launch, for grids that live in L2): what Engine(resident=None)
-# means.  FDTD_RESIDENT=0/1 overrides it for experiments.
-RESIDENT_DEFAULT = False
+# means when the caller also left the launch geometry and temporal blocking alone.  FDTD_RESIDENT=0/1 overrides it.
+# On since its first B200 run (profiles/r1_resident_*): bit-identical, 7-9 us per call instead of 43-63 us.
+RESIDENT_DEFAULT = True
 
 
 def _resident_default():

@@ -8,16 +8,13 @@ can show: the cooperative launch, grid.sync between calls, the generation ping-p
 import contextlib
 import io
 import itertools
-import os
 
 import numpy as np
 import pytest
 
 from oracle import restated as R, scenarios as SC
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FDTD_TEST_RESIDENT", "0") == "0",
-                                 reason="resident mode awaits its first GPU run: set FDTD_TEST_RESIDENT=1")]
+pytestmark = pytest.mark.gpu
 
 WALLS = list(itertools.product([False, True], repeat=4))
 
@@ -45,6 +42,13 @@ def _same(e, f, where=""):
 
 def _has_wrapping_line(setup):
     return any(p.direction == "right" and p.col == 0 for p in setup.pulses)
+
+
+def _without_wrapping_lines(setup):
+    """A TF/SF "right" line at column 0 keeps a scene on the per-call path (fdtd2d.cu resident_eligible); random cases
+    on narrow grids draw one often.  Dropped where the test is about the resident kernel itself."""
+    setup.pulses = [p for p in setup.pulses if not (p.direction == "right" and p.col == 0)]
+    return setup
 
 
 @pytest.mark.parametrize("shape", [(3, 3), (4, 7), (9, 5), (33, 33), (40, 70), (67, 131), (139, 139), (300, 200)])
@@ -84,6 +88,7 @@ def test_random_cases_run_loop_bitwise(shape):
 def test_all_wall_combinations(walls):
     for shape in [(6, 6), (17, 12), (20, 150)]:
         f, setup, times = SC.random_case(shape[0], shape[1], 11, walls=walls, n_steps=7)
+        setup = _without_wrapping_lines(setup)
         e = _engine_for(f, setup, times, resident=True)
         assert e.resident_active()
         R.run(f, setup, times)
@@ -120,6 +125,7 @@ def test_single_calls_every_step_bitwise(shape):
     for seed in (1, 2, 4):
         walls = WALLS[(seed * 5 + rows + cols) % 16]
         f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=10)
+        setup = _without_wrapping_lines(setup)
         e = _engine_for(f, setup, times, resident=True)
         assert e.resident_active()
         for n, t in enumerate(times):
