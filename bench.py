@@ -180,7 +180,8 @@ def workload_config(args, n_gpus):
             "kernel": "%s vec=%d tile_rows=%d warps=%d" % (
                 "stepK_stream (%d steps per HBM pass) + masked step_stream frame passes" % args.temporal
                 if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
-            "temporal_blocking": args.temporal}
+            "temporal_blocking": args.temporal,
+            "frame_mode": int(getattr(args, "frame_mode", None) or 0)}
 
 
 def main():
@@ -195,6 +196,9 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = library default)")
     ap.add_argument("--temporal", type=int, default=6, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="leapfrog steps per HBM pass (>1 = temporal blocking)")
+    ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2],
+                    help="frame of a temporal-blocking group: 0 masked single-step passes, 1/2 one frame_window launch "
+                         "next to / behind the K-step kernel (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -226,7 +230,8 @@ def main():
     n_calls = 2 * (args.steps + args.warmup) + 64
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
-                          tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal)
+                          tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal,
+                          frame_mode=args.frame_mode)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:

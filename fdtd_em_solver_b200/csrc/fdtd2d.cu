@@ -6,6 +6,7 @@
 #include "fdtd2d.h"
 #include "kernels.cuh"
 #include "resident.cuh"
+#include "window.cuh"
 
 #include <dlfcn.h>
 
@@ -60,12 +61,15 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     unsigned char* d_skip = nullptr; unsigned char* d_mask[8] = {};
     std::vector<int2> h_list[8];                 // compact (block column, row tile) launch lists of the frame passes
     int2* d_list[8] = {};
-    size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
+    std::vector<int2> h_tiles;                   // frame tiles (column tile, row tile) for frame_window (window.cuh)
+    int2* d_tiles = nullptr;
+    size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0, d_tiles_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
     int frame_tile_rows = 0, frame_vec = 0, frame_nty = 0;   // the frame passes use smaller tiles than the K-step kernel
     int64_t k_row_lo = 0, k_row_hi = 0;                      // rows the K-step tiles own
     void release() {
         if (d_skip) cudaFree(d_skip);
+        if (d_tiles) cudaFree(d_tiles);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
     }
 };
@@ -114,6 +118,10 @@ struct fdtd_ctx {
     void* rs_count = nullptr; void* rs_last = nullptr; void* rs_src = nullptr;   // per-call pulse records on the device
     bool rs_valid = false;
     int rs_stride = 0, res_blocks_max = 0;
+
+    // how the frame of a temporal-blocking group advances: 0 = K masked single-step passes (step_stream), 1 = ONE
+    // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
+    int frame_mode = 0;
 
     fdtd_stats stats{};
     std::string err;
@@ -435,6 +443,10 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
                         if (y >= 0 && y < ntyF && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
                     }
             }
+    m.h_tiles.clear();
+    for (int ty = 0; ty < ntyF; ++ty)
+        for (int tx = 0; tx < ntx1; ++tx)
+            if (m.h_mask[0][(size_t)ty * ntx1 + tx]) m.h_tiles.push_back(make_int2(tx, ty));
     const int w = g.block_warps, nbx = (ntx1 + w - 1) / w;
     for (int d = 0; d < K; ++d)
         for (int ty = 0; ty < ntyF; ++ty)
@@ -494,6 +506,12 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         }
         m.d_mask_cap = mask_bytes; m.d_list_cap = longest;
     }
+    if (m.d_tiles_cap < m.h_tiles.size()) {
+        if (m.d_tiles) cudaFree(m.d_tiles);
+        CK(cudaMalloc(&m.d_tiles, m.h_tiles.size() * sizeof(int2))); m.d_tiles_cap = m.h_tiles.size();
+    }
+    if (!m.h_tiles.empty())
+        CK(cudaMemcpyAsync(m.d_tiles, m.h_tiles.data(), m.h_tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(m.d_skip, m.h_skip.data(), m.h_skip.size(), cudaMemcpyHostToDevice, c->stream));
     for (int d = 0; d < K; ++d) {
         CK(cudaMemcpyAsync(m.d_mask[d], m.h_mask[d].data(), mask_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -681,7 +699,81 @@ int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
     return c->cfg.dtype == FDTD_F64 ? resident_run<double>(c, n, g) : resident_run<float>(c, n, g);
 }
 
+// ---- temporal blocking with the frame in ONE launch (window.cuh) ------------------------------------------
+bool frame_window_eligible(const fdtd_ctx* c, int K) {
+    if (c->frame_mode == 0 || c->comm || K > fdtd::WIN_MAX_CALLS) return false;
+    if (c->cfg.row_begin != 0 || c->cfg.row_end != c->cfg.rows) return false;            // whole grid on this GPU
+    if (c->n_src > FDTD_MAX_SRC) return false;
+    for (int p = 0; p < c->n_src; ++p)
+        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
+    return true;
+}
+
+// Steps n .. n+K-1: A -> B.  stepK_stream advances every tile whose K-step cone is plain; frame_window advances every
+// other tile K calls in shared memory from one load of A (tile + K+1 cells of apron).  Both read only A and write
+// disjoint tiles of B (cells of a frame tile that a K-step tile also covers get the same bits from both), so they need
+// no ordering between them and no scratch generations.
+template <typename T>
+int group_window(fdtd_ctx* c, int64_t n, int K) {
+    if (int rc = build_frame_maps<T>(c, n, K)) return rc;
+    if (int rc = resident_tables<T>(c)) return rc;
+    const FrameMaps& m = c->fm[K];
+    const int A = c->cur, B = (A + 1) % c->ngen;
+    const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
+    if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
+    const bool side = c->frame_mode == 1 && m.nty > 0 && !m.h_tiles.empty();
+    if (side) {
+        CK(cudaEventRecord(c->ev_int, c->stream));              // everything before this group
+        CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
+    }
+    if (m.nty > 0) {
+        StepParams<T> PK;
+        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
+        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
+        switch (K) {
+            case 2: launch_stepK<T, 2>(PK, c); break;
+            case 3: launch_stepK<T, 3>(PK, c); break;
+            case 4: launch_stepK<T, 4>(PK, c); break;
+            case 5: launch_stepK<T, 5>(PK, c); break;
+            case 6: launch_stepK<T, 6>(PK, c); break;
+            case 7: launch_stepK<T, 7>(PK, c); break;
+            default: launch_stepK<T, 8>(PK, c); break;
+        }
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    if (!m.h_tiles.empty()) {
+        StepParams<T> PF;
+        if (int rc = fill_params<T>(c, PF, n, A, B)) return rc;
+        PF.n_src = 0; PF.last_mag = T(0);                        // the kernel reads the K calls' records itself
+        PF.row_lo = (int)lo; PF.row_hi = (int)hi;
+        if (c->n_probe) PF.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+        const int tile_rows = m.frame_tile_rows, tile_cols = 32 * m.frame_vec, apron = fdtd::window_apron(K);
+        const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
+        if (bytes > 200 * 1024) return fail(c, FDTD_ERR_ARG, "frame_window: window does not fit shared memory");
+        if (bytes > 48 * 1024)
+            CK(cudaFuncSetAttribute(fdtd::frame_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+        fdtd::frame_window<T><<<(unsigned)m.h_tiles.size(), fdtd::WIN_THREADS, bytes, side ? c->edge_stream : c->stream>>>(
+            PF, m.d_tiles, tile_rows, tile_cols, K, R, (long long)n);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    if (side) {
+        CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // main-stream order = "all of B written"
+    }
+    CK(cudaEventRecord(c->ev_int, c->stream));
+    c->cur = B;
+    if (c->n_probe) c->probe_count += K;
+    c->stats.steps += K;
+    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
+    return 0;
+}
+
 int group_any(fdtd_ctx* c, int64_t n, int K) {
+    if (frame_window_eligible(c, K))
+        return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
     return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
 
@@ -908,6 +1000,13 @@ int fdtd_set_resident(fdtd_handle c, int32_t enable, int64_t max_cells) {
     if (max_cells < 0) return fail(c, FDTD_ERR_ARG, "max_cells must be >= 0 (0 keeps the default)");
     c->resident = enable ? 1 : 0;
     if (max_cells > 0) c->resident_max_cells = max_cells;
+    return 0;
+}
+
+int fdtd_set_frame_mode(fdtd_handle c, int32_t mode) {
+    if (!c) return FDTD_ERR_ARG;
+    if (mode < 0 || mode > 2) return fail(c, FDTD_ERR_ARG, "frame mode must be 0, 1 or 2");
+    c->frame_mode = mode;
     return 0;
 }
 

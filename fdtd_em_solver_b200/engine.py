@@ -80,7 +80,7 @@ def build_source_tables(pulses, times):
 class Engine:
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None, frame_mode=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
@@ -122,6 +122,11 @@ class Engine:
         self.temporal = 1
         if temporal > 1:
             self.enable_temporal_blocking(temporal)
+        # frame of a temporal-blocking group: 0 = masked single-step passes (validated default), 1 / 2 = one
+        # frame_window launch next to / behind the K-step kernel (experimental until its first GPU run)
+        self.frame_mode = int(os.environ.get("FDTD_FRAME_MODE", "0") or 0) if frame_mode is None else int(frame_mode)
+        if self.frame_mode:
+            L.check(self.lib, self.handle, self.lib.fdtd_set_frame_mode(self.handle, self.frame_mode))
         if resident is None:                # default: only when the caller left the launch strategy to the library
             resident = (_resident_default() and temporal <= 1 and kernel == "stream"
                         and not (tile_rows or vec or block_warps))

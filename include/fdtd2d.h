@@ -129,6 +129,15 @@ int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 int fdtd_set_resident(fdtd_handle h, int32_t enable, int64_t max_cells);
 int fdtd_resident_active(fdtd_handle h);
 
+/* How the FRAME of a temporal-blocking group (the tiles stepK_stream leaves out) advances:
+ *   0  K masked single-step launches through the scratch generations (default);
+ *   1  ONE launch of frame_window (csrc/window.cuh: each frame tile + K+1 cells of apron advanced K calls in shared
+ *      memory from one load of generation A) on a side stream next to the K-step kernel;
+ *   2  the same launch queued behind the K-step kernel.
+ * Modes 1/2 apply when the context owns the whole grid, no halo transport is active and no TF/SF "right" line sits at
+ * column 0; otherwise the group silently uses mode 0.  Results are bit-identical in every mode. */
+int fdtd_set_frame_mode(fdtd_handle h, int32_t mode);
+
 /* The frame plan of temporal blocking as pure host logic (no CUDA call, works without a GPU; used by the tests).
  * cfg: rows, cols, row_begin, row_end, dtype, tile_rows (> 0) and block_warps (> 0) are read.  boxes: n_boxes x
  * {r0, r1, c0, c1} INCLUSIVE cell boxes that the K-step kernel must stay away from (sources, reflectors, probes).

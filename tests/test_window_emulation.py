@@ -1,0 +1,170 @@
+"""CPU check of frame_window's K-call window algorithm (fdtd_em_solver_b200/csrc/window.cuh) against the oracle.
+
+The kernel advances the FRAME tiles of a temporal-blocking group (walls, pulse lines, reflectors, probes) K calls in
+shared memory from one load of "tile + (K+1) cells of apron".  Its per-cell phase functions are __host__ __device__;
+tests/host_emul/window_emul.cu runs them with plain loops, so the algorithm is pinned bit-for-bit here without a GPU:
+
+  * K = 1..8 with every tile covering the grid (1x1, 2x3, 5x32, 8x64 tiles), all wall combinations, all pulse kinds,
+    reflectors, probes: generation B must equal the oracle after K calls EVERYWHERE;
+  * the apron K+1 is tight: K cells are not enough;
+  * with the real frame plan of the library (fdtd_plan_frame): exactly the frame tiles are written, with the oracle's
+    values, the rest of generation B is left to the K-step kernel.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import restated as R, scenarios as SC
+
+import resident_emul as E
+
+pytestmark = pytest.mark.skipif(not E.available(), reason="nvcc not found (the emulation is compiled from window.cuh)")
+
+WALLS = list(itertools.product([False, True], repeat=4))
+
+
+def _eligible(setup):
+    """A TF/SF "right" line at column 0 (python's h[:, col-1] wraps to the far column) is outside the window algorithm;
+    the library keeps such scenes on the masked single-step passes."""
+    setup.pulses = [p for p in setup.pulses if not (p.direction == "right" and p.col == 0)]
+    return setup
+
+
+def _all_tiles(rows, cols, tr, tc):
+    return [(tx, ty) for ty in range(-(-(rows + 1) // tr)) for tx in range(-(-(cols + 1) // tc))]
+
+
+def _check(got, f, where, only=None):
+    for name, a, b in zip(("h", "ex", "ey"), got[:3], (f.h, f.ex, f.ey)):
+        if only is not None:
+            m = only[name]
+            a, b = a[m], b[m]
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError("%s differs %s: %d cells, first %s" % (name, where, len(bad), bad[0]))
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("tile", [(1, 1), (2, 3), (5, 32), (8, 64)])
+def test_k_calls_every_tile_bitwise(K, tile):
+    tr, tc = tile
+    shapes = [(3, 3), (9, 5), (23, 41)] if tile in ((1, 1), (2, 3)) else [(9, 5), (40, 70), (67, 131)]
+    for shape in shapes:
+        rows, cols = shape
+        for seed in (1, 2):
+            walls = WALLS[(seed * 5 + rows + cols + K) % 16]
+            f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=K + 3)
+            setup = _eligible(setup)
+            cells = [(0, 0), (rows - 1, cols - 1), (rows // 2, cols // 3)]
+            f.raw_probes = [(i, j, []) for i, j in cells]
+            first = seed                                      # the launch does not start at call 0
+            for t in times[:first]:
+                R.leapfrog(f, setup, t)
+            for c in f.raw_probes:
+                c[2].clear()
+            got = E.window_emulate(f, setup, times, first, K, _all_tiles(rows, cols, tr, tc), tr, tc, order=(seed + K) % 3,
+                                   probe_cells=cells)
+            for t in times[first:first + K]:
+                R.leapfrog(f, setup, t)
+            _check(got, f, "K %d tile %s shape %s seed %d walls %s" % (K, tile, shape, seed, walls))
+            for c, (i, j, series) in enumerate(f.raw_probes):
+                assert np.array_equal(got[3][:, c, :], np.array(series))
+
+
+@pytest.mark.parametrize("walls", WALLS)
+def test_all_wall_combinations(walls):
+    for shape, tile, K in (((6, 6), (1, 1), 4), ((17, 12), (2, 3), 6), ((12, 70), (8, 64), 6)):
+        f, setup, times = SC.random_case(shape[0], shape[1], 11, walls=walls, n_steps=K)
+        setup = _eligible(setup)
+        got = E.window_emulate(f, setup, times, 0, K, _all_tiles(shape[0], shape[1], *tile), tile[0], tile[1])
+        R.run(f, setup, times)
+        _check(got, f, "walls %s shape %s" % (walls, shape))
+
+
+def test_the_apron_is_tight():
+    """K cells of apron instead of K+1 must go wrong somewhere (1x1 tiles at an absorbing wall: the first hop inward
+    from a wall is two cells)."""
+    K, wrong = 4, 0
+    for seed in range(4):
+        f, setup, times = SC.random_case(9, 9, seed, walls=(False, False, False, False), n_steps=K)
+        setup = _eligible(setup)
+        got = E.window_emulate(f, setup, times, 0, K, _all_tiles(9, 9, 1, 1), 1, 1, apron=K)
+        ok = E.window_emulate(f, setup, times, 0, K, _all_tiles(9, 9, 1, 1), 1, 1, apron=K + 1)
+        R.run(f, setup, times)
+        _check(ok, f, "apron K+1")
+        wrong += int(not all(np.array_equal(a, b) for a, b in zip(got[:3], (f.h, f.ex, f.ey))))
+    assert wrong > 0
+
+
+def _frame_plan(rows, cols, K, tile_rows, block_warps, boxes, row_begin=0, row_end=None):
+    from fdtd_em_solver_b200 import _lib as L
+    lib = L.load()
+    cfg = L.Config()
+    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, row_begin, rows if row_end is None else row_end
+    cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, block_warps
+    plan = L.FramePlan()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 4))
+    rc = lib.fdtd_plan_frame(C.byref(cfg), K, len(b), b.ctypes.data if len(b) else None, C.byref(plan), None, None)
+    assert rc == 0
+    masks = np.zeros((K, plan.frame_tiles_y, plan.frame_tiles_x), dtype=np.uint8)
+    skip = np.zeros((max(plan.k_tiles_y, 1), plan.k_tiles_x), dtype=np.uint8)
+    rc = lib.fdtd_plan_frame(C.byref(cfg), K, len(b), b.ctypes.data if len(b) else None, C.byref(plan),
+                             skip.ctypes.data, masks.ctypes.data)
+    assert rc == 0
+    return plan, masks
+
+
+def _boxes(setup, rows, cols, probe_cells):
+    """The inclusive boxes fdtd2d.cu build_frame_maps hands to the planner (all pulses counted as live)."""
+    BIG = 1 << 40
+    out = []
+    for p in setup.pulses:
+        if p.direction is None:
+            out.append((p.row, p.row, p.col, p.col))
+        elif p.direction in ("right", "left"):
+            out.append((-BIG, BIG, p.col, p.col))
+        elif p.direction == "up":
+            out.append((p.row + 1, p.row + 1, -BIG, BIG))
+        else:
+            out.append((p.row, p.row, -BIG, BIG))
+    for rect in setup.reflectors:
+        for shape in ((rows, cols), (rows + 1, cols), (rows, cols + 1)):
+            r0, r1, c0, c1 = E.clip_rect(rect, *shape)
+            if r1 > r0 and c1 > c0:
+                out.append((r0, r1 - 1, c0, c1 - 1))
+    for i, j in probe_cells:
+        out.append((i, i, j, j))
+    return out
+
+
+@pytest.mark.parametrize("K,tile_rows", [(2, 8), (4, 16), (6, 48), (8, 56)])
+def test_frame_tiles_of_the_library_plan(K, tile_rows):
+    """The frame of a real plan: frame_window writes exactly the frame tiles, with the oracle's values after K calls."""
+    rows, cols = 300, 700
+    f, setup, times = SC.random_case(rows, cols, 4, walls=(False, True, False, False), n_steps=K + 2)
+    setup = _eligible(setup)
+    cells = [(rows // 2, cols // 2), (5, cols // 3)]
+    f.raw_probes = [(i, j, []) for i, j in cells]
+    plan, masks = _frame_plan(rows, cols, K, tile_rows, 1, _boxes(setup, rows, cols, cells))
+    tr, tc = plan.frame_tile_rows, plan.frame_tile_cols
+    tiles = [(tx, ty) for ty, tx in np.argwhere(masks[0] != 0)]
+    assert 0 < len(tiles) < masks[0].size                     # there is a frame, and there are K-step tiles
+    R.leapfrog(f, setup, times[0])
+    for c in f.raw_probes:
+        c[2].clear()
+    got = E.window_emulate(f, setup, times, 1, K, tiles, tr, tc, order=K % 3, probe_cells=cells)
+    for t in times[1:1 + K]:
+        R.leapfrog(f, setup, t)
+    covered = {}
+    for name, arr in zip(("h", "ex", "ey"), (f.h, f.ex, f.ey)):
+        m = np.zeros(arr.shape, dtype=bool)
+        for tx, ty in tiles:
+            m[ty * tr:(ty + 1) * tr, tx * tc:(tx + 1) * tc] = True
+        covered[name] = m
+    _check(got, f, "frame tiles, K %d" % K, only=covered)
+    for name, a in zip(("h", "ex", "ey"), got[:3]):
+        assert np.isnan(a[~covered[name]]).all()              # nothing outside the frame tiles was written
+    for c, (i, j, series) in enumerate(f.raw_probes):
+        assert np.array_equal(got[3][:, c, :], np.array(series))
