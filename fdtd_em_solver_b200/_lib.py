@@ -68,6 +68,8 @@ SIGNATURES = {
     "fdtd_last_error": (C.c_char_p, [_P]),
     "fdtd_bind_buffers": (C.c_int, [_P] * 9),
     "fdtd_plan_frame": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P]),
+    "fdtd_plan_frame_split": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P,
+                                        C.POINTER(C.c_int32), _P]),
     "fdtd_bind_scratch": (C.c_int, [_P, _P, _P, _P]),
     "fdtd_set_temporal_blocking": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_resident": (C.c_int, [_P, C.c_int32, C.c_int64]),

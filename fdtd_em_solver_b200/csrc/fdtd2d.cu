@@ -381,10 +381,20 @@ int step_impl(fdtd_ctx* c, int64_t step) {
 // ---- temporal blocking (K steps per HBM pass) ----------------------------------------------------------
 template <typename T> constexpr int kvec() { return sizeof(T) == 8 ? 2 : 4; }     // columns per lane of stepK_stream
 
+// Can frame_window (window.cuh) take the frame tiles of a K-step group of this context?  (Which of them it takes is
+// decided per tile by plan_frame: all of them on a whole grid, all but the interface strips on a y-slab.)
+bool frame_window_usable(const fdtd_ctx* c, int K) {
+    if (c->frame_mode == 0 || K > fdtd::WIN_MAX_CALLS || c->n_src > FDTD_MAX_SRC) return false;
+    for (int p = 0; p < c->n_src; ++p)
+        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
+    return true;
+}
+template <typename T> int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_t st);
+
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
 struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
-struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; };
+struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false; };
 
 void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
     const int K = g.K, V2 = g.V2;
@@ -433,6 +443,23 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
                 if (covered) m.h_mask[0][(size_t)fy * ntx1 + t1] = 0;
             }
     }
+    // frame_window (window.cuh) takes every frame tile whose window -- the tile + K+1 rows of apron -- lies inside the
+    // rows this slab OWNS (or beyond a real wall of the grid); the masks then keep only the rest, i.e. the interface
+    // strips of a y-slab, which still need one halo exchange per step and so stay on the masked single-step passes.
+    m.h_tiles.clear();
+    if (g.fused) {
+        const int64_t A = K + 1;
+        for (int ty = 0; ty < ntyF; ++ty) {
+            const int64_t ta = lo + (int64_t)ty * TRF, tb = std::min<int64_t>(ta + TRF, hi);
+            const bool rows_ok = (g.row_begin == 0 || ta - A >= g.row_begin) && (g.row_end == NR || tb + A <= g.row_end);
+            if (!rows_ok) continue;
+            for (int tx = 0; tx < ntx1; ++tx)
+                if (m.h_mask[0][(size_t)ty * ntx1 + tx]) {
+                    m.h_tiles.push_back(make_int2(tx, ty));
+                    m.h_mask[0][(size_t)ty * ntx1 + tx] = 0;
+                }
+        }
+    }
     for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one frame tile
         for (int ty = 0; ty < ntyF; ++ty)
             for (int tx = 0; tx < ntx1; ++tx) {
@@ -443,10 +470,6 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
                         if (y >= 0 && y < ntyF && x >= 0 && x < ntx1) m.h_mask[d][(size_t)y * ntx1 + x] = 1;
                     }
             }
-    m.h_tiles.clear();
-    for (int ty = 0; ty < ntyF; ++ty)
-        for (int tx = 0; tx < ntx1; ++tx)
-            if (m.h_mask[0][(size_t)ty * ntx1 + tx]) m.h_tiles.push_back(make_int2(tx, ty));
     const int w = g.block_warps, nbx = (ntx1 + w - 1) / w;
     for (int d = 0; d < K; ++d)
         for (int ty = 0; ty < ntyF; ++ty)
@@ -467,7 +490,8 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
         key.push_back(live);
     }
-    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K}) {
+    const bool fused = frame_window_usable(c, K);
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused}) {
         key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
     }
     if (key == m.key && m.d_skip) return 0;
@@ -486,7 +510,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
             if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
     plan_frame(FrameGeom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
-                         c->cfg.block_warps, K, kvec<T>()}, mods, m);
+                         c->cfg.block_warps, K, kvec<T>(), fused}, mods, m);
     const int ntyF = m.frame_nty, ntx1 = m.ntx1;
     size_t longest = 1;
     for (int d = 0; d < K; ++d) longest = std::max(longest, m.h_list[d].size());
@@ -580,7 +604,14 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
             }
             if (m.nty > 0) c->stats.kernel_launches++;
             CK(cudaGetLastError());
-            if (!on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // passes 1..K-1 done
+            if (!m.h_tiles.empty()) {
+                // frame tiles away from the slab interfaces: K calls in ONE launch from generation A, independent of the
+                // passes and of the K-step kernel (frame mode 1: on the edge stream behind passes 1..K-1; 2: behind the
+                // K-step kernel)
+                if (int rc = launch_frame_window<T>(c, n, K, A, B, c->frame_mode == 1 ? c->edge_stream : c->stream)) return rc;
+                if (c->frame_mode == 1) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+            }
+            if (!on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // passes 1..K-1 (and the window launch) done
         }
         StepParams<T> P;
         if (int rc = fill_params<T>(c, P, n + p - 1, src, dst)) return rc;
@@ -700,13 +731,28 @@ int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
 }
 
 // ---- temporal blocking with the frame in ONE launch (window.cuh) ------------------------------------------
-bool frame_window_eligible(const fdtd_ctx* c, int K) {
-    if (c->frame_mode == 0 || c->comm || K > fdtd::WIN_MAX_CALLS) return false;
-    if (c->cfg.row_begin != 0 || c->cfg.row_end != c->cfg.rows) return false;            // whole grid on this GPU
-    if (c->n_src > FDTD_MAX_SRC) return false;
-    for (int p = 0; p < c->n_src; ++p)
-        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
-    return true;
+template <typename T>
+int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_t st) {
+    const FrameMaps& m = c->fm[K];
+    if (m.h_tiles.empty()) return 0;
+    if (int rc = resident_tables<T>(c)) return rc;
+    StepParams<T> PF;
+    if (int rc = fill_params<T>(c, PF, n, A, B)) return rc;
+    PF.n_src = 0; PF.last_mag = T(0);                            // the kernel reads the K calls' records itself
+    PF.row_lo = (int)c->cfg.row_begin;
+    PF.row_hi = (int)(c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0));
+    if (c->n_probe) PF.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    const int tile_rows = m.frame_tile_rows, tile_cols = 32 * m.frame_vec, apron = fdtd::window_apron(K);
+    const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
+    if (bytes > 200 * 1024) return fail(c, FDTD_ERR_ARG, "frame_window: window does not fit shared memory");
+    if (bytes > 48 * 1024)
+        CK(cudaFuncSetAttribute(fdtd::frame_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+    fdtd::frame_window<T><<<(unsigned)m.h_tiles.size(), fdtd::WIN_THREADS, bytes, st>>>(
+        PF, m.d_tiles, tile_rows, tile_cols, K, R, (long long)n);
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // Steps n .. n+K-1: A -> B.  stepK_stream advances every tile whose K-step cone is plain; frame_window advances every
@@ -716,10 +762,8 @@ bool frame_window_eligible(const fdtd_ctx* c, int K) {
 template <typename T>
 int group_window(fdtd_ctx* c, int64_t n, int K) {
     if (int rc = build_frame_maps<T>(c, n, K)) return rc;
-    if (int rc = resident_tables<T>(c)) return rc;
     const FrameMaps& m = c->fm[K];
     const int A = c->cur, B = (A + 1) % c->ngen;
-    const int64_t lo = c->cfg.row_begin, hi = c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
     if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
     const bool side = c->frame_mode == 1 && m.nty > 0 && !m.h_tiles.empty();
     if (side) {
@@ -742,23 +786,7 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
-    if (!m.h_tiles.empty()) {
-        StepParams<T> PF;
-        if (int rc = fill_params<T>(c, PF, n, A, B)) return rc;
-        PF.n_src = 0; PF.last_mag = T(0);                        // the kernel reads the K calls' records itself
-        PF.row_lo = (int)lo; PF.row_hi = (int)hi;
-        if (c->n_probe) PF.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
-        const int tile_rows = m.frame_tile_rows, tile_cols = 32 * m.frame_vec, apron = fdtd::window_apron(K);
-        const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
-        if (bytes > 200 * 1024) return fail(c, FDTD_ERR_ARG, "frame_window: window does not fit shared memory");
-        if (bytes > 48 * 1024)
-            CK(cudaFuncSetAttribute(fdtd::frame_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
-        fdtd::frame_window<T><<<(unsigned)m.h_tiles.size(), fdtd::WIN_THREADS, bytes, side ? c->edge_stream : c->stream>>>(
-            PF, m.d_tiles, tile_rows, tile_cols, K, R, (long long)n);
-        c->stats.kernel_launches++;
-        CK(cudaGetLastError());
-    }
+    if (int rc = launch_frame_window<T>(c, n, K, A, B, side ? c->edge_stream : c->stream)) return rc;
     if (side) {
         CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // main-stream order = "all of B written"
@@ -772,7 +800,9 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
 }
 
 int group_any(fdtd_ctx* c, int64_t n, int K) {
-    if (frame_window_eligible(c, K))
+    // a whole grid on one GPU: no interface strips, so no pass chain at all; y-slabs go through group_impl, which adds
+    // the window launch to its chain of interface passes
+    if (frame_window_usable(c, K) && !c->comm && c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)
         return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
     return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
@@ -941,8 +971,9 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
     return 0;
 }
 
-int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
-                    fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks) {
+static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                             fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, bool fused, int32_t* n_window_tiles,
+                             int32_t* window_tiles_xy) {
     fdtd_ctx* c = nullptr;
     if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes))
         return fail(c, FDTD_ERR_ARG, "bad argument");
@@ -953,7 +984,7 @@ int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_bo
     for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
     const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
-    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2}, mods, m);
+    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, fused}, mods, m);
     const int margin = (K + V2 - 1) / V2;
     plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
     plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
@@ -964,7 +995,21 @@ int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_bo
     if (masks)
         for (int d = 0; d < K; ++d)
             std::memcpy(masks + (size_t)d * m.frame_nty * m.ntx1, m.h_mask[d].data(), (size_t)m.frame_nty * m.ntx1);
+    if (n_window_tiles) *n_window_tiles = (int32_t)m.h_tiles.size();
+    if (window_tiles_xy)
+        for (size_t k = 0; k < m.h_tiles.size(); ++k) { window_tiles_xy[2 * k] = m.h_tiles[k].x; window_tiles_xy[2 * k + 1] = m.h_tiles[k].y; }
     return 0;
+}
+
+int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                    fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks) {
+    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, false, nullptr, nullptr);
+}
+
+int fdtd_plan_frame_split(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                          fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, int32_t* n_window_tiles,
+                          int32_t* window_tiles_xy) {
+    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, true, n_window_tiles, window_tiles_xy);
 }
 
 int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {

@@ -17,7 +17,9 @@
 //   E  reflector zeroing of ex, ey; h walls (from the old h, later walls win) into hn; probes; on the last call the
 //      store of the tile's cells                                                                         :221-242, :246-255
 // then h and hn swap roles.  Dependency cone: one cell per call, two inward from a wall on the first hop, so K calls need
-// K+1 cells of apron; what the window computes outside the cone of the tile is never read by a stored value.
+// K+1 cells of apron; what the window computes outside the cone of the tile is never read by a stored value.  Call m
+// runs on the window shrunk by m cells (window_margin); phases C / D are skipped when the window holds no wall row /
+// column.
 //
 // As in resident.cuh the per-cell functions are __host__ __device__ and tests/host_emul/window_emul.cu pins them bitwise
 // to the oracle on the CPU (test infrastructure; never linked into the package).
@@ -182,16 +184,36 @@ FDTD_HD void window_cell(const StepParams<T>& P, const StepRec<T>& Q, const Win<
 
 FDTD_HD int window_apron(int K) { return K + 1; }
 
+// Call m (0-based) of a launch only has to be exact on the tile + (K-m) cells: a cell at distance d from the tile reads
+// cells at distance <= max(d+1, 2) (one cell per call; two inward from a wall, which exceeds d+1 only for d = 0).  So
+// call m runs on the window shrunk by m cells on every side; what lies outside goes stale and is never read by a value
+// that matters.
+FDTD_HD int window_margin(int m) { return m; }
+
+// Phases C / D do something only if the window holds a row / column an absorbing wall writes.
+template <typename T>
+FDTD_HD bool window_has_ud_wall(const StepParams<T>& P, const Win<T>& W) {
+    const int r0 = W.wa, r1 = W.wa + W.WR;                     // window rows [r0, r1)
+    return (P.absorb_u && r0 <= 0 && r1 > 0) || (P.absorb_d && r0 <= P.NR && r1 > P.NR - 1);
+}
+template <typename T>
+FDTD_HD bool window_has_lr_wall(const StepParams<T>& P, const Win<T>& W) {
+    const int c0 = W.ca, c1 = W.ca + W.WC;
+    return (P.absorb_l && c0 <= 0 && c1 > 0) || (P.absorb_r && c0 <= P.NC && c1 > P.NC - 1);
+}
+
 #if defined(__CUDACC__)
 constexpr int WIN_THREADS = 256;
 constexpr int WIN_MAX_CALLS = 8;
 
+// one phase of call m over the window shrunk by `margin` cells: warps take rows, lanes take columns (no division)
 template <typename T, char PHASE>
-__device__ __forceinline__ void window_phase(const StepParams<T>& P, const StepRec<T>& Q, const Win<T>& W, int ta, int tb,
-                                             int ja, int jb, bool store, double* probe_out) {
-    const int cells = W.WR * W.WC;
-    for (int idx = threadIdx.x; idx < cells; idx += WIN_THREADS)
-        window_cell<T, PHASE>(P, Q, W, idx / W.WC, idx % W.WC, ta, tb, ja, jb, store, probe_out);
+__device__ __forceinline__ void window_phase(const StepParams<T>& P, const StepRec<T>& Q, const Win<T>& W, int margin,
+                                             int ta, int tb, int ja, int jb, bool store, double* probe_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int li = margin + warp; li < W.WR - margin; li += WIN_THREADS / 32)
+        for (int lj = margin + lane; lj < W.WC - margin; lj += 32)
+            window_cell<T, PHASE>(P, Q, W, li, lj, ta, tb, ja, jb, store, probe_out);
     __syncthreads();
 }
 
@@ -238,13 +260,15 @@ __global__ void __launch_bounds__(WIN_THREADS) frame_window(const __grid_constan
         }
     }
     __syncthreads();
+    const bool ud = window_has_ud_wall<T>(P0, W), lr = window_has_lr_wall<T>(P0, W);
     for (int m = 0; m < K; ++m) {
         double* const probe_out = P0.probe_out ? P0.probe_out + (size_t)m * P0.n_probe * 3 : nullptr;
-        window_phase<T, 'A'>(P0, rec[m], W, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'B'>(P0, rec[m], W, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'C'>(P0, rec[m], W, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'D'>(P0, rec[m], W, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'E'>(P0, rec[m], W, ta, tb, ja, jb, m == K - 1, probe_out);
+        const int mg = window_margin(m);
+        window_phase<T, 'A'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        window_phase<T, 'B'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        if (ud) window_phase<T, 'C'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        if (lr) window_phase<T, 'D'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        window_phase<T, 'E'>(P0, rec[m], W, mg, ta, tb, ja, jb, m == K - 1, probe_out);
         T* const t = W.h; W.h = W.hn; W.hn = t;                  // the new h is the next call's old h
     }
 }

@@ -134,8 +134,10 @@ int fdtd_resident_active(fdtd_handle h);
  *   1  ONE launch of frame_window (csrc/window.cuh: each frame tile + K+1 cells of apron advanced K calls in shared
  *      memory from one load of generation A) on a side stream next to the K-step kernel;
  *   2  the same launch queued behind the K-step kernel.
- * Modes 1/2 apply when the context owns the whole grid, no halo transport is active and no TF/SF "right" line sits at
- * column 0; otherwise the group silently uses mode 0.  Results are bit-identical in every mode. */
+ * On a y-slab the frame tiles within K+1 rows of a slab interface still need one halo exchange per step and stay on
+ * the masked passes; all other frame tiles go through frame_window.  Modes 1/2 do not apply (the group silently uses
+ * mode 0) when a TF/SF "right" line sits at column 0 or more than 16 pulses exist.  Results are bit-identical in
+ * every mode. */
 int fdtd_set_frame_mode(fdtd_handle h, int32_t mode);
 
 /* The frame plan of temporal blocking as pure host logic (no CUDA call, works without a GPU; used by the tests).
@@ -151,6 +153,13 @@ typedef struct fdtd_frame_plan {
 } fdtd_frame_plan;
 int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
                     fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks);
+
+/* The same plan in frame modes 1/2: window_tiles_xy receives the (column tile, row tile) pairs of the frame tiles that
+ * frame_window advances (up to frame_tiles_y * frame_tiles_x pairs; may be NULL), n_window_tiles their number, and
+ * masks then cover only the remaining frame tiles -- the interface strips of a y-slab (none on a whole grid). */
+int fdtd_plan_frame_split(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
+                          fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, int32_t* n_window_tiles,
+                          int32_t* window_tiles_xy);
 
 /* Host arrays handed to fdtd_upload_coeffs / fdtd_set_fields / fdtd_get_fields normally start at global
  * row 0.  A rank that keeps only its slab on the host declares the global row its host arrays start at. */

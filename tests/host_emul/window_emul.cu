@@ -3,7 +3,8 @@
 // CPU emulation of frame_window (fdtd_em_solver_b200/csrc/window.cuh): the kernel's own __host__ __device__ phase
 // functions, driven by plain loops instead of CUDA threads, so that tests/test_window_emulation.py can pin the K-call
 // window algorithm (apron K+1, phases A..E, h/hn swap, per-call pulse records, probes, tile-only stores) bitwise to the
-// oracle without a GPU.  Cell order inside a phase: 0 ascending, 1 descending, 2 a fixed pseudo-random permutation
+// oracle without a GPU.  margin_override: -1 = the kernel's rule (call m runs on the window shrunk by window_margin(m)
+// cells), otherwise the shrink per call to try instead (0 = never shrink, 2 = too greedy).  Cell order inside a phase: 0 ascending, 1 descending, 2 a fixed pseudo-random permutation
 // (the kernel's threads run a phase's cells in no particular order, so the result must not depend on it).
 #include "window.cuh"
 
@@ -36,7 +37,7 @@ struct WinEmuScene {
 };
 
 int window_emulate_f64(const WinEmuScene* sc, int n_tiles, const int32_t* tiles_xy, int tile_rows, int tile_cols,
-                       int K, int apron_override, int order, long long first_step) {
+                       int K, int apron_override, int order, long long first_step, int margin_override) {
     static_assert(sizeof(WinEmuSource) == sizeof(SrcStep<double>), "record layout");
     if (!sc || K < 1 || K > 8 || order < 0 || order > 2) return -1;
     StepParams<double> P{};
@@ -83,12 +84,18 @@ int window_emulate_f64(const WinEmuScene* sc, int n_tiles, const int32_t* tiles_
         W.wa = ta - apron; W.ca = ja - apron;
         for (int k = 0; k < cells; ++k)
             window_put<double>(W, perm[k], window_fetch<double>(P, W.wa + perm[k] / W.WC, W.ca + perm[k] % W.WC));
+        const bool ud = window_has_ud_wall<double>(P, W), lr = window_has_lr_wall<double>(P, W);
         for (int m = 0; m < K; ++m) {
             double* const po = P.probe_out ? P.probe_out + (size_t)m * P.n_probe * 3 : nullptr;
-#define WIN_PHASE(PH, ST, PO) for (int k = 0; k < cells; ++k) \
-    window_cell<double, PH>(P, rec[m], W, perm[k] / W.WC, perm[k] % W.WC, ta, tb, ja, jb, ST, PO);
-            WIN_PHASE('A', false, nullptr) WIN_PHASE('B', false, nullptr) WIN_PHASE('C', false, nullptr)
-            WIN_PHASE('D', false, nullptr) WIN_PHASE('E', m == K - 1, po)
+            const int mg = margin_override >= 0 ? margin_override * m : window_margin(m);      // cells outside the box are skipped
+#define WIN_PHASE(PH, ST, PO) for (int k = 0; k < cells; ++k) { \
+        const int li = perm[k] / W.WC, lj = perm[k] % W.WC; \
+        if (li >= mg && li < W.WR - mg && lj >= mg && lj < W.WC - mg) \
+            window_cell<double, PH>(P, rec[m], W, li, lj, ta, tb, ja, jb, ST, PO); }
+            WIN_PHASE('A', false, nullptr) WIN_PHASE('B', false, nullptr)
+            if (ud) { WIN_PHASE('C', false, nullptr) }
+            if (lr) { WIN_PHASE('D', false, nullptr) }
+            WIN_PHASE('E', m == K - 1, po)
 #undef WIN_PHASE
             std::swap(W.h, W.hn);
         }

@@ -168,15 +168,17 @@ def load_window():
         _win = C.CDLL(_build(WIN_SRC, WIN_OUT))
         _win.window_emulate_f64.restype = C.c_int
         _win.window_emulate_f64.argtypes = [C.POINTER(WinEmuScene), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                            C.c_int, C.c_int, C.c_longlong]
+                                            C.c_int, C.c_int, C.c_longlong, C.c_int]
     return _win
 
 
 def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, order=0, probe_cells=(),
-                   apron=0, row_begin=0, row_end=None, fill=np.nan):
+                   apron=0, row_begin=0, row_end=None, fill=np.nan, poison_halo=False, shrink=-1):
     """Advance the frame tiles `tiles` ([(tx, ty), ...] of the (tile_rows x tile_cols) grid that starts at row
     `row_begin`) by K calls with the emulated frame_window kernel, reading the oracle-style fields `f` as generation A.
     With row_begin/row_end the context stores only that y-slab (one halo row above, the ex row below), like the library.
+    shrink: cells the active box loses per call (-1 = the kernel's rule, window.cuh window_margin).
+    poison_halo: the halo rows of generation A (which the library fills by halo exchange) hold NaN instead.
     Returns (h, ex, ey, probe_records) of generation B as GLOBAL arrays pre-filled with `fill`: cells the kernel did not
     store keep it."""
     lib = load_window()
@@ -196,6 +198,12 @@ def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, 
     if row_end < NR:
         ga[0][-1, :] = 0.0                                   # the last local row holds ONLY ex[row_end]
         ga[2][-1, :] = 0.0
+    if poison_halo:
+        for a in ga:
+            if row_begin > 0:
+                a[0, :] = np.nan
+            if row_end < NR:
+                a[-1, :] = np.nan
     gb = [plane(None, fill) for _ in range(3)]
     muc, epc = plane(setup.mu_coef), plane(setup.eps_coef)
     sc = WinEmuScene()
@@ -223,7 +231,8 @@ def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, 
     if len(setup.pulses):
         sc.count, sc.last, sc.src, sc.stride = count.ctypes.data, last.ctypes.data, C.addressof(rec), stride
     t = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 2))
-    rc = lib.window_emulate_f64(C.byref(sc), len(t), t.ctypes.data, tile_rows, tile_cols, K, apron, order, first_step)
+    rc = lib.window_emulate_f64(C.byref(sc), len(t), t.ctypes.data, tile_rows, tile_cols, K, apron, order, first_step,
+                                shrink)
     assert rc == 0, "emulation failed"
 
     def globalise(p, rows, cols):

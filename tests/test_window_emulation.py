@@ -98,6 +98,24 @@ def test_the_apron_is_tight():
     assert wrong > 0
 
 
+def test_the_shrinking_active_box_is_tight():
+    """Call m runs on the window shrunk by m cells (window_margin).  Never shrinking gives the same bits; shrinking by
+    two cells per call must go wrong."""
+    K, wrong = 5, 0
+    for seed in range(4):
+        f, setup, times = SC.random_case(11, 13, seed, walls=(False, False, False, False), n_steps=K)
+        setup = _eligible(setup)
+        tiles = _all_tiles(11, 13, 2, 3)
+        rule = E.window_emulate(f, setup, times, 0, K, tiles, 2, 3)
+        never = E.window_emulate(f, setup, times, 0, K, tiles, 2, 3, shrink=0)
+        greedy = E.window_emulate(f, setup, times, 0, K, tiles, 2, 3, shrink=2)
+        R.run(f, setup, times)
+        _check(rule, f, "kernel rule")
+        _check(never, f, "no shrink")
+        wrong += int(not all(np.array_equal(a, b) for a, b in zip(greedy[:3], (f.h, f.ex, f.ey))))
+    assert wrong > 0
+
+
 def _frame_plan(rows, cols, K, tile_rows, block_warps, boxes, row_begin=0, row_end=None):
     from fdtd_em_solver_b200 import _lib as L
     lib = L.load()
@@ -168,3 +186,69 @@ def test_frame_tiles_of_the_library_plan(K, tile_rows):
         assert np.isnan(a[~covered[name]]).all()              # nothing outside the frame tiles was written
     for c, (i, j, series) in enumerate(f.raw_probes):
         assert np.array_equal(got[3][:, c, :], np.array(series))
+
+
+def _frame_plan_split(rows, cols, K, tile_rows, block_warps, boxes, row_begin, row_end):
+    from fdtd_em_solver_b200 import _lib as L
+    lib = L.load()
+    cfg = L.Config()
+    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, row_begin, row_end
+    cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, block_warps
+    plan = L.FramePlan()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 4))
+    bp = b.ctypes.data if len(b) else None
+    assert lib.fdtd_plan_frame(C.byref(cfg), K, len(b), bp, C.byref(plan), None, None) == 0
+    full = np.zeros((K, plan.frame_tiles_y, plan.frame_tiles_x), dtype=np.uint8)
+    assert lib.fdtd_plan_frame(C.byref(cfg), K, len(b), bp, C.byref(plan), None, full.ctypes.data) == 0
+    chain = np.zeros_like(full)
+    n = C.c_int32(0)
+    xy = np.zeros((plan.frame_tiles_y * plan.frame_tiles_x, 2), dtype=np.int32)
+    assert lib.fdtd_plan_frame_split(C.byref(cfg), K, len(b), bp, C.byref(plan), None, chain.ctypes.data,
+                                     C.byref(n), xy.ctypes.data) == 0
+    return plan, full, chain, [tuple(t) for t in xy[:n.value]]
+
+
+@pytest.mark.parametrize("K,tile_rows", [(2, 8), (4, 16), (6, 48)])
+@pytest.mark.parametrize("n_slabs", [1, 2, 3])
+def test_y_slabs_window_tiles_and_interface_chain(K, tile_rows, n_slabs):
+    """Frame modes 1/2 on y-slabs: frame_window takes the frame tiles whose window lies inside the rows the slab owns
+    (the halo rows hold NaN here: they must not be read), the masked passes keep exactly the interface strips."""
+    rows, cols = 330, 500
+    f, setup, times = SC.random_case(rows, cols, 7, walls=(False, False, True, False), n_steps=K + 1)
+    setup = _eligible(setup)
+    boxes = _boxes(setup, rows, cols, [])
+    g = R.Fields(f.h.copy(), f.ex.copy(), f.ey.copy())
+    for t in times[:K]:
+        R.leapfrog(g, setup, t)
+    edges = [rows * s // n_slabs for s in range(n_slabs + 1)]
+    for b, e in zip(edges[:-1], edges[1:]):
+        plan, full, chain, tiles = _frame_plan_split(rows, cols, K, tile_rows, 1, boxes, b, e)
+        tr, tc = plan.frame_tile_rows, plan.frame_tile_cols
+        win = np.zeros_like(full[0])
+        for tx, ty in tiles:
+            win[ty, tx] = 1
+        assert np.array_equal(win | chain[0], full[0]) and not (win & chain[0]).any()      # a partition of the frame
+        A = K + 1
+        for tx, ty in tiles:                                  # every window inside the owned rows, or beyond a real wall
+            ta, tb = b + ty * tr, min(b + (ty + 1) * tr, e + (1 if e == rows else 0))
+            assert b == 0 or ta - A >= b
+            assert e == rows or tb + A <= e
+        if n_slabs == 1:
+            assert not chain.any() and len(tiles) == int(full[0].sum())
+        else:
+            assert chain[0].any() and len(tiles) > 0
+            interface_rows = [r for r in (b, e - 1) if 0 < r < rows - 1]
+            for r in interface_rows:                          # the rows next to a slab interface stay on the passes
+                assert chain[0][(r - b) // tr].all()
+        got = E.window_emulate(f, setup, times, 0, K, tiles, tr, tc, row_begin=b, row_end=e, poison_halo=True)
+        covered = {}
+        for name, arr in zip(("h", "ex", "ey"), (g.h, g.ex, g.ey)):
+            m = np.zeros(arr.shape, dtype=bool)
+            for tx, ty in tiles:
+                m[b + ty * tr:min(b + (ty + 1) * tr, arr.shape[0]), tx * tc:(tx + 1) * tc] = True
+            if name != "ex" or e < rows:
+                m[e:] = False
+            covered[name] = m
+        _check(got, g, "slab [%d,%d) K %d" % (b, e, K), only=covered)
+        for name, a in zip(("h", "ex", "ey"), got[:3]):
+            assert np.isnan(a[~covered[name]]).all()

@@ -16,12 +16,19 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-for rows, cols, n_steps, kw in [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
+# frame modes 1/2 (frame_window + interface pass chain, window.cuh) join the list with FDTD_SLAB_CHECK_FRAME=1
+FRAME_CASES = [(1500, 4100, 26, dict(temporal=4, frame_mode=1)), (2000, 9000, 27, dict(temporal=6, tile_rows=16, frame_mode=1)),
+               (2000, 9000, 27, dict(temporal=6, tile_rows=16, frame_mode=2)), (1500, 4100, 33, dict(temporal=8, frame_mode=2)),
+               (97, 300, 13, dict(tile_rows=4, temporal=2, frame_mode=1))] if os.environ.get("FDTD_SLAB_CHECK_FRAME") == "1" else []
+
+for rows, cols, n_steps, kw in FRAME_CASES + [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
                                 (97, 300, 13, dict(tile_rows=4, temporal=2)), (1500, 4100, 25, dict(temporal=2)),
                                 (2000, 9000, 16, dict(temporal=2, block_warps=2)),
                                 (1500, 4100, 26, dict(temporal=4)), (2000, 9000, 19, dict(temporal=3, block_warps=2)),
                                 (2000, 9000, 27, dict(temporal=6, tile_rows=16)), (1500, 4100, 33, dict(temporal=8))]:
     f, setup, times = SC.random_case(rows, cols, 3, walls=(False, False, False, True), n_steps=n_steps)
+    if kw.get("frame_mode"):         # a TF/SF line at column 0 would keep the whole frame on the masked passes
+        setup.pulses = [p for p in setup.pulses if not (p.direction == "right" and p.col == 0)]
     b, e_ = SL.split_rows(rows, world)[rank]
     S = setup.courant
     eng = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, row_begin=b,
