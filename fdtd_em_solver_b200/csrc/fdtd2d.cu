@@ -118,6 +118,8 @@ struct fdtd_ctx {
     void* rs_count = nullptr; void* rs_last = nullptr; void* rs_src = nullptr;   // per-call pulse records on the device
     bool rs_valid = false;
     int rs_stride = 0, res_blocks_max = 0;
+    int resident_depth = 1;          // calls per grid barrier: 1 = step_resident, 2..8 = resident_window (window.cuh)
+    int resw_blocks_max = 0, resw_depth = 0;
 
     // how the frame of a temporal-blocking group advances: 0 = K masked single-step passes (step_stream), 1 = ONE
     // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
@@ -691,10 +693,51 @@ int resident_tables(fdtd_ctx* c) {
     return 0;
 }
 
+// calls n .. n+g-1 in ONE cooperative launch with M = resident_depth calls per grid barrier (resident_window)
+template <typename T>
+int resident_window_run(fdtd_ctx* c, int64_t n, int64_t g) {
+    if (int rc = resident_tables<T>(c)) return rc;
+    const int M = c->resident_depth;
+    const int A = c->cur, B = next_gen(c, A);
+    StepParams<T> P;
+    if (int rc = fill_params<T>(c, P, n, A, B)) return rc;
+    P.n_src = 0; P.last_mag = T(0);
+    P.row_lo = 0; P.row_hi = (int)c->cfg.rows + 1;
+    if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    int tile_rows = 8, tile_cols = 64;
+    const int apron = fdtd::window_apron(M);
+    const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
+    if (c->resw_depth != M) {
+        int coop = 0, sms = 0, per_sm = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        if (bytes > 48 * 1024)
+            CK(cudaFuncSetAttribute(fdtd::resident_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdtd::resident_window<T>, fdtd::WIN_THREADS, bytes));
+        if (!coop || per_sm < 1) return fail(c, FDTD_ERR_CUDA, "cooperative launch unavailable for resident_window");
+        c->resw_blocks_max = per_sm * sms; c->resw_depth = M;
+    }
+    const int tiles = (int)(((c->cfg.cols + 1 + tile_cols - 1) / tile_cols) * ((c->cfg.rows + 1 + tile_rows - 1) / tile_rows));
+    const int blocks = std::min(tiles, c->resw_blocks_max);
+    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+    long long first = n;
+    int ns = (int)g, depth = M;
+    void* args[] = {&P, &tile_rows, &tile_cols, &depth, &R, &first, &ns};
+    CK(cudaLaunchCooperativeKernel((void*)fdtd::resident_window<T>, dim3((unsigned)blocks), dim3(fdtd::WIN_THREADS), args, bytes, c->stream));
+    c->stats.kernel_launches++;
+    const int64_t intervals = (g + M - 1) / M;
+    c->cur = (intervals & 1) ? B : A;
+    if (c->n_probe) c->probe_count += g;
+    c->stats.steps += g;
+    c->stats.cell_updates += g * c->owned * c->cfg.cols;
+    return 0;
+}
+
 // calls n .. n+g-1 in ONE cooperative launch
 template <typename T>
 int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
     using G = fdtd::ResGeom;
+    if (c->resident_depth > 1 && g > 1) return resident_window_run<T>(c, n, g);
     if (int rc = resident_tables<T>(c)) return rc;
     const int A = c->cur, B = next_gen(c, A);
     StepParams<T> P;
@@ -1045,6 +1088,13 @@ int fdtd_set_resident(fdtd_handle c, int32_t enable, int64_t max_cells) {
     if (max_cells < 0) return fail(c, FDTD_ERR_ARG, "max_cells must be >= 0 (0 keeps the default)");
     c->resident = enable ? 1 : 0;
     if (max_cells > 0) c->resident_max_cells = max_cells;
+    return 0;
+}
+
+int fdtd_set_resident_depth(fdtd_handle c, int32_t calls_per_barrier) {
+    if (!c) return FDTD_ERR_ARG;
+    if (calls_per_barrier < 1 || calls_per_barrier > fdtd::WIN_MAX_CALLS) return fail(c, FDTD_ERR_ARG, "calls_per_barrier must be 1..8");
+    c->resident_depth = calls_per_barrier;
     return 0;
 }
 

@@ -58,8 +58,9 @@ FDTD_HD void window_load_record(StepRec<T>& Q, const ResSources<T>& R, long long
     Q.last_mag = last;
 }
 
-// old values of one window cell; zeros outside the arrays and outside the rows this context stores
-template <typename T>
+// old values of one window cell; zeros outside the arrays and outside the rows this context stores.  COHERENT: the
+// fields are rewritten by other CTAs during the launch (resident_window), so they are read through L2.
+template <typename T, bool COHERENT = false>
 FDTD_HD ResCell<T> window_fetch(const StepParams<T>& P, int i, int j) {
     const bool stored = i >= P.row_off && i < P.row_off + P.lrows;
     const bool in_h = stored && i >= 0 && i < P.NR && j >= 0 && j < P.NC;
@@ -68,9 +69,9 @@ FDTD_HD ResCell<T> window_fetch(const StepParams<T>& P, int i, int j) {
     const long long o = (long long)(i - P.row_off) * P.pitch + j;
     ResCell<T> v;
     v.h = v.mu = v.ep = v.ex = v.ey = T(0);
-    if (in_h) { v.h = r_ld_const(P.h + o); v.mu = r_ld_const(P.muc + o); v.ep = r_ld_const(P.epc + o); }
-    if (in_ex) v.ex = r_ld_const(P.ex + o);
-    if (in_ey) v.ey = r_ld_const(P.ey + o);
+    if (in_h) { v.h = COHERENT ? r_ld_field(P.h + o) : r_ld_const(P.h + o); v.mu = r_ld_const(P.muc + o); v.ep = r_ld_const(P.epc + o); }
+    if (in_ex) v.ex = COHERENT ? r_ld_field(P.ex + o) : r_ld_const(P.ex + o);
+    if (in_ey) v.ey = COHERENT ? r_ld_field(P.ey + o) : r_ld_const(P.ey + o);
     return v;
 }
 
@@ -217,41 +218,35 @@ __device__ __forceinline__ void window_phase(const StepParams<T>& P, const StepR
     __syncthreads();
 }
 
-// tiles[b] = (column tile, row tile) of the frame-tile grid: rows P0.row_lo + ty*tile_rows .., cols tx*tile_cols ..
-// P0: generation A in h/ex/ey, generation B in hn/exn/eyn, probe_out = record of call first_step.
+// K pulse records into shared memory in one memory round trip: thread m*16+s copies pulse s of call m, thread 128+m its
+// header.  The caller synchronises before the records are read.
 template <typename T>
-__global__ void __launch_bounds__(WIN_THREADS) frame_window(const __grid_constant__ StepParams<T> P0,
-                                                            const int2* __restrict__ tiles, int tile_rows, int tile_cols,
-                                                            int K, const ResSources<T> R, long long first_step) {
-    extern __shared__ __align__(16) unsigned char win_raw[];
-    __shared__ StepRec<T> rec[WIN_MAX_CALLS];
-    const int apron = window_apron(K);
-    const int2 tile = tiles[blockIdx.x];
-    const int ta = P0.row_lo + tile.y * tile_rows, ja = tile.x * tile_cols;
-    const int tb = min(ta + tile_rows, P0.row_hi), jb = min(ja + tile_cols, P0.NC + 1);
+__device__ __forceinline__ void window_load_records(StepRec<T>* rec, const ResSources<T>& R, long long first_step, int K) {
+    const int t = threadIdx.x;
+    const int m = t / FDTD_MAX_SRC, s = t % FDTD_MAX_SRC;
+    if (m < K && s < R.stride) rec[m].src[s] = R.src[(first_step + m) * R.stride + s];
+    if (t >= 128 && t - 128 < K) {
+        rec[t - 128].n_src = R.count ? R.count[first_step + t - 128] : 0;
+        rec[t - 128].last_mag = R.count ? R.last[first_step + t - 128] : T(0);
+    }
+}
+
+// One tile: load the window (tile + apron) of P's generation A, run K calls on it, store the tile into generation B.
+// probe0 = probe record of the first of the K calls (or null).
+template <typename T, bool COHERENT>
+__device__ __forceinline__ void window_tile(const StepParams<T>& P, const StepRec<T>* rec, T* base, int ta, int tb, int ja,
+                                            int jb, int tile_rows, int tile_cols, int apron, int K, double* probe0) {
     Win<T> W;
     W.WR = tile_rows + 2 * apron; W.WC = tile_cols + 2 * apron;
     W.wa = ta - apron; W.ca = ja - apron;
     const int cells = W.WR * W.WC;
-    T* base = reinterpret_cast<T*>(win_raw);
     W.h = base; W.hn = base + cells; W.ex = base + 2 * cells; W.ey = base + 3 * cells; W.mu = base + 4 * cells; W.ep = base + 5 * cells;
-
-    {   // the K pulse records, one memory round trip: thread m*16+s copies pulse s of call m, thread 128+m its header
-        const int t = threadIdx.x;
-        const int m = t / FDTD_MAX_SRC, s = t % FDTD_MAX_SRC;
-        if (m < K && s < R.stride) rec[m].src[s] = R.src[(first_step + m) * R.stride + s];
-        if (t >= 128 && t - 128 < K) {
-            rec[t - 128].n_src = R.count ? R.count[first_step + t - 128] : 0;
-            rec[t - 128].last_mag = R.count ? R.last[first_step + t - 128] : T(0);
-        }
-    }
-    // the window of generation A, four cells per thread and round trip
-    for (int b = 0; b < cells; b += 4 * WIN_THREADS) {
+    for (int b = 0; b < cells; b += 4 * WIN_THREADS) {          // four cells per thread and memory round trip
         ResCell<T> v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = b + k * WIN_THREADS + threadIdx.x;
-            if (idx < cells) v[k] = window_fetch<T>(P0, W.wa + idx / W.WC, W.ca + idx % W.WC);
+            if (idx < cells) v[k] = window_fetch<T, COHERENT>(P, W.wa + idx / W.WC, W.ca + idx % W.WC);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -260,16 +255,71 @@ __global__ void __launch_bounds__(WIN_THREADS) frame_window(const __grid_constan
         }
     }
     __syncthreads();
-    const bool ud = window_has_ud_wall<T>(P0, W), lr = window_has_lr_wall<T>(P0, W);
+    const bool ud = window_has_ud_wall<T>(P, W), lr = window_has_lr_wall<T>(P, W);
     for (int m = 0; m < K; ++m) {
-        double* const probe_out = P0.probe_out ? P0.probe_out + (size_t)m * P0.n_probe * 3 : nullptr;
+        double* const probe_out = probe0 ? probe0 + (size_t)m * P.n_probe * 3 : nullptr;
         const int mg = window_margin(m);
-        window_phase<T, 'A'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'B'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
-        if (ud) window_phase<T, 'C'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
-        if (lr) window_phase<T, 'D'>(P0, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
-        window_phase<T, 'E'>(P0, rec[m], W, mg, ta, tb, ja, jb, m == K - 1, probe_out);
+        window_phase<T, 'A'>(P, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        window_phase<T, 'B'>(P, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        if (ud) window_phase<T, 'C'>(P, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        if (lr) window_phase<T, 'D'>(P, rec[m], W, mg, ta, tb, ja, jb, false, nullptr);
+        window_phase<T, 'E'>(P, rec[m], W, mg, ta, tb, ja, jb, m == K - 1, probe_out);
         T* const t = W.h; W.h = W.hn; W.hn = t;                  // the new h is the next call's old h
+    }
+}
+
+// tiles[b] = (column tile, row tile) of the frame-tile grid: rows P0.row_lo + ty*tile_rows .., cols tx*tile_cols ..
+// P0: generation A in h/ex/ey, generation B in hn/exn/eyn, probe_out = record of call first_step.
+template <typename T>
+__global__ void __launch_bounds__(WIN_THREADS) frame_window(const __grid_constant__ StepParams<T> P0,
+                                                            const int2* __restrict__ tiles, int tile_rows, int tile_cols,
+                                                            int K, const ResSources<T> R, long long first_step) {
+    extern __shared__ __align__(16) unsigned char win_raw[];
+    __shared__ StepRec<T> rec[WIN_MAX_CALLS];
+    const int2 tile = tiles[blockIdx.x];
+    const int ta = P0.row_lo + tile.y * tile_rows, ja = tile.x * tile_cols;
+    const int tb = min(ta + tile_rows, P0.row_hi), jb = min(ja + tile_cols, P0.NC + 1);
+    window_load_records<T>(rec, R, first_step, K);
+    window_tile<T, false>(P0, rec, reinterpret_cast<T*>(win_raw), ta, tb, ja, jb, tile_rows, tile_cols, window_apron(K), K,
+                          P0.probe_out);
+}
+
+// Resident mode with M calls per grid barrier (the many-calls-per-launch kernel of resident.cuh, built from the K-call
+// window): every CTA strides over the tiles of the whole index space; per interval of M calls it loads tile + M+1 cells
+// of apron, runs the M calls in shared memory and stores the tile into the other generation, then the grid synchronises.
+// One barrier, one window load and one store per M calls instead of per call, for (tile + 2(M+1))^2 / tile work.
+// P0: generation 0 in h/ex/ey (read by the first interval), generation 1 in hn/exn/eyn.
+template <typename T>
+__global__ void __launch_bounds__(WIN_THREADS) resident_window(const __grid_constant__ StepParams<T> P0, int tile_rows,
+                                                               int tile_cols, int M, const ResSources<T> R,
+                                                               long long first_step, int n_steps) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char win_raw[];
+    __shared__ StepRec<T> rec[WIN_MAX_CALLS];
+    __shared__ StepParams<T> P;
+    if (threadIdx.x == 0) P = P0;
+    const int ntx = (P0.NC + 1 + tile_cols - 1) / tile_cols, nty = (P0.NR + 1 + tile_rows - 1) / tile_rows;
+    const int apron = window_apron(M);
+    int interval = 0;
+    for (int s = 0; s < n_steps; s += M, ++interval) {
+        const int K = min(M, n_steps - s);
+        __syncthreads();                                         // everyone is done with the previous interval's P and records
+        if (threadIdx.x == 0) {
+            const bool odd = interval & 1;
+            P.h = odd ? P0.hn : P0.h; P.ex = odd ? P0.exn : P0.ex; P.ey = odd ? P0.eyn : P0.ey;
+            P.hn = odd ? const_cast<T*>(P0.h) : P0.hn; P.exn = odd ? const_cast<T*>(P0.ex) : P0.exn;
+            P.eyn = odd ? const_cast<T*>(P0.ey) : P0.eyn;
+        }
+        window_load_records<T>(rec, R, first_step + s, K);
+        __syncthreads();
+        double* const probe0 = P0.probe_out ? P0.probe_out + (size_t)s * P0.n_probe * 3 : nullptr;
+        for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {
+            const int ta = (t / ntx) * tile_rows, ja = (t % ntx) * tile_cols;
+            const int tb = min(ta + tile_rows, P0.NR + 1), jb = min(ja + tile_cols, P0.NC + 1);
+            window_tile<T, true>(P, rec, reinterpret_cast<T*>(win_raw), ta, tb, ja, jb, tile_rows, tile_cols, apron, K, probe0);
+        }
+        if (s + M < n_steps) grid.sync();                        // the other generation is complete and visible
     }
 }
 #endif  // __CUDACC__

@@ -128,6 +128,10 @@ int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
  * either way.  fdtd_resident_active reports whether fdtd_run would use it for the current scene (1/0). */
 int fdtd_set_resident(fdtd_handle h, int32_t enable, int64_t max_cells);
 int fdtd_resident_active(fdtd_handle h);
+/* Calls per grid-wide barrier in resident mode: 1 (default) = step_resident; 2..8 = resident_window (csrc/window.cuh):
+ * each CTA advances tile + (M+1) cells of apron M calls in shared memory between two barriers, i.e. one barrier, one
+ * window load and one store per M calls for a larger window.  Bit-identical.  (Experimental until its first GPU run.) */
+int fdtd_set_resident_depth(fdtd_handle h, int32_t calls_per_barrier);
 
 /* How the FRAME of a temporal-blocking group (the tiles stepK_stream leaves out) advances:
  *   0  K masked single-step launches through the scratch generations (default);

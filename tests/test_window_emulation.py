@@ -252,3 +252,31 @@ def test_y_slabs_window_tiles_and_interface_chain(K, tile_rows, n_slabs):
         _check(got, g, "slab [%d,%d) K %d" % (b, e, K), only=covered)
         for name, a in zip(("h", "ex", "ey"), got[:3]):
             assert np.isnan(a[~covered[name]]).all()
+
+
+@pytest.mark.parametrize("M", [2, 3, 4, 8])
+@pytest.mark.parametrize("name,n_calls", [("waveguide", 61), ("tutorial", 45), ("mixed", 38)])
+def test_resident_window_intervals_of_m_calls(name, n_calls, M):
+    """resident_window (resident mode with M calls per grid barrier): the script scenes advanced interval by interval,
+    8 x 64 tiles with M+1 cells of apron, a shorter last interval on the same window size, probes every call."""
+    sc = SC.spec(name)
+    f, setup, times, info = SC.restate(sc)
+    rows = cols = info["size"]
+    cells = [(i, j) for i, j, _ in f.probes] or [(rows // 2, cols // 2)]
+    f.probes = []
+    f.raw_probes = [(i, j, []) for i, j in cells]
+    g = R.Fields(f.h.copy(), f.ex.copy(), f.ey.copy())
+    records = []
+    tiles = _all_tiles(rows, cols, 8, 64)
+    for n in range(0, n_calls, M):
+        K = min(M, n_calls - n)
+        h, ex, ey, rec = E.window_emulate(g, setup, times, n, K, tiles, 8, 64, apron=M + 1, order=(n // M) % 3,
+                                          probe_cells=cells)
+        g = R.Fields(h, ex, ey)
+        records.append(rec)
+    for t in times[:n_calls]:
+        R.leapfrog(f, setup, t)
+    _check((g.h, g.ex, g.ey), f, "%s, %d calls per barrier" % (name, M))
+    rec = np.concatenate(records)
+    for c, (i, j, series) in enumerate(f.raw_probes):
+        assert np.array_equal(rec[:, c, :], np.array(series))
