@@ -1339,7 +1339,11 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
             }
             n += std::max<int64_t>(g, 1);
         }
+        if (c->frame_mode != 0)                          // frame_window reads the pulse records of resident mode
+            if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     }
+    if (resident)                                        // upload the pulse records before the timed region, too
+        if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     CK(cudaEventRecord(c->ev_t0, c->stream));
     const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
