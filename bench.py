@@ -185,6 +185,7 @@ def workload_config(args, n_gpus):
 
 
 def main():
+    global ROWS_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -196,6 +197,9 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = library default)")
     ap.add_argument("--temporal", type=int, default=6, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="leapfrog steps per HBM pass (>1 = temporal blocking)")
+    ap.add_argument("--total-rows", type=int, default=0,
+                    help="STRONG scaling: fix the grid at this many rows (e.g. 65536, BASELINE config 5) and give each GPU "
+                         "total/N of them; default 0 = weak scaling, %d rows per GPU" % ROWS_PER_GPU)
     ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2],
                     help="frame of a temporal-blocking group: 0 masked single-step passes, 1/2 one frame_window launch "
                          "next to / behind the K-step kernel (default: the library's)")
@@ -209,6 +213,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.total_rows:
+        if args.total_rows % world or args.total_rows // world < 64:
+            raise SystemExit("--total-rows must be a multiple of the number of GPUs, at least 64 rows per GPU")
+        ROWS_PER_GPU = args.total_rows // world
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -334,7 +342,8 @@ def main():
     achieved = per_gpu_gcells * bpc
     line = {
         "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.total_rows else "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n_gpus),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
