@@ -31,6 +31,25 @@ def _resident_default():
     return RESIDENT_DEFAULT if v is None or v == "" else v not in ("0", "false", "no")
 
 
+def empty_hugepages(shape):
+    """np.empty(shape, float64) whose pages the kernel may back with transparent huge pages (MADV_HUGEPAGE).  A snapshot
+    stack is written exactly once, front to back, by the library's copy thread, so its cost is first-touch page faults:
+    with THP in `madvise` mode (this image) huge pages make that 3.4x faster (1.07 -> 3.6 GB/s on the build host,
+    measured with 814 KB snapshots).  Any failure is ignored: it is only a hint."""
+    a = np.empty(shape, dtype=np.float64)
+    if a.nbytes >= (8 << 20):
+        try:
+            page = 4096
+            lo = (a.ctypes.data + page - 1) & ~(page - 1)
+            n = (a.ctypes.data + a.nbytes - lo) & ~(page - 1)
+            if n > 0:
+                libc = C.CDLL("libc.so.6", use_errno=True)
+                libc.madvise(C.c_void_p(lo), C.c_size_t(n), 14)          # MADV_HUGEPAGE
+        except Exception:
+            pass
+    return a
+
+
 def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
@@ -256,7 +275,7 @@ class Engine:
             n_snaps = (first_step + n_steps) // k - first_step // k
             if n_snaps:
                 shape = (n_snaps, self.owned, self.cols)
-                snaps = np.empty(shape, dtype=np.float64) if alloc is None else alloc(shape)
+                snaps = empty_hugepages(shape) if alloc is None else alloc(shape)
                 if (snaps.shape != shape or snaps.dtype != np.float64 or not snaps.flags.c_contiguous
                         or not snaps.flags.writeable):
                     raise ValueError("alloc() must return a writeable C-contiguous float64 array of shape %r" % (shape,))

@@ -23,7 +23,7 @@ import sys
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, empty_hugepages
 
 C = 2.99 * (10 ** 8)
 MU = 1.26 * (10 ** (-6))
@@ -258,7 +258,7 @@ class Solver:
         if self.save_file and not self.h_list and nbytes >= STREAM_SNAPSHOT_BYTES:
             self._streamed = self._npy_path()
             return np.lib.format.open_memmap(self._streamed, mode="w+", dtype=np.float64, shape=tuple(shape))
-        return np.empty(shape, dtype=np.float64)
+        return empty_hugepages(shape)
 
     _streamed = None
 

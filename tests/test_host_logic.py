@@ -202,3 +202,14 @@ def test_c_abi_argument_validation_needs_no_gpu():
     # NULL handles are rejected, never dereferenced
     assert lib.fdtd_step(None, 0) == -1 and lib.fdtd_sync(None) == -1 and lib.fdtd_destroy(None) == 0
     assert lib.fdtd_set_temporal_blocking(None, 2) == -1 and lib.fdtd_current_generation(None) == -1
+
+
+def test_snapshot_stack_allocator_is_a_plain_float64_array():
+    """engine.empty_hugepages: np.empty + a MADV_HUGEPAGE hint (only a hint: never an error, never a different array)."""
+    from fdtd_em_solver_b200.engine import empty_hugepages
+    for shape in ((3, 5, 7), (40, 255, 255), (0, 4, 4)):
+        a = empty_hugepages(shape)
+        assert a.shape == shape and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable
+        if a.size:
+            a[...] = 1.5
+            assert float(a.sum()) == 1.5 * a.size
