@@ -210,8 +210,13 @@ __global__ void __launch_bounds__(256) step_exact(const __grid_constant__ StepPa
 #endif
 
 // V consecutive elements, 128-bit (V*sizeof(T)==16) or 256-bit (==32) per lane
+// (FDTD_HOST_EMUL: tests/host_emul/simt.h runs this file's device code on the CPU, lane by lane, to pin kernel edits
+// bitwise against the oracle without a GPU; the product build never defines it, so the PTX paths below are what ships)
 template <typename T, int V>
 __device__ __forceinline__ void ldvec(T (&r)[V], const T* p) {
+#if defined(FDTD_HOST_EMUL)
+    for (int v = 0; v < V; ++v) r[v] = p[v];
+#else
     if constexpr (sizeof(T) == 8 && V == 2)
         asm("ld.global" FDTD_LD_MOD ".v2.f64 {%0,%1}, [%2];" : "=d"(r[0]), "=d"(r[1]) : "l"(p));
     else if constexpr (sizeof(T) == 8 && V == 4)
@@ -221,10 +226,14 @@ __device__ __forceinline__ void ldvec(T (&r)[V], const T* p) {
     else
         asm("ld.global" FDTD_LD_MOD ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+#endif
 }
 
 template <typename T, int V>
 __device__ __forceinline__ void stvec(T* p, const T (&r)[V]) {
+#if defined(FDTD_HOST_EMUL)
+    for (int v = 0; v < V; ++v) p[v] = r[v];
+#else
     if constexpr (sizeof(T) == 8 && V == 2)
         asm volatile("st.global" FDTD_ST_MOD ".v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(r[0]), "d"(r[1]) : "memory");
     else if constexpr (sizeof(T) == 8 && V == 4)
@@ -234,6 +243,7 @@ __device__ __forceinline__ void stvec(T* p, const T (&r)[V]) {
     else
         asm volatile("st.global" FDTD_ST_MOD ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]),
                      "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+#endif
 }
 
 template <typename T, int V>
@@ -592,11 +602,17 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
 // K = 2, while K >= 3 needs the deeper ring: K = 4 went from 243 to 315 Gcell/s, profiles/sweep_r1l_ring.jsonl)
 template <int K> struct KRing { static constexpr int ROWS = (K <= 2) ? 0 : 4; };
 
+#if defined(FDTD_HOST_EMUL)          // the copy lands at once: ordering bugs around wait_group are not modelled
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 template <int K, int V> struct KGeom {
     static constexpr int MARGIN = (K + V - 1) / V;           // sacrificial lanes on each side

@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by or reachable from the package.
+//
+// The device code of the streaming kernels (kernels.cuh: step_stream and stepK_stream with their tile functions) run on
+// the CPU through tests/host_emul/simt.h, one warp at a time.  tests/test_stream_emulation.py compares the result with
+// the oracle, so a kernel edit can be pinned bitwise BEFORE it costs GPU time (and profiles/validated_sass.json tells
+// whether an edit changed the shipped device code at all).
+#define FDTD_HOST_EMUL 1
+#include "simt.h"
+#include "kernels.cuh"
+
+namespace fdtd { alignas(16) unsigned char ring_raw[256 * 1024]; }   // the dynamic shared memory of stepK_stream
+
+using namespace fdtd;
+
+extern "C" {
+
+struct EmuSrc { int32_t kind, row, col, pad; double mag, magz; };
+
+struct StreamScene {
+    const double* a[3];         // generation A: h, ex, ey ((rows+1) x pitch each, whole grid)
+    double* b[3];               // generation B
+    const double* muc; const double* epc;
+    int64_t pitch;
+    int32_t NR, NC;
+    int32_t absorb[4];
+    double S, oms, last_mag;
+    int32_t n_src; EmuSrc src[FDTD_MAX_SRC];
+    int32_t n_rect;
+    int32_t rh[FDTD_MAX_RECT][4], rex[FDTD_MAX_RECT][4], rey[FDTD_MAX_RECT][4];
+};
+
+static void fill(StepParams<double>& P, const StreamScene& sc) {
+    std::memset(&P, 0, sizeof(P));
+    P.h = sc.a[0]; P.ex = sc.a[1]; P.ey = sc.a[2]; P.hn = sc.b[0]; P.exn = sc.b[1]; P.eyn = sc.b[2];
+    P.muc = sc.muc; P.epc = sc.epc; P.pitch = sc.pitch; P.NR = sc.NR; P.NC = sc.NC;
+    P.row_off = 0; P.lrows = sc.NR + 1;
+    P.absorb_u = sc.absorb[0]; P.absorb_d = sc.absorb[1]; P.absorb_l = sc.absorb[2]; P.absorb_r = sc.absorb[3];
+    P.S = sc.S; P.oms = sc.oms; P.last_mag = sc.last_mag;
+    P.n_src = sc.n_src;
+    for (int s = 0; s < sc.n_src; ++s) {
+        P.src[s].kind = sc.src[s].kind; P.src[s].row = sc.src[s].row; P.src[s].col = sc.src[s].col; P.src[s].pad = 0;
+        P.src[s].mag = sc.src[s].mag; P.src[s].magz = sc.src[s].magz;
+    }
+    P.n_rect = sc.n_rect;
+    for (int r = 0; r < sc.n_rect; ++r) {
+        P.rh[r] = RectI{sc.rh[r][0], sc.rh[r][1], sc.rh[r][2], sc.rh[r][3]};
+        P.rex[r] = RectI{sc.rex[r][0], sc.rex[r][1], sc.rex[r][2], sc.rex[r][3]};
+        P.rey[r] = RectI{sc.rey[r][0], sc.rey[r][1], sc.rey[r][2], sc.rey[r][3]};
+    }
+}
+
+// One launch of step_stream<double, V> over rows [row_lo, row_hi): the kernel body itself, grid and all.
+int emul_step_stream(const StreamScene* sc, int V, int tile_rows, int warps, int row_lo, int row_hi) {
+    StepParams<double> P;
+    fill(P, *sc);
+    P.row_lo = row_lo; P.row_hi = row_hi; P.tile_rows = tile_rows;
+    const int W = 32 * V;
+    const int gx = (P.NC + 1 + W * warps - 1) / (W * warps), gy = (row_hi - row_lo + tile_rows - 1) / tile_rows;
+    simt::g_block_dim = simt::Idx{(unsigned)(warps * 32), 1, 1};
+    simt::g_grid_dim = simt::Idx{(unsigned)gx, (unsigned)gy, 1};
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            simt::g_block_idx = simt::Idx{(unsigned)bx, (unsigned)by, 0};
+            for (int w = 0; w < warps; ++w) {
+                if (V == 2) simt::run_warp(w, [&] { step_stream<double, 2>(P); });
+                else if (V == 4) simt::run_warp(w, [&] { step_stream<double, 4>(P); });
+                else return -1;
+            }
+        }
+    return 0;
+}
+
+// One launch of stepK_stream<double, 2, K>: K calls for every tile of rows [row_lo, row_hi) whose skip byte is 0.
+// skip: (tiles_y x tiles_x) bytes, as fdtd_plan_frame returns them.
+int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, int row_lo, int row_hi,
+                      const unsigned char* skip, int tiles_x, int tiles_y) {
+    StepParams<double> P;
+    fill(P, *sc);
+    P.n_src = 0; P.n_rect = 0;                                   // as group_impl launches it
+    P.row_lo = row_lo; P.row_hi = row_hi; P.tile_rows = tile_rows;
+    const int gx = (tiles_x + warps - 1) / warps;
+    simt::g_block_dim = simt::Idx{(unsigned)(warps * 32), 1, 1};
+    simt::g_grid_dim = simt::Idx{(unsigned)gx, (unsigned)tiles_y, 1};
+    for (int by = 0; by < tiles_y; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            simt::g_block_idx = simt::Idx{(unsigned)bx, (unsigned)by, 0};
+            for (int w = 0; w < warps; ++w) {
+                switch (K) {
+                    case 2: simt::run_warp(w, [&] { stepK_stream<double, 2, 2>(P, skip, tiles_x); }); break;
+                    case 3: simt::run_warp(w, [&] { stepK_stream<double, 2, 3>(P, skip, tiles_x); }); break;
+                    case 4: simt::run_warp(w, [&] { stepK_stream<double, 2, 4>(P, skip, tiles_x); }); break;
+                    case 5: simt::run_warp(w, [&] { stepK_stream<double, 2, 5>(P, skip, tiles_x); }); break;
+                    case 6: simt::run_warp(w, [&] { stepK_stream<double, 2, 6>(P, skip, tiles_x); }); break;
+                    case 7: simt::run_warp(w, [&] { stepK_stream<double, 2, 7>(P, skip, tiles_x); }); break;
+                    case 8: simt::run_warp(w, [&] { stepK_stream<double, 2, 8>(P, skip, tiles_x); }); break;
+                    default: return -1;
+                }
+            }
+        }
+    return 0;
+}
+
+}  // extern "C"
