@@ -181,7 +181,8 @@ def workload_config(args, n_gpus):
                 "stepK_stream (%d steps per HBM pass) + masked step_stream frame passes" % args.temporal
                 if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
             "temporal_blocking": args.temporal,
-            "frame_mode": int(getattr(args, "frame_mode", None) or 0)}
+            "frame_mode": int(getattr(args, "frame_mode", None) or 0),
+            "kstep_variant": int(getattr(args, "kstep_variant", None) or 0)}
 
 
 def main():
@@ -203,6 +204,8 @@ def main():
     ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2],
                     help="frame of a temporal-blocking group: 0 masked single-step passes, 1/2 one frame_window launch "
                          "next to / behind the K-step kernel (default: the library's)")
+    ap.add_argument("--kstep-variant", type=int, default=None, choices=[0, 1],
+                    help="K-step kernel: 0 stepK_stream, 1 stepK_lean (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -239,7 +242,7 @@ def main():
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
                           tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal,
-                          frame_mode=args.frame_mode)
+                          frame_mode=args.frame_mode, kstep_variant=args.kstep_variant)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:

@@ -75,6 +75,7 @@ SIGNATURES = {
     "fdtd_set_resident": (C.c_int, [_P, C.c_int32, C.c_int64]),
     "fdtd_resident_active": (C.c_int, [_P]),
     "fdtd_set_frame_mode": (C.c_int, [_P, C.c_int32]),
+    "fdtd_set_kstep_variant": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_resident_depth": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),
     "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),

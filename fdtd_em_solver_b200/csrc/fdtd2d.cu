@@ -124,6 +124,7 @@ struct fdtd_ctx {
     // how the frame of a temporal-blocking group advances: 0 = K masked single-step passes (step_stream), 1 = ONE
     // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
     int frame_mode = 0;
+    int kstep_variant = 0;           // 0 = stepK_stream (GPU-validated), 1 = stepK_lean (same bits, fewer issue slots; experimental)
 
     fdtd_stats stats{};
     std::string err;
@@ -555,6 +556,14 @@ void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
     const FrameMaps& m = c->fm[K];
     const int w = std::min(c->cfg.block_warps, 4);
     dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)m.nty);
+    if (c->kstep_variant == 1) {                                 // experimental: fewer issue slots per row (kernels.cuh stepK_lean)
+        constexpr int ring_rows = fdtd::KRing<K>::ROWS > 0 ? fdtd::KRing<K>::ROWS : 4;
+        const size_t lean_bytes = (size_t)w * ring_rows * 5 * 32 * V2 * sizeof(T);
+        if (lean_bytes > 48 * 1024)
+            cudaFuncSetAttribute(fdtd::stepK_lean<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_bytes);
+        fdtd::stepK_lean<T, V2, K><<<grid, w * 32, lean_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
+        return;
+    }
     const size_t ring_bytes = (size_t)w * fdtd::KRing<K>::ROWS * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
     if (ring_bytes > 48 * 1024)
         cudaFuncSetAttribute(fdtd::stepK_stream<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
@@ -1095,6 +1104,13 @@ int fdtd_set_resident_depth(fdtd_handle c, int32_t calls_per_barrier) {
     if (!c) return FDTD_ERR_ARG;
     if (calls_per_barrier < 1 || calls_per_barrier > fdtd::WIN_MAX_CALLS) return fail(c, FDTD_ERR_ARG, "calls_per_barrier must be 1..8");
     c->resident_depth = calls_per_barrier;
+    return 0;
+}
+
+int fdtd_set_kstep_variant(fdtd_handle c, int32_t variant) {
+    if (!c) return FDTD_ERR_ARG;
+    if (variant < 0 || variant > 1) return fail(c, FDTD_ERR_ARG, "K-step kernel variant must be 0 or 1");
+    c->kstep_variant = variant;
     return 0;
 }
 

@@ -674,6 +674,10 @@ __device__ __forceinline__ void run_tileK(const StepParams<T>& P, int ta, int tb
     } else {
         load(cur, i_first);
     }
+#if defined(FDTD_K_UNROLL)           // experiment hook (tools/sass_loop_mix.py): unroll so that the latch / delay-line copies rename
+    constexpr int ROW_UNROLL = FDTD_K_UNROLL;
+#pragma unroll ROW_UNROLL
+#endif
     for (int i = i_first; i <= i_last; ++i) {                // stage s works on row i-(s-1)
         Row<T, V> nxt;
         if constexpr (RING > 0) {
@@ -747,6 +751,137 @@ __global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_stream(cons
     const int tb = min(ta + P.tile_rows, P.row_hi);
     if (ta >= tb) return;
     run_tileK<T, V, K, KRing<K>::ROWS>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+}
+
+// ---------------------------------------------------------------------------
+// stepK_lean: the same K-stage pipeline with fewer issue slots per row (EXPERIMENTAL: CPU-pinned through
+// tests/host_emul/simt.h, not yet run on a GPU; selected with fdtd_set_kstep_variant(h, 1), stepK_stream stays the
+// default).  The shipped row loop of stepK_stream<double,2,6> issues 367 instructions per row, of which only 132 are
+// the DADD/DMUL of the update: 125 are register moves (latch and delay-line copies) and ~70 are address arithmetic
+// ((i - row_off) * pitch per array and row, ring slot modulo) -- profiles/r1_stepK_unroll_sass_mix.txt.  Here
+//   * the row loop is unrolled by two, so the latch copies become register renaming (ptxas: 125 -> 29 moves per row),
+//   * every global address is a running pointer advanced by one pitch per row, and the ring slot is a wrapping counter.
+// Same operations in the same order on the same operands => bit-identical to stepK_stream.
+// ---------------------------------------------------------------------------
+template <typename T, int V, int K, int RING>
+__device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    const unsigned full = 0xffffffffu;
+    constexpr int MARGIN = KGeom<K, V>::MARGIN;
+    static_assert(RING > 0 && V * sizeof(T) == 16, "the lean variant always prefetches through the cp.async ring");
+    const int j = jw + lane * V;
+    const long long pitch = P.pitch;
+    const int i_first = ta - K + 1, i_last = tb + K - 2;
+    const long long o_first = (long long)(i_first - P.row_off) * pitch + j;      // element offset of row i_first
+
+    T ex0c[V];
+    T hnp[K][V];
+    T Lh[K][V], Lex[K][V], Ley[K][V];
+    T Cmu[K][V], Cep[K][V];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int v = 0; v < V; ++v) hnp[s][v] = Lh[s][v] = Lex[s][v] = Ley[s][v] = Cmu[s][v] = Cep[s][v] = T(0);
+    {   // prologue: hn_1 of row ta-K and ex0 of row ta-K+1 (same as run_tileK)
+        T h[V], mu[V], exm[V], ey[V];
+        ldvec<T, V>(h, P.h + o_first - pitch); ldvec<T, V>(mu, P.muc + o_first - pitch); ldvec<T, V>(exm, P.ex + o_first - pitch);
+        ldvec<T, V>(ex0c, P.ex + o_first); ldvec<T, V>(ey, P.ey + o_first - pitch);
+        const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+            hnp[0][v] = add(h[v], mul(mu[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
+        }
+    }
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    constexpr int SLOT = 5 * 32 * V;                             // elements per ring slot (5 arrays x one warp row)
+    T* const ring = reinterpret_cast<T*>(ring_raw) + (size_t)(threadIdx.x >> 5) * (RING * SLOT) + lane * V;
+    // running state of the prefetcher: next row to issue, its global offset, its ring slot
+    int i_issue = i_first;
+    long long o_issue = o_first;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (i_issue <= i_last) {
+            T* slot = ring + s_issue * SLOT;
+            cp_async16(slot + 0 * 32 * V, P.h + o_issue); cp_async16(slot + 1 * 32 * V, P.muc + o_issue);
+            cp_async16(slot + 2 * 32 * V, P.epc + o_issue); cp_async16(slot + 3 * 32 * V, P.ex + o_issue + pitch);
+            cp_async16(slot + 4 * 32 * V, P.ey + o_issue);
+        }
+        cp_async_commit();
+        ++i_issue; o_issue += pitch;
+        s_issue = (s_issue + 1 == RING) ? 0 : s_issue + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < RING; ++d) issue();
+    int s_read = 0;                                              // ring slot of row i
+    long long o_store = o_first - (long long)(K - 1) * pitch;    // offset of row i-(K-1), the row the last stage produces
+    constexpr int ROW_UNROLL = 2;
+#pragma unroll ROW_UNROLL
+    for (int i = i_first; i <= i_last; ++i) {
+        Row<T, V> cur;
+        cp_async_wait<RING - 1>();
+        {
+            const T* slot = ring + s_read * SLOT;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                cur.h[v] = slot[0 * 32 * V + v]; cur.mu[v] = slot[1 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
+                cur.exn[v] = slot[3 * 32 * V + v]; cur.ey[v] = slot[4 * 32 * V + v];
+            }
+        }
+        T oh[V], oex[V], oey[V];
+        auto stage = [&](const T (&h)[V], const T (&exc)[V], const T (&exn)[V], const T (&ey)[V], const T (&mu)[V],
+                         const T (&ep)[V], T (&hp)[V]) {
+            const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+                oh[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
+            }
+            const T lf = __shfl_up_sync(full, oh[V - 1], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T hl = (v == 0) ? lf : oh[v > 0 ? v - 1 : 0];
+                oex[v] = add(exc[v], mul(ep[v], sub(oh[v], hp[v])));
+                oey[v] = sub(ey[v], mul(ep[v], sub(oh[v], hl)));
+                hp[v] = oh[v];
+            }
+        };
+        stage(cur.h, ex0c, cur.exn, cur.ey, cur.mu, cur.ep, hnp[0]);
+#pragma unroll
+        for (int s = 1; s < K; ++s) {
+            T ph[V], pex[V], pey[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { ph[v] = oh[v]; pex[v] = oex[v]; pey[v] = oey[v]; }
+            stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }
+        }
+        if (i - (K - 1) >= ta && lane >= MARGIN && lane < 32 - MARGIN) {
+            stvec<T, V>(P.hn + o_store, oh); stvec<T, V>(P.exn + o_store, oex); stvec<T, V>(P.eyn + o_store, oey);
+        }
+        o_store += pitch;
+#pragma unroll
+        for (int s = K - 1; s >= 2; --s)
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
+        s_read = (s_read + 1 == RING) ? 0 : s_read + 1;
+        issue();                                                 // refill the slot just consumed
+    }
+}
+
+template <typename T, int V, int K>
+__global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_lean(const __grid_constant__ StepParams<T> P,
+                                                     const unsigned char* __restrict__ skip, int skip_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tx >= skip_stride) return;
+    if (skip[(long long)blockIdx.y * skip_stride + tx]) return;
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    constexpr int RING = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;      // K = 2 prefetches through the ring here, too
+    run_tileK_lean<T, V, K, RING>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 }
 
 // ---------------------------------------------------------------------------

@@ -99,7 +99,7 @@ def build_source_tables(pulses, times):
 class Engine:
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None, frame_mode=None):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None, frame_mode=None, kstep_variant=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
@@ -146,6 +146,11 @@ class Engine:
         self.frame_mode = int(os.environ.get("FDTD_FRAME_MODE", "0") or 0) if frame_mode is None else int(frame_mode)
         if self.frame_mode:
             L.check(self.lib, self.handle, self.lib.fdtd_set_frame_mode(self.handle, self.frame_mode))
+        # K-step kernel of temporal blocking: 0 = stepK_stream (validated default), 1 = stepK_lean (experimental)
+        self.kstep_variant = (int(os.environ.get("FDTD_KSTEP_VARIANT", "0") or 0) if kstep_variant is None
+                              else int(kstep_variant))
+        if self.kstep_variant:
+            L.check(self.lib, self.handle, self.lib.fdtd_set_kstep_variant(self.handle, self.kstep_variant))
         if resident is None:                # default: only when the caller left the launch strategy to the library
             resident = (_resident_default() and temporal <= 1 and kernel == "stream"
                         and not (tile_rows or vec or block_warps))

@@ -133,6 +133,12 @@ int fdtd_resident_active(fdtd_handle h);
  * window load and one store per M calls for a larger window.  Bit-identical.  (Experimental until its first GPU run.) */
 int fdtd_set_resident_depth(fdtd_handle h, int32_t calls_per_barrier);
 
+/* Which K-step kernel fdtd_run launches for the plain tiles of a temporal-blocking group: 0 = stepK_stream (default),
+ * 1 = stepK_lean: the same pipeline with the row loop unrolled by two and running pointers instead of per-row address
+ * arithmetic (about a third fewer issue slots per row).  Same operations in the same order: bit-identical.
+ * (Experimental until its first GPU run.) */
+int fdtd_set_kstep_variant(fdtd_handle h, int32_t variant);
+
 /* How the FRAME of a temporal-blocking group (the tiles stepK_stream leaves out) advances:
  *   0  K masked single-step launches through the scratch generations (default);
  *   1  ONE launch of frame_window (csrc/window.cuh: each frame tile + K+1 cells of apron advanced K calls in shared

@@ -72,8 +72,9 @@ int emul_step_stream(const StreamScene* sc, int V, int tile_rows, int warps, int
 
 // One launch of stepK_stream<double, 2, K>: K calls for every tile of rows [row_lo, row_hi) whose skip byte is 0.
 // skip: (tiles_y x tiles_x) bytes, as fdtd_plan_frame returns them.
+// variant 0 = stepK_stream (shipped), 1 = stepK_lean (unrolled row loop, running pointers).
 int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, int row_lo, int row_hi,
-                      const unsigned char* skip, int tiles_x, int tiles_y) {
+                      const unsigned char* skip, int tiles_x, int tiles_y, int variant) {
     StepParams<double> P;
     fill(P, *sc);
     P.n_src = 0; P.n_rect = 0;                                   // as group_impl launches it
@@ -85,6 +86,19 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
         for (int bx = 0; bx < gx; ++bx) {
             simt::g_block_idx = simt::Idx{(unsigned)bx, (unsigned)by, 0};
             for (int w = 0; w < warps; ++w) {
+                if (variant == 1) {
+                    switch (K) {
+                        case 2: simt::run_warp(w, [&] { stepK_lean<double, 2, 2>(P, skip, tiles_x); }); break;
+                        case 3: simt::run_warp(w, [&] { stepK_lean<double, 2, 3>(P, skip, tiles_x); }); break;
+                        case 4: simt::run_warp(w, [&] { stepK_lean<double, 2, 4>(P, skip, tiles_x); }); break;
+                        case 5: simt::run_warp(w, [&] { stepK_lean<double, 2, 5>(P, skip, tiles_x); }); break;
+                        case 6: simt::run_warp(w, [&] { stepK_lean<double, 2, 6>(P, skip, tiles_x); }); break;
+                        case 7: simt::run_warp(w, [&] { stepK_lean<double, 2, 7>(P, skip, tiles_x); }); break;
+                        case 8: simt::run_warp(w, [&] { stepK_lean<double, 2, 8>(P, skip, tiles_x); }); break;
+                        default: return -1;
+                    }
+                    continue;
+                }
                 switch (K) {
                     case 2: simt::run_warp(w, [&] { stepK_stream<double, 2, 2>(P, skip, tiles_x); }); break;
                     case 3: simt::run_warp(w, [&] { stepK_stream<double, 2, 3>(P, skip, tiles_x); }); break;

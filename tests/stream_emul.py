@@ -62,7 +62,7 @@ def load():
         _lib.emul_step_stream.restype = C.c_int
         _lib.emul_step_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5
         _lib.emul_stepK_stream.restype = C.c_int
-        _lib.emul_stepK_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int]
+        _lib.emul_stepK_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
     return _lib
 
 
@@ -122,11 +122,11 @@ def step_stream(f, setup, times, n, vec=2, tile_rows=8, warps=1):
     return s.result()
 
 
-def stepK_stream(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip):
-    """One launch of stepK_stream<double, 2, K> with the skip map of the frame plan."""
+def stepK_stream(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip, variant=0):
+    """One launch of stepK_stream<double, 2, K> (variant 1: stepK_lean) with the skip map of the frame plan."""
     s = Scene(f, setup, times, n)
     skip = np.ascontiguousarray(skip, dtype=np.uint8)
     rc = load().emul_stepK_stream(C.byref(s.sc), K, tile_rows, warps, row_lo, row_hi, skip.ctypes.data,
-                                  skip.shape[1], skip.shape[0])
+                                  skip.shape[1], skip.shape[0], variant)
     assert rc == 0
     return s.result()

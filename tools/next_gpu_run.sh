@@ -2,16 +2,20 @@
 # First GPU call of the next round (about 4 minutes of box time; every leg has its own timeout and log under gpurun_out/):
 # the kernels that were built and CPU-pinned after round 1's GPU budget had run out get their first run, and the two
 # new kernels of round 1 get their ncu profiles.
-#   gpurun --timeout 420 -- 'bash tools/next_gpu_run.sh'
+#   gpurun --timeout 600 -- 'bash tools/next_gpu_run.sh'
 mkdir -p gpurun_out
-export FDTD_TEST_FRAME_WINDOW=1 FDTD_TEST_RESIDENT_DEPTH=1
-# 1. parity of frame_window (frame modes 1/2) and of resident_window (2..8 calls per barrier)
-timeout 150 python -m pytest tests/test_gpu_frame_window.py tests/test_gpu_resident.py -q -p no:cacheprovider --durations=8 \
+export FDTD_TEST_FRAME_WINDOW=1 FDTD_TEST_RESIDENT_DEPTH=1 FDTD_TEST_KSTEP_LEAN=1
+# 1. parity of stepK_lean, of frame_window (frame modes 1/2) and of resident_window (2..8 calls per barrier)
+timeout 200 python -m pytest tests/test_gpu_kstep_lean.py tests/test_gpu_frame_window.py tests/test_gpu_resident.py -q -p no:cacheprovider --durations=8 \
     > gpurun_out/next_new_kernels_tests.log 2>&1; echo "rc=$?" >> gpurun_out/next_new_kernels_tests.log
 # 2. what they buy: the C5 slab with the frame as masked passes / next to / behind the K-step kernel
 for fm in 0 1 2; do
     timeout 60 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 --frame-mode $fm > gpurun_out/next_bench_frame_mode$fm.json \
         2> gpurun_out/next_bench_frame_mode$fm.err
+done
+# 2b. the lean K-step kernel (about 30 % fewer issue slots per row), alone and with the frame in one launch
+for v in "--kstep-variant 1" "--kstep-variant 1 --frame-mode 1" "--kstep-variant 1 --temporal 8" "--kstep-variant 1 --temporal 4"; do
+    n=$(echo $v | tr -d ' -'); timeout 60 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 $v > gpurun_out/next_bench_$n.json 2> gpurun_out/next_bench_$n.err
 done
 # 3. the script configs with 1 / 2 / 4 calls per grid barrier
 for d in 1 2 4; do
@@ -23,4 +27,4 @@ timeout 120 ncu --set full --clock-control none --import-source on -k regex:step
     python tools/resident_times.py waveguide > gpurun_out/next_ncu_resident.log 2>&1
 timeout 180 ncu --set full --clock-control none --import-source on -k regex:frame_window -c 1 -o gpurun_out/next_frame_window \
     python bench.py --no-cpu --no-e2e --steps 12 --warmup 6 --frame-mode 1 > gpurun_out/next_ncu_frame_window.log 2>&1
-tail -3 gpurun_out/next_new_kernels_tests.log; cat gpurun_out/next_bench_frame_mode*.json | cut -c1-300; cat gpurun_out/next_resident_depth*.jsonl | cut -c1-400
+tail -3 gpurun_out/next_new_kernels_tests.log; cat gpurun_out/next_bench_*.json | cut -c1-300; cat gpurun_out/next_resident_depth*.jsonl | cut -c1-400
