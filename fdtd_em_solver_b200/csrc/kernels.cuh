@@ -32,6 +32,12 @@
 #ifndef FDTD_CHUNK
 #define FDTD_CHUNK 4
 #endif
+#ifndef FDTD_LEAN_UNROLL
+#define FDTD_LEAN_UNROLL 2
+#endif
+#ifndef FDTD_LEAN_MIN_BLOCKS_K6
+#define FDTD_LEAN_MIN_BLOCKS_K6 3
+#endif
 
 namespace fdtd {
 
@@ -814,7 +820,9 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
     for (int d = 0; d < RING; ++d) issue();
     int s_read = 0;                                              // ring slot of row i
     long long o_store = o_first - (long long)(K - 1) * pitch;    // offset of row i-(K-1), the row the last stage produces
-    constexpr int ROW_UNROLL = 2;
+    // 2: the latch copies rename (K = 6: 367 -> 263 instructions per row); 2*(K-1) would also rename the coefficient delay
+    // line (-> ~242) at five times the code size -- a build knob for the GPU sweep: FDTD_NVCC_EXTRA=-DFDTD_LEAN_UNROLL=10
+    constexpr int ROW_UNROLL = FDTD_LEAN_UNROLL;
 #pragma unroll ROW_UNROLL
     for (int i = i_first; i <= i_last; ++i) {
         Row<T, V> cur;
@@ -870,8 +878,12 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
     }
 }
 
+// K = 6 at three CTAs per SM (168 registers) spills a dozen values per two rows in the lean variant; two CTAs per SM
+// (255 registers, 8 warps instead of 12) is the other candidate: -DFDTD_LEAN_MIN_BLOCKS_K6=2
+template <int K> struct KBoundsLean { static constexpr int MIN_BLOCKS = (K == 6) ? FDTD_LEAN_MIN_BLOCKS_K6 : KBounds<K>::MIN_BLOCKS; };
+
 template <typename T, int V, int K>
-__global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_lean(const __grid_constant__ StepParams<T> P,
+__global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(const __grid_constant__ StepParams<T> P,
                                                      const unsigned char* __restrict__ skip, int skip_stride) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
