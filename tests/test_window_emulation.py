@@ -280,3 +280,44 @@ def test_resident_window_intervals_of_m_calls(name, n_calls, M):
     rec = np.concatenate(records)
     for c, (i, j, series) in enumerate(f.raw_probes):
         assert np.array_equal(rec[:, c, :], np.array(series))
+
+
+@pytest.mark.parametrize("K,tile_rows,variant", [(2, 8, 0), (4, 16, 1), (6, 16, 1), (6, 48, 0), (8, 24, 1)])
+def test_whole_group_k_step_kernel_plus_frame_window_covers_the_grid(K, tile_rows, variant):
+    """One temporal-blocking group as fdtd2d.cu group_window launches it: the K-step kernel (stepK_stream / stepK_lean,
+    device code run by the SIMT emulator) on the plain tiles and frame_window on the frame tiles, both from generation A
+    into the same generation B.  Together they must write EVERY cell, with the oracle's values after K calls."""
+    import stream_emul as SE
+    if not SE.available():
+        pytest.skip("needs g++ and the CUDA headers")
+    rows, cols = 260, 420
+    f, setup, times = SC.random_case(rows, cols, 5, walls=(False, True, False, False), n_steps=K + 1)
+    setup = _eligible(setup)
+    R.leapfrog(f, setup, times[0])                             # generation A = the state after call 0
+    from fdtd_em_solver_b200 import _lib as L
+    lib = L.load()
+    cfg = L.Config()
+    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, 0, rows
+    cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, 2
+    boxes = np.ascontiguousarray(np.asarray(_boxes(setup, rows, cols, []), dtype=np.int64).reshape(-1, 4))
+    plan = L.FramePlan()
+    n = C.c_int32(0)
+    assert lib.fdtd_plan_frame_split(C.byref(cfg), K, len(boxes), boxes.ctypes.data, C.byref(plan), None, None,
+                                     C.byref(n), None) == 0
+    skip = np.zeros((max(plan.k_tiles_y, 1), plan.k_tiles_x), dtype=np.uint8)
+    xy = np.zeros((plan.frame_tiles_y * plan.frame_tiles_x, 2), dtype=np.int32)
+    masks = np.zeros((K, plan.frame_tiles_y, plan.frame_tiles_x), dtype=np.uint8)
+    assert lib.fdtd_plan_frame_split(C.byref(cfg), K, len(boxes), boxes.ctypes.data, C.byref(plan), skip.ctypes.data,
+                                     masks.ctypes.data, C.byref(n), xy.ctypes.data) == 0
+    assert not masks.any() and n.value > 0 and plan.k_tiles_y > 0 and not skip.all()
+    tiles = [tuple(t) for t in xy[:n.value]]
+    by_k = SE.stepK_stream(f, setup, times, 1, K, tile_rows, 2, plan.k_row_lo, plan.k_row_hi, skip, variant=variant)
+    by_w = E.window_emulate(f, setup, times, 1, K, tiles, plan.frame_tile_rows, plan.frame_tile_cols)[:3]
+    for t in times[1:1 + K]:
+        R.leapfrog(f, setup, t)
+    for name, a, b, want in zip(("h", "ex", "ey"), by_k, by_w, (f.h, f.ex, f.ey)):
+        both = ~np.isnan(a) & ~np.isnan(b)
+        assert np.array_equal(a[both], b[both]), name         # where they overlap they agree
+        merged = np.where(np.isnan(a), b, a)
+        assert not np.isnan(merged).any(), "%s: %d cells written by neither kernel" % (name, int(np.isnan(merged).sum()))
+        assert np.array_equal(merged, want), name
