@@ -172,6 +172,15 @@ class Solver:
     def ready(self):
         return len(self.pulses) > 0
 
+    def update_reflect(self):
+        """reference solver.py:164-167: zero h inside every reflector.  update() applies this on the device as part of
+        the step; the method is kept for callers that invoke it by hand between steps (it edits the host view, which
+        is uploaded before the next step)."""
+        h = np.array(self.h)
+        for top, bottom, left, right in self.reflectors:
+            h[top:bottom, left:right] = 0
+        self.h = h
+
     def record_energy(self, location):
         row, col = (self.convert(v) for v in location)
         self.recorded_energies.append({"i": row, "j": col, "location": location, "energies": []})

@@ -190,3 +190,47 @@ def test_streamed_file_is_removed_when_the_loop_raises(S, monkeypatch, tmp_path)
     with pytest.raises(IndexError):
         _quiet(s.solve, realtime=False)
     assert not os.path.exists(str(tmp_path / "broken") + ".npy") and s._streamed is None
+
+
+def test_update_reflect_by_hand_matches_the_reference(S):
+    """solver.py:164-167 is public in the reference; called between steps it zeroes h inside the reflectors."""
+    sc = SC.spec("waveguide")
+    f, setup, times, info = SC.restate(sc)
+    s = _quiet(SC.drive, S, sc)
+    for t in times[:30]:
+        R.leapfrog(f, setup, t)
+        s.update(t)
+    s.h = s.h + 1.0                                         # something visible inside the reflectors
+    f.h = f.h + 1.0
+    s.update_reflect()
+    for top, bottom, left, right in s.reflectors:
+        f.h[top:bottom, left:right] = 0
+        assert not s.h[top:bottom, left:right].any()
+    assert np.array_equal(s.h, f.h)
+    t = times[30]
+    R.leapfrog(f, setup, t)                                 # the edited h is what the next step starts from
+    assert np.array_equal(s.update(t), f.h)
+
+
+def test_public_surface_matches_the_reference_signatures():
+    """every public method of the reference's classes exists here with the same leading parameters
+    (extra keywords with defaults are allowed).  Needs /root/reference (build container only)."""
+    import inspect
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference sources not present on this box")
+    ref_solver, ref_analyser = ref_import.load()[:2]
+    from fdtd_em_solver_b200 import solver, analyser
+    for ref_mod, mod in ((ref_solver, solver), (ref_analyser, analyser)):
+        for cname, cls in inspect.getmembers(ref_mod, inspect.isclass):
+            if cls.__module__ != ref_mod.__name__:
+                continue
+            mine = getattr(mod, cname)
+            for name, fn in inspect.getmembers(cls, inspect.isfunction):
+                theirs = list(inspect.signature(fn).parameters.values())
+                ours = list(inspect.signature(getattr(mine, name)).parameters.values())
+                assert [(p.name, p.default) for p in ours[:len(theirs)]] == [(p.name, p.default) for p in theirs], \
+                    (cname, name)
+                assert all(p.default is not inspect.Parameter.empty for p in ours[len(theirs):]), (cname, name)
+    for const in ("C", "MU", "EPSILON"):
+        assert getattr(solver, const) == getattr(ref_solver, const)
