@@ -1284,6 +1284,7 @@ int fdtd_set_probes(fdtd_handle c, int32_t n, const int64_t* ij) {
     if (!c) return FDTD_ERR_ARG;
     for (FrameMaps& m : c->fm) m.key.clear();
     if (n < 0 || n > FDTD_MAX_PROBE) return fail(c, FDTD_ERR_ARG, "at most 16 probes");
+    if (n > 0 && !ij) return fail(c, FDTD_ERR_ARG, "null probe list");
     cudaSetDevice(c->cfg.device);
     if (c->probe_dev) { cudaStreamSynchronize(c->stream); cudaFree(c->probe_dev); c->probe_dev = nullptr; }
     c->probe_cap = 0; c->probe_count = 0;
@@ -1330,11 +1331,10 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     if (n_steps < 0) return fail(c, FDTD_ERR_ARG, "negative step count");
     const bool snaps = snapshot_every > 0 && snapshots_host != nullptr;
     if (snaps) {
-        for (int s = 0; s < 2; ++s)
-            if (!c->snap_dev[s]) {
-                CK(cudaMalloc(&c->snap_dev[s], (size_t)c->owned * c->cfg.cols * 8));
-                CK(cudaHostAlloc(&c->snap_pin[s], (size_t)c->owned * c->cfg.cols * 8, cudaHostAllocDefault));
-            }
+        for (int s = 0; s < 2; ++s) {                   // each checked on its own: a failed half is retried next call
+            if (!c->snap_dev[s]) CK(cudaMalloc(&c->snap_dev[s], (size_t)c->owned * c->cfg.cols * 8));
+            if (!c->snap_pin[s]) CK(cudaHostAlloc(&c->snap_pin[s], (size_t)c->owned * c->cfg.cols * 8, cudaHostAllocDefault));
+        }
     }
     if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
     int64_t k = 0;
