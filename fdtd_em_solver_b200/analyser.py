@@ -159,3 +159,16 @@ class DataCollector:
         plt.plot(self.fft_frequencies, self.fft_amplitude)
         if show:
             plt.show()
+
+
+class ProbeCollector(DataCollector):
+    """NOT in the reference: a `DataCollector` whose series was sampled by an on-device probe during the run
+    (`Solver.record_field`) instead of being sliced out of a saved snapshot stack -- same attributes, `fft()` and
+    plots, no `.npy` needed."""
+
+    def __init__(self, samples, location, constants):
+        self._samples = np.asarray(samples, dtype=np.float64)
+        super().__init__(self._samples, location, constants)        # len(matrix) = number of samples
+
+    def collect_all(self):
+        self.data = self._samples

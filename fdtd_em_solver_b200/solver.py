@@ -86,6 +86,7 @@ class Solver:
 
         self.recorded_energies = []
         self.energy_vector = []
+        self.recorded_fields = []          # record_field(): h series sampled by on-device probes (no snapshots needed)
 
         # device side
         self._dtype, self._device, self._kernel = dtype, device, kernel
@@ -185,6 +186,24 @@ class Solver:
         row, col = (self.convert(v) for v in location)
         self.recorded_energies.append({"i": row, "j": col, "location": location, "energies": []})
 
+    def record_field(self, location):
+        """NOT in the reference: the series a `DataCollector` would extract from the saved snapshot
+        stack at `location` (analyser.py:117-124: cell int(x / ds), one sample every `step_frequency` calls), sampled
+        by an on-device probe instead -- so an analysis run needs no snapshots at all (`solve(solve_only=True)`).
+        Returns the index to pass to `field_collector()` after the run."""
+        self.recorded_fields.append({"location": location, "samples": []})
+        return len(self.recorded_fields) - 1
+
+    def field_collector(self, index=0):
+        """`analyser.DataCollector` over the series of `record_field(...)` number `index`: same `.data`, `.time_vector`,
+        `.fft()` and plots as `FileLoader(name).create_data_collector(location)` after a saved run, bit for bit."""
+        from .analyser import ProbeCollector
+        d = self.recorded_fields[index]
+        return ProbeCollector(d["samples"], d["location"], self._run_constants())
+
+    def _field_cells(self):
+        return [(int(d["location"][0] / self.ds), int(d["location"][1] / self.ds)) for d in self.recorded_fields]
+
     def save(self, file_name):
         self.save_file_name = file_name
         self.save_file = True
@@ -226,7 +245,7 @@ class Solver:
         e = self._engine
         static = (id(self.eps_coefficient_arr), id(self.mu_coefficient_arr),
                   tuple(map(tuple, self.reflectors)) if self.reflect else (),
-                  tuple((d["i"], d["j"]) for d in self.recorded_energies),
+                  tuple((d["i"], d["j"]) for d in self.recorded_energies), tuple(self._field_cells()),
                   tuple(id(p) for p in self.pulses), np.asarray(times).tobytes())
         if static != self._static_key:
             if isinstance(self.eps_coefficient_arr, tuple):          # painted on the device from the recorded shapes
@@ -234,7 +253,7 @@ class Solver:
             else:
                 e.upload_coefficients(self.eps_coefficient_arr, self.mu_coefficient_arr)
             e.set_reflectors(self.reflectors if self.reflect else [])
-            e.set_probes([(d["i"], d["j"]) for d in self.recorded_energies])
+            e.set_probes([(d["i"], d["j"]) for d in self.recorded_energies] + self._field_cells())
             e.set_sources(self.pulses, times)
             self._static_key = static
             self._probe_seen = 0
@@ -243,19 +262,53 @@ class Solver:
             self._pending = None
 
     def _collect_probes(self):
-        """Energy formula of reference solver.py:251-255, evaluated on the host from raw device probes."""
-        if not self.recorded_energies:
+        """Energy formula of reference solver.py:251-255, evaluated on the host from raw device probes; and the h
+        samples of record_field()."""
+        if not (self.recorded_energies or self.recorded_fields):
             return
         raw = self._engine.probes()
+        new = raw[self._probe_seen:]
         cells = [self.material.cell(d["i"], d["j"]) for d in self.recorded_energies]
         # scalar arithmetic on purpose: np.float64 ** 2 is libm pow(), which is NOT always the correctly rounded x*x
         # that a vectorised `array ** 2` computes -- the reference's energies are the scalar kind (solver.py:251-255)
         for k, d in enumerate(self.recorded_energies):
             eps_ij, mu_ij = cells[k]
             out = d["energies"]
-            for hv, exv, eyv in raw[self._probe_seen:, k]:           # iterating float64 rows yields np.float64 scalars
+            for hv, exv, eyv in new[:, k]:                           # iterating float64 rows yields np.float64 scalars
                 out.append(0.5 * ((eps_ij * (exv ** 2 + eyv ** 2) + mu_ij * hv ** 2)))
+        if self.recorded_fields and len(new):
+            # record r of `new` was written by the call that left self.step at `calls[r]`; plot_and_save keeps the
+            # field after every call with step % step_frequency == 0 (solver.py:334-337)
+            calls = np.arange(self.step - len(new) + 1, self.step + 1)
+            keep = np.nonzero(calls % self.step_frequency == 0)[0]
+            ne = len(self.recorded_energies)
+            for k, (cell, d) in enumerate(zip(self._field_cells(), self.recorded_fields)):
+                for r in keep:
+                    aliased = self._aliased_source_value(cell, int(calls[r]))
+                    d["samples"].append(new[r, ne + k, 0] if aliased is None else aliased)
         self._probe_seen = len(raw)
+
+    def _aliased_source_value(self, cell, next_step):
+        """App. A-Q8: h_list holds REFERENCES to self.h, so the NEXT call's hard point-source write (solver.py:180)
+        lands in the snapshot taken before it.  Value a saved snapshot shows at `cell` instead of the computed h, or
+        None.  (Same rule as the device's snapshot pack: only if a next call exists.)"""
+        times = self.time_vector
+        if times is None or next_step >= len(times):
+            return None
+        value = None
+        for p in self.pulses:
+            if p.get_direction() is None and (p.get_row(), p.get_col()) == tuple(cell) \
+                    and p.get_start_time() < times[next_step] < p.get_end_time() \
+                    and next_step < len(p._magnitude_vector):
+                value = p.magnitude(next_step)
+                if self._dtype == "float32":
+                    value = np.float64(np.float32(value))            # the array it is written into is float32
+        return value
+
+    def _run_constants(self):
+        """The scalar run constants save_to_json writes (reference solver.py:68-75)."""
+        return {key: getattr(self, key) for key in ('dt', 'ds', 'length_x', 'length_y', 'stability', 'omega_max',
+                                                     'end_time', 'step_frequency')}
 
     def _npy_path(self):
         name = self.save_file_name

@@ -234,3 +234,47 @@ def test_public_surface_matches_the_reference_signatures():
                 assert all(p.default is not inspect.Parameter.empty for p in ours[len(theirs):]), (cname, name)
     for const in ("C", "MU", "EPSILON"):
         assert getattr(solver, const) == getattr(ref_solver, const)
+
+
+@pytest.mark.parametrize("name,n_calls", [("tutorial", 700), ("waveguide", 600)])
+def test_record_field_equals_the_data_collector_of_a_saved_run(S, name, n_calls, tmp_path):
+    """the on-device probe series == DataCollector over the saved snapshot stack, bit for bit --
+    also AT the point source, where a saved snapshot shows the NEXT call's source write (App. A-Q8)."""
+    from fdtd_em_solver_b200 import analyser
+    sc = SC.spec(name)
+    times = SC.restate(sc)[2][:n_calls]
+
+    def driven():
+        s = _quiet(SC.drive, S, sc)
+        s.end_time = float(times[-1]) + 0.5 * s.dt
+        return s
+
+    saved = driven()
+    saved.save(str(tmp_path / name))
+    _quiet(saved.solve, realtime=False, step_frequency=sc["step_frequency"])
+    loader = _quiet(analyser.FileLoader, str(tmp_path / name))
+
+    probed = driven()
+    src = probed.pulses[0]
+    at_source = ((src.get_row() + 0.5) * probed.ds, (src.get_col() + 0.5) * probed.ds)
+    assert (int(at_source[0] / probed.ds), int(at_source[1] / probed.ds)) == (src.get_row(), src.get_col())
+    places = [at_source, (0.4 * probed.length_x, 0.6 * probed.length_y), (0.0, 0.0)]
+    for loc in places:
+        probed.record_field(loc)
+    _quiet(probed.solve, solve_only=True, step_frequency=sc["step_frequency"])
+    assert probed.h_list == [] and np.array_equal(probed.h, saved.h)
+    some_aliased = False
+    for k, loc in enumerate(places):
+        want = loader.create_data_collector(loc)
+        got = probed.field_collector(k)
+        assert got.data.shape == want.data.shape and np.array_equal(got.data, want.data), (name, loc)
+        assert np.array_equal(got.time_vector, want.time_vector) and (got.i_pos, got.j_pos) == (want.i_pos, want.j_pos)
+        got.fft(); want.fft()
+        assert np.array_equal(got.fft_amplitude, want.fft_amplitude)
+        assert np.array_equal(got.fft_frequencies, want.fft_frequencies)
+    # the source cell really exercises the aliasing rule: its saved samples are pulse magnitudes, not computed h
+    d = probed.recorded_fields[0]["samples"]
+    some_aliased = any(d[m] == src.magnitude((m + 1) * sc["step_frequency"]) and d[m] != 0 for m in range(len(d) - 1))
+    assert some_aliased
+    if probed.recorded_energies:                           # energy probes and field probes share the device probe list
+        assert probed.recorded_energies[0]["energies"] == saved.recorded_energies[0]["energies"]
