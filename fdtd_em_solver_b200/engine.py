@@ -317,6 +317,11 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         L.check(self.lib, self.handle, self.lib.fdtd_comm_init(self.handle, C.cast(buf, C.c_void_p), rank, nranks))
 
+    @staticmethod
+    def comm_unique_id():
+        """The 128-byte NCCL id rank 0 creates and every rank passes to comm_init()."""
+        return comm_unique_id()
+
     def halo_exchange(self):
         L.check(self.lib, self.handle, self.lib.fdtd_halo_exchange(self.handle))
 

@@ -15,15 +15,21 @@ temporal_block=1 (leapfrog steps per HBM pass in solve(); 2..8 = temporal
 blocking, worthwhile for grids far larger than L2, bit-identical results),
 resident=None (True/False: all calls between two snapshots in ONE cooperative
 launch for grids that live in L2, i.e. every script of the reference; None =
-engine.RESIDENT_DEFAULT / $FDTD_RESIDENT; bit-identical results).
+engine.RESIDENT_DEFAULT / $FDTD_RESIDENT; bit-identical results),
+sharded=None (None: under `torchrun --nproc-per-node N` every rank builds the same
+Solver and owns one y-slab of rows on its own GPU, halo rows travel over NCCL
+inside the library -- see shard.py; False: never; results bit-identical to one GPU).
 """
 import json
 import math
+import os
 import sys
 
 import numpy as np
 
+from . import shard as _shard
 from .engine import Engine, empty_hugepages
+from .slab import split_rows
 
 C = 2.99 * (10 ** 8)
 MU = 1.26 * (10 ** (-6))
@@ -36,7 +42,7 @@ STREAM_SNAPSHOT_BYTES = 1 << 30
 
 
 def _say(*a):
-    if VERBOSE:
+    if VERBOSE and os.environ.get("RANK", "0") == "0":       # a sharded (torchrun) run talks through rank 0 only
         print(*a)
 
 
@@ -50,7 +56,7 @@ class Solver:
 
     def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
                  dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=1,
-                 resident=None):
+                 resident=None, sharded=None):
         self.points_per_wavelength = points_per_wavelength
         self.stability = stability
         self.n_max = math.sqrt(eps_r_max * mu_r_max)
@@ -93,6 +99,9 @@ class Solver:
         self._material_on_device = material_on_device
         self._temporal_block = int(temporal_block)      # leapfrog steps per HBM pass in the run loops (1..8)
         self._resident = resident                       # None = the engine's default
+        self._sharded = sharded                         # None = shard under torchrun (shard.context)
+        self._shard_ctx = None                          # shard.Shard of the current engine, or None
+        self._slabs = None                              # [(row_begin, row_end)] per rank of a sharded engine
         self._engine = None
         self._engine_key = None
         self._host = None           # (h, ex, ey) host copies valid for the current step, or None
@@ -116,8 +125,16 @@ class Solver:
 
     # field views: host copies of the device state (the reference keeps them on the host)
     def _fetch(self):
+        """COLLECTIVE in a sharded run: every rank ends up with the whole arrays (slabs gathered over torch.distributed)."""
         if self._host is None:
-            self._host = self._engine.get_fields()
+            got = self._engine.get_fields()
+            sh = self._shard_ctx
+            if sh is not None:
+                b, e = self._slabs[sh.rank]
+                last = 1 if e == self.size else 0                    # the last slab also owns ex[size]
+                parts = sh.all_gather((got[0][b:e], got[1][b:e + last], got[2][b:e]))
+                got = tuple(np.concatenate([part[k] for part in parts]) for k in range(3))
+            self._host = got
         return self._host
 
     h = property(lambda self: None if self.size is None else self._fetch()[0])
@@ -228,16 +245,28 @@ class Solver:
     def _sync_engine(self, times):
         """(Re)build the device state from the host-side description when it changed."""
         courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
+        sh = _shard.context(self._sharded)
         key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant,
-               self._temporal_block, self._resident)
+               self._temporal_block, self._resident, None if sh is None else (sh.rank, sh.world))
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 if self._pending is None:
                     self._pending = self._fetch()
                 self._engine.close()
-            self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
-                                  device=self._device, reflect=self.boundaries, kernel=self._kernel,
-                                  temporal=self._temporal_block, resident=self._resident)
+            if sh is None:
+                self._slabs = None
+                self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
+                                      device=self._device, reflect=self.boundaries, kernel=self._kernel,
+                                      temporal=self._temporal_block, resident=self._resident)
+            else:                   # one y-slab per rank, each on its own GPU; the library exchanges the halo rows itself
+                self._slabs = split_rows(self.size, sh.world)
+                b, e = self._slabs[sh.rank]
+                self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
+                                      device=sh.local_rank, reflect=self.boundaries, kernel=self._kernel,
+                                      temporal=self._temporal_block, resident=False, row_begin=b, row_end=e)
+                self._engine.comm_init(sh.rank, sh.world,
+                                       sh.broadcast(self._engine.comm_unique_id() if sh.rank == 0 else None))
+            self._shard_ctx = sh
             self._engine_key = key
             self._static_key = None
             self._probe_seen = 0
@@ -267,6 +296,13 @@ class Solver:
         if not (self.recorded_energies or self.recorded_fields):
             return
         raw = self._engine.probes()
+        sh = self._shard_ctx
+        if sh is not None:          # a probe cell is written by the rank that owns its row; the others hold zeros there
+            cells = [(d["i"], d["j"]) for d in self.recorded_energies] + self._field_cells()
+            theirs = sh.all_gather(raw)
+            raw = raw.copy()
+            for k, (i, _) in enumerate(cells):
+                raw[:, k, :] = theirs[_shard.owner_of_row(self._slabs, i)][:, k, :]
         new = raw[self._probe_seen:]
         cells = [self.material.cell(d["i"], d["j"]) for d in self.recorded_energies]
         # scalar arithmetic on purpose: np.float64 ** 2 is libm pow(), which is NOT always the correctly rounded x*x
@@ -317,7 +353,7 @@ class Solver:
     def _snapshot_alloc(self, shape):
         """Where the snapshot stack of a run lives: RAM, or the .npy file itself for big stacks."""
         nbytes = 8 * int(np.prod(shape))
-        if self.save_file and not self.h_list and nbytes >= STREAM_SNAPSHOT_BYTES:
+        if self._shard_ctx is None and self.save_file and not self.h_list and nbytes >= STREAM_SNAPSHOT_BYTES:
             self._streamed = self._npy_path()
             return np.lib.format.open_memmap(self._streamed, mode="w+", dtype=np.float64, shape=tuple(shape))
         return empty_hugepages(shape)
@@ -338,7 +374,28 @@ class Solver:
             self.step = first + (done - self._steps_seen)
             self._steps_seen = done
             self._collect_probes()
-        return stack
+        return self._whole_stack(stack)
+
+    def _whole_stack(self, stack):
+        """Sharded runs: the engine returned this rank's rows of every snapshot.  COLLECTIVE.  A fresh saving run puts
+        the slabs straight into <name>.npy (rank 0 creates the file, every rank writes its rows and then maps the whole
+        stack -- one node, one page cache); otherwise the slabs are gathered in RAM."""
+        sh = self._shard_ctx
+        if sh is None or stack is None:
+            return stack
+        b, e = self._slabs[sh.rank]
+        if self.save_file and not self.h_list:
+            path, shape = self._npy_path(), (stack.shape[0], self.size, stack.shape[2])
+            if sh.rank == 0:
+                np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=shape).flush()
+            sh.barrier()
+            whole = np.lib.format.open_memmap(path, mode="r+")
+            whole[:, b:e, :] = stack
+            whole.flush()
+            sh.barrier()
+            self._streamed = path
+            return whole
+        return np.concatenate(sh.all_gather(stack), axis=1)
 
     def update(self, time):
         """One leapfrog step (reference solver.py:169-257); returns the new h as a host array."""
@@ -389,11 +446,15 @@ class Solver:
                 raise Exception("Must create a save file name for non-realtime simulation")
             self.plot_and_save(step_frequency=step_frequency)
             _say("Saving to npy file...")
-            if self._streamed is None:
+            writer = self._shard_ctx is None or self._shard_ctx.rank == 0      # sharded: every rank holds the same data
+            if self._streamed is None and writer:
                 np.save(self.save_file_name, self._stack if self._stack is not None else self.h_list)
             self._streamed = None             # (a streamed stack already IS the file; the page cache keeps it coherent)
             _say("Saving to txt file...")
-            self.save_to_json()
+            if writer:
+                self.save_to_json()
+            if self._shard_ctx is not None:
+                self._shard_ctx.barrier()     # the files exist on return, on every rank
             _say("Complete!")
 
     def _loop(self, snapshot_every):
@@ -408,7 +469,7 @@ class Solver:
                     frames.append(self.h)
             if frames:
                 stack = np.array(frames)
-        if self.steps and VERBOSE:
+        if self.steps and VERBOSE and os.environ.get("RANK", "0") == "0":
             sys.stdout.write("\r%d%%" % (100 * self.step // self.steps))
             sys.stdout.flush()
         return stack
@@ -421,7 +482,6 @@ class Solver:
             stack = self._loop(step_frequency if self.save_file else 0)
         except BaseException:
             if self._streamed is not None:         # the reference writes no file when the loop raises
-                import os
                 path, self._streamed = self._streamed, None
                 if os.path.exists(path):
                     os.remove(path)
@@ -434,6 +494,8 @@ class Solver:
 
     def plot_and_show(self):
         """reference solver.py:309-329: one update per animation frame."""
+        if _shard.context(self._sharded) is not None:
+            raise Exception("realtime plotting is not available in a sharded run: save() and solve(realtime=False)")
         plt = _pyplot()
         import matplotlib.animation as animation
         fig, ax1 = plt.subplots(figsize=(6, 6))
