@@ -224,3 +224,27 @@ def test_snapshot_stack_allocator_is_a_plain_float64_array():
         if a.size:
             a[...] = 1.5
             assert float(a.sum()) == 1.5 * a.size
+
+
+def test_integration_md_stub_compiles_and_matches_the_abi():
+    """INTEGRATION.md's reference-side binding must not drift from include/fdtd2d.h / _lib.py: its code block compiles,
+    its ctypes structures have the library's field lists, and every fdtd_* symbol it calls is exported."""
+    import ast
+    import re
+    from fdtd_em_solver_b200 import _lib as L
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = max(blocks, key=len)
+    tree = ast.parse(stub)                                     # compiles
+    fields = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef):
+            for stmt in node.body:
+                if isinstance(stmt, ast.Assign) and stmt.targets[0].id == "_fields_":
+                    fields[node.name] = [elt.elts[0].value for elt in stmt.value.elts]
+    assert fields["Config"] == [f[0] for f in L.Config._fields_]
+    assert fields["Source"] == [f[0] for f in L.Source._fields_]
+    called = set(re.findall(r"lib\.(fdtd_\w+)", stub))
+    assert called and called <= set(L.SIGNATURES), called - set(L.SIGNATURES)
+    direction_kinds = ast.literal_eval(re.search(r"KIND = (\{.*?\})", stub).group(1))
+    assert direction_kinds == L.DIRECTION_KIND
