@@ -89,6 +89,10 @@ class Solver:
         self.save_file = False
         self.save_dict_json = dict()
         self.step_frequency = 5
+        # NOT in the reference: update() calls per animation frame of plot_and_show.  1 = the
+        # reference's one call per frame; n > 1 runs n calls in one device run and shows every n-th field, which keeps
+        # the interactive view usable on grids where drawing, not stepping, sets the pace
+        self.frame_stride = 1
 
         self.recorded_energies = []
         self.energy_vector = []
@@ -360,11 +364,13 @@ class Solver:
 
     _streamed = None
 
-    def _run_device(self, times, snapshot_every=0):
-        """The loops of solver.py:288-292 / :331-337 for calls self.step .. len(times)-1."""
+    def _run_device(self, times, snapshot_every=0, n_calls=None):
+        """The loops of solver.py:288-292 / :331-337 for calls self.step .. len(times)-1 (or the next n_calls of them)."""
         self._sync_engine(times)
         first = self.step
         n = len(times) - first
+        if n_calls is not None:
+            n = max(0, min(n, int(n_calls)))
         self._host = None
         try:
             stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
@@ -506,13 +512,19 @@ class Solver:
         ax1.xaxis.set_label_position('top')
         fig.colorbar(im, ax=ax1)
 
+        stride = max(1, int(self.frame_stride))
+
         def animate(time):
-            if self.step % self.step_frequency == 0:
+            if self.step % self.step_frequency == 0 or stride > 1:
                 fig.suptitle("Time Step = {}".format(self.step))
-            im.set_array(self.update(time))
+            if stride == 1:
+                im.set_array(self.update(time))
+            else:                           # `stride` calls in one device run, then one readback for the picture
+                self._run_device(self.time_vector, n_calls=stride)
+                im.set_array(self.h)
             return im,
 
-        self._anim = animation.FuncAnimation(fig, animate, frames=self.time_vector, interval=1, blit=False,
+        self._anim = animation.FuncAnimation(fig, animate, frames=self.time_vector[::stride], interval=1, blit=False,
                                              repeat=False)
         plt.show()
 

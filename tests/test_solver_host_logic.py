@@ -157,6 +157,21 @@ def test_realtime_path_updates_once_per_frame(S, monkeypatch):
         R.leapfrog(f, setup, t)
     assert len(shown) == 61 and s.step == 61 and np.array_equal(shown[-1], f.h)
 
+    # frame_stride = 7: seven calls per frame in one device run, the same fields at the frames shown
+    del shown[:]
+    f7, setup7, _, _ = SC.restate(sc)
+    s7 = _quiet(SC.drive, S, sc)
+    s7.end_time = 60.5 * s7.dt
+    s7.frame_stride = 7
+    _quiet(s7.solve)
+    want = []
+    for n, t in enumerate(times[:61]):
+        R.leapfrog(f7, setup7, t)
+        if (n + 1) % 7 == 0 or n == 60:
+            want.append(f7.h.copy())
+    assert s7.step == 61 and len(shown) == len(want) == 9
+    assert all(np.array_equal(a, b) for a, b in zip(shown, want))
+
 
 def test_big_snapshot_stacks_stream_into_the_npy_file(S, monkeypatch, tmp_path):
     """above STREAM_SNAPSHOT_BYTES the stack is an open_memmap of <name>.npy, never a RAM copy +
