@@ -570,6 +570,19 @@ void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
     fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
 }
 
+template <typename T>
+void launch_stepK_any(const StepParams<T>& P, fdtd_ctx* c, int K) {      // K = 2..8 (fdtd_set_temporal_blocking checks)
+    switch (K) {
+        case 2: launch_stepK<T, 2>(P, c); break;
+        case 3: launch_stepK<T, 3>(P, c); break;
+        case 4: launch_stepK<T, 4>(P, c); break;
+        case 5: launch_stepK<T, 5>(P, c); break;
+        case 6: launch_stepK<T, 6>(P, c); break;
+        case 7: launch_stepK<T, 7>(P, c); break;
+        default: launch_stepK<T, 8>(P, c); break;
+    }
+}
+
 // Steps n .. n+K-1 in one HBM pass: A -> B.  The frame (walls, sources, reflectors, probes, slab interface strips)
 // goes A -> S -> S' -> ... -> B with K masked, compact single-step launches: passes 1..K-1 (frame dilated by a ring
 // of tiles wide enough for the K-p cells of validity still needed) run on the high-priority edge stream
@@ -604,15 +617,7 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
             StepParams<T> PK;                                   // the K-step kernel: everything but the frame
             if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
             PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
-            if (m.nty > 0) switch (K) {
-                case 2: launch_stepK<T, 2>(PK, c); break;
-                case 3: launch_stepK<T, 3>(PK, c); break;
-                case 4: launch_stepK<T, 4>(PK, c); break;
-                case 5: launch_stepK<T, 5>(PK, c); break;
-                case 6: launch_stepK<T, 6>(PK, c); break;
-                case 7: launch_stepK<T, 7>(PK, c); break;
-                default: launch_stepK<T, 8>(PK, c); break;
-            }
+            if (m.nty > 0) launch_stepK_any<T>(PK, c, K);
             if (m.nty > 0) c->stats.kernel_launches++;
             CK(cudaGetLastError());
             if (!m.h_tiles.empty()) {
@@ -826,15 +831,7 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
         StepParams<T> PK;
         if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
         PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
-        switch (K) {
-            case 2: launch_stepK<T, 2>(PK, c); break;
-            case 3: launch_stepK<T, 3>(PK, c); break;
-            case 4: launch_stepK<T, 4>(PK, c); break;
-            case 5: launch_stepK<T, 5>(PK, c); break;
-            case 6: launch_stepK<T, 6>(PK, c); break;
-            case 7: launch_stepK<T, 7>(PK, c); break;
-            default: launch_stepK<T, 8>(PK, c); break;
-        }
+        launch_stepK_any<T>(PK, c, K);
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
