@@ -859,3 +859,19 @@ class Pulse:
     def get_row(self): return self._index_location[0]
     def get_col(self): return self._index_location[1]
     def get_type(self): return self._type
+
+
+def test():
+    """The reference's built-in demo scene (solver.py:645-665): a point pulse next to an eps_r = mu_r = 3 block, shown
+    in the realtime view (needs matplotlib and a display, like the reference)."""
+    solver = Solver(points_per_wavelength=10, stability=0.1, eps_r_max=4, mu_r_max=3, simulation_size=3,
+                    simulation_time=2.5e-8)
+    _say(C / 5e9)
+    solver.add_oscillating_pulse(1e9, (0.8, 0.4), 5e9)
+    solver.create_material().set_material_rect((2, 2), (2.8, 2.8), 3, 3)
+    solver.solve(step_frequency=50)
+    return solver
+
+
+if __name__ == '__main__':
+    test()
