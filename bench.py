@@ -182,7 +182,8 @@ def workload_config(args, n_gpus):
                 if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
             "temporal_blocking": args.temporal,
             "frame_mode": int(getattr(args, "frame_mode", None) or 0),
-            "kstep_variant": int(getattr(args, "kstep_variant", None) or 0)}
+            "kstep_variant": int(getattr(args, "kstep_variant", None) or 0),
+            "halo_depth": int(getattr(args, "halo_depth", None) or 1)}
 
 
 def main():
@@ -207,6 +208,9 @@ def main():
                          "next to / behind the K-step kernel (default: the library's)")
     ap.add_argument("--kstep-variant", type=int, default=None, choices=[0, 1],
                     help="K-step kernel: 0 stepK_stream, 1 stepK_lean (default: the library's)")
+    ap.add_argument("--halo-depth", type=int, default=None,
+                    help="y-slabs: rows stored from each neighbouring slab; 1 = one row exchanged every step, K+1 = deep "
+                         "halos with ONE exchange per K-step group (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -243,7 +247,7 @@ def main():
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
                           tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal,
-                          frame_mode=args.frame_mode, kstep_variant=args.kstep_variant)
+                          frame_mode=args.frame_mode, kstep_variant=args.kstep_variant, halo_depth=args.halo_depth)
     if world > 1:
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -293,13 +297,16 @@ def main():
     if not args.no_e2e:
         owned = ROWS_PER_GPU
         tdt = torch.float64
-        lo = 1 if rank > 0 else 0                        # halo row above the slab travels with the coefficient planes
+        deep = e.halo_depth if e.halo_depth > 1 else 0
+        lo = (deep or 1) if rank > 0 else 0              # halo rows above the slab travel with the coefficient planes
+        hb = deep if rank + 1 < world else 0             # ... and, with deep halos, the ones below it
         # host-resident inputs of this slab: the two coefficient planes, pinned, float64 (what
         # Solver.solve hands over, solver.py:278-279); built once outside the timed region
-        eps_slab = torch.empty((owned + 1, COLS), dtype=tdt, pin_memory=True)
-        mu_slab = torch.empty((owned + 1, COLS), dtype=tdt, pin_memory=True)
-        eps_slab[:owned + lo].copy_(e.buffers[6][:owned + lo, :COLS].to(tdt))
-        mu_slab[:owned + lo].copy_(e.buffers[7][:owned + lo, :COLS].to(tdt))
+        stored = owned + lo + hb
+        eps_slab = torch.empty((stored + 1, COLS), dtype=tdt, pin_memory=True)
+        mu_slab = torch.empty((stored + 1, COLS), dtype=tdt, pin_memory=True)
+        eps_slab[:stored].copy_(e.buffers[6][:stored, :COLS].to(tdt))
+        mu_slab[:stored].copy_(e.buffers[7][:stored, :COLS].to(tdt))
         h_out = torch.empty((owned, COLS), dtype=tdt, pin_memory=True)
         torch.cuda.synchronize()
         import ctypes as C
@@ -323,7 +330,7 @@ def main():
             t = torch.tensor([sec], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
-        h2d = 2 * (owned + lo) * COLS * 8
+        h2d = 2 * stored * COLS * 8
         d2h = owned * COLS * 8
         e2e = {"value": cells * args.steps / sec / 1e9, "unit": "Gcell-updates/s",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,

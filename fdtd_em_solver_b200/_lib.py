@@ -99,6 +99,11 @@ SIGNATURES = {
     "fdtd_comm_init": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     "fdtd_halo_exchange": (C.c_int, [_P]),
     "fdtd_halo_rows": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "fdtd_local_rows_halo": (C.c_int64, [C.POINTER(Config), C.c_int32]),
+    "fdtd_set_halo_depth": (C.c_int, [_P, C.c_int32]),
+    "fdtd_plan_frame_halo": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P,
+                                       C.POINTER(C.c_int32), _P]),
+    "fdtd_halo_blocks": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
 }
 
 

@@ -76,7 +76,10 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
 
 struct fdtd_ctx {
     fdtd_config cfg{};
-    int64_t pitch = 0, lrows = 0, halo_top = 0, row_off = 0, owned = 0, host_row0 = 0;
+    int64_t pitch = 0, lrows = 0, halo_top = 0, halo_bot = 0, row_off = 0, owned = 0, host_row0 = 0;
+    int halo_depth = 1;             // rows of h/ex/ey kept from each neighbouring slab: 1 = one row above + ex[row_end]
+                                    // (exchange every step); D >= 2 = D rows above AND below (deep halos: ONE exchange
+                                    // per temporal-blocking group of up to D-1 steps, fdtd_set_halo_depth)
     size_t esize = 8;
     void* gen[4][3] = {};           // [generation][h,ex,ey]: 2 for ping-pong, +1 / +2 scratch for temporal blocking
     int ngen = 2;                   // generations bound
@@ -311,9 +314,34 @@ int ensure_probe_capacity(fdtd_ctx* c, int64_t extra_steps) {
 
 int nccl_dtype(fdtd_ctx* c) { return c->cfg.dtype == FDTD_F64 ? 8 : 7; }
 
+// Deep halos: refresh the D rows of h/ex/ey stored from each neighbour with that neighbour's D outermost owned rows
+// of generation g -- one contiguous block of D x pitch elements per array and direction.
+int exchange_deep(fdtd_ctx* c, int g, cudaStream_t s) {
+    const int64_t D = c->halo_depth;
+    const size_t es = c->esize, count = (size_t)(D * c->pitch);
+    auto row = [&](int f, int64_t grow) { return (char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * es; };
+    const bool has_up = c->rank > 0, has_down = c->rank + 1 < c->nranks;
+    const int dt = nccl_dtype(c);
+    NCK(g_nccl.GroupStart());
+    for (int f = 0; f < 3; ++f) {
+        if (has_down) {
+            NCK(g_nccl.Send(row(f, c->cfg.row_end - D), count, dt, c->rank + 1, c->comm, s));
+            NCK(g_nccl.Recv(row(f, c->cfg.row_end), count, dt, c->rank + 1, c->comm, s));
+        }
+        if (has_up) {
+            NCK(g_nccl.Send(row(f, c->cfg.row_begin), count, dt, c->rank - 1, c->comm, s));
+            NCK(g_nccl.Recv(row(f, c->cfg.row_begin - D), count, dt, c->rank - 1, c->comm, s));
+        }
+    }
+    NCK(g_nccl.GroupEnd());
+    c->stats.halo_bytes_sent += (int64_t)((has_down ? 3 : 0) + (has_up ? 3 : 0)) * (int64_t)(D * c->cfg.cols * es);
+    return 0;
+}
+
 // Exchange the halo rows of generation g on `s` (3 rows down, 1 row up).
 int exchange(fdtd_ctx* c, int g, cudaStream_t s) {
     if (!c->comm) return 0;
+    if (c->halo_depth > 1) return exchange_deep(c, g, s);
     const int64_t NC = c->cfg.cols;
     const size_t es = c->esize;
     auto row = [&](int f, int64_t grow) { return (char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * es; };
@@ -352,6 +380,16 @@ int step_impl(fdtd_ctx* c, int64_t step) {
     if (c->auto_tile_rows) P.tile_rows = 6;        // cfg.tile_rows follows the K-step kernel; a lone single step wants short tiles
     if (!c->comm) {
         if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
+    } else if (c->halo_depth > 1) {
+        // deep halos: single steps are the exception here (remainders, snapshot cadence), so no strip overlap -- all
+        // owned rows in one launch once the previous exchange has landed, then the D-row blocks travel
+        CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        if (int rc = launch_rows<T>(c, P, lo, hi, c->stream)) return rc;
+        CK(cudaEventRecord(c->ev_p3, c->stream));
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_p3, 0));
+        if (int rc = exchange(c, dst, c->comm_stream)) return rc;
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+        CK(cudaEventRecord(c->ev_int, c->stream));
     } else {
         // Interface strips on a high-priority stream, their rows sent over NCCL on the comm stream, the
         // interior on the main stream -- all three overlap.  Dependencies of step n (A -> B):
@@ -387,7 +425,8 @@ template <typename T> constexpr int kvec() { return sizeof(T) == 8 ? 2 : 4; }   
 // Can frame_window (window.cuh) take the frame tiles of a K-step group of this context?  (Which of them it takes is
 // decided per tile by plan_frame: all of them on a whole grid, all but the interface strips on a y-slab.)
 bool frame_window_usable(const fdtd_ctx* c, int K) {
-    if (c->frame_mode == 0 || K > fdtd::WIN_MAX_CALLS || c->n_src > FDTD_MAX_SRC) return false;
+    // (deep halos have no pass chain to fall back on: there frame_window is THE frame kernel, whatever the mode says)
+    if ((c->frame_mode == 0 && c->halo_depth <= 1) || K > fdtd::WIN_MAX_CALLS || c->n_src > FDTD_MAX_SRC) return false;
     for (int p = 0; p < c->n_src; ++p)
         if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
     return true;
@@ -397,7 +436,8 @@ template <typename T> int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
 struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
-struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false; };
+struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false;
+                   int64_t halo_top = 0, halo_bot = 0; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
 
 void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
     const int K = g.K, V2 = g.V2;
@@ -413,8 +453,11 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
     if (TR <= 8) TRF = (TR % 2 == 0 && TR >= 8) ? TR / 2 : TR;
     // K-step tiles own rows [loK, hiK): they start K rows (rounded up to a frame tile) below the slab top and stop K
     // rows above its bottom, so that only a thin band of rows at the top/bottom (or at a slab interface) is frame.
-    const int64_t loK = lo + ((K + TRF - 1) / TRF) * (int64_t)TRF;
-    int64_t hiK = std::min<int64_t>(g.row_end, NR) - K;            // tb+K-1 <= row_end-1 and tb+K-2 <= NR-2
+    // Deep halos store K rows (and one more) of the neighbouring slab, so at an INTERFACE the K-step tiles reach the
+    // slab's first / last owned row; at a real wall of the grid nothing changes.
+    const bool deep_top = g.row_begin > 0 && g.halo_top >= K, deep_bot = g.row_end < NR && g.halo_bot >= K + 1;
+    const int64_t loK = deep_top ? lo : lo + ((K + TRF - 1) / TRF) * (int64_t)TRF;
+    int64_t hiK = deep_bot ? g.row_end : std::min<int64_t>(g.row_end, NR) - K;   // tb+K-1 <= last stored row - 1 and tb+K-2 <= NR-2
     hiK = hiK > lo ? lo + ((hiK - lo) / TRF) * TRF : lo;
     const int nty = hiK > loK ? (int)((hiK - loK + TR - 1) / TR) : 0, ntyF = (int)((hi - lo + TRF - 1) / TRF);
     const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT), ntx1 = (int)((NC + 1 + W1 - 1) / W1);
@@ -427,8 +470,8 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
     for (int ty = 0; ty < nty; ++ty) {
         const int64_t ta = loK + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hiK);
         // every row a stage touches (ta-K .. tb+K-1) is an OWNED plain interior row of this slab (by construction)
-        const bool rows_ok = ta - K >= std::max<int64_t>(g.row_begin, 0) && ta - (K - 1) >= 1 &&
-                             tb + K - 2 <= NR - 2 && tb + K - 1 <= g.row_end - 1;
+        const bool rows_ok = ta - K >= std::max<int64_t>(g.row_begin - g.halo_top, 0) && ta - (K - 1) >= 1 &&
+                             tb + K - 2 <= NR - 2 && tb + K - 1 <= g.row_end + g.halo_bot - 1;
         for (int tx = 0; tx < ntx2; ++tx) {
             const int64_t jw = (int64_t)tx * OUT - (int64_t)MARGIN * V2;
             bool mixed = !rows_ok || jw < 1 || jw + LD - 1 > NC - 2;
@@ -454,7 +497,8 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
         const int64_t A = K + 1;
         for (int ty = 0; ty < ntyF; ++ty) {
             const int64_t ta = lo + (int64_t)ty * TRF, tb = std::min<int64_t>(ta + TRF, hi);
-            const bool rows_ok = (g.row_begin == 0 || ta - A >= g.row_begin) && (g.row_end == NR || tb + A <= g.row_end);
+            const bool rows_ok = (g.row_begin == 0 || ta - A >= g.row_begin - g.halo_top) &&
+                                 (g.row_end == NR || tb + A <= g.row_end + g.halo_bot);
             if (!rows_ok) continue;
             for (int tx = 0; tx < ntx1; ++tx)
                 if (m.h_mask[0][(size_t)ty * ntx1 + tx]) {
@@ -494,7 +538,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         key.push_back(live);
     }
     const bool fused = frame_window_usable(c, K);
-    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused}) {
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused, c->halo_depth}) {
         key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
     }
     if (key == m.key && m.d_skip) return 0;
@@ -512,8 +556,9 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
             if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
+    const bool deep = c->halo_depth > 1;
     plan_frame(FrameGeom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
-                         c->cfg.block_warps, K, kvec<T>(), fused}, mods, m);
+                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0}, mods, m);
     const int ntyF = m.frame_nty, ntx1 = m.ntx1;
     size_t longest = 1;
     for (int d = 0; d < K; ++d) longest = std::max(longest, m.h_list[d].size());
@@ -823,6 +868,7 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
     const int A = c->cur, B = (A + 1) % c->ngen;
     if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
     const bool side = c->frame_mode == 1 && m.nty > 0 && !m.h_tiles.empty();
+    if (c->comm) CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));      // deep halos: the neighbours' rows of A have landed
     if (side) {
         CK(cudaEventRecord(c->ev_int, c->stream));              // everything before this group
         CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
@@ -841,6 +887,12 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // main-stream order = "all of B written"
     }
     CK(cudaEventRecord(c->ev_int, c->stream));
+    if (c->comm) {                                              // deep halos: ONE exchange per group, of generation B
+        CK(cudaEventRecord(c->ev_p3, c->stream));
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_p3, 0));
+        if (int rc = exchange(c, B, c->comm_stream)) return rc;
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    }
     c->cur = B;
     if (c->n_probe) c->probe_count += K;
     c->stats.steps += K;
@@ -848,16 +900,27 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
     return 0;
 }
 
-int group_any(fdtd_ctx* c, int64_t n, int K) {
-    // a whole grid on one GPU: no interface strips, so no pass chain at all; y-slabs go through group_impl, which adds
-    // the window launch to its chain of interface passes
-    if (frame_window_usable(c, K) && !c->comm && c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)
-        return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
-    return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
-}
-
 int step_any(fdtd_ctx* c, int64_t step) {
     return c->cfg.dtype == FDTD_F64 ? step_impl<double>(c, step) : step_impl<float>(c, step);
+}
+
+int group_any(fdtd_ctx* c, int64_t n, int K) {
+    const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
+    if (c->halo_depth > 1 && !whole) {
+        // deep halos: the slab stores D rows of each neighbour, so a group of K <= D-1 steps needs nothing from them
+        // while it runs -- K-step kernel + frame_window, then one exchange.  No pass chain exists in this mode; a scene
+        // frame_window cannot take (or a deeper group) is stepped call by call instead.
+        if (K <= c->halo_depth - 1 && frame_window_usable(c, K))
+            return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
+        for (int k = 0; k < K; ++k)
+            if (int rc = step_any(c, n + k)) return rc;
+        return 0;
+    }
+    // a whole grid on one GPU: no interface strips, so no pass chain at all; y-slabs go through group_impl, which adds
+    // the window launch to its chain of interface passes
+    if (frame_window_usable(c, K) && !c->comm && whole)
+        return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
+    return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
 
 template <typename T>
@@ -908,6 +971,13 @@ int64_t fdtd_default_pitch(int64_t cols, int32_t /*dtype*/) { return ((cols + 1 
 int64_t fdtd_local_rows(const fdtd_config* cfg) {
     if (!cfg) return 0;
     return (cfg->row_end - cfg->row_begin) + (cfg->row_begin > 0 ? 1 : 0) + 1;
+}
+
+int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth) {
+    if (!cfg) return 0;
+    if (halo_depth <= 1) return fdtd_local_rows(cfg);
+    return (cfg->row_end - cfg->row_begin) + (cfg->row_begin > 0 ? halo_depth : 0) +
+           (cfg->row_end < cfg->rows ? halo_depth : 0) + 1;
 }
 
 const char* fdtd_last_error(fdtd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1022,7 +1092,7 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
 
 static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
                              fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, bool fused, int32_t* n_window_tiles,
-                             int32_t* window_tiles_xy) {
+                             int32_t* window_tiles_xy, int32_t halo_depth = 1) {
     fdtd_ctx* c = nullptr;
     if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes))
         return fail(c, FDTD_ERR_ARG, "bad argument");
@@ -1033,7 +1103,10 @@ static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int
     for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
     const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
-    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, fused}, mods, m);
+    const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
+    const int64_t hb = (halo_depth > 1 && cfg->row_end < cfg->rows) ? halo_depth : 0;
+    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, fused,
+                         ht, hb}, mods, m);
     const int margin = (K + V2 - 1) / V2;
     plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
     plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
@@ -1061,6 +1134,14 @@ int fdtd_plan_frame_split(const fdtd_config* cfg, int32_t steps_per_pass, int32_
     return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, true, n_window_tiles, window_tiles_xy);
 }
 
+int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes,
+                         const int64_t* boxes, fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks,
+                         int32_t* n_window_tiles, int32_t* window_tiles_xy) {
+    if (halo_depth < 1 || halo_depth > 9) return fail(nullptr, FDTD_ERR_ARG, "halo depth must be 1..9");
+    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, true, n_window_tiles, window_tiles_xy,
+                             halo_depth);
+}
+
 int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
     if (!c) return FDTD_ERR_ARG;
     for (void* p : {h2, ex2, ey2}) {
@@ -1085,6 +1166,22 @@ int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     static const int rows_for_k[9] = {6, 6, 8, 12, 16, 32, 48, 48, 56};
     if (c->auto_tile_rows) c->cfg.tile_rows = rows_for_k[steps_per_pass];
     if (c->auto_warps) c->cfg.block_warps = steps_per_pass == 1 ? 4 : (steps_per_pass == 4 ? 2 : 1);
+    for (FrameMaps& m : c->fm) m.key.clear();
+    return 0;
+}
+
+int fdtd_set_halo_depth(fdtd_handle c, int32_t depth) {
+    if (!c) return FDTD_ERR_ARG;
+    if (c->bound) return fail(c, FDTD_ERR_STATE, "set the halo depth before fdtd_bind_buffers (it sizes the arrays)");
+    if (depth < 1 || depth > 9) return fail(c, FDTD_ERR_ARG, "halo depth must be 1..9");
+    const bool up = c->cfg.row_begin > 0, down = c->cfg.row_end < c->cfg.rows;
+    if (depth > 1 && (up || down) && c->owned < depth)
+        return fail(c, FDTD_ERR_ARG, "a slab must own at least as many rows as its halos are deep");
+    c->halo_depth = depth;
+    c->halo_top = up ? depth : 0;
+    c->halo_bot = (depth > 1 && down) ? depth : 0;
+    c->row_off = c->cfg.row_begin - c->halo_top;
+    c->lrows = fdtd_local_rows_halo(&c->cfg, depth);
     for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
@@ -1133,7 +1230,7 @@ int fdtd_set_host_row_origin(fdtd_handle c, int64_t first_global_row) {
 int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_coef, int64_t host_ld) {
     NEED_BOUND();
     if (!eps_coef || !mu_coef || host_ld < c->cfg.cols) return fail(c, FDTD_ERR_ARG, "bad coefficient arrays");
-    const int64_t g0 = c->row_off, n = c->cfg.row_end - c->row_off;
+    const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off;     // every stored h-row
     int rc;
     if (c->cfg.dtype == FDTD_F64) {
         if ((rc = h2d_plane<double>(c, c->epc, eps_coef, host_ld, g0, n, c->cfg.cols))) return rc;
@@ -1203,7 +1300,7 @@ int fdtd_zero_fields(fdtd_handle c) {
 
 int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const double* ey) {
     NEED_BOUND();
-    const int64_t g0 = c->row_off, n = c->cfg.row_end - c->row_off, NC = c->cfg.cols;
+    const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off, NC = c->cfg.cols;
     const int a = c->cur;
     int rc;
     if (c->cfg.dtype == FDTD_F64) {
@@ -1337,7 +1434,10 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     int64_t k = 0;
     int rc = 0;
     const bool resident = resident_eligible(c);
-    const int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
+    // steps per group: what the caller asked for, what the bound scratch generations allow, and -- on a slab with deep
+    // halos -- what the halos cover (a group of K steps reads K+1 rows of the neighbours)
+    int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
+    if (c->halo_depth > 1 && !(c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)) kmax_pre = std::min(kmax_pre, c->halo_depth - 1);
     if (kmax_pre >= 2 && !resident) {
         // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
         bool seen[9] = {};
@@ -1352,13 +1452,13 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
             }
             n += std::max<int64_t>(g, 1);
         }
-        if (c->frame_mode != 0)                          // frame_window reads the pulse records of resident mode
+        if (c->frame_mode != 0 || c->halo_depth > 1)     // frame_window reads the pulse records of resident mode
             if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     }
     if (resident)                                        // upload the pulse records before the timed region, too
         if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     CK(cudaEventRecord(c->ev_t0, c->stream));
-    const int kmax = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
+    const int kmax = kmax_pre;
     for (int64_t n = first_step; n < first_step + n_steps; ++n) {
         // largest group that ends no later than the run, the next snapshot and the source tables
         int64_t g = std::min<int64_t>(kmax, first_step + n_steps - n);
@@ -1477,6 +1577,24 @@ int fdtd_halo_rows(fdtd_handle c, void* send_down[3], void* recv_up[3], void** s
     if (send_up) *send_up = row(1, c->cfg.row_begin);
     if (recv_down) *recv_down = row(1, c->cfg.row_end);
     if (counts) { counts[0] = c->cfg.cols; counts[1] = c->cfg.cols; counts[2] = c->cfg.cols + 1; }
+    return 0;
+}
+
+int fdtd_halo_blocks(fdtd_handle c, void* send_down[3], void* recv_down[3], void* send_up[3], void* recv_up[3],
+                     int64_t* count) {
+    NEED_BOUND();
+    if (c->halo_depth <= 1) return fail(c, FDTD_ERR_STATE, "fdtd_halo_blocks needs deep halos (fdtd_set_halo_depth > 1)");
+    const int g = c->cur;
+    const int64_t D = c->halo_depth;
+    auto row = [&](int f, int64_t grow) { return (void*)((char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * c->esize); };
+    const bool up = c->cfg.row_begin > 0, down = c->cfg.row_end < c->cfg.rows;
+    for (int f = 0; f < 3; ++f) {
+        if (send_down) send_down[f] = down ? row(f, c->cfg.row_end - D) : nullptr;
+        if (recv_down) recv_down[f] = down ? row(f, c->cfg.row_end) : nullptr;
+        if (send_up) send_up[f] = up ? row(f, c->cfg.row_begin) : nullptr;
+        if (recv_up) recv_up[f] = up ? row(f, c->cfg.row_begin - D) : nullptr;
+    }
+    if (count) *count = D * c->pitch;
     return 0;
 }
 

@@ -99,7 +99,8 @@ def build_source_tables(pulses, times):
 class Engine:
     def __init__(self, rows, cols=None, *, courant, one_minus_courant=None, dtype="float64", device=0,
                  reflect=(False, False, False, False), row_begin=0, row_end=None, kernel="stream",
-                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None, frame_mode=None, kstep_variant=None):
+                 tile_rows=0, vec=0, block_warps=0, temporal=1, resident=None, frame_mode=None, kstep_variant=None,
+                 halo_depth=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("fdtd_em_solver_b200 needs a CUDA device: the field update exists only as "
@@ -126,9 +127,19 @@ class Engine:
         cfg.one_minus_courant = float(1 - courant) if one_minus_courant is None else float(one_minus_courant)
         self.cfg = cfg
         self.pitch = int(self.lib.fdtd_default_pitch(self.cols, cfg.dtype))
-        self.lrows = int(self.lib.fdtd_local_rows(C.byref(cfg)))
+        # y-slabs: rows of h/ex/ey stored from each neighbouring slab.  1 = one row, exchanged every step (validated
+        # default); D >= 2 = deep halos, ONE exchange per temporal-blocking group of up to D-1 steps (experimental until
+        # its first multi-GPU run; the frame of a group then always goes through frame_window)
+        self.halo_depth = (int(os.environ.get("FDTD_HALO_DEPTH", "1") or 1) if halo_depth is None else int(halo_depth))
+        self.lrows = int(self.lib.fdtd_local_rows_halo(C.byref(cfg), self.halo_depth))
         self.handle = C.c_void_p()
         L.check(self.lib, None, self.lib.fdtd_create(C.byref(cfg), C.byref(self.handle)))
+        if self.halo_depth != 1:
+            L.check(self.lib, self.handle, self.lib.fdtd_set_halo_depth(self.handle, self.halo_depth))
+        deep = self.halo_depth > 1
+        self.halo_top = (self.halo_depth if deep else 1) if self.row_begin > 0 else 0      # stored rows above the slab
+        self.halo_bot = self.halo_depth if (deep and self.row_end < self.rows) else 0      # ... and below (deep only)
+        self.row_off = self.row_begin - self.halo_top                                      # global row of local row 0
         tdt = torch.float64 if self.dtype == np.float64 else torch.float32
         dev = torch.device("cuda", int(device))
         self.device = dev

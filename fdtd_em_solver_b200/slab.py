@@ -107,3 +107,65 @@ def exchange(plan, arrays, dist, group=None):
     for view, buf in landing:
         if buf is not view:
             view.copy_(buf)
+
+
+# ---- deep halos (fdtd_set_halo_depth): D rows of h/ex/ey stored from each neighbour, ONE exchange per K-step group ------
+@dataclass(frozen=True)
+class DeepPlan:
+    rank: int
+    world: int
+    row_begin: int
+    row_end: int
+    rows: int
+    depth: int
+
+    @property
+    def halo_top(self):
+        return self.depth if self.row_begin > 0 else 0
+
+    @property
+    def halo_bot(self):
+        return self.depth if self.row_end < self.rows else 0
+
+    @property
+    def row_off(self):
+        return self.row_begin - self.halo_top
+
+    @property
+    def local_rows(self):
+        return (self.row_end - self.row_begin) + self.halo_top + self.halo_bot + 1          # fdtd_local_rows_halo
+
+    def blocks(self):
+        """[(peer, first global row sent, first global row received)]: D rows of every field each way per interface."""
+        out = []
+        if self.row_end < self.rows:
+            out.append((self.rank + 1, self.row_end - self.depth, self.row_end))
+        if self.row_begin > 0:
+            out.append((self.rank - 1, self.row_begin, self.row_begin - self.depth))
+        return out
+
+
+def deep_plan_for(rank, world, rows, depth):
+    b, e = split_rows(rows, world, min_rows=depth)[rank]        # a slab must own at least as many rows as its halos are deep
+    return DeepPlan(rank, world, b, e, rows, depth)
+
+
+def exchange_deep(plan, arrays, dist, group=None):
+    """The library's exchange_deep (csrc/fdtd2d.cu) over torch.distributed: `arrays` as in exchange()."""
+    ops, landing = [], []
+    for peer, send_row, recv_row in plan.blocks():
+        for f in FIELDS:
+            a = arrays[f]
+            ops.append(dist.P2POp(dist.isend, a[send_row - plan.row_off:send_row - plan.row_off + plan.depth].contiguous(),
+                                  peer, group))
+            view = a[recv_row - plan.row_off:recv_row - plan.row_off + plan.depth]
+            buf = view if view.is_contiguous() else view.contiguous()
+            landing.append((view, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for view, buf in landing:
+        if buf is not view:
+            view.copy_(buf)

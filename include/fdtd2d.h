@@ -246,6 +246,26 @@ int fdtd_halo_exchange(fdtd_handle h);
 int fdtd_halo_rows(fdtd_handle h, void* send_down[3], void* recv_up[3], void** send_up, void** recv_down,
                    int64_t counts[3]);
 
+/* Deep halos (BASELINE.json north_star (3): "k-row halo exchange under temporal blocking").  With depth D >= 2 a slab
+ * stores D rows of h/ex/ey (and of the coefficient planes) of EACH neighbouring slab:
+ *   local row l  <->  global row  row_begin - (row_begin > 0 ? D : 0) + l,   fdtd_local_rows_halo() rows in all,
+ * so a temporal-blocking group of K <= D-1 steps needs nothing from the neighbours while it runs: the K-step kernel
+ * reaches the slab's first/last owned row, frame_window (K+1 cells of apron) takes every frame tile, and the D-row blocks
+ * are exchanged ONCE per group (one contiguous D x pitch block per array and direction) instead of one row per step and
+ * masked pass.  Call fdtd_set_halo_depth right after fdtd_create, before the buffers are sized and bound; every slab
+ * next to an interface must own >= D rows.  Results are bit-identical to depth 1. */
+int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth);
+int fdtd_set_halo_depth(fdtd_handle h, int32_t halo_depth);
+/* fdtd_plan_frame_split for a context with deep halos (pure host logic, no GPU). */
+int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes,
+                         const int64_t* boxes, fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks,
+                         int32_t* n_window_tiles, int32_t* window_tiles_xy);
+/* Block pointers of the current generation for an external transport: send_down = the last D owned rows, recv_down = the
+ * D rows stored from the slab below, send_up = the first D owned rows, recv_up = the D rows stored from the slab above
+ * (NULL where there is no neighbour); *count = elements per block (D x pitch). */
+int fdtd_halo_blocks(fdtd_handle h, void* send_down[3], void* recv_down[3], void* send_up[3], void* recv_up[3],
+                     int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

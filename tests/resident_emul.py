@@ -173,20 +173,25 @@ def load_window():
 
 
 def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, order=0, probe_cells=(),
-                   apron=0, row_begin=0, row_end=None, fill=np.nan, poison_halo=False, shrink=-1):
+                   apron=0, row_begin=0, row_end=None, fill=np.nan, poison_halo=False, shrink=-1, halo_depth=1):
     """Advance the frame tiles `tiles` ([(tx, ty), ...] of the (tile_rows x tile_cols) grid that starts at row
     `row_begin`) by K calls with the emulated frame_window kernel, reading the oracle-style fields `f` as generation A.
     With row_begin/row_end the context stores only that y-slab (one halo row above, the ex row below), like the library.
     shrink: cells the active box loses per call (-1 = the kernel's rule, window.cuh window_margin).
     poison_halo: the halo rows of generation A (which the library fills by halo exchange) hold NaN instead.
+    halo_depth D >= 2: deep halos (fdtd_set_halo_depth) -- the context stores D valid rows of each neighbouring slab; every
+    other row it does not own holds NaN.
     Returns (h, ex, ey, probe_records) of generation B as GLOBAL arrays pre-filled with `fill`: cells the kernel did not
     store keep it."""
     lib = load_window()
     NR, NC = f.h.shape
     row_end = NR if row_end is None else row_end
     pitch = ((NC + 1 + 31) // 32) * 32
-    row_off = row_begin - (1 if row_begin > 0 else 0)
-    lrows = (row_end - row_begin) + (1 if row_begin > 0 else 0) + 1       # fdtd_local_rows
+    deep = halo_depth > 1
+    ht = (halo_depth if row_begin > 0 else 0) if deep else (1 if row_begin > 0 else 0)
+    hb = halo_depth if (deep and row_end < NR) else 0
+    row_off = row_begin - ht
+    lrows = (row_end - row_begin) + ht + hb + 1                          # fdtd_local_rows / fdtd_local_rows_halo
 
     def plane(a, value=0.0):
         p = np.full((lrows, pitch), value)
@@ -195,9 +200,12 @@ def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, 
             p[:n, :a.shape[1]] = a[row_off:row_off + n]
         return p
     ga = [plane(f.h), plane(f.ex), plane(f.ey)]
-    if row_end < NR:
+    if row_end < NR and not deep:
         ga[0][-1, :] = 0.0                                   # the last local row holds ONLY ex[row_end]
         ga[2][-1, :] = 0.0
+    if row_end < NR and deep:
+        for a in ga:
+            a[-1, :] = np.nan                                # row_end + D is stored but never exchanged
     if poison_halo:
         for a in ga:
             if row_begin > 0:

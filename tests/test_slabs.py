@@ -141,3 +141,63 @@ def test_nccl_slabs_under_torchrun_match_single_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SLAB_CHECK_OK" in res.stdout
+
+
+# ------------------------------------------------------------------------------------------ deep halos (CPU, gloo)
+def _deep_worker(rank, world, port, rows, cols, seed, K, n_steps, out_dir):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    f, setup, times = SC.random_case(rows, cols, seed, walls=(False, False, True, False), n_steps=n_steps)
+    D = K + 1
+    plan = SL.deep_plan_for(rank, world, rows, D)
+    off, b, e = plan.row_off, plan.row_begin, plan.row_end
+    hi = e + plan.halo_bot
+    fl = R.Fields(f.h[off:hi].copy(), f.ex[off:hi + 1].copy(), f.ey[off:hi].copy(), step=f.step)
+    assert fl.ex.shape[0] == plan.local_rows
+    sl = OS.local_setup(setup, off, fl.h.shape[0], rows)
+    n = 0
+    while n < n_steps:
+        g = K if n_steps - n >= K else 1                     # whole groups without any exchange inside, then single steps
+        for t in times[n:n + g]:
+            fl.step = n
+            OS.leapfrog_slab(fl, sl, t, rows, off)
+            n += 1
+        arrays = {"h": torch.from_numpy(fl.h), "ex": torch.from_numpy(fl.ex), "ey": torch.from_numpy(fl.ey)}
+        SL.exchange_deep(plan, arrays, dist)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), h=fl.h[b - off:e - off],
+             ex=fl.ex[b - off:e - off + (1 if e == rows else 0)], ey=fl.ey[b - off:e - off])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,K", [(2, 3), (3, 2), (3, 6)])
+def test_deep_halo_scheme_over_gloo_matches_monolithic_oracle(world, K, tmp_path):
+    """K+1 rows of each neighbour, ONE exchange per group of K steps (and one per leftover single step): the owned rows
+    stay bit-identical to the monolithic run -- what the stale edge of the stored rows computes moves one row per step
+    and so never reaches an owned row inside a group."""
+    import torch.multiprocessing as mp
+    rows, cols, seed, n_steps = 61, 29, 2, 3 * K + 2
+    mp.spawn(_deep_worker, args=(world, _free_port(), rows, cols, seed, K, n_steps, str(tmp_path)), nprocs=world, join=True)
+    f, setup, times = SC.random_case(rows, cols, seed, walls=(False, False, True, False), n_steps=n_steps)
+    for t in times:
+        R.leapfrog(f, setup, t)
+    parts = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(world)]
+    assert np.array_equal(np.concatenate([p["h"] for p in parts]), f.h)
+    assert np.array_equal(np.concatenate([p["ex"] for p in parts]), f.ex)
+    assert np.array_equal(np.concatenate([p["ey"] for p in parts]), f.ey)
+
+
+def test_deep_plan_matches_the_library_layout():
+    from fdtd_em_solver_b200 import _lib as L
+    import ctypes as C
+    lib = L.load()
+    for world, rows, depth in ((2, 100, 7), (3, 61, 4), (8, 65536, 7)):
+        for r in range(world):
+            p = SL.deep_plan_for(r, world, rows, depth)
+            cfg = L.Config()
+            cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end, cfg.dtype = rows, 40, p.row_begin, p.row_end, L.F64
+            assert p.local_rows == lib.fdtd_local_rows_halo(C.byref(cfg), depth)
+            for peer, send_row, recv_row in p.blocks():
+                q = SL.deep_plan_for(peer, world, rows, depth)
+                assert (r, recv_row, send_row) in [(x[0], x[1], x[2]) for x in q.blocks()]     # my receive is its send

@@ -321,3 +321,66 @@ def test_whole_group_k_step_kernel_plus_frame_window_covers_the_grid(K, tile_row
         merged = np.where(np.isnan(a), b, a)
         assert not np.isnan(merged).any(), "%s: %d cells written by neither kernel" % (name, int(np.isnan(merged).sum()))
         assert np.array_equal(merged, want), name
+
+
+def _frame_plan_halo(rows, cols, K, depth, tile_rows, block_warps, boxes, row_begin, row_end):
+    from fdtd_em_solver_b200 import _lib as L
+    lib = L.load()
+    cfg = L.Config()
+    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, row_begin, row_end
+    cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, block_warps
+    plan = L.FramePlan()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 4))
+    bp = b.ctypes.data if len(b) else None
+    n = C.c_int32(0)
+    assert lib.fdtd_plan_frame_halo(C.byref(cfg), K, depth, len(b), bp, C.byref(plan), None, None, C.byref(n), None) == 0
+    skip = np.zeros((max(plan.k_tiles_y, 1), plan.k_tiles_x), dtype=np.uint8)
+    masks = np.zeros((K, plan.frame_tiles_y, plan.frame_tiles_x), dtype=np.uint8)
+    xy = np.zeros((plan.frame_tiles_y * plan.frame_tiles_x, 2), dtype=np.int32)
+    assert lib.fdtd_plan_frame_halo(C.byref(cfg), K, depth, len(b), bp, C.byref(plan), skip.ctypes.data, masks.ctypes.data,
+                                    C.byref(n), xy.ctypes.data) == 0
+    return plan, skip[:plan.k_tiles_y], masks, [tuple(t) for t in xy[:n.value]]
+
+
+@pytest.mark.parametrize("K,tile_rows,variant", [(2, 8, 0), (4, 16, 1), (6, 16, 0), (6, 48, 1), (8, 24, 0)])
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_deep_halo_slabs_need_no_exchange_inside_a_group(K, tile_rows, variant, n_slabs):
+    """Deep halos (fdtd_set_halo_depth(K+1)): every slab stores K+1 valid rows of each neighbour and NOTHING else of
+    them (NaN here).  The library's plan for that layout has no pass chain left -- the K-step tiles reach the slab's
+    first and last owned row, frame_window takes every frame tile -- and the two kernels (device code of the K-step
+    kernel through the SIMT emulator, the window algorithm through its emulation) write every owned cell with the
+    oracle's values after K calls, reading no row beyond the halos."""
+    import stream_emul as SE
+    if not SE.available():
+        pytest.skip("needs g++ and the CUDA headers")
+    rows, cols, D = 264, 420, K + 1
+    f, setup, times = SC.random_case(rows, cols, 7, walls=(False, True, False, False), n_steps=K + 1)
+    setup = _eligible(setup)
+    R.leapfrog(f, setup, times[0])                             # generation A = the state after call 0
+    g = R.Fields(f.h.copy(), f.ex.copy(), f.ey.copy(), step=f.step)
+    for t in times[1:1 + K]:
+        R.leapfrog(g, setup, t)
+    edges = [(rows * s // n_slabs) // 8 * 8 for s in range(n_slabs)] + [rows]
+    boxes = _boxes(setup, rows, cols, [])
+    for b, e in zip(edges[:-1], edges[1:]):
+        plan, skip, masks, tiles = _frame_plan_halo(rows, cols, K, D, tile_rows, 2, boxes, b, e)
+        assert not masks.any() and tiles                      # no interface strips on a pass chain: all frame tiles are window tiles
+        if b > 0:
+            assert plan.k_row_lo == b                         # K-step tiles start at the first owned row of an interface
+        if e < rows:
+            assert plan.k_row_hi > e - plan.frame_tile_rows   # ... and end at the last (up to frame-tile alignment)
+        stored_lo, stored_hi = (b - D if b > 0 else 0), (e + D if e < rows else rows + 1)
+        poisoned = R.Fields(f.h.copy(), f.ex.copy(), f.ey.copy(), step=f.step)
+        for a in (poisoned.h, poisoned.ex, poisoned.ey):
+            a[:stored_lo] = np.nan
+            a[stored_hi:] = np.nan
+        by_k = SE.stepK_stream(poisoned, setup, times, 1, K, tile_rows, 2, plan.k_row_lo, plan.k_row_hi, skip, variant=variant)
+        by_w = E.window_emulate(f, setup, times, 1, K, tiles, plan.frame_tile_rows, plan.frame_tile_cols, row_begin=b,
+                                row_end=e, halo_depth=D)[:3]
+        for name, a, w, want in zip(("h", "ex", "ey"), by_k, by_w, (g.h, g.ex, g.ey)):
+            hi = e + (1 if (name == "ex" and e == rows) else 0)
+            a, w, want = a[b:hi], w[b:hi], want[b:hi]
+            merged = np.where(np.isnan(a), w, a)
+            assert not np.isnan(merged).any(), "%s slab [%d,%d): %d owned cells unwritten or poisoned" % (
+                name, b, e, int(np.isnan(merged).sum()))
+            assert np.array_equal(merged, want), (name, b, e)

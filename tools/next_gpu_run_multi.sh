@@ -10,10 +10,11 @@ port=29611
 run() { name=$1; n=$2; shift 2; port=$((port + 1));
         if [ "$n" = 1 ]; then timeout 240 python $B --gpus 1 "$@" > gpurun_out/multi_$name.json 2> gpurun_out/multi_$name.err
         else timeout 240 $TR --nproc-per-node $n --master-port $port $B --gpus $n "$@" > gpurun_out/multi_$name.json 2> gpurun_out/multi_$name.err; fi; }
-FDTD_SLAB_CHECK_FRAME=1 timeout 600 $TR --nproc-per-node 4 --master-port $port tools/slab_check.py > gpurun_out/multi_slab_check.log 2>&1
+FDTD_SLAB_CHECK_FRAME=1 FDTD_SLAB_CHECK_DEEP=1 timeout 600 $TR --nproc-per-node 4 --master-port $port tools/slab_check.py > gpurun_out/multi_slab_check.log 2>&1
 port=$((port + 1)); timeout 300 $TR --nproc-per-node 4 --master-port $port tools/solver_sharded_check.py > gpurun_out/multi_solver_sharded.log 2>&1
 for n in 1 2 4 8; do run weak_f64_n$n $n; run weak_f32_n$n $n --dtype f32; done
 for n in 4 8; do run strong_f64_n$n $n --total-rows 65536; done
+for n in 2 4 8; do run deep_f64_n$n $n --halo-depth 7; run deep_window_f64_n$n $n --halo-depth 7 --frame-mode 1; done   # one exchange per K = 6 group
 for n in 2 4 8; do run strong_f32_n$n $n --total-rows 65536 --dtype f32; done
 timeout 300 python tools/cpu_baseline_sizes.py > gpurun_out/multi_cpu_baseline_sizes.json 2> gpurun_out/multi_cpu_baseline_sizes.err
 tail -2 gpurun_out/multi_slab_check.log; tail -3 gpurun_out/multi_solver_sharded.log; for f in gpurun_out/multi_*_n*.json; do echo "$f: $(cut -c1-160 $f)"; done

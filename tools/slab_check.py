@@ -21,13 +21,18 @@ FRAME_CASES = [(1500, 4100, 26, dict(temporal=4, frame_mode=1)), (2000, 9000, 27
                (2000, 9000, 27, dict(temporal=6, tile_rows=16, frame_mode=2)), (1500, 4100, 33, dict(temporal=8, frame_mode=2)),
                (97, 300, 13, dict(tile_rows=4, temporal=2, frame_mode=1))] if os.environ.get("FDTD_SLAB_CHECK_FRAME") == "1" else []
 
-for rows, cols, n_steps, kw in FRAME_CASES + [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
+# deep halos (one exchange per K-step group, fdtd_set_halo_depth) join with FDTD_SLAB_CHECK_DEEP=1
+DEEP_CASES = [(1500, 4100, 26, dict(temporal=4, halo_depth=5)), (2000, 9000, 27, dict(temporal=6, tile_rows=16, halo_depth=7)),
+              (2000, 9000, 29, dict(temporal=6, halo_depth=7, frame_mode=1)), (1500, 4100, 35, dict(temporal=8, halo_depth=9)),
+              (97, 300, 13, dict(tile_rows=4, temporal=2, halo_depth=3))] if os.environ.get("FDTD_SLAB_CHECK_DEEP") == "1" else []
+
+for rows, cols, n_steps, kw in DEEP_CASES + FRAME_CASES + [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
                                 (97, 300, 13, dict(tile_rows=4, temporal=2)), (1500, 4100, 25, dict(temporal=2)),
                                 (2000, 9000, 16, dict(temporal=2, block_warps=2)),
                                 (1500, 4100, 26, dict(temporal=4)), (2000, 9000, 19, dict(temporal=3, block_warps=2)),
                                 (2000, 9000, 27, dict(temporal=6, tile_rows=16)), (1500, 4100, 33, dict(temporal=8))]:
     f, setup, times = SC.random_case(rows, cols, 3, walls=(False, False, False, True), n_steps=n_steps)
-    if kw.get("frame_mode"):         # a TF/SF line at column 0 would keep the whole frame on the masked passes
+    if kw.get("frame_mode") or kw.get("halo_depth"):         # a TF/SF line at column 0 would keep the whole frame on the masked passes
         setup.pulses = [p for p in setup.pulses if not (p.direction == "right" and p.col == 0)]
     b, e_ = SL.split_rows(rows, world)[rank]
     S = setup.courant
@@ -47,7 +52,8 @@ for rows, cols, n_steps, kw in FRAME_CASES + [(97, 300, 12, dict(tile_rows=4)), 
     parts = [None] * world
     dist.all_gather_object(parts, (b, e_, h[b:e_], ex[b:e_ + (1 if e_ == rows else 0)], ey[b:e_]))
     if rank == 0:
-        whole = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, device=local, **kw)
+        whole = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, device=local,
+                       **{k: v for k, v in kw.items() if k != "halo_depth"})
         whole.upload_coefficients(setup.eps_coef, setup.mu_coef)
         whole.set_sources(setup.pulses, times)
         whole.set_reflectors(setup.reflectors)
