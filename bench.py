@@ -176,7 +176,10 @@ def workload_config(args, n_gpus):
             "l2": "inputs_exceed_l2 (%d arrays x %.1f GiB per GPU, no flush needed)"
                   % (8 if args.temporal == 1 else (11 if args.temporal == 2 else 14),
                      ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
-            "parallelism": "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus if n_gpus > 1 else "1 GPU",
+            "parallelism": ("1 GPU" if n_gpus == 1 else
+                            "y-slab x%d, %d halo rows of h/ex/ey each way ONCE per K-step group over NCCL"
+                            % (n_gpus, args.halo_depth) if (getattr(args, "halo_depth", None) or 1) > 1 else
+                            "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus),
             "kernel": "%s vec=%d tile_rows=%d warps=%d" % (
                 "stepK_stream (%d steps per HBM pass) + masked step_stream frame passes" % args.temporal
                 if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
