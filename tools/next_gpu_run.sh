@@ -4,9 +4,10 @@
 # new kernels of round 1 get their ncu profiles.
 #   gpurun --timeout 600 -- 'bash tools/next_gpu_run.sh'
 mkdir -p gpurun_out
-export FDTD_TEST_FRAME_WINDOW=1 FDTD_TEST_RESIDENT_DEPTH=1 FDTD_TEST_KSTEP_LEAN=1
-# 1. parity of stepK_lean, of frame_window (frame modes 1/2) and of resident_window (2..8 calls per barrier)
-timeout 200 python -m pytest tests/test_gpu_kstep_lean.py tests/test_gpu_frame_window.py tests/test_gpu_resident.py -q -p no:cacheprovider --durations=8 \
+export FDTD_TEST_FRAME_WINDOW=1 FDTD_TEST_RESIDENT_DEPTH=1 FDTD_TEST_KSTEP_LEAN=1 FDTD_TEST_DEEP_HALO=1
+# 1. parity of stepK_lean, of frame_window (frame modes 1/2), of resident_window (2..8 calls per barrier), of deep-halo slabs
+#    (several slab contexts on this one GPU) and of Solver.record_field
+timeout 260 python -m pytest tests/test_gpu_kstep_lean.py tests/test_gpu_frame_window.py tests/test_gpu_resident.py tests/test_gpu_deep_halo.py tests/test_zz_gpu_record_field.py -q -p no:cacheprovider --durations=8 \
     > gpurun_out/next_new_kernels_tests.log 2>&1; echo "rc=$?" >> gpurun_out/next_new_kernels_tests.log
 # 2. what they buy: the C5 slab with the frame as masked passes / next to / behind the K-step kernel
 for fm in 0 1 2; do
