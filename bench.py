@@ -214,6 +214,10 @@ def main():
     ap.add_argument("--halo-depth", type=int, default=None,
                     help="y-slabs: rows stored from each neighbouring slab; 1 = one row exchanged every step, K+1 = deep "
                          "halos with ONE exchange per K-step group (default: the library's)")
+    ap.add_argument("--snapshot-every", type=int, default=0,
+                    help="also time the K steps WITH an h snapshot every N steps read back to the host (device pack -> "
+                         "pinned ring -> async D2H on the copy stream -> host stack), SURVEY.md 8(d) 'with and without "
+                         "snapshot D2H'; reported as `with_snapshots`")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -295,6 +299,27 @@ def main():
     value = cells * args.steps / (ms * 1e-3) / 1e9
     halo_bytes = st["halo_bytes_sent"]
 
+    # ---- the same K steps with field snapshots streamed to the host ------------------------------
+    with_snapshots = None
+    if args.snapshot_every > 0:
+        fence()
+        t0 = time.perf_counter()
+        stack = e.run(step, args.steps, snapshot_every=args.snapshot_every)       # returns after the last copy has landed
+        fence()
+        sec = time.perf_counter() - t0
+        step += args.steps
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        n_snap = 0 if stack is None else int(stack.shape[0])
+        with_snapshots = {"every": args.snapshot_every, "snapshots": n_snap, "value": cells * args.steps / sec / 1e9,
+                          "unit": "Gcell-updates/s", "seconds": sec,
+                          "d2h_bytes_per_gpu": n_snap * ROWS_PER_GPU * COLS * 8,
+                          "what": "wall clock of fdtd_run incl. the first-touch of the pageable host stack; pack kernel + "
+                                  "2-slot pinned ring + copy stream, stepping continues while a snapshot drains"}
+        del stack
+
     # ---- end to end through the host-facing API ("e2e") -----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -375,6 +400,8 @@ def main():
                      "steps_per_launch": args.temporal},
         "wall_s_timed_region": wall,
     }
+    if with_snapshots is not None:
+        line["with_snapshots"] = with_snapshots
     if n_gpus > 1:
         line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}

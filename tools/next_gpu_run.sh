@@ -18,6 +18,8 @@ done
 for v in "--kstep-variant 1" "--kstep-variant 1 --frame-mode 1" "--kstep-variant 1 --temporal 8" "--kstep-variant 1 --temporal 4"; do
     n=$(echo $v | tr -d ' -'); timeout 60 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 $v > gpurun_out/next_bench_$n.json 2> gpurun_out/next_bench_$n.err
 done
+# 2c. SURVEY.md 8(d) "with and without snapshot D2H": four 4.3 GB snapshots streamed to the host during 240 steps
+timeout 120 python bench.py --no-cpu --no-e2e --steps 240 --warmup 6 --snapshot-every 60 > gpurun_out/next_bench_snapshots.json 2> gpurun_out/next_bench_snapshots.err
 # 3. the script configs with 1 / 2 / 4 calls per grid barrier
 for d in 1 2 4; do
     FDTD_RESIDENT_DEPTH=$d timeout 40 python tools/resident_times.py waveguide lens tutorial doubleslit \
