@@ -302,6 +302,7 @@ def main():
     # ---- the same K steps with field snapshots streamed to the host ------------------------------
     with_snapshots = None
     if args.snapshot_every > 0:
+        e.run(step, 2, snapshot_every=2); step += 2      # untimed: allocates the device/pinned snapshot ring (GBs of cudaHostAlloc)
         fence()
         t0 = time.perf_counter()
         stack = e.run(step, args.steps, snapshot_every=args.snapshot_every)       # returns after the last copy has landed
