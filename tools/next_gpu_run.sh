@@ -18,6 +18,12 @@ done
 for v in "--kstep-variant 1" "--kstep-variant 1 --frame-mode 1" "--kstep-variant 1 --temporal 8" "--kstep-variant 1 --temporal 4"; do
     n=$(echo $v | tr -d ' -'); timeout 60 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 $v > gpurun_out/next_bench_$n.json 2> gpurun_out/next_bench_$n.err
 done
+# 2b'. the two build knobs of stepK_lean (side-by-side libraries, ~30 s of nvcc each unless they travelled with the snapshot):
+#      two CTAs per SM at K = 6 (255 registers, no spills) and the row loop unrolled by ten (delay line renamed too)
+FDTD_LIB_SUFFIX=_mb2 FDTD_NVCC_EXTRA=-DFDTD_LEAN_MIN_BLOCKS_K6=2 timeout 150 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 --kstep-variant 1 \
+    > gpurun_out/next_bench_lean_minblocks2.json 2> gpurun_out/next_bench_lean_minblocks2.err
+FDTD_LIB_SUFFIX=_u10 FDTD_NVCC_EXTRA=-DFDTD_LEAN_UNROLL=10 timeout 150 python bench.py --no-cpu --no-e2e --steps 120 --warmup 12 --kstep-variant 1 \
+    > gpurun_out/next_bench_lean_unroll10.json 2> gpurun_out/next_bench_lean_unroll10.err
 # 2c. SURVEY.md 8(d) "with and without snapshot D2H": four 4.3 GB snapshots streamed to the host during 240 steps
 timeout 120 python bench.py --no-cpu --no-e2e --steps 240 --warmup 6 --snapshot-every 60 > gpurun_out/next_bench_snapshots.json 2> gpurun_out/next_bench_snapshots.err
 # 3. the script configs with 1 / 2 / 4 calls per grid barrier
