@@ -595,36 +595,43 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     return 0;
 }
 
+// K-step tile rows [ty0, ty0 + ny) of the plan (ny < 0: all of them) on stream st (null: the main stream)
 template <typename T, int K>
-void launch_stepK(const StepParams<T>& P, fdtd_ctx* c) {
+void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1, cudaStream_t st = nullptr) {
     constexpr int V2 = kvec<T>();
     const FrameMaps& m = c->fm[K];
     const int w = std::min(c->cfg.block_warps, 4);
-    dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)m.nty);
+    if (ny < 0) ny = m.nty - ty0;
+    if (ny <= 0) return;
+    if (!st) st = c->stream;
+    StepParams<T> P = P0;                                        // the kernel derives a tile's rows from row_lo and blockIdx.y
+    P.row_lo = P0.row_lo + ty0 * P0.tile_rows;
+    const unsigned char* skip = m.d_skip + (size_t)ty0 * m.ntx2;
+    dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)ny);
     if (c->kstep_variant == 1) {                                 // experimental: fewer issue slots per row (kernels.cuh stepK_lean)
         constexpr int ring_rows = fdtd::KRing<K>::ROWS > 0 ? fdtd::KRing<K>::ROWS : 4;
         const size_t lean_bytes = (size_t)w * ring_rows * 5 * 32 * V2 * sizeof(T);
         if (lean_bytes > 48 * 1024)
             cudaFuncSetAttribute(fdtd::stepK_lean<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_bytes);
-        fdtd::stepK_lean<T, V2, K><<<grid, w * 32, lean_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
+        fdtd::stepK_lean<T, V2, K><<<grid, w * 32, lean_bytes, st>>>(P, skip, m.ntx2);
         return;
     }
     const size_t ring_bytes = (size_t)w * fdtd::KRing<K>::ROWS * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
     if (ring_bytes > 48 * 1024)
         cudaFuncSetAttribute(fdtd::stepK_stream<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
-    fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, c->stream>>>(P, m.d_skip, m.ntx2);
+    fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, st>>>(P, skip, m.ntx2);
 }
 
 template <typename T>
-void launch_stepK_any(const StepParams<T>& P, fdtd_ctx* c, int K) {      // K = 2..8 (fdtd_set_temporal_blocking checks)
-    switch (K) {
-        case 2: launch_stepK<T, 2>(P, c); break;
-        case 3: launch_stepK<T, 3>(P, c); break;
-        case 4: launch_stepK<T, 4>(P, c); break;
-        case 5: launch_stepK<T, 5>(P, c); break;
-        case 6: launch_stepK<T, 6>(P, c); break;
-        case 7: launch_stepK<T, 7>(P, c); break;
-        default: launch_stepK<T, 8>(P, c); break;
+void launch_stepK_any(const StepParams<T>& P, fdtd_ctx* c, int K, int ty0 = 0, int ny = -1, cudaStream_t st = nullptr) {
+    switch (K) {                                                 // K = 2..8 (fdtd_set_temporal_blocking checks)
+        case 2: launch_stepK<T, 2>(P, c, ty0, ny, st); break;
+        case 3: launch_stepK<T, 3>(P, c, ty0, ny, st); break;
+        case 4: launch_stepK<T, 4>(P, c, ty0, ny, st); break;
+        case 5: launch_stepK<T, 5>(P, c, ty0, ny, st); break;
+        case 6: launch_stepK<T, 6>(P, c, ty0, ny, st); break;
+        case 7: launch_stepK<T, 7>(P, c, ty0, ny, st); break;
+        default: launch_stepK<T, 8>(P, c, ty0, ny, st); break;
     }
 }
 
@@ -857,6 +864,46 @@ int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_
     return 0;
 }
 
+// A K-step group on a y-slab with deep halos and a communicator (maps built, probe capacity ensured by group_window).
+// Only what lies next to an interface depends on the neighbours, and only that is what they wait for:
+//   main stream : the INTERIOR K-step tile rows -- they read owned rows only, so they start at once
+//   edge stream : (after the previous exchange has landed) the K-step tile rows within D rows of an interface and
+//                 every window tile, on the high-priority stream
+//   comm stream : (after the edge work) the D-row blocks of B to both neighbours -- while the interior still runs
+// The main stream joins the edge stream at the end, so main-stream order again means "all of B written".
+template <typename T>
+int group_window_slab(fdtd_ctx* c, int64_t n, int K, int A, int B) {
+    const FrameMaps& m = c->fm[K];
+    const int TR = c->cfg.tile_rows, D = c->halo_depth;
+    const int e_top = c->cfg.row_begin > 0 ? std::min(m.nty, (D + TR - 1) / TR) : 0;
+    const int e_bot = c->cfg.row_end < c->cfg.rows ? std::min(m.nty - e_top, (D + TR - 1) / TR + 1) : 0;   // (+1: the last tile row may be short)
+    StepParams<T> PK;
+    if (m.nty > 0) {
+        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
+        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
+    }
+    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this group
+    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
+    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0));     // the neighbours' rows of A have landed
+    const int n_int = m.nty - e_top - e_bot;
+    if (n_int > 0) { launch_stepK_any<T>(PK, c, K, e_top, n_int, c->stream); c->stats.kernel_launches++; }
+    if (e_top > 0) { launch_stepK_any<T>(PK, c, K, 0, e_top, c->edge_stream); c->stats.kernel_launches++; }
+    if (e_bot > 0) { launch_stepK_any<T>(PK, c, K, m.nty - e_bot, e_bot, c->edge_stream); c->stats.kernel_launches++; }
+    CK(cudaGetLastError());
+    if (int rc = launch_frame_window<T>(c, n, K, A, B, c->edge_stream)) return rc;
+    CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+    CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+    if (int rc = exchange(c, B, c->comm_stream)) return rc;     // ONE exchange per group
+    CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
+    CK(cudaEventRecord(c->ev_int, c->stream));
+    c->cur = B;
+    if (c->n_probe) c->probe_count += K;
+    c->stats.steps += K;
+    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
+    return 0;
+}
+
 // Steps n .. n+K-1: A -> B.  stepK_stream advances every tile whose K-step cone is plain; frame_window advances every
 // other tile K calls in shared memory from one load of A (tile + K+1 cells of apron).  Both read only A and write
 // disjoint tiles of B (cells of a frame tile that a K-step tile also covers get the same bits from both), so they need
@@ -867,8 +914,8 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
     const FrameMaps& m = c->fm[K];
     const int A = c->cur, B = (A + 1) % c->ngen;
     if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
+    if (c->comm) return group_window_slab<T>(c, n, K, A, B);
     const bool side = c->frame_mode == 1 && m.nty > 0 && !m.h_tiles.empty();
-    if (c->comm) CK(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));      // deep halos: the neighbours' rows of A have landed
     if (side) {
         CK(cudaEventRecord(c->ev_int, c->stream));              // everything before this group
         CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
@@ -887,12 +934,6 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // main-stream order = "all of B written"
     }
     CK(cudaEventRecord(c->ev_int, c->stream));
-    if (c->comm) {                                              // deep halos: ONE exchange per group, of generation B
-        CK(cudaEventRecord(c->ev_p3, c->stream));
-        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_p3, 0));
-        if (int rc = exchange(c, B, c->comm_stream)) return rc;
-        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
-    }
     c->cur = B;
     if (c->n_probe) c->probe_count += K;
     c->stats.steps += K;
