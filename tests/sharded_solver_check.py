@@ -1,10 +1,10 @@
 """Run under torchrun on 2+ GPUs: the drop-in Solver, launched unchanged, shards itself (shard.py: one y-slab per rank,
 halo rows over NCCL inside libfdtd2d) and must leave the same .npy / fields / probe series as the same script on ONE GPU.
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/solver_sharded_check.py
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/sharded_solver_check.py
 
 The one-GPU run (Solver(..., sharded=False) on every rank's own GPU) is the reference here: it is the path the GPU
-parity suite pins bitwise to the oracle.  oracle.scenarios only supplies the scene descriptions (inputs)."""
+parity suite pins bitwise to the oracle.  Test infrastructure: oracle.scenarios supplies the scene descriptions."""
 import contextlib
 import io
 import os

@@ -93,3 +93,21 @@ def test_single_process_runs_are_not_sharded(monkeypatch):
     with pytest.raises(RuntimeError):
         shard.context(True)
     assert shard.owner_of_row([(0, 4), (4, 7), (7, 10)], 6) == 1
+
+
+@pytest.mark.gpu
+def test_sharded_solver_under_torchrun_matches_one_gpu():
+    """The real thing: the drop-in Solver sharding itself under torchrun (NCCL inside the library) against the same
+    scenes on one GPU.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on the one-GPU box of the round-end run."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % min(n, 4),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(root, "tests", "sharded_solver_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "SOLVER_SHARDED_OK" in res.stdout

@@ -19,7 +19,7 @@ run() { name=$1; n=$2; shift 2; port=$((port + 1));
         else timeout 200 $TR --nproc-per-node $n --master-port $port $B --gpus $n "$@" > gpurun_out/multi_$name.json 2> gpurun_out/multi_$name.err; fi; }
 if [ "$N" = 2 ]; then
     FDTD_SLAB_CHECK_FRAME=1 FDTD_SLAB_CHECK_DEEP=1 timeout 420 $TR --nproc-per-node 2 --master-port $port tools/slab_check.py > gpurun_out/multi_slab_check.log 2>&1
-    port=$((port + 1)); timeout 240 $TR --nproc-per-node 2 --master-port $port tools/solver_sharded_check.py > gpurun_out/multi_solver_sharded.log 2>&1
+    port=$((port + 1)); timeout 240 $TR --nproc-per-node 2 --master-port $port tests/sharded_solver_check.py > gpurun_out/multi_solver_sharded.log 2>&1
     run weak_f64_n1 1; run weak_f32_n1 1 --dtype f32                  # the same-box N = 1 lines the efficiencies refer to
     timeout 300 python tools/cpu_baseline_sizes.py > gpurun_out/multi_cpu_baseline_sizes.json 2> gpurun_out/multi_cpu_baseline_sizes.err
 fi
