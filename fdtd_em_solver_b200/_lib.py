@@ -120,21 +120,36 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> fdtd_em_solver_b200/libfdtd2d.so (in tree)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> fdtd_em_solver_b200/libfdtd2d.so (in tree).
+
+    Safe under torchrun: the build runs under an exclusive file lock (ranks that lose the race find a fresh library when
+    they get the lock and return), and nvcc writes to a per-process temporary that is renamed into place, so no process
+    can ever map a half-written library."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfdtd2d.so (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + NVCC_EXTRA + ["-I", INCLUDE_DIR] + sources() + ["-o", LIB_PATH + ".tmp"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():          # another rank built it while this one waited for the lock
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + NVCC_EXTRA + ["-I", INCLUDE_DIR] + sources() + ["-o", tmp]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -148,9 +163,14 @@ def load():
         return _lib
     try:
         build()
-    except RuntimeError:
-        if not os.path.isfile(LIB_PATH):
+    except RuntimeError as exc:
+        # A library older than its sources may not match SIGNATURES below: never load it silently.  It is used only
+        # when no compiler exists at all (a deployment box that received a prebuilt library), and loudly.
+        if not os.path.isfile(LIB_PATH) or "nvcc not found" not in str(exc):
             raise
+        import warnings
+        warnings.warn("libfdtd2d.so is older than its sources and nvcc is missing: loading the prebuilt library as is",
+                      RuntimeWarning)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError if the .so lacks a declared symbol

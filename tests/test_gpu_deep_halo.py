@@ -10,9 +10,7 @@ import pytest
 from oracle import restated as R, scenarios as SC
 from fdtd_em_solver_b200 import slab as SL
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FDTD_TEST_DEEP_HALO", "0") == "0",
-                                 reason="deep halos have not had their first GPU run yet (FDTD_TEST_DEEP_HALO=1)")]
+pytestmark = [pytest.mark.gpu]           # first B200 run: round 2 (green); over NCCL: profiles/r2_slab_check_n2.log
 
 
 def _eligible(setup):

@@ -13,9 +13,7 @@ import pytest
 
 from oracle import restated as R, scenarios as SC
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FDTD_TEST_KSTEP_LEAN", "0") == "0",
-                                 reason="stepK_lean awaits its first GPU run: set FDTD_TEST_KSTEP_LEAN=1")]
+pytestmark = [pytest.mark.gpu]           # first B200 run: round 2, profiles/r2_first_run_new_kernels_tests.log (all green)
 
 WALLS = list(itertools.product([False, True], repeat=4))
 

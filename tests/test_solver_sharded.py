@@ -96,8 +96,6 @@ def test_single_process_runs_are_not_sharded(monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("FDTD_TEST_SHARDED_SOLVER", "0") == "0",
-                    reason="the sharded Solver has not had its first multi-GPU run yet (FDTD_TEST_SHARDED_SOLVER=1)")
 def test_sharded_solver_under_torchrun_matches_one_gpu():
     """The real thing: the drop-in Solver sharding itself under torchrun (NCCL inside the library) against the same
     scenes on one GPU.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on the one-GPU box of the round-end run."""
