@@ -37,7 +37,7 @@ ROWS_PER_GPU = 8192
 COLS = 65536
 BYTES_PER_CELL = {"f64": 64, "f32": 32}      # 5 words read + 3 written
 METRIC = "Gcell-updates/s (2D Yee leapfrog, C5 synthetic slab)"
-CPU_SAMPLE = (2048, 2048)
+CPU_SAMPLE = (512, 65536)           # rows x cols of the CPU arm's sample: a thin slab of the real rows
 
 
 def measured_peak_gbs():
@@ -97,26 +97,81 @@ class ClockSampler:
                 "power_w_max": max(watts) if watts else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _reference_module():
+    """The UNMODIFIED reference solver.py, if __graft_entry__.build() found /root/reference and put a copy under the
+    git-ignored baseline/_ref/ (it travels to the GPU box with the snapshot; /root/reference itself does not)."""
+    path = os.path.join(ROOT, "baseline", "_ref", "solver.py")
+    if not os.path.isfile(path):
+        return None
+    try:
+        from oracle import ref_import
+        ref_import.install_matplotlib_stub()
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_fdtd_reference_solver_bench", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:
+        return None
+
+
 def cpu_baseline(steps_budget_s=15.0):
-    """The oracle port of the reference numpy step, timed on this host (bounded sample)."""
+    """The reference's CPU implementation of the step on a bounded, slab-shaped sample of the C5 workload (CPU_SAMPLE
+    rows of the real 65536-column rows), timed on this host.  With baseline/_ref/solver.py present it is the reference's
+    own Solver.update() (kind "reference"): a reference Solver object whose arrays, coefficient planes and pulses are
+    replaced by the sample's (update() only reads attributes, /root/reference/solver.py:169-257); otherwise the oracle
+    port oracle/restated.py, bit-identical to it (kind "port").  Returns (Gcell/s, steps, seconds, kind)."""
     from oracle import restated as R
     from fdtd_em_solver_b200 import synthetic as SY
     rows, cols = CPU_SAMPLE
     epc, muc = R.synthetic_coefficients(rows, cols, SY.DT, SY.DS, seed=0, total_cols=COLS)
     n_calls = 512                                    # upper bound; the time budget below ends the loop (10-30 s of CPU work)
-    pulses = [R.PulseSpec("table", p.direction, p.row, p.col, p.start, p.end, p.table)
-              for p in SY.pulses(rows, cols, n_calls)]
+    specs = SY.pulses(rows, cols, n_calls)
+    t = SY.times(n_calls)
+    ref = _reference_module()
+    if ref is not None:
+        try:
+            import contextlib
+            import io
+            quiet = contextlib.redirect_stdout(io.StringIO())    # the reference prints pulse info: keep stdout one JSON line
+            quiet.__enter__()
+            sol = ref.Solver(points_per_wavelength=10, stability=0.1, eps_r_max=4, mu_r_max=1, simulation_size=1,
+                             simulation_time=1e-9)
+            sol.dt, sol.ds = SY.DT, SY.DS
+            sol.h, sol.ex, sol.ey = np.zeros((rows, cols)), np.zeros((rows + 1, cols)), np.zeros((rows, cols + 1))
+            sol.eps_coefficient_arr, sol.mu_coefficient_arr = epc, muc
+            sol.boundaries = [False, False, False, False]
+            sol.pulses = []
+            for p in specs:
+                q = ref.Pulse(sigma_w=SY.SIGMA_W, dt=SY.DT, location=[p.row, p.col], omega_0=SY.OMEGA_0, start_time=0,
+                              type="oscillate", sim_end_time=float(t[-1]) + SY.DT, direction=p.direction,
+                              real_location=[0, 0])
+                q._magnitude_vector = np.asarray(p.table)                # the C5 recipe's tables and windows
+                q._start_time, q._end_time = p.start, p.end
+                sol.pulses.append(q)
+            quiet.__exit__(None, None, None)
+            sol.step = 0
+            sol.update(t[0])                         # warm-up
+            n, t0 = 0, time.perf_counter()
+            while n < n_calls - 1 and (n < 3 or time.perf_counter() - t0 < steps_budget_s):
+                sol.update(t[n + 1])
+                n += 1
+            dt = time.perf_counter() - t0
+            return rows * cols * n / dt / 1e9, n, dt, "reference"
+        except Exception as exc:                     # an API mismatch must not cost the bench line: fall back to the port
+            sys.stdout = sys.__stdout__
+            sys.stderr.write("bench.py: live reference unusable (%r), timing the oracle port instead\n" % (exc,))
+    pulses = [R.PulseSpec("table", p.direction, p.row, p.col, p.start, p.end, p.table) for p in specs]
     S = (SY.C0 * SY.DT / SY.DS)
     setup = R.Setup(eps_coef=epc, mu_coef=muc, courant=S, pulses=pulses)
     f = R.Fields.zeros(rows, cols)
-    t = SY.times(n_calls)
     R.leapfrog(f, setup, t[0])                       # warm-up
     n, t0 = 0, time.perf_counter()
     while n < n_calls - 1 and (n < 3 or time.perf_counter() - t0 < steps_budget_s):
         R.leapfrog(f, setup, t[n + 1])
         n += 1
     dt = time.perf_counter() - t0
-    return rows * cols * n / dt / 1e9, n, dt
+    return rows * cols * n / dt / 1e9, n, dt, "port"
 
 
 def cpu_baseline_c(budget_s=5.0):
@@ -152,14 +207,19 @@ def cpu_baseline_c(budget_s=5.0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    value, n, dt = cpu_baseline(steps_budget_s=max(5.0, min(60.0, 0.2 * (args.steps + args.warmup))))
-    sample = "%dx%d sub-grid of the C5 slab recipe, %d numpy steps in %.1f s" % (CPU_SAMPLE + (n, dt))
+    value, n, dt, kind = cpu_baseline(steps_budget_s=max(5.0, min(60.0, 0.2 * (args.steps + args.warmup))))
+    sample = "%d x %d slab of the C5 recipe (the real row length), %d steps of %s in %.1f s" % (
+        CPU_SAMPLE + (n, "the reference's own Solver.update (baseline/_ref/solver.py)" if kind == "reference"
+                      else "the numpy oracle port (bit-identical to the reference)", dt))
+    cfg = workload_config(args, 1)
+    cfg["workload"] += "; CPU arm: a %d x %d sample of it, throughput scaled per cell" % CPU_SAMPLE
+    cfg["sampled_shape"] = list(CPU_SAMPLE)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores": os.cpu_count(), "threaded_c_port": cpu_baseline_c(),
                          "note": "numpy elementwise ufuncs are single-threaded; oracle/restated.py is bit-identical "
                                  "to reference solver.py:169-257 (tests/test_oracle_vs_reference.py)"},
@@ -168,7 +228,19 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n_gpus):
+def workload_config(args, n_gpus, engine=None):
+    frame_mode = engine.frame_mode if engine is not None else int(getattr(args, "frame_mode", None) or 0)
+    variant = engine.kstep_variant if engine is not None else int(getattr(args, "kstep_variant", None) or 0)
+    halo = engine.halo_depth if engine is not None else int(getattr(args, "halo_depth", None) or 1)
+    kvec = 2 if args.dtype == "f64" else 4
+    if args.temporal > 1:
+        frame = {0: "masked step_stream frame passes", 1: "one frame_window launch beside it", 2: "one frame_window launch behind it",
+                 3: "stepK_edge for the wall / source / reflector tiles"}[frame_mode]
+        kernel = "%s<%s,%d,%d> (%d steps per HBM pass, %d columns per lane) + %s; tile_rows=%d warps=%d" % (
+            "stepK_lean" if variant == 1 else "stepK_stream", "double" if args.dtype == "f64" else "float", kvec, args.temporal,
+            args.temporal, kvec, frame, args.tile_rows, args.warps)
+    else:
+        kernel = "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)
     return {"workload": "C5 synthetic: %d x %d Yee grid (%d rows per GPU, y-slab sharded), heterogeneous eps_r=1+3u "
                         "(splitmix64), mu_r=1, 4 absorbing walls, 1 point source per slab + 1 TF/SF line at col 7"
                         % (ROWS_PER_GPU * n_gpus, COLS, ROWS_PER_GPU),
@@ -178,15 +250,11 @@ def workload_config(args, n_gpus):
                      ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "y-slab x%d, %d halo rows of h/ex/ey each way ONCE per K-step group over NCCL"
-                            % (n_gpus, args.halo_depth) if (getattr(args, "halo_depth", None) or 1) > 1 else
+                            % (n_gpus, halo) if halo > 1 else
                             "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus),
-            "kernel": "%s vec=%d tile_rows=%d warps=%d" % (
-                "stepK_stream (%d steps per HBM pass) + masked step_stream frame passes" % args.temporal
-                if args.temporal > 1 else "step_stream", args.vec, args.tile_rows, args.warps),
+            "kernel": kernel,
             "temporal_blocking": args.temporal,
-            "frame_mode": int(getattr(args, "frame_mode", None) or 0),
-            "kstep_variant": int(getattr(args, "kstep_variant", None) or 0),
-            "halo_depth": int(getattr(args, "halo_depth", None) or 1)}
+            "frame_mode": frame_mode, "kstep_variant": variant, "halo_depth": halo}
 
 
 def main():
@@ -206,7 +274,7 @@ def main():
     ap.add_argument("--total-rows", type=int, default=0,
                     help="STRONG scaling: fix the grid at this many rows (e.g. 65536, BASELINE config 5) and give each GPU "
                          "total/N of them; default 0 = weak scaling, %d rows per GPU" % ROWS_PER_GPU)
-    ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2],
+    ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2, 3],
                     help="frame of a temporal-blocking group: 0 masked single-step passes, 1/2 one frame_window launch "
                          "next to / behind the K-step kernel (default: the library's)")
     ap.add_argument("--kstep-variant", type=int, default=None, choices=[0, 1],
@@ -218,6 +286,9 @@ def main():
                     help="also time the K steps WITH an h snapshot every N steps read back to the host (device pack -> "
                          "pinned ring -> async D2H on the copy stream -> host stack), SURVEY.md 8(d) 'with and without "
                          "snapshot D2H'; reported as `with_snapshots`")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="how often the timed --steps region is repeated back to back; the line reports the median "
+                         "(0 = 5 repetitions, 3 for runs longer than 2000 steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -250,7 +321,7 @@ def main():
     n_gpus = world
     rows = ROWS_PER_GPU * n_gpus
     dtype = "float64" if args.dtype == "f64" else "float32"
-    n_calls = 2 * (args.steps + args.warmup) + 64
+    n_calls = 8 * (args.steps + args.warmup) + 256
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
                           tile_rows=args.tile_rows, vec=args.vec, block_warps=args.warps, temporal=args.temporal,
@@ -280,21 +351,38 @@ def main():
         args.warps = args.warps or (4 if args.temporal == 1 else (2 if args.temporal == 4 else 1))
 
     # ---- device-resident timing ("value") -------------------------------------------------
+    # Warm-up: the W steps asked for, then one untimed pass with the GROUP STRUCTURE of the timed region (full K-step
+    # groups, the remainder group, every launch shape and exchange pattern once), so that no first-ever launch of a
+    # kernel variant, no lazy module load and no NCCL channel set-up can land inside the timed region -- a 20-step run
+    # is three K = 6 groups and one K = 2 group, and a 5-step warm-up alone exercises neither.
+    K = max(1, args.temporal)
     step = 0
     e.run(step, args.warmup); step += args.warmup
+    structural = args.steps if args.steps <= 4 * K else 2 * K + args.steps % K
+    e.run(step, structural); step += structural
     fence()
+    # The timed region: exactly --steps leapfrog steps, R times back to back (each bracketed by barrier + synchronize,
+    # device-timed by CUDA events on the library's stream, max over ranks); value = the MEDIAN repetition.
+    reps = args.repeats if args.repeats > 0 else (5 if args.steps <= 2000 else 3)
+    e.kernel_timing(True)
     launches0 = e.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     wall0 = time.perf_counter()
-    e.run(step, args.steps); step += args.steps           # events on the library stream bracket exactly K steps
-    fence()
+    rep_ms = []
+    for _ in range(reps):
+        fence()
+        e.run(step, args.steps); step += args.steps       # events on the library stream bracket exactly --steps steps
+        fence()
+        rep_ms.append(max_over_ranks(e.stats()["last_run_ms"]))
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
+    kt = e.kernel_timing_fetch()
+    e.kernel_timing(False)
     st = e.stats()
-    ms = max_over_ranks(st["last_run_ms"])
-    launches = st["kernel_launches"] - launches0
+    ms = float(np.median(rep_ms))
+    launches = (st["kernel_launches"] - launches0) // reps
     cells = rows * COLS
     value = cells * args.steps / (ms * 1e-3) / 1e9
     halo_bytes = st["halo_bytes_sent"]
@@ -378,27 +466,44 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     bpc = BYTES_PER_CELL[args.dtype]
-    per_gpu_gcells = value / n_gpus
-    achieved = per_gpu_gcells * bpc
+    tname = "double" if args.dtype == "f64" else "float"
+    kvec = 2 if args.dtype == "f64" else 4
+    if args.temporal > 1 and kt["launches"] > 0:
+        # the dominant kernel's OWN duration: CUDA events around every launch of the plain K-step kernel on the stream it
+        # is launched on, inside the timed region (fdtd_kernel_timing); its algorithmic bytes = the cell-updates those
+        # launches advanced (plain tiles x K steps, counted by the library from its tile plan) x 64 / 32 B
+        launch_ms = kt["total_ms"] / kt["launches"]
+        alg_bytes = kt["cell_updates"] / kt["launches"] * bpc
+        kname = ("fdtd::%s<%s,%d,%d>: one launch advances its tiles %d steps (algorithmic bytes are counted per step, so "
+                 "frac > 1 is the temporal-blocking gain; the DRAM-level view is traffic / dram_frac)"
+                 % ("stepK_lean" if e.kstep_variant == 1 else "stepK_stream", tname, kvec, args.temporal, args.temporal))
+    else:
+        launch_ms = ms / args.steps
+        alg_bytes = ROWS_PER_GPU * COLS * bpc
+        kname = "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
+            tname, args.vec, "; 3 launches with halo overlap" if n_gpus > 1 else "")
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.total_rows else "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n_gpus),
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n_gpus, e),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "repeats": {"n": reps, "ms_per_step": [m / args.steps for m in rep_ms],
+                    "value_min": cells * args.steps / (max(rep_ms) * 1e-3) / 1e9,
+                    "value_max": cells * args.steps / (min(rep_ms) * 1e-3) / 1e9,
+                    "what": "value = median of n back-to-back repetitions of the timed --steps region",
+                    "warmup_steps_run": args.warmup + structural},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ROWS_PER_GPU * COLS * bpc * args.temporal,
-                     "kernel": ("fdtd::stepK_stream<%s,%d,%d>: one launch advances %d steps (algorithmic bytes are counted per "
-                                "step, so frac > 1 is the temporal-blocking gain; DRAM-level traffic is in `traffic`)"
-                                % ("double" if args.dtype == "f64" else "float", 2 if args.dtype == "f64" else 4,
-                                   args.temporal, args.temporal))
-                     if args.temporal > 1 else
-                     "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
-                         "double" if args.dtype == "f64" else "float", args.vec,
-                         "; 3 launches with halo overlap" if n_gpus > 1 else ""),
-                     "launch_ms": ms / args.steps * args.temporal,
-                     "steps_per_launch": args.temporal},
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": kname,
+                     "launch_ms": launch_ms,
+                     "launch_ms_min_max": [kt["min_ms"], kt["max_ms"]] if kt["launches"] else None,
+                     "launches_timed": kt["launches"],
+                     "kernel_share_of_step": (kt["total_ms"] / (sum(rep_ms)) if kt["launches"] else 1.0),
+                     "steps_per_launch": args.temporal,
+                     "whole_step_achieved": value / n_gpus * bpc, "whole_step_frac": value / n_gpus * bpc / peak},
         "wall_s_timed_region": wall,
     }
     if with_snapshots is not None:
@@ -406,21 +511,22 @@ def main():
     if n_gpus > 1:
         line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s.json" % (args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else ""))
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s%s.json" % (
+        args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else "", "_lean" if e.kstep_variant == 1 else ""))
     if os.path.isfile(traffic_file):
         try:
             rf = line["roofline"]
             rf["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
             # DRAM-level view of the same launch: the ncu bytes over the live launch time.  With temporal blocking the
             # algorithmic fraction above exceeds 1 by design; THIS one cannot, and says how close the pass is to the bus.
-            rf["dram_achieved"] = rf["traffic"] / (rf["launch_ms"] * 1e-3) / 1e9
+            rf["dram_achieved"] = rf["traffic"] / (rf["launch_ms"] * 1e-3) / 1e9          # the kernel's own event time
             rf["dram_frac"] = rf["dram_achieved"] / peak
         except Exception:
             pass
     if n_gpus == 1 and not args.no_cpu:
-        v, n, dt = cpu_baseline()
-        line["cpu_baseline"] = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": "port",
-                                "sample": "%dx%d sub-grid of the C5 recipe, %d numpy steps in %.1f s (host has %d cores; "
+        v, n, dt, kind = cpu_baseline()
+        line["cpu_baseline"] = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": kind,
+                                "sample": "%d x %d slab of the C5 recipe, %d numpy steps in %.1f s (host has %d cores; "
                                           "numpy ufuncs use 1)" % (CPU_SAMPLE + (n, dt, os.cpu_count())),
                                 "threaded_c_port": cpu_baseline_c()}
     print(json.dumps(line), flush=True)

@@ -93,6 +93,8 @@ SIGNATURES = {
     "fdtd_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "fdtd_set_tuning": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "fdtd_sync": (C.c_int, [_P]),
+    "fdtd_kernel_timing": (C.c_int, [_P, C.c_int32]),
+    "fdtd_kernel_timing_fetch": (C.c_int, [_P, C.POINTER(C.c_int32), _D, _D, _D, C.POINTER(C.c_int64)]),
     "fdtd_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "fdtd_current_generation": (C.c_int, [_P]),
     "fdtd_comm_unique_id": (C.c_int, [_P]),
@@ -103,6 +105,8 @@ SIGNATURES = {
     "fdtd_set_halo_depth": (C.c_int, [_P, C.c_int32]),
     "fdtd_plan_frame_halo": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P,
                                        C.POINTER(C.c_int32), _P]),
+    "fdtd_plan_edge": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P,
+                                 C.POINTER(C.c_int32), _P, C.c_int32]),
     "fdtd_halo_blocks": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
 }
 

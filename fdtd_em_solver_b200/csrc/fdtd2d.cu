@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "resident.cuh"
 #include "window.cuh"
+#include "edge.cuh"
 
 #include <dlfcn.h>
 
@@ -63,13 +64,19 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     int2* d_list[8] = {};
     std::vector<int2> h_tiles;                   // frame tiles (column tile, row tile) for frame_window (window.cuh)
     int2* d_tiles = nullptr;
+    std::vector<fdtd::EdgeTile> h_edge;          // frame mode 3: the tiles of stepK_edge (edge.cuh), those next to a slab
+    fdtd::EdgeTile* d_edge = nullptr;            // interface first (n_edge_near of them)
+    size_t d_edge_cap = 0;
+    int n_edge_near = 0;
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0, d_tiles_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
+    std::vector<int64_t> row_cells;      // cells the plain K-step kernel advances per tile row (measurement hook)
     int frame_tile_rows = 0, frame_vec = 0, frame_nty = 0;   // the frame passes use smaller tiles than the K-step kernel
     int64_t k_row_lo = 0, k_row_hi = 0;                      // rows the K-step tiles own
     void release() {
         if (d_skip) cudaFree(d_skip);
         if (d_tiles) cudaFree(d_tiles);
+        if (d_edge) cudaFree(d_edge);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
     }
 };
@@ -128,6 +135,13 @@ struct fdtd_ctx {
     // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
     int frame_mode = 0;
     int kstep_variant = 0;           // 0 = stepK_stream (GPU-validated), 1 = stepK_lean (same bits, fewer issue slots; experimental)
+
+    // optional: CUDA events around every launch of the plain K-step kernel on its own stream (bench.py: the roofline
+    // line wants the dominant kernel's own duration, measured live in the timed region)
+    bool ktime_on = false;
+    std::vector<cudaEvent_t> kt_ev;
+    int kt_n = 0;
+    int64_t kt_cell_steps = 0;       // cell-updates of the timed launches
 
     fdtd_stats stats{};
     std::string err;
@@ -433,11 +447,23 @@ bool frame_window_usable(const fdtd_ctx* c, int K) {
 }
 template <typename T> int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_t st);
 
+// Frame mode 3: can stepK_edge (edge.cuh) take every non-plain tile of a K-step group of this context?  It handles all
+// walls, pulse kinds, reflectors and probes; what it needs is the whole grid on this GPU or, on a y-slab, halos deep
+// enough for the group (K+1 rows), and no TF/SF "right" line at column 0 (python's h[:, col-1] wraps to the far column).
+bool edge_usable(const fdtd_ctx* c, int K) {
+    if (c->frame_mode != 3 || c->n_src > FDTD_MAX_SRC || K < 2 || K > 8) return false;
+    const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
+    if (!whole && c->halo_depth < K + 1) return false;
+    for (int p = 0; p < c->n_src; ++p)
+        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;
+    return true;
+}
+
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
 struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
 struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false;
-                   int64_t halo_top = 0, halo_bot = 0; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
+                   int64_t halo_top = 0, halo_bot = 0; bool edge = false; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
 
 void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
     const int K = g.K, V2 = g.V2;
@@ -527,6 +553,57 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
             }
 }
 
+// Frame mode 3: every tile of the slab is a K-step tile.  Tiles whose K-step cone touches nothing special go to the
+// plain kernel (skip map, as above); ALL the others -- the K-row bands at the top / bottom wall, the wall and TF/SF
+// columns, tiles near sources, reflectors and probes -- go to stepK_edge, which folds those features into the same
+// pipeline as predicates (edge.cuh).  No masks, no pass chain, no scratch generations.  At a slab interface the stored
+// halo rows (deep halos, >= K+1 of them) let both kinds of tile reach the slab's first / last owned row.
+void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
+    const int K = g.K, V2 = g.V2;
+    const int MARGIN = (K + V2 - 1) / V2, OUT = (32 - 2 * MARGIN) * V2, LD = 32 * V2;
+    const int64_t NR = g.rows, NC = g.cols;
+    const int64_t lo = g.row_begin, hi = g.row_end + (g.row_end == NR ? 1 : 0);
+    const int TR = g.tile_rows;
+    const bool top_wall = g.row_begin == 0, bot_wall = g.row_end == NR;
+    // plain tiles own rows [loK, hiK): K rows away from a wall of the grid, right up to a slab interface
+    int64_t loK = top_wall ? lo + K : lo, hiK = bot_wall ? NR - K : g.row_end;
+    if (hiK < loK) { loK = lo; hiK = lo; }
+    const int nty = hiK > loK ? (int)((hiK - loK + TR - 1) / TR) : 0;
+    const int ntx2 = (int)((NC + 1 + OUT - 1) / OUT);
+    int ntx_e = ntx2;                     // a tile whose loaded columns reach past column NC owns everything right of it
+    while (ntx_e > 1 && (int64_t)(ntx_e - 2) * OUT - (int64_t)MARGIN * V2 + LD > NC) --ntx_e;
+    m.nty = nty; m.ntx2 = ntx2; m.ntx1 = 0; m.frame_tile_rows = TR; m.frame_vec = V2; m.frame_nty = 0;
+    m.k_row_lo = loK; m.k_row_hi = hiK;
+    m.h_skip.assign((size_t)std::max(nty, 1) * ntx2, 1);
+    for (int d = 0; d < 8; ++d) { m.h_mask[d].clear(); m.h_list[d].clear(); }
+    m.h_tiles.clear();
+    std::vector<fdtd::EdgeTile> near, far;
+    const int64_t D = std::max<int64_t>(g.halo_top, g.halo_bot);
+    auto push = [&](int tx, int64_t ta, int64_t tb) {
+        const bool is_near = (!top_wall && ta < lo + D) || (!bot_wall && tb > g.row_end - D);
+        (is_near ? near : far).push_back(fdtd::EdgeTile{tx, (int)ta, (int)tb, 0});
+    };
+    if (loK > lo) for (int tx = 0; tx < ntx_e; ++tx) push(tx, lo, loK);
+    for (int ty = 0; ty < nty; ++ty) {
+        const int64_t ta = loK + (int64_t)ty * TR, tb = std::min<int64_t>(ta + TR, hiK);
+        const bool rows_ok = ta - K >= std::max<int64_t>(g.row_begin - g.halo_top, 0) && ta - (K - 1) >= 1 &&
+                             tb + K - 2 <= NR - 2 && tb + K - 1 <= g.row_end + g.halo_bot - 1;
+        for (int tx = 0; tx < ntx2; ++tx) {
+            const int64_t jw = (int64_t)tx * OUT - (int64_t)MARGIN * V2;
+            bool mixed = !rows_ok || jw < 1 || jw + LD - 1 > NC - 2;
+            if (!mixed)
+                for (const FrameBox& q : mods)
+                    if (q.r0 <= tb + K && q.r1 >= ta - K - 1 && q.c0 <= jw + LD && q.c1 >= jw - 1) { mixed = true; break; }
+            m.h_skip[(size_t)ty * ntx2 + tx] = mixed;
+            if (mixed && tx < ntx_e) push(tx, ta, tb);
+        }
+    }
+    if (hi > hiK && hiK >= loK) for (int tx = 0; tx < ntx_e; ++tx) push(tx, std::max(hiK, lo), hi);
+    m.n_edge_near = (int)near.size();
+    m.h_edge = near;
+    m.h_edge.insert(m.h_edge.end(), far.begin(), far.end());
+}
+
 template <typename T>
 int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     FrameMaps& m = c->fm[K];
@@ -537,8 +614,9 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         for (int64_t t = n; t < n + K; ++t) if (t < c->table_len && c->active[(size_t)p * c->table_len + t]) live = 1;
         key.push_back(live);
     }
-    const bool fused = frame_window_usable(c, K);
-    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused, c->halo_depth}) {
+    const bool edge = edge_usable(c, K);
+    const bool fused = !edge && frame_window_usable(c, K);
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused + 2 * (int)edge, c->halo_depth}) {
         key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
     }
     if (key == m.key && m.d_skip) return 0;
@@ -557,8 +635,9 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
             if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
     const bool deep = c->halo_depth > 1;
-    plan_frame(FrameGeom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
-                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0}, mods, m);
+    const FrameGeom geom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
+                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge};
+    if (edge) plan_edge(geom, mods, m); else plan_frame(geom, mods, m);
     const int ntyF = m.frame_nty, ntx1 = m.ntx1;
     size_t longest = 1;
     for (int d = 0; d < K; ++d) longest = std::max(longest, m.h_list[d].size());
@@ -569,8 +648,14 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         if (m.d_skip) cudaFree(m.d_skip);
         CK(cudaMalloc(&m.d_skip, m.h_skip.size())); m.d_skip_cap = m.h_skip.size();
     }
+    if (m.d_edge_cap < m.h_edge.size()) {
+        if (m.d_edge) cudaFree(m.d_edge);
+        CK(cudaMalloc(&m.d_edge, m.h_edge.size() * sizeof(fdtd::EdgeTile))); m.d_edge_cap = m.h_edge.size();
+    }
+    if (edge && !m.h_edge.empty())
+        CK(cudaMemcpyAsync(m.d_edge, m.h_edge.data(), m.h_edge.size() * sizeof(fdtd::EdgeTile), cudaMemcpyHostToDevice, c->stream));
     const size_t mask_bytes = (size_t)ntyF * ntx1;
-    if (m.d_mask_cap < mask_bytes || m.d_list_cap < longest) {
+    if (!edge && (m.d_mask_cap < mask_bytes || m.d_list_cap < longest)) {
         for (int d = 0; d < K; ++d) {
             if (m.d_mask[d]) cudaFree(m.d_mask[d]);
             if (m.d_list[d]) cudaFree(m.d_list[d]);
@@ -585,12 +670,22 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     if (!m.h_tiles.empty())
         CK(cudaMemcpyAsync(m.d_tiles, m.h_tiles.data(), m.h_tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(m.d_skip, m.h_skip.data(), m.h_skip.size(), cudaMemcpyHostToDevice, c->stream));
-    for (int d = 0; d < K; ++d) {
+    for (int d = 0; d < K && !edge; ++d) {
         CK(cudaMemcpyAsync(m.d_mask[d], m.h_mask[d].data(), mask_bytes, cudaMemcpyHostToDevice, c->stream));
         if (!m.h_list[d].empty())
             CK(cudaMemcpyAsync(m.d_list[d], m.h_list[d].data(), m.h_list[d].size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
+    {
+        const int V2 = kvec<T>(), OUT = (32 - 2 * ((K + V2 - 1) / V2)) * V2;
+        m.row_cells.assign((size_t)std::max(m.nty, 0), 0);
+        for (int ty = 0; ty < m.nty; ++ty) {
+            const int64_t ta = m.k_row_lo + (int64_t)ty * c->cfg.tile_rows, tb = std::min<int64_t>(ta + c->cfg.tile_rows, m.k_row_hi);
+            int plain = 0;
+            for (int tx = 0; tx < m.ntx2; ++tx) plain += m.h_skip[(size_t)ty * m.ntx2 + tx] ? 0 : 1;
+            m.row_cells[ty] = (int64_t)plain * OUT * (tb - ta);
+        }
+    }
     m.key = key;
     return 0;
 }
@@ -608,6 +703,16 @@ void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1
     P.row_lo = P0.row_lo + ty0 * P0.tile_rows;
     const unsigned char* skip = m.d_skip + (size_t)ty0 * m.ntx2;
     dim3 grid((unsigned)((m.ntx2 + w - 1) / w), (unsigned)ny);
+    struct Timed {                                               // event pair around this launch, if asked for (only the
+        fdtd_ctx* c; cudaStream_t st; bool on;                   // configured group size: remainder groups are not the headline)
+        Timed(fdtd_ctx* c_, cudaStream_t st_, bool want) : c(c_), st(st_),
+            on(want && c_->ktime_on && 2 * c_->kt_n + 1 < (int)c_->kt_ev.size()) {
+            if (on) cudaEventRecord(c->kt_ev[2 * c->kt_n], st);
+        }
+        ~Timed() { if (on) { cudaEventRecord(c->kt_ev[2 * c->kt_n + 1], st); c->kt_n++; } }
+    } timed(c, st, K == c->temporal);
+    if (timed.on)
+        for (int ty = ty0; ty < ty0 + ny && ty < (int)m.row_cells.size(); ++ty) c->kt_cell_steps += m.row_cells[ty] * K;
     if (c->kstep_variant == 1) {                                 // experimental: fewer issue slots per row (kernels.cuh stepK_lean)
         constexpr int ring_rows = fdtd::KRing<K>::ROWS > 0 ? fdtd::KRing<K>::ROWS : 4;
         const size_t lean_bytes = (size_t)w * ring_rows * 5 * 32 * V2 * sizeof(T);
@@ -941,12 +1046,98 @@ int group_window(fdtd_ctx* c, int64_t n, int K) {
     return 0;
 }
 
+// ---- frame mode 3: plain K-step tiles + stepK_edge tiles, nothing else ------------------------------------------------
+template <typename T, int K>
+void launch_edge_k(const StepParams<T>& P, const fdtd::EdgeTile* tiles, int n, const fdtd::ResSources<T>& R, long long first,
+                   cudaStream_t st) {
+    fdtd::stepK_edge<T, kvec<T>(), K><<<(unsigned)n, 32, 0, st>>>(P, tiles, n, R, first);
+}
+
+// edge tiles [first_tile, first_tile + n_tiles) of the plan
+template <typename T>
+int launch_edge(fdtd_ctx* c, int64_t n, int K, int A, int B, int first_tile, int n_tiles, cudaStream_t st) {
+    const FrameMaps& m = c->fm[K];
+    if (n_tiles <= 0) return 0;
+    if (int rc = resident_tables<T>(c)) return rc;
+    StepParams<T> PE;
+    if (int rc = fill_params<T>(c, PE, n, A, B)) return rc;
+    PE.n_src = 0; PE.last_mag = T(0);                            // the kernel reads the K calls' records itself
+    PE.row_lo = (int)c->cfg.row_begin;
+    PE.row_hi = (int)(c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0));
+    if (c->n_probe) PE.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+    const fdtd::EdgeTile* tiles = m.d_edge + first_tile;
+    switch (K) {
+        case 2: launch_edge_k<T, 2>(PE, tiles, n_tiles, R, n, st); break;
+        case 3: launch_edge_k<T, 3>(PE, tiles, n_tiles, R, n, st); break;
+        case 4: launch_edge_k<T, 4>(PE, tiles, n_tiles, R, n, st); break;
+        case 5: launch_edge_k<T, 5>(PE, tiles, n_tiles, R, n, st); break;
+        case 6: launch_edge_k<T, 6>(PE, tiles, n_tiles, R, n, st); break;
+        case 7: launch_edge_k<T, 7>(PE, tiles, n_tiles, R, n, st); break;
+        default: launch_edge_k<T, 8>(PE, tiles, n_tiles, R, n, st); break;
+    }
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Steps n .. n+K-1: A -> B in two launches that read only A and write disjoint tiles of B.  The edge tiles (long-running
+// single warps) start first, on the high-priority stream, next to the plain kernel.  On a y-slab with a communicator the
+// tiles next to an interface (plain tile rows and edge tiles within D rows of it) run on that stream, too, once the
+// previous exchange has landed; the D-row blocks of B leave as soon as they are done, while the interior still runs.
+template <typename T>
+int group_edge(fdtd_ctx* c, int64_t n, int K) {
+    if (int rc = build_frame_maps<T>(c, n, K)) return rc;
+    const FrameMaps& m = c->fm[K];
+    const int A = c->cur, B = (A + 1) % c->ngen;
+    if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
+    StepParams<T> PK;
+    if (m.nty > 0) {
+        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
+        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
+    }
+    const int n_edge = (int)m.h_edge.size();
+    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this group
+    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
+    if (!c->comm) {
+        if (int rc = launch_edge<T>(c, n, K, A, B, 0, n_edge, c->edge_stream)) return rc;
+        if (m.nty > 0) { launch_stepK_any<T>(PK, c, K); c->stats.kernel_launches++; CK(cudaGetLastError()); }
+    } else {
+        const int TR = c->cfg.tile_rows, D = c->halo_depth;
+        const int e_top = c->cfg.row_begin > 0 ? std::min(m.nty, (D + TR - 1) / TR) : 0;
+        const int e_bot = c->cfg.row_end < c->cfg.rows ? std::min(m.nty - e_top, (D + TR - 1) / TR + 1) : 0;
+        const int n_int = m.nty - e_top - e_bot;
+        // tiles away from the interfaces read owned rows only: they start at once
+        if (int rc = launch_edge<T>(c, n, K, A, B, m.n_edge_near, n_edge - m.n_edge_near, c->edge_stream)) return rc;
+        if (n_int > 0) { launch_stepK_any<T>(PK, c, K, e_top, n_int, c->stream); c->stats.kernel_launches++; }
+        CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0)); // the neighbours' rows of A have landed
+        if (int rc = launch_edge<T>(c, n, K, A, B, 0, m.n_edge_near, c->edge_stream)) return rc;
+        if (e_top > 0) { launch_stepK_any<T>(PK, c, K, 0, e_top, c->edge_stream); c->stats.kernel_launches++; }
+        if (e_bot > 0) { launch_stepK_any<T>(PK, c, K, m.nty - e_bot, e_bot, c->edge_stream); c->stats.kernel_launches++; }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
+    if (c->comm) {
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
+        if (int rc = exchange(c, B, c->comm_stream)) return rc; // ONE exchange per group
+        CK(cudaEventRecord(c->ev_comm, c->comm_stream));
+    }
+    CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));           // main-stream order = "all of B written"
+    CK(cudaEventRecord(c->ev_int, c->stream));
+    c->cur = B;
+    if (c->n_probe) c->probe_count += K;
+    c->stats.steps += K;
+    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
+    return 0;
+}
+
 int step_any(fdtd_ctx* c, int64_t step) {
     return c->cfg.dtype == FDTD_F64 ? step_impl<double>(c, step) : step_impl<float>(c, step);
 }
 
 int group_any(fdtd_ctx* c, int64_t n, int K) {
     const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
+    if (edge_usable(c, K)) return c->cfg.dtype == FDTD_F64 ? group_edge<double>(c, n, K) : group_edge<float>(c, n, K);
     if (c->halo_depth > 1 && !whole) {
         // deep halos: the slab stores D rows of each neighbour, so a group of K <= D-1 steps needs nothing from them
         // while it runs -- K-step kernel + frame_window, then one exchange.  No pass chain exists in this mode; a scene
@@ -1105,6 +1296,7 @@ int fdtd_destroy(fdtd_handle c) {
     if (c->stage) cudaFree(c->stage);
     resident_free_tables(c);
     for (FrameMaps& m : c->fm) m.release();
+    for (cudaEvent_t e : c->kt_ev) cudaEventDestroy(e);
     for (int s = 0; s < 2; ++s) {
         if (c->snap_dev[s]) cudaFree(c->snap_dev[s]);
         if (c->snap_pin[s]) cudaFreeHost(c->snap_pin[s]);
@@ -1183,6 +1375,41 @@ int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t
                              halo_depth);
 }
 
+int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes, const int64_t* boxes,
+                   fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles, int32_t* edge_tiles, int32_t max_edge_tiles) {
+    fdtd_ctx* c = nullptr;
+    if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes) ||
+        halo_depth < 1 || halo_depth > 9)
+        return fail(c, FDTD_ERR_ARG, "bad argument");
+    if (cfg->rows < 3 || cfg->cols < 3 || cfg->tile_rows <= 0 || cfg->row_begin < 0 || cfg->row_end > cfg->rows ||
+        cfg->row_end <= cfg->row_begin)
+        return fail(c, FDTD_ERR_ARG, "bad geometry");
+    const bool whole = cfg->row_begin == 0 && cfg->row_end == cfg->rows;
+    if (!whole && halo_depth < steps_per_pass + 1)
+        return fail(c, FDTD_ERR_ARG, "a y-slab needs halos of steps_per_pass + 1 rows for the edge plan");
+    std::vector<FrameBox> mods;
+    for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
+    const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+    FrameMaps m;
+    const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
+    const int64_t hb = (halo_depth > 1 && cfg->row_end < cfg->rows) ? halo_depth : 0;
+    plan_edge(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, std::max(cfg->block_warps, 1), K, V2,
+                        false, ht, hb, true}, mods, m);
+    const int margin = (K + V2 - 1) / V2;
+    plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
+    plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
+    plan->k_row_lo = m.k_row_lo; plan->k_row_hi = m.k_row_hi;
+    plan->frame_tile_rows = 0; plan->frame_tile_cols = 0; plan->frame_tiles_y = 0; plan->frame_tiles_x = 0;
+    if (skip && m.nty > 0) std::memcpy(skip, m.h_skip.data(), (size_t)m.nty * m.ntx2);
+    if (n_edge_tiles) *n_edge_tiles = (int32_t)m.h_edge.size();
+    if (edge_tiles)
+        for (size_t k = 0; k < m.h_edge.size() && (int32_t)k < max_edge_tiles; ++k) {
+            edge_tiles[4 * k] = m.h_edge[k].tx; edge_tiles[4 * k + 1] = m.h_edge[k].ta; edge_tiles[4 * k + 2] = m.h_edge[k].tb;
+            edge_tiles[4 * k + 3] = (int)k < m.n_edge_near ? 1 : 0;
+        }
+    return 0;
+}
+
 int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
     if (!c) return FDTD_ERR_ARG;
     for (void* p : {h2, ex2, ey2}) {
@@ -1251,7 +1478,7 @@ int fdtd_set_kstep_variant(fdtd_handle c, int32_t variant) {
 
 int fdtd_set_frame_mode(fdtd_handle c, int32_t mode) {
     if (!c) return FDTD_ERR_ARG;
-    if (mode < 0 || mode > 2) return fail(c, FDTD_ERR_ARG, "frame mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(c, FDTD_ERR_ARG, "frame mode must be 0, 1, 2 or 3");
     c->frame_mode = mode;
     return 0;
 }
@@ -1552,6 +1779,41 @@ int fdtd_set_tuning(fdtd_handle c, int32_t tile_rows, int32_t vec, int32_t block
     if (vec) c->cfg.vec = vec;
     if (block_warps) { c->cfg.block_warps = block_warps; c->auto_warps = false; }
     for (FrameMaps& m : c->fm) m.key.clear();
+    return 0;
+}
+
+int fdtd_kernel_timing(fdtd_handle c, int32_t enable) {
+    if (!c) return FDTD_ERR_ARG;
+    CK(cudaSetDevice(c->cfg.device));
+    if (enable && c->kt_ev.empty()) {
+        c->kt_ev.resize(2 * 4096);
+        for (cudaEvent_t& e : c->kt_ev) CK(cudaEventCreate(&e));
+    }
+    c->ktime_on = enable != 0;
+    c->kt_n = 0;
+    c->kt_cell_steps = 0;
+    return 0;
+}
+
+int fdtd_kernel_timing_fetch(fdtd_handle c, int32_t* n_launches, double* total_ms, double* min_ms, double* max_ms,
+                             int64_t* cell_updates) {
+    if (!c) return FDTD_ERR_ARG;
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->edge_stream));
+    double tot = 0, lo = 0, hi = 0;
+    for (int k = 0; k < c->kt_n; ++k) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->kt_ev[2 * k], c->kt_ev[2 * k + 1]));
+        tot += ms;
+        lo = k == 0 ? ms : std::min<double>(lo, ms);
+        hi = std::max<double>(hi, ms);
+    }
+    if (n_launches) *n_launches = c->kt_n;
+    if (total_ms) *total_ms = tot;
+    if (min_ms) *min_ms = lo;
+    if (max_ms) *max_ms = hi;
+    if (cell_updates) *cell_updates = c->kt_cell_steps;
     return 0;
 }
 

@@ -317,6 +317,16 @@ class Engine:
     def clear_probes(self):
         L.check(self.lib, self.handle, self.lib.fdtd_probe_clear(self.handle))
 
+    def kernel_timing(self, enable=True):
+        """Bracket every launch of the plain K-step kernel with CUDA events on its stream (measurement hook)."""
+        L.check(self.lib, self.handle, self.lib.fdtd_kernel_timing(self.handle, 1 if enable else 0))
+
+    def kernel_timing_fetch(self):
+        n, tot, lo, hi, cu = C.c_int32(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+        L.check(self.lib, self.handle, self.lib.fdtd_kernel_timing_fetch(self.handle, C.byref(n), C.byref(tot), C.byref(lo),
+                                                                        C.byref(hi), C.byref(cu)))
+        return dict(launches=n.value, total_ms=tot.value, min_ms=lo.value, max_ms=hi.value, cell_updates=cu.value)
+
     def stats(self):
         s = L.Stats()
         L.check(self.lib, self.handle, self.lib.fdtd_get_stats(self.handle, C.byref(s)))

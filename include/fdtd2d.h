@@ -226,6 +226,15 @@ int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapsho
 /* Launch geometry of the streaming kernel (0 keeps the current value); results never depend on it. */
 int fdtd_set_tuning(fdtd_handle h, int32_t tile_rows, int32_t vec, int32_t block_warps);
 
+/* Measurement hook: with enable != 0 every launch of the plain K-step kernel (the dominant kernel of fdtd_run with
+ * temporal blocking) is bracketed by CUDA events on the stream it is launched on (at most 4096 launches are kept; the
+ * counters restart at every call; only launches of the configured group size count).  fdtd_kernel_timing_fetch waits for
+ * the streams and returns the number of launches timed, their total, shortest and longest duration in ms, and the
+ * cell-updates (cells x steps) those launches advanced. */
+int fdtd_kernel_timing(fdtd_handle h, int32_t enable);
+int fdtd_kernel_timing_fetch(fdtd_handle h, int32_t* n_launches, double* total_ms, double* min_ms, double* max_ms,
+                             int64_t* cell_updates);
+
 int fdtd_sync(fdtd_handle h);
 int fdtd_get_stats(fdtd_handle h, fdtd_stats* out);
 
@@ -260,6 +269,14 @@ int fdtd_set_halo_depth(fdtd_handle h, int32_t halo_depth);
 int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes,
                          const int64_t* boxes, fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks,
                          int32_t* n_window_tiles, int32_t* window_tiles_xy);
+/* The tile plan of frame mode 3 as pure host logic (no CUDA call).  Every tile of the slab is a K-step tile: skip
+ * (k_tiles_y x k_tiles_x bytes) = 0 for the tiles of the plain K-step kernel; every other tile is listed in edge_tiles
+ * as {column tile tx, first row, end row, next-to-an-interface flag} for stepK_edge (csrc/edge.cuh), which folds walls,
+ * pulses, reflectors and probes into the same register pipeline -- incl. the K-row bands at the top / bottom wall that
+ * the plain tile grid (rows k_row_lo .. k_row_hi) leaves out.  A y-slab needs halo_depth >= steps_per_pass + 1.
+ * *n_edge_tiles receives the number of edge tiles; at most max_edge_tiles quadruples are written to edge_tiles. */
+int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes, const int64_t* boxes,
+                   fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles, int32_t* edge_tiles, int32_t max_edge_tiles);
 /* Block pointers of the current generation for an external transport: send_down = the last D owned rows, recv_down = the
  * D rows stored from the slab below, send_up = the first D owned rows, recv_up = the D rows stored from the slab above
  * (NULL where there is no neighbour); *count = elements per block (D x pitch). */

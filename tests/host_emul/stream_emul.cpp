@@ -7,6 +7,7 @@
 #define FDTD_HOST_EMUL 1
 #include "simt.h"
 #include "kernels.cuh"
+#include "edge.cuh"
 
 namespace fdtd { alignas(16) unsigned char ring_raw[256 * 1024]; }   // the dynamic shared memory of stepK_stream
 
@@ -111,6 +112,45 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
                 }
             }
         }
+    return 0;
+}
+
+// One launch of stepK_edge<double, 2, K>: K calls for every listed tile (tiles: n x {tx, ta, tb, 0}).  The pulse records
+// of the K calls come as the device tables of resident mode do: count[K], last[K], src[K][stride].
+int emul_stepK_edge(const StreamScene* sc, int K, const int32_t* tiles, int n_tiles, const int32_t* count, const double* last,
+                    const EmuSrc* src, int stride, int n_probe, const int32_t* probe_ij, double* probe_out) {
+    StepParams<double> P;
+    fill(P, *sc);
+    P.n_src = 0;                                                 // the kernel reads the records itself
+    P.row_lo = 0; P.row_hi = P.NR + 1; P.tile_rows = 0;
+    P.n_probe = n_probe;
+    for (int k = 0; k < n_probe; ++k) { P.probe_i[k] = probe_ij[2 * k]; P.probe_j[k] = probe_ij[2 * k + 1]; }
+    P.probe_out = probe_out;
+    std::vector<SrcStep<double>> recs((size_t)K * std::max(stride, 1));
+    for (int m = 0; m < K; ++m)
+        for (int k = 0; k < stride; ++k) {
+            const EmuSrc& e = src[(size_t)m * stride + k];
+            SrcStep<double>& q = recs[(size_t)m * stride + k];
+            q.kind = e.kind; q.row = e.row; q.col = e.col; q.pad = 0; q.mag = e.mag; q.magz = e.magz;
+        }
+    ResSources<double> R{stride ? count : nullptr, last, recs.data(), stride};
+    simt::g_block_dim = simt::Idx{32, 1, 1};
+    simt::g_grid_dim = simt::Idx{(unsigned)n_tiles, 1, 1};
+    const EdgeTile* tl = reinterpret_cast<const EdgeTile*>(tiles);
+    for (int b = 0; b < n_tiles; ++b) {
+        simt::g_block_idx = simt::Idx{(unsigned)b, 0, 0};
+        switch (K) {
+            case 1: simt::run_warp(0, [&] { stepK_edge<double, 2, 1>(P, tl, n_tiles, R, 0); }); break;
+            case 2: simt::run_warp(0, [&] { stepK_edge<double, 2, 2>(P, tl, n_tiles, R, 0); }); break;
+            case 3: simt::run_warp(0, [&] { stepK_edge<double, 2, 3>(P, tl, n_tiles, R, 0); }); break;
+            case 4: simt::run_warp(0, [&] { stepK_edge<double, 2, 4>(P, tl, n_tiles, R, 0); }); break;
+            case 5: simt::run_warp(0, [&] { stepK_edge<double, 2, 5>(P, tl, n_tiles, R, 0); }); break;
+            case 6: simt::run_warp(0, [&] { stepK_edge<double, 2, 6>(P, tl, n_tiles, R, 0); }); break;
+            case 7: simt::run_warp(0, [&] { stepK_edge<double, 2, 7>(P, tl, n_tiles, R, 0); }); break;
+            case 8: simt::run_warp(0, [&] { stepK_edge<double, 2, 8>(P, tl, n_tiles, R, 0); }); break;
+            default: return -1;
+        }
+    }
     return 0;
 }
 

@@ -39,7 +39,7 @@ def available():
 
 
 def build():
-    deps = [SRC, os.path.join(HERE, "host_emul", "simt.h"), os.path.join(CSRC, "kernels.cuh")]
+    deps = [SRC, os.path.join(HERE, "host_emul", "simt.h")] + [os.path.join(CSRC, f) for f in ("kernels.cuh", "edge.cuh", "resident.cuh")]
     if os.path.isfile(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
@@ -63,6 +63,9 @@ def load():
         _lib.emul_step_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5
         _lib.emul_stepK_stream.restype = C.c_int
         _lib.emul_stepK_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.emul_stepK_edge.restype = C.c_int
+        _lib.emul_stepK_edge.argtypes = [C.POINTER(StreamScene), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -70,7 +73,7 @@ class Scene:
     """Generation A = the oracle-style fields `f`; generation B pre-filled with `fill`.  The pulse record is the one of
     call `n` (what fdtd2d.cu fill_params puts into StepParams for a single-step launch)."""
 
-    def __init__(self, f, setup, times, n, fill=np.nan):
+    def __init__(self, f, setup, times, n, fill=np.nan, pad=0.0):
         from fdtd_em_solver_b200.engine import build_source_tables
         NR, NC = f.h.shape
         self.NR, self.NC = NR, NC
@@ -81,9 +84,9 @@ class Scene:
             if a is not None:
                 p[:a.shape[0], :a.shape[1]] = a
             return p
-        self.a = [plane(f.h), plane(f.ex), plane(f.ey)]
+        self.a = [plane(f.h, pad), plane(f.ex, pad), plane(f.ey, pad)]          # pad: what lies outside the arrays
         self.b = [plane(None, fill) for _ in range(3)]
-        self.muc, self.epc = plane(setup.mu_coef), plane(setup.eps_coef)
+        self.muc, self.epc = plane(setup.mu_coef, pad), plane(setup.eps_coef, pad)
         sc = StreamScene()
         for k in range(3):
             sc.a[k], sc.b[k] = self.a[k].ctypes.data, self.b[k].ctypes.data
@@ -130,3 +133,32 @@ def stepK_stream(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip, 
                                   skip.shape[1], skip.shape[0], variant)
     assert rc == 0
     return s.result()
+
+
+def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan):
+    """One launch of stepK_edge<double, 2, K>: calls n .. n+K-1 for every listed tile (tx, ta, tb).  Returns the fields
+    of generation B (cells no tile owns keep `fill`) and the probe records (K, n_probe, 3)."""
+    from fdtd_em_solver_b200.engine import build_source_tables
+    s = Scene(f, setup, times, n, fill=fill, pad=np.nan)          # NaN outside the arrays: nothing read there may be kept
+    s.sc.n_src = 0
+    srcs, mag, magz, active, last, _ = build_source_tables(setup.pulses, times)
+    stride = len(setup.pulses)
+    count = np.zeros(K, dtype=np.int32)
+    lastv = np.zeros(K)
+    recs = (EmuSrc * max(K * stride, 1))()
+    for m in range(K):
+        k = 0
+        for p in range(stride):
+            if active[p, n + m]:
+                q = recs[m * stride + k]
+                q.kind, q.row, q.col, q.mag, q.magz = srcs[p].kind, srcs[p].row, srcs[p].col, mag[p, n + m], magz[p, n + m]
+                k += 1
+        count[m] = k
+        lastv[m] = last[n + m] if stride else 0.0
+    tl = np.ascontiguousarray([[tx, ta, tb, 0] for tx, ta, tb in tiles], dtype=np.int32).reshape(-1, 4)
+    pij = np.ascontiguousarray(np.asarray(probes, dtype=np.int32).reshape(-1, 2))
+    pout = np.full((K, max(len(pij), 1), 3), np.nan)
+    rc = load().emul_stepK_edge(C.byref(s.sc), K, tl.ctypes.data, len(tl), count.ctypes.data, lastv.ctypes.data,
+                                C.cast(recs, C.c_void_p), stride, len(pij), pij.ctypes.data, pout.ctypes.data)
+    assert rc == 0
+    return s.result(), pout[:, :len(pij)]

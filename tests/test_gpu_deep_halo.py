@@ -34,9 +34,10 @@ def _copy_blocks(engines):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("frame_mode", [None, 3], ids=["frame_window", "stepK_edge"])
 @pytest.mark.parametrize("world,K,shape,tile_rows", [(2, 4, (300, 700), 16), (3, 6, (400, 900), 16), (2, 2, (97, 300), 8),
-                                                    (4, 6, (700, 2100), 48)])
-def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows):
+                                                    (4, 6, (700, 2100), 48), (3, 8, (500, 1300), 24)])
+def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows, frame_mode):
     from fdtd_em_solver_b200.engine import Engine
     rows, cols = shape
     n_steps = 3 * K + 2
@@ -46,7 +47,7 @@ def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows)
     engines = []
     for b, e_ in SL.split_rows(rows, world):
         e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, row_begin=b, row_end=e_,
-                   temporal=K, tile_rows=tile_rows, halo_depth=K + 1)
+                   temporal=K, tile_rows=tile_rows, halo_depth=K + 1, frame_mode=frame_mode)
         e.upload_coefficients(setup.eps_coef, setup.mu_coef)
         e.set_sources(setup.pulses, times)
         e.set_reflectors(setup.reflectors)

@@ -45,7 +45,7 @@ def _without_wrapping_lines(setup):
     return setup
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("temporal", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("shape,tile_rows,warps", [((200, 900), 8, 4), ((131, 517), 4, 2), ((64, 300), 16, 1)])
 def test_k_steps_per_pass_with_the_frame_in_one_launch(shape, tile_rows, warps, temporal, mode):
@@ -75,7 +75,7 @@ def test_k_steps_per_pass_with_the_frame_in_one_launch(shape, tile_rows, warps, 
         e.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_wrapping_line_keeps_the_masked_passes(mode):
     """A TF/SF "right" line at column 0 is outside the window algorithm: the group silently uses mode 0."""
     f, setup, times = SC.random_case(131, 517, 3, n_steps=13)          # seed % 3 == 0: has the column-0 line
@@ -87,7 +87,7 @@ def test_wrapping_line_keeps_the_masked_passes(mode):
     e.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_fp32_same_bits_as_single_stepping(mode):
     from fdtd_em_solver_b200.engine import Engine
     f, setup, times = SC.random_case(150, 1200, 10, n_steps=13)
@@ -108,7 +108,7 @@ def test_fp32_same_bits_as_single_stepping(mode):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_2048_grid_default_geometry_vs_oracle(mode):
     f, setup, times = SC.random_case(2048, 2048, 21, walls=(False, False, False, False), n_steps=20)
     setup = _without_wrapping_lines(setup)

@@ -24,7 +24,11 @@ FRAME_CASES = [(1500, 4100, 26, dict(temporal=4, frame_mode=1)), (2000, 9000, 27
 # deep halos (one exchange per K-step group, fdtd_set_halo_depth) join with FDTD_SLAB_CHECK_DEEP=1
 DEEP_CASES = [(1500, 4100, 26, dict(temporal=4, halo_depth=5)), (2000, 9000, 27, dict(temporal=6, tile_rows=16, halo_depth=7)),
               (2000, 9000, 29, dict(temporal=6, halo_depth=7, frame_mode=1)), (1500, 4100, 35, dict(temporal=8, halo_depth=9)),
-              (97, 300, 13, dict(tile_rows=4, temporal=2, halo_depth=3))] if os.environ.get("FDTD_SLAB_CHECK_DEEP") == "1" else []
+              (97, 300, 13, dict(tile_rows=4, temporal=2, halo_depth=3)),
+              # frame mode 3: plain K-step tiles + stepK_edge tiles, nothing else
+              (1500, 4100, 26, dict(temporal=4, halo_depth=5, frame_mode=3)), (2000, 9000, 29, dict(temporal=6, halo_depth=7, frame_mode=3)),
+              (1500, 4100, 35, dict(temporal=8, halo_depth=9, frame_mode=3, kstep_variant=1)),
+              (97, 300, 13, dict(tile_rows=4, temporal=2, halo_depth=3, frame_mode=3))] if os.environ.get("FDTD_SLAB_CHECK_DEEP") == "1" else []
 
 for rows, cols, n_steps, kw in DEEP_CASES + FRAME_CASES + [(97, 300, 12, dict(tile_rows=4)), (1500, 4100, 25, dict()),
                                 (97, 300, 13, dict(tile_rows=4, temporal=2)), (1500, 4100, 25, dict(temporal=2)),
