@@ -229,9 +229,11 @@ def run_reference(args, rank):
 
 
 def workload_config(args, n_gpus, engine=None):
-    frame_mode = engine.frame_mode if engine is not None else int(getattr(args, "frame_mode", None) or 0)
-    variant = engine.kstep_variant if engine is not None else int(getattr(args, "kstep_variant", None) or 0)
-    halo = engine.halo_depth if engine is not None else int(getattr(args, "halo_depth", None) or 1)
+    fm, kv, hd = getattr(args, "frame_mode", None), getattr(args, "kstep_variant", None), getattr(args, "halo_depth", None)
+    frame_mode = engine.frame_mode if engine is not None else (3 if fm is None else int(fm))
+    variant = engine.kstep_variant if engine is not None else (1 if kv is None else int(kv))
+    halo = engine.halo_depth if engine is not None else (1 if hd is None else int(hd))
+    n_arrays = len(engine.buffers) if engine is not None else 8
     kvec = 2 if args.dtype == "f64" else 4
     if args.temporal > 1:
         frame = {0: "masked step_stream frame passes", 1: "one frame_window launch beside it", 2: "one frame_window launch behind it",
@@ -246,7 +248,7 @@ def workload_config(args, n_gpus, engine=None):
                         % (ROWS_PER_GPU * n_gpus, COLS, ROWS_PER_GPU),
             "rows": ROWS_PER_GPU * n_gpus, "cols": COLS, "rows_per_gpu": ROWS_PER_GPU,
             "l2": "inputs_exceed_l2 (%d arrays x %.1f GiB per GPU, no flush needed)"
-                  % (8 if args.temporal == 1 else (11 if args.temporal == 2 else 14),
+                  % (n_arrays,
                      ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "y-slab x%d, %d halo rows of h/ex/ey each way ONCE per K-step group over NCCL"
@@ -269,7 +271,7 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0, help="rows per warp tile (0 = library default for the chosen --temporal)")
     ap.add_argument("--vec", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0, help="warps per CTA (0 = library default)")
-    ap.add_argument("--temporal", type=int, default=6, choices=[1, 2, 3, 4, 5, 6, 7, 8],
+    ap.add_argument("--temporal", type=int, default=8, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="leapfrog steps per HBM pass (>1 = temporal blocking)")
     ap.add_argument("--total-rows", type=int, default=0,
                     help="STRONG scaling: fix the grid at this many rows (e.g. 65536, BASELINE config 5) and give each GPU "
@@ -346,9 +348,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if args.tile_rows == 0 or args.warps == 0:
-        args.tile_rows = args.tile_rows or {1: 6, 2: 8, 3: 12, 4: 16, 5: 32, 6: 48, 7: 48, 8: 56}[args.temporal]
-        args.warps = args.warps or (4 if args.temporal == 1 else (2 if args.temporal == 4 else 1))
+    tuning = e.tuning()                      # what the library picked where the flags left it open
+    args.tile_rows, args.warps = tuning["tile_rows"], tuning["block_warps"]
 
     # ---- device-resident timing ("value") -------------------------------------------------
     # Warm-up: the W steps asked for, then one untimed pass with the GROUP STRUCTURE of the timed region (full K-step

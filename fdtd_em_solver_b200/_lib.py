@@ -92,6 +92,7 @@ SIGNATURES = {
     "fdtd_step": (C.c_int, [_P, C.c_int64]),
     "fdtd_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "fdtd_set_tuning": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fdtd_get_tuning": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "fdtd_sync": (C.c_int, [_P]),
     "fdtd_kernel_timing": (C.c_int, [_P, C.c_int32]),
     "fdtd_kernel_timing_fetch": (C.c_int, [_P, C.POINTER(C.c_int32), _D, _D, _D, C.POINTER(C.c_int64)]),

@@ -133,8 +133,9 @@ struct fdtd_ctx {
 
     // how the frame of a temporal-blocking group advances: 0 = K masked single-step passes (step_stream), 1 = ONE
     // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
-    int frame_mode = 0;
-    int kstep_variant = 0;           // 0 = stepK_stream (GPU-validated), 1 = stepK_lean (same bits, fewer issue slots; experimental)
+    int frame_mode = 3;              // (3 = stepK_edge takes every non-plain tile: default since its B200 runs, profiles/r2_sweep_*)
+    int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
+    int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
 
     // optional: CUDA events around every launch of the plain K-step kernel on its own stream (bench.py: the roofline
     // line wants the dominant kernel's own duration, measured live in the timed region)
@@ -203,7 +204,7 @@ int h2d_plane(fdtd_ctx* c, void* base, const double* host, int64_t host_ld, int6
         const int64_t m = std::min(chunk, n - a);
         CK(cudaMemcpy2DAsync(c->stage, ncols * 8, src + a * host_ld, host_ld * 8, ncols * 8, m,
                              cudaMemcpyHostToDevice, c->stream));
-        dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)m);
+        dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)std::min<int64_t>(m, 65535));
         fdtd::plane_from_f64<T><<<grid, 256, 0, c->stream>>>(dst + a * c->pitch, c->pitch,
                                                              (const double*)c->stage, ncols, (int)m, (int)ncols);
         c->stats.kernel_launches++;
@@ -227,7 +228,7 @@ int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int6
     fdtd::PatchList none; none.n = 0;
     for (int64_t a = 0; a < n; a += chunk) {
         const int64_t m = std::min(chunk, n - a);
-        dim3 block(64, 4), grid((unsigned)((ncols + 63) / 64), (unsigned)((m + 3) / 4));
+        dim3 block(64, 4), grid((unsigned)((ncols + 63) / 64), (unsigned)std::min<int64_t>((m + 3) / 4, 65535));
         fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>((double*)c->stage, ncols, src + a * c->pitch, c->pitch,
                                                              (int)m, (int)ncols, 0, none);
         c->stats.kernel_launches++;
@@ -293,7 +294,7 @@ int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, c
     if (P.tile_list && n_list == 0) return 0;
     P.row_lo = (int)row_lo; P.row_hi = (int)row_hi;
     if (c->cfg.kernel == FDTD_KERNEL_EXACT) {
-        dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)(row_hi - row_lo));
+        dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)std::min<int64_t>(row_hi - row_lo, 65535));
         fdtd::step_exact<T><<<grid, 256, 0, s>>>(P);
     } else {
         const int v = vec_override ? vec_override : c->cfg.vec, w = c->cfg.block_warps;
@@ -463,7 +464,7 @@ bool edge_usable(const fdtd_ctx* c, int K) {
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
 struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
 struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false;
-                   int64_t halo_top = 0, halo_bot = 0; bool edge = false; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
+                   int64_t halo_top = 0, halo_bot = 0; bool edge = false; int edge_rows = 32; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
 
 void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
     const int K = g.K, V2 = g.V2;
@@ -579,9 +580,16 @@ void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps&
     m.h_tiles.clear();
     std::vector<fdtd::EdgeTile> near, far;
     const int64_t D = std::max<int64_t>(g.halo_top, g.halo_bot);
-    auto push = [&](int tx, int64_t ta, int64_t tb) {
-        const bool is_near = (!top_wall && ta < lo + D) || (!bot_wall && tb > g.row_end - D);
-        (is_near ? near : far).push_back(fdtd::EdgeTile{tx, (int)ta, (int)tb, 0});
+    // Edge tiles are single warps that march (rows + 2K + 1) iterations of a slow pipeline: they are cut into pieces of
+    // at most edge_rows rows, independent of the height of the plain tiles (which like to be tall), so that the few
+    // thousand of them spread over the SMs and finish well inside the plain kernel's run.
+    const int ER = std::max(g.edge_rows, 1);
+    auto push = [&](int tx, int64_t ta0, int64_t tb0) {
+        for (int64_t ta = ta0; ta < tb0; ta += ER) {
+            const int64_t tb = std::min<int64_t>(ta + ER, tb0);
+            const bool is_near = (!top_wall && ta < lo + D) || (!bot_wall && tb > g.row_end - D);
+            (is_near ? near : far).push_back(fdtd::EdgeTile{tx, (int)ta, (int)tb, 0});
+        }
     };
     if (loK > lo) for (int tx = 0; tx < ntx_e; ++tx) push(tx, lo, loK);
     for (int ty = 0; ty < nty; ++ty) {
@@ -636,7 +644,8 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
     const bool deep = c->halo_depth > 1;
     const FrameGeom geom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
-                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge};
+                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge,
+                         c->edge_rows};
     if (edge) plan_edge(geom, mods, m); else plan_frame(geom, mods, m);
     const int ntyF = m.frame_nty, ntx1 = m.ntx1;
     size_t longest = 1;
@@ -1170,7 +1179,7 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     }
     const int64_t rows = c->owned, cols = c->cfg.cols;
     CK(cudaStreamWaitEvent(c->stream, c->ev_free[slot], 0));
-    dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 3) / 4));
+    dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)std::min<int64_t>((rows + 3) / 4, 65535));
     fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>(c->snap_dev[slot], cols,
         plane<T>(c->gen[c->cur][0], c, c->cfg.row_begin), c->pitch, (int)rows, (int)cols, (int)c->cfg.row_begin, pl);
     c->stats.kernel_launches++;
@@ -1234,6 +1243,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(c, FDTD_ERR_ARG, "bad device ordinal");
     c = new fdtd_ctx();
     c->cfg = *cfg;
+    if (const char* er = std::getenv("FDTD_EDGE_ROWS")) { const int v = std::atoi(er); if (v >= 1 && v <= 4096) c->edge_rows = v; }
     c->esize = cfg->dtype == FDTD_F64 ? 8 : 4;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
     if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
@@ -1423,17 +1433,39 @@ int fdtd_bind_scratch(fdtd_handle c, void* h2, void* ex2, void* ey2) {
     return 0;
 }
 
+// Launch geometry the library picks when the caller left it open (cfg.tile_rows / block_warps <= 0 at fdtd_create).
+static void auto_geometry(fdtd_ctx* c) {
+    const int steps_per_pass = c->temporal;
+    // measured on the 8192 x 65536 slab (profiles/sweep_r1*.jsonl, r2_sweep_*): the K-step kernel wants taller tiles as K
+    // grows (its prologue is 2K-1 rows) and one warp per CTA; with the edge tiles cut to their own short height (frame
+    // mode 3) K = 7, 8 like them much taller still (K = 8: 56 rows 552, 128 rows 607, 512 rows 632 Gcell/s)
+    static const int rows_for_k[9] = {6, 6, 8, 12, 16, 32, 48, 48, 56};
+    static const int rows_for_k_edge[9] = {6, 6, 8, 12, 16, 32, 48, 256, 512};
+    if (c->auto_tile_rows) {
+        int tr = rows_for_k[steps_per_pass];
+        if (c->frame_mode == 3 && rows_for_k_edge[steps_per_pass] > tr) {
+            // ... as long as the plain tiles still fill the GPU several times over (8 single-warp CTAs per SM at 250
+            // registers): a grid much smaller than the 8192 x 65536 slab keeps shorter tiles
+            const int V2 = c->cfg.dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+            const int64_t out_cols = (32 - 2 * ((K + V2 - 1) / V2)) * V2;
+            const int64_t ntx = (c->cfg.cols + 1 + out_cols - 1) / out_cols;
+            const int64_t want_nty = (4 * 8 * 148 + ntx - 1) / ntx;
+            const int64_t fit = (c->owned / std::max<int64_t>(want_nty, 1)) / 8 * 8;
+            tr = (int)std::min<int64_t>(rows_for_k_edge[steps_per_pass], std::max<int64_t>(tr, fit));
+        }
+        c->cfg.tile_rows = tr;
+    }
+    if (c->auto_warps) c->cfg.block_warps = steps_per_pass == 1 ? 4 : (steps_per_pass == 4 ? 2 : 1);
+}
+
 int fdtd_set_temporal_blocking(fdtd_handle c, int32_t steps_per_pass) {
     if (!c) return FDTD_ERR_ARG;
     if (steps_per_pass < 1 || steps_per_pass > 8) return fail(c, FDTD_ERR_ARG, "steps_per_pass must be 1..8");
-    const int need = steps_per_pass == 1 ? 2 : (steps_per_pass == 2 ? 3 : 4);
-    if (c->ngen < need) return fail(c, FDTD_ERR_STATE, "temporal blocking needs fdtd_bind_scratch (once for 2 steps per pass, twice for 3..8)");
+    // Scratch generations (fdtd_bind_scratch) are needed only by the masked pass chain (frame mode 0, one-row halos, a
+    // TF/SF "right" line at column 0).  Frame mode 3 reads generation A and writes generation B and nothing else; a run
+    // that finds neither stepK_edge usable nor the scratch bound steps call by call (fdtd_run).
     c->temporal = steps_per_pass;
-    // measured on the 8192 x 65536 slab (profiles/sweep_r1*.jsonl): the K-step kernel wants taller tiles as K grows
-    // (its prologue is 2K-1 rows) and one warp per CTA
-    static const int rows_for_k[9] = {6, 6, 8, 12, 16, 32, 48, 48, 56};
-    if (c->auto_tile_rows) c->cfg.tile_rows = rows_for_k[steps_per_pass];
-    if (c->auto_warps) c->cfg.block_warps = steps_per_pass == 1 ? 4 : (steps_per_pass == 4 ? 2 : 1);
+    auto_geometry(c);
     for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
@@ -1480,6 +1512,8 @@ int fdtd_set_frame_mode(fdtd_handle c, int32_t mode) {
     if (!c) return FDTD_ERR_ARG;
     if (mode < 0 || mode > 3) return fail(c, FDTD_ERR_ARG, "frame mode must be 0, 1, 2 or 3");
     c->frame_mode = mode;
+    auto_geometry(c);
+    for (FrameMaps& m : c->fm) m.key.clear();
     return 0;
 }
 
@@ -1513,7 +1547,7 @@ int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_c
 
 int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, double epsilon0, double mu0) {
     NEED_BOUND();
-    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)c->lrows);
+    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
     if (c->cfg.dtype == FDTD_F64)
         fdtd::synth_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0);
@@ -1540,7 +1574,7 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
     fdtd::ShapeDev* dev = nullptr;
     CK(cudaMalloc(&dev, host.size() * sizeof(fdtd::ShapeDev)));
     CK(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(fdtd::ShapeDev), cudaMemcpyHostToDevice, c->stream));
-    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)c->lrows);
+    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
     if (c->cfg.dtype == FDTD_F64)
         fdtd::paint_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
@@ -1556,8 +1590,18 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
     return 0;
 }
 
+// Host-side accessors must not race with work still in flight on the side streams (a halo block of the last exchange
+// landing after an upload, a frame / edge launch still writing): they wait for all of them first.
+static int quiesce(fdtd_ctx* c) {
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->edge_stream));
+    CK(cudaStreamSynchronize(c->comm_stream));
+    return 0;
+}
+
 int fdtd_zero_fields(fdtd_handle c) {
     NEED_BOUND();
+    if (int rc = quiesce(c)) return rc;
     for (int g = 0; g < c->ngen; ++g)
         for (int f = 0; f < 3; ++f)
             CK(cudaMemsetAsync(c->gen[g][f], 0, (size_t)c->lrows * c->pitch * c->esize, c->stream));
@@ -1568,6 +1612,7 @@ int fdtd_zero_fields(fdtd_handle c) {
 
 int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const double* ey) {
     NEED_BOUND();
+    if (int rc = quiesce(c)) return rc;
     const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off, NC = c->cfg.cols;
     const int a = c->cur;
     int rc;
@@ -1586,6 +1631,7 @@ int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const dou
 
 int fdtd_get_fields(fdtd_handle c, double* hh, double* ex, double* ey) {
     NEED_BOUND();
+    if (int rc = quiesce(c)) return rc;
     const int64_t g0 = c->cfg.row_begin, n = c->owned, NC = c->cfg.cols;
     const int64_t nex = n + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
     const int a = c->cur;
@@ -1704,8 +1750,10 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     const bool resident = resident_eligible(c);
     // steps per group: what the caller asked for, what the bound scratch generations allow, and -- on a slab with deep
     // halos -- what the halos cover (a group of K steps reads K+1 rows of the neighbours)
-    int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? std::min(c->temporal, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1)) : 1;
+    int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? c->temporal : 1;
     if (c->halo_depth > 1 && !(c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)) kmax_pre = std::min(kmax_pre, c->halo_depth - 1);
+    if (kmax_pre >= 2 && !edge_usable(c, kmax_pre))      // only the pass chain needs the scratch generations
+        kmax_pre = std::min(kmax_pre, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1));
     if (kmax_pre >= 2 && !resident) {
         // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
         bool seen[9] = {};
@@ -1779,6 +1827,14 @@ int fdtd_set_tuning(fdtd_handle c, int32_t tile_rows, int32_t vec, int32_t block
     if (vec) c->cfg.vec = vec;
     if (block_warps) { c->cfg.block_warps = block_warps; c->auto_warps = false; }
     for (FrameMaps& m : c->fm) m.key.clear();
+    return 0;
+}
+
+int fdtd_get_tuning(fdtd_handle c, int32_t out[8]) {
+    if (!c || !out) return FDTD_ERR_ARG;
+    const int v[8] = {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->temporal, c->frame_mode, c->kstep_variant,
+                      c->halo_depth, c->ngen};
+    for (int k = 0; k < 8; ++k) out[k] = v[k];
     return 0;
 }
 

@@ -194,15 +194,16 @@ struct Exact {
 template <typename T>
 __global__ void __launch_bounds__(256) step_exact(const __grid_constant__ StepParams<T> P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = P.row_lo + blockIdx.y;
-    if (j > P.NC || i >= P.row_hi) return;
+    if (j > P.NC) return;
     const Exact<T> X(P);
-    const long long o = (long long)(i - P.row_off) * P.pitch + j;
-    T hv = T(0), exv = T(0), eyv = T(0);
-    if (i < P.NR && j < P.NC) { hv = X.h_final(i, j); P.hn[o] = hv; }
-    if (j < P.NC) { exv = X.ex_final(i, j); P.exn[o] = exv; }
-    if (i < P.NR) { eyv = X.ey_final(i, j); P.eyn[o] = eyv; }
-    if (P.n_probe) X.probe(i, j, hv, exv, eyv);
+    for (int i = P.row_lo + blockIdx.y; i < P.row_hi; i += gridDim.y) {      // grid.y is capped at 65535 rows
+        const long long o = (long long)(i - P.row_off) * P.pitch + j;
+        T hv = T(0), exv = T(0), eyv = T(0);
+        if (i < P.NR && j < P.NC) { hv = X.h_final(i, j); P.hn[o] = hv; }
+        if (j < P.NC) { exv = X.ex_final(i, j); P.exn[o] = exv; }
+        if (i < P.NR) { eyv = X.ey_final(i, j); P.eyn[o] = eyv; }
+        if (P.n_probe) X.probe(i, j, hv, exv, eyv);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -903,8 +904,8 @@ __global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(co
 template <typename T>
 __global__ void plane_from_f64(T* dst, long long pitch, const double* src, long long src_ld, int rows, int cols) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j < cols && i < rows) dst[(long long)i * pitch + j] = (T)src[(long long)i * src_ld + j];
+    if (j >= cols) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) dst[(long long)i * pitch + j] = (T)src[(long long)i * src_ld + j];
 }
 
 // pitched T plane -> dense double plane, with the snapshot aliasing patches applied
@@ -915,12 +916,13 @@ template <typename T>
 __global__ void plane_to_f64(double* dst, long long dst_ld, const T* src, long long pitch, int rows, int cols,
                              int row_global0, const __grid_constant__ PatchList patches) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (j >= cols || i >= rows) return;
-    double v = (double)src[(long long)i * pitch + j];
-    for (int k = 0; k < patches.n; ++k)
-        if (patches.p[k].row == row_global0 + i && patches.p[k].col == j) v = patches.p[k].value;
-    dst[(long long)i * dst_ld + j] = v;
+    if (j >= cols) return;
+    for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < rows; i += gridDim.y * blockDim.y) {
+        double v = (double)src[(long long)i * pitch + j];
+        for (int k = 0; k < patches.n; ++k)
+            if (patches.p[k].row == row_global0 + i && patches.p[k].col == j) v = patches.p[k].value;
+        dst[(long long)i * dst_ld + j] = v;
+    }
 }
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
@@ -936,16 +938,18 @@ template <typename T>
 __global__ void synth_coeffs(T* epc, T* muc, long long pitch, int lrows, int cols, int row_off, int NR, long long NC,
                              unsigned long long seed, double dtds, double eps0, double mu0) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
-    const int i = row_off + l;
-    if (j >= cols || l >= lrows || i >= NR) return;
-    const unsigned long long bits = splitmix64(seed + (unsigned long long)i * (unsigned long long)NC + (unsigned long long)j);
-    const double u = __dmul_rn((double)(bits >> 11), 1.1102230246251565e-16);      // 2^-53
-    const double eps_r = __dadd_rn(1.0, __dmul_rn(3.0, u));
-    const double eps = __dmul_rn(eps_r, eps0);
-    const double mu = __dmul_rn(1.0, mu0);
-    epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
-    muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
+    if (j >= cols) return;
+    for (int l = blockIdx.y; l < lrows; l += gridDim.y) {
+        const int i = row_off + l;
+        if (i < 0 || i >= NR) continue;
+        const unsigned long long bits = splitmix64(seed + (unsigned long long)i * (unsigned long long)NC + (unsigned long long)j);
+        const double u = __dmul_rn((double)(bits >> 11), 1.1102230246251565e-16);      // 2^-53
+        const double eps_r = __dadd_rn(1.0, __dmul_rn(3.0, u));
+        const double eps = __dmul_rn(eps_r, eps0);
+        const double mu = __dmul_rn(1.0, mu0);
+        epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
+        muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
+    }
 }
 
 struct ShapeDev { int kind, pad; long long a[6]; double eps, mu; };
@@ -972,22 +976,24 @@ template <typename T>
 __global__ void paint_coeffs(T* epc, T* muc, long long pitch, int lrows, int cols, int row_off, int NR,
                              const ShapeDev* __restrict__ shapes, int n_shapes, double eps_bg, double mu_bg, double dtds) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
-    const long long i = (long long)row_off + l;
-    if (j >= cols || l >= lrows || i >= NR) return;
-    double eps = eps_bg, mu = mu_bg;
-    for (int k = 0; k < n_shapes; ++k) {
-        const ShapeDev& s = shapes[k];
-        bool hit;
-        if (s.kind == 0) hit = i >= s.a[0] && i < s.a[1] && j >= s.a[2] && j < s.a[3];
-        else if (s.kind == 1) {
-            const long long x = i - s.a[0], y = (long long)j - s.a[1], d2 = x * x + y * y, in = s.a[2] - s.a[3];
-            hit = s.a[2] * s.a[2] > d2 && d2 > in * in && x < 0 && y > 0;
-        } else hit = convex_hit(s, i, j);
-        if (hit) { eps = s.eps; mu = s.mu; }
+    if (j >= cols) return;
+    for (int l = blockIdx.y; l < lrows; l += gridDim.y) {
+        const long long i = (long long)row_off + l;
+        if (i < 0 || i >= NR) continue;
+        double eps = eps_bg, mu = mu_bg;
+        for (int k = 0; k < n_shapes; ++k) {
+            const ShapeDev& s = shapes[k];
+            bool hit;
+            if (s.kind == 0) hit = i >= s.a[0] && i < s.a[1] && j >= s.a[2] && j < s.a[3];
+            else if (s.kind == 1) {
+                const long long x = i - s.a[0], y = (long long)j - s.a[1], d2 = x * x + y * y, in = s.a[2] - s.a[3];
+                hit = s.a[2] * s.a[2] > d2 && d2 > in * in && x < 0 && y > 0;
+            } else hit = convex_hit(s, i, j);
+            if (hit) { eps = s.eps; mu = s.mu; }
+        }
+        epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
+        muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
     }
-    epc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, eps));
-    muc[(long long)l * pitch + j] = (T)__dmul_rn(dtds, __ddiv_rn(1.0, mu));
 }
 
 }  // namespace fdtd

@@ -127,10 +127,15 @@ class Engine:
         cfg.one_minus_courant = float(1 - courant) if one_minus_courant is None else float(one_minus_courant)
         self.cfg = cfg
         self.pitch = int(self.lib.fdtd_default_pitch(self.cols, cfg.dtype))
-        # y-slabs: rows of h/ex/ey stored from each neighbouring slab.  1 = one row, exchanged every step (validated
-        # default); D >= 2 = deep halos, ONE exchange per temporal-blocking group of up to D-1 steps (experimental until
-        # its first multi-GPU run; the frame of a group then always goes through frame_window)
-        self.halo_depth = (int(os.environ.get("FDTD_HALO_DEPTH", "1") or 1) if halo_depth is None else int(halo_depth))
+        # y-slabs: rows of h/ex/ey stored from each neighbouring slab.  1 = one row, exchanged every step; D >= 2 = deep
+        # halos, ONE exchange per temporal-blocking group of up to D-1 steps.  Default: K+1 under temporal blocking (what
+        # stepK_edge needs at a slab interface; bit-exact on 2 GPUs since profiles/r2_slab_check_n2.log), else 1.
+        slab = self.row_begin > 0 or self.row_end < self.rows
+        if halo_depth is None:
+            env = os.environ.get("FDTD_HALO_DEPTH", "")
+            halo_depth = int(env) if env else (min(int(temporal) + 1, 9) if (slab and temporal > 1 and kernel == "stream"
+                                                                             and self.owned >= int(temporal) + 1) else 1)
+        self.halo_depth = int(halo_depth)
         self.lrows = int(self.lib.fdtd_local_rows_halo(C.byref(cfg), self.halo_depth))
         self.handle = C.c_void_p()
         L.check(self.lib, None, self.lib.fdtd_create(C.byref(cfg), C.byref(self.handle)))
@@ -149,19 +154,21 @@ class Engine:
         L.check(self.lib, self.handle, self.lib.fdtd_bind_buffers(self.handle, *[C.c_void_p(b.data_ptr()) for b in self.buffers]))
         self.first_bad = None
         self._keep = None
+        # frame of a temporal-blocking group: 3 = stepK_edge (library default), 0 = masked single-step passes through
+        # scratch generations, 1 / 2 = one frame_window launch next to / behind the K-step kernel
+        if frame_mode is None and os.environ.get("FDTD_FRAME_MODE", "") != "":
+            frame_mode = int(os.environ["FDTD_FRAME_MODE"])
+        if frame_mode is not None:
+            L.check(self.lib, self.handle, self.lib.fdtd_set_frame_mode(self.handle, int(frame_mode)))
+        # K-step kernel of temporal blocking: 1 = stepK_lean (library default), 0 = stepK_stream
+        if kstep_variant is None and os.environ.get("FDTD_KSTEP_VARIANT", "") != "":
+            kstep_variant = int(os.environ["FDTD_KSTEP_VARIANT"])
+        if kstep_variant is not None:
+            L.check(self.lib, self.handle, self.lib.fdtd_set_kstep_variant(self.handle, int(kstep_variant)))
+        self.frame_mode, self.kstep_variant = self.tuning()["frame_mode"], self.tuning()["kstep_variant"]
         self.temporal = 1
         if temporal > 1:
             self.enable_temporal_blocking(temporal)
-        # frame of a temporal-blocking group: 0 = masked single-step passes (validated default), 1 / 2 = one
-        # frame_window launch next to / behind the K-step kernel (experimental until its first GPU run)
-        self.frame_mode = int(os.environ.get("FDTD_FRAME_MODE", "0") or 0) if frame_mode is None else int(frame_mode)
-        if self.frame_mode:
-            L.check(self.lib, self.handle, self.lib.fdtd_set_frame_mode(self.handle, self.frame_mode))
-        # K-step kernel of temporal blocking: 0 = stepK_stream (validated default), 1 = stepK_lean (experimental)
-        self.kstep_variant = (int(os.environ.get("FDTD_KSTEP_VARIANT", "0") or 0) if kstep_variant is None
-                              else int(kstep_variant))
-        if self.kstep_variant:
-            L.check(self.lib, self.handle, self.lib.fdtd_set_kstep_variant(self.handle, self.kstep_variant))
         if resident is None:                # default: only when the caller left the launch strategy to the library
             resident = (_resident_default() and temporal <= 1 and kernel == "stream"
                         and not (tile_rows or vec or block_warps))
@@ -188,18 +195,31 @@ class Engine:
         """Would run() use the resident kernel for the scene as it is now?"""
         return bool(self.lib.fdtd_resident_active(self.handle))
 
-    def enable_temporal_blocking(self, steps_per_pass=2):
-        """K leapfrog steps per HBM pass in run(): needs scratch generations of h/ex/ey (3 more buffers for K=2,
-        6 more for K=3..8)."""
+    def tuning(self):
+        """What the library runs with, its own defaults included (fdtd_get_tuning)."""
+        out = (C.c_int32 * 8)()
+        L.check(self.lib, self.handle, self.lib.fdtd_get_tuning(self.handle, out))
+        return dict(zip(("tile_rows", "vec", "block_warps", "temporal", "frame_mode", "kstep_variant", "halo_depth",
+                         "generations"), (int(v) for v in out)))
+
+    def enable_temporal_blocking(self, steps_per_pass=2, scratch=None):
+        """K leapfrog steps per HBM pass in run().  Scratch generations of h/ex/ey (3 more buffers for K=2, 6 more for
+        K=3..8) are only needed by the masked pass chain (frame mode 0; y-slabs with fewer than K+1 halo rows): frame
+        mode 3 reads one generation and writes the other.  scratch=None allocates them only where that chain can run
+        (a scene stepK_edge cannot take -- a TF/SF "right" line at column 0 -- then steps call by call); True forces."""
         torch = self.torch
-        need = 8 if steps_per_pass <= 1 else (11 if steps_per_pass == 2 else 14)
+        K = int(steps_per_pass)
+        slab = self.row_begin > 0 or self.row_end < self.rows
+        if scratch is None:
+            scratch = self.frame_mode != 3 or (slab and self.halo_depth < K + 1)
+        need = 8 if (K <= 1 or not scratch) else (11 if K == 2 else 14)
         while len(self.buffers) < need:
             extra = [torch.zeros((self.lrows, self.pitch), dtype=self.buffers[0].dtype, device=self.device) for _ in range(3)]
             torch.cuda.synchronize(self.device)
             L.check(self.lib, self.handle, self.lib.fdtd_bind_scratch(self.handle, *[C.c_void_p(b.data_ptr()) for b in extra]))
             self.buffers += extra
-        L.check(self.lib, self.handle, self.lib.fdtd_set_temporal_blocking(self.handle, int(steps_per_pass)))
-        self.temporal = int(steps_per_pass)
+        L.check(self.lib, self.handle, self.lib.fdtd_set_temporal_blocking(self.handle, K))
+        self.temporal = K
 
     # ---- static inputs -------------------------------------------------------------------
     def upload_coefficients(self, eps_coef, mu_coef):

@@ -1,7 +1,7 @@
 """Sharded runs of the drop-in `Solver` (no reference counterpart -- SURVEY.md 8(e)).
 
-Launched as one process per GPU (`torchrun --nproc-per-node N script.py`, the script unchanged), every rank builds the
-same `Solver`; the grid's rows are split into y-slabs (slab.split_rows), each rank's `Engine` owns one slab and the C
+Launched as one process per GPU (`FDTD_SHARDED=1 torchrun --nproc-per-node N script.py`, the script unchanged, or
+`Solver(..., sharded=True)`), every rank builds the same `Solver`; the grid's rows are split into y-slabs (slab.split_rows), each rank's `Engine` owns one slab and the C
 library exchanges the halo rows over NCCL by itself (fdtd_comm_init).  `torch.distributed` is only the control plane:
 it carries the 128-byte NCCL id, the slabs when the script reads `solver.h`, and the probe records of the owning rank.
 
@@ -31,20 +31,27 @@ class Shard:
 def context(enable=None):
     """The `Shard` of this process, or None for an ordinary single-process run.
 
-    enable=None : shard iff a process group with more than one rank is up, or the process was started by torchrun
-                  (WORLD_SIZE > 1), in which case the group is initialised here (NCCL with a GPU, gloo without).
-    enable=False: never.   enable=True: as None, but a single-process launch is an error."""
+    enable=None : opt-in by environment -- with FDTD_SHARDED=1 shard iff a process group with more than one rank is up or
+                  the process was started by torchrun (WORLD_SIZE > 1), so `FDTD_SHARDED=1 torchrun ... script.py` shards
+                  an unchanged script; without it never (a torchrun launch of INDEPENDENT simulations per rank stays
+                  independent).
+    enable=False: never.
+    enable=True : shard; a single-process launch is an error.
+    Under torchrun the process group is initialised here if it is not up yet (NCCL with a GPU, gloo without)."""
     if enable is False:
+        return None
+    strict = enable is True
+    if enable is None and os.environ.get("FDTD_SHARDED", "") in ("", "0", "false", "no"):
         return None
     import torch
     import torch.distributed as dist
     if not dist.is_available():
-        if enable:
+        if strict:
             raise RuntimeError("sharded=True needs torch.distributed")
         return None
     if not dist.is_initialized():
         if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
-            if enable:
+            if strict:
                 raise RuntimeError("sharded=True needs a torchrun launch (WORLD_SIZE > 1) or an initialised process group")
             return None
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -56,7 +63,7 @@ def context(enable=None):
             dist.init_process_group("gloo")
     world = dist.get_world_size()
     if world <= 1:
-        if enable:
+        if strict:
             raise RuntimeError("sharded=True needs more than one rank")
         return None
     local = int(os.environ.get("LOCAL_RANK", str(dist.get_rank())))

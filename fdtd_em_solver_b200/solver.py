@@ -11,14 +11,17 @@ Solver.solve (:288-292, :319-337) -- see engine.py / csrc/.
 Extra, optional constructor keywords (defaults keep reference scripts
 unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact",
 material_on_device=False (paint eps/mu on the GPU from the recorded shapes),
-temporal_block=1 (leapfrog steps per HBM pass in solve(); 2..8 = temporal
-blocking, worthwhile for grids far larger than L2, bit-identical results),
+temporal_block=None (leapfrog steps per HBM pass in solve(); 2..8 = temporal
+blocking, bit-identical results; None = 8 on grids beyond 512 x 512 cells,
+which are HBM-bound, 1 on the script-sized ones),
 resident=None (True/False: all calls between two snapshots in ONE cooperative
 launch for grids that live in L2, i.e. every script of the reference; None =
 engine.RESIDENT_DEFAULT / $FDTD_RESIDENT; bit-identical results),
-sharded=None (None: under `torchrun --nproc-per-node N` every rank builds the same
-Solver and owns one y-slab of rows on its own GPU, halo rows travel over NCCL
-inside the library -- see shard.py; False: never; results bit-identical to one GPU).
+sharded=None (True, or None with FDTD_SHARDED=1 in the environment: under
+`torchrun --nproc-per-node N` every rank builds the same Solver and owns one
+y-slab of rows on its own GPU, halo rows travel over NCCL inside the library --
+see shard.py; False / None without the flag: never, every process is its own
+simulation; results bit-identical to one GPU).
 """
 import json
 import math
@@ -55,7 +58,7 @@ class Solver:
     """reference solver.py:14-349."""
 
     def __init__(self, points_per_wavelength, stability, eps_r_max, mu_r_max, simulation_size, simulation_time=1,
-                 dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=1,
+                 dtype="float64", device=0, kernel="stream", material_on_device=False, temporal_block=None,
                  resident=None, sharded=None):
         self.points_per_wavelength = points_per_wavelength
         self.stability = stability
@@ -101,9 +104,11 @@ class Solver:
         # device side
         self._dtype, self._device, self._kernel = dtype, device, kernel
         self._material_on_device = material_on_device
-        self._temporal_block = int(temporal_block)      # leapfrog steps per HBM pass in the run loops (1..8)
+        # leapfrog steps per HBM pass in the run loops (1..8); None = 8 on grids beyond resident mode's reach (> 512 x 512
+        # cells: HBM-bound, where temporal blocking pays), 1 on the script-sized ones.  Same bits either way.
+        self._temporal_block = None if temporal_block is None else int(temporal_block)
         self._resident = resident                       # None = the engine's default
-        self._sharded = sharded                         # None = shard under torchrun (shard.context)
+        self._sharded = sharded                         # None = shard only if FDTD_SHARDED=1 (shard.context)
         self._shard_ctx = None                          # shard.Shard of the current engine, or None
         self._slabs = None                              # [(row_begin, row_end)] per rank of a sharded engine
         self._engine = None
@@ -250,8 +255,11 @@ class Solver:
         """(Re)build the device state from the host-side description when it changed."""
         courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
         sh = _shard.context(self._sharded)
+        temporal = self._temporal_block
+        if temporal is None:
+            temporal = 8 if (self.size + 1) ** 2 > 512 * 512 and self._kernel == "stream" else 1
         key = (self.size, self._dtype, self._device, self._kernel, tuple(bool(b) for b in self.boundaries), courant,
-               self._temporal_block, self._resident, None if sh is None else (sh.rank, sh.world))
+               temporal, self._resident, None if sh is None else (sh.rank, sh.world))
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 if self._pending is None:
@@ -261,13 +269,13 @@ class Solver:
                 self._slabs = None
                 self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
                                       device=self._device, reflect=self.boundaries, kernel=self._kernel,
-                                      temporal=self._temporal_block, resident=self._resident)
+                                      temporal=temporal, resident=self._resident)
             else:                   # one y-slab per rank, each on its own GPU; the library exchanges the halo rows itself
                 self._slabs = split_rows(self.size, sh.world)
                 b, e = self._slabs[sh.rank]
                 self._engine = Engine(self.size, courant=courant, one_minus_courant=(1 - courant), dtype=self._dtype,
                                       device=sh.local_rank, reflect=self.boundaries, kernel=self._kernel,
-                                      temporal=self._temporal_block, resident=False, row_begin=b, row_end=e)
+                                      temporal=temporal, resident=False, row_begin=b, row_end=e)
                 self._engine.comm_init(sh.rank, sh.world,
                                        sh.broadcast(self._engine.comm_unique_id() if sh.rank == 0 else None))
             self._shard_ctx = sh
@@ -372,14 +380,26 @@ class Solver:
         if n_calls is not None:
             n = max(0, min(n, int(n_calls)))
         self._host = None
-        try:
-            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
-                                     alloc=self._snapshot_alloc if snapshot_every else None)
-        finally:
+        def account(collect):
             done = self._engine.stats()["steps"]
             self.step = first + (done - self._steps_seen)
             self._steps_seen = done
-            self._collect_probes()
+            if collect:
+                self._collect_probes()
+
+        try:
+            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
+                                     alloc=self._snapshot_alloc if snapshot_every else None)
+        except IndexError:
+            # a pulse outliving its table (App. A-Q10): found on the host from the same tables on every rank, so the
+            # collective probe gather of a sharded run is still matched; the records up to the failing call are kept
+            account(True)
+            raise
+        except BaseException:
+            # anything else may have hit ONE rank only: no collective on the way out (the other ranks would never match it)
+            account(self._shard_ctx is None)
+            raise
+        account(True)
         return self._whole_stack(stack)
 
     def _whole_stack(self, stack):

@@ -109,12 +109,15 @@ const char* fdtd_last_error(fdtd_handle h);          /* h may be NULL: last erro
 int fdtd_bind_buffers(fdtd_handle h, void* h0, void* h1, void* ex0, void* ex1, void* ey0, void* ey1,
                       void* eps_coef, void* mu_coef);
 
-/* Temporal blocking (BASELINE.json north_star (1)): with scratch generations of h/ex/ey bound (fdtd_bind_scratch: once
- * for 2 steps per pass, twice for 3..8), fdtd_run advances K leapfrog steps per HBM pass wherever the K-step dependency
- * cone touches no wall, source, reflector, probe or slab interface (kernel stepK_stream), and advances the remaining
- * frame of tiles with K masked single-step launches through the scratch generations.  Results are bit-identical to
- * single stepping.  With fdtd_comm_init active the slab interface strips belong to the frame and exchange halo rows
- * every step.  Groups never straddle a snapshot. */
+/* Temporal blocking (BASELINE.json north_star (1)): fdtd_run advances K leapfrog steps per HBM pass.  Tiles whose K-step
+ * dependency cone touches no wall, source, reflector, probe or slab edge go through the plain K-step kernel (stepK_lean);
+ * all other tiles go through stepK_edge, the same register pipeline with those features folded in as tile predicates
+ * (frame mode 3, the default) -- two launches per group that read generation A and write generation B, no scratch.
+ * Scratch generations of h/ex/ey (fdtd_bind_scratch: once for 2 steps per pass, twice for 3..8) are needed only by the
+ * fallback, frame mode 0: K masked single-step launches through the scratch generations for the non-plain tiles, used
+ * when stepK_edge cannot take the scene (a TF/SF "right" line at column 0, more than 16 pulses) or a y-slab stores
+ * fewer than K+1 halo rows (fdtd_set_halo_depth); without scratch such runs step call by call.  Results are
+ * bit-identical to single stepping in every mode.  Groups never straddle a snapshot. */
 int fdtd_bind_scratch(fdtd_handle h, void* h2, void* ex2, void* ey2);
 int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
 
@@ -133,20 +136,22 @@ int fdtd_resident_active(fdtd_handle h);
  * window load and one store per M calls for a larger window.  Bit-identical.  (Experimental until its first GPU run.) */
 int fdtd_set_resident_depth(fdtd_handle h, int32_t calls_per_barrier);
 
-/* Which K-step kernel fdtd_run launches for the plain tiles of a temporal-blocking group: 0 = stepK_stream (default),
- * 1 = stepK_lean: the same pipeline with the row loop unrolled by two and running pointers instead of per-row address
- * arithmetic (about a third fewer issue slots per row).  Same operations in the same order: bit-identical.
- * (Experimental until its first GPU run.) */
+/* Which K-step kernel fdtd_run launches for the plain tiles of a temporal-blocking group: 1 = stepK_lean (default): the
+ * stage pipeline with the row loop unrolled by two and running pointers instead of per-row address arithmetic (about a
+ * third fewer issue slots per row); 0 = stepK_stream, the first version of the same pipeline.  Same operations in the
+ * same order: bit-identical. */
 int fdtd_set_kstep_variant(fdtd_handle h, int32_t variant);
 
-/* How the FRAME of a temporal-blocking group (the tiles stepK_stream leaves out) advances:
- *   0  K masked single-step launches through the scratch generations (default);
+/* How the tiles the plain K-step kernel leaves out (the FRAME: wall bands and columns, pulse lines, sources, reflectors,
+ * probes) advance in a temporal-blocking group:
+ *   3  ONE launch of stepK_edge (csrc/edge.cuh) next to the plain kernel (default);
+ *   0  K masked single-step launches through the scratch generations (needs fdtd_bind_scratch);
  *   1  ONE launch of frame_window (csrc/window.cuh: each frame tile + K+1 cells of apron advanced K calls in shared
  *      memory from one load of generation A) on a side stream next to the K-step kernel;
  *   2  the same launch queued behind the K-step kernel.
- * On a y-slab the frame tiles within K+1 rows of a slab interface still need one halo exchange per step and stay on
- * the masked passes; all other frame tiles go through frame_window.  Modes 1/2 do not apply (the group silently uses
- * mode 0) when a TF/SF "right" line sits at column 0 or more than 16 pulses exist.  Results are bit-identical in
+ * Modes 1-3 do not apply (the group silently uses mode 0, or single steps without scratch) when a TF/SF "right" line
+ * sits at column 0 or more than 16 pulses exist; on a y-slab mode 3 needs K+1 halo rows (fdtd_set_halo_depth), and in
+ * modes 1/2 the frame tiles within K+1 rows of a slab interface stay on the masked passes.  Results are bit-identical in
  * every mode. */
 int fdtd_set_frame_mode(fdtd_handle h, int32_t mode);
 
@@ -225,6 +230,9 @@ int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapsho
 
 /* Launch geometry of the streaming kernel (0 keeps the current value); results never depend on it. */
 int fdtd_set_tuning(fdtd_handle h, int32_t tile_rows, int32_t vec, int32_t block_warps);
+/* What the library runs with (the defaults it picked included): out = {tile_rows, vec, block_warps, steps_per_pass,
+ * frame_mode, kstep_variant, halo_depth, field generations bound}. */
+int fdtd_get_tuning(fdtd_handle h, int32_t out[8]);
 
 /* Measurement hook: with enable != 0 every launch of the plain K-step kernel (the dominant kernel of fdtd_run with
  * temporal blocking) is bracketed by CUDA events on the stream it is launched on (at most 4096 launches are kept; the

@@ -21,6 +21,9 @@ from . import ref_import, scenarios as SC
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 TRUNCATE = {"doubleslit": 3000, "solver_test": 600}       # calls; full runs otherwise
+# ... and the full-length doubleslit run (31 938 calls, 6 387 snapshots = 5.2 GB stack) as a second fixture that keeps only
+# hashes, the final h and one series:  python -m oracle.make_golden full
+FULL = ("doubleslit",)
 DIR_CODE = {None: 0, "right": 1, "left": 2, "up": 3, "down": 4}
 
 
@@ -28,11 +31,11 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def scenario_fixture(ref, name):
+def scenario_fixture(ref, name, truncate=True):
     sc = SC.spec(name)
     with contextlib.redirect_stdout(io.StringIO()):
         s = SC.drive(ref, sc)
-        n_calls = TRUNCATE.get(name)
+        n_calls = TRUNCATE.get(name) if truncate else None
         if n_calls is not None:
             full = np.arange(0, s.end_time, s.dt)
             s.end_time = float(full[n_calls - 1]) + 0.5 * s.dt
@@ -104,8 +107,17 @@ def random_fixture(ref, rows, cols, seed, walls):
 
 
 def main():
+    import sys
     ref = ref_import.load()[0]
     os.makedirs(OUT, exist_ok=True)
+    if "full" in sys.argv[1:]:
+        for name in FULL:
+            d = scenario_fixture(ref, name, truncate=False)
+            for big in ("snap_first", "snap_mid", "eps", "mu"):              # the truncated fixture carries these already
+                d.pop(big, None)
+            np.savez_compressed(os.path.join(OUT, "scenario_%s_full.npz" % name), **d)
+            print("wrote", name, "full length:", len(d["times"]), "calls,", int(d["n_snapshots"]), "snapshots")
+        return
     for name in ("tutorial", "doubleslit", "lens", "waveguide", "waveguide_mixed_walls", "mixed", "solver_test"):
         np.savez_compressed(os.path.join(OUT, "scenario_%s.npz" % name), **scenario_fixture(ref, name))
         print("wrote", name)

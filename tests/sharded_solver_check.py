@@ -26,17 +26,17 @@ for name, n_calls, kw in [("waveguide", 900, {}), ("tutorial", 1200, {}), ("doub
                           ("lens", 700, {"temporal_block": 4}), ("mixed", 600, {"dtype": "float32"})]:
     sc = SC.spec(name)
     runs = []
-    for sharded in (None, False):
+    for sharded in (True, False):
         with contextlib.redirect_stdout(io.StringIO()):
             s = SC.drive(S, sc, sharded=sharded, device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
             s.end_time = (n_calls - 0.5) * s.dt
             k = s.record_field((0.5 * s.length_x, 0.25 * s.length_y))
-            path = os.path.join(tmp, "%s_%s_r%d" % (name, "sharded" if sharded is None else "single", 0 if sharded is None else rank))
+            path = os.path.join(tmp, "%s_%s_r%d" % (name, "sharded" if sharded else "single", 0 if sharded else rank))
             s.save(path)
             t0 = time.perf_counter()
             s.solve(realtime=False, step_frequency=sc["step_frequency"])
             dt = time.perf_counter() - t0
-        assert (s._shard_ctx is not None) == (sharded is None)
+        assert (s._shard_ctx is not None) == sharded
         runs.append((np.load(path + ".npy"), s.h, s.ex, s.ey, s.field_collector(k).data,
                      [d["energies"] for d in s.recorded_energies], dt))
     a, b = runs

@@ -30,6 +30,7 @@ def _worker(rank, world, port, name, n_calls, out_dir):
     from fake_engine import FakeSlabEngine
     from fdtd_em_solver_b200 import solver as S, analyser as A
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    os.environ["FDTD_SHARDED"] = "1"              # the opt-in an unchanged script gets its sharding from
     S.Engine = FakeSlabEngine
     sc = SC.spec(name)
     f, setup, times, info = SC.restate(sc)
@@ -89,9 +90,15 @@ def test_sharded_solver_over_gloo_equals_the_monolithic_oracle(world, name, n_ca
 def test_single_process_runs_are_not_sharded(monkeypatch):
     from fdtd_em_solver_b200 import shard
     monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("FDTD_SHARDED", raising=False)
     assert shard.context(None) is None and shard.context(False) is None
     with pytest.raises(RuntimeError):
         shard.context(True)
+    monkeypatch.setenv("FDTD_SHARDED", "1")       # the opt-in by environment never fails a single-process run
+    assert shard.context(None) is None
+    monkeypatch.setenv("WORLD_SIZE", "2")         # ... and without it a torchrun launch stays unsharded (independent runs)
+    monkeypatch.delenv("FDTD_SHARDED")
+    assert shard.context(None) is None
     assert shard.owner_of_row([(0, 4), (4, 7), (7, 10)], 6) == 1
 
 
