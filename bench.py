@@ -236,8 +236,7 @@ def workload_config(args, n_gpus, engine=None):
     n_arrays = len(engine.buffers) if engine is not None else 8
     kvec = 2 if args.dtype == "f64" else 4
     if args.temporal > 1:
-        frame = {0: "masked step_stream frame passes", 1: "one frame_window launch beside it", 2: "one frame_window launch behind it",
-                 3: "stepK_edge for the wall / source / reflector tiles"}[frame_mode]
+        frame = {0: "masked step_stream frame passes", 3: "stepK_edge for the wall / source / reflector tiles"}[frame_mode]
         kernel = "%s<%s,%d,%d> (%d steps per HBM pass, %d columns per lane) + %s; tile_rows=%d warps=%d" % (
             "stepK_lean" if variant == 1 else "stepK_stream", "double" if args.dtype == "f64" else "float", kvec, args.temporal,
             args.temporal, kvec, frame, args.tile_rows, args.warps)
@@ -276,9 +275,9 @@ def main():
     ap.add_argument("--total-rows", type=int, default=0,
                     help="STRONG scaling: fix the grid at this many rows (e.g. 65536, BASELINE config 5) and give each GPU "
                          "total/N of them; default 0 = weak scaling, %d rows per GPU" % ROWS_PER_GPU)
-    ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 1, 2, 3],
-                    help="frame of a temporal-blocking group: 0 masked single-step passes, 1/2 one frame_window launch "
-                         "next to / behind the K-step kernel (default: the library's)")
+    ap.add_argument("--frame-mode", type=int, default=None, choices=[0, 3],
+                    help="non-plain tiles of a temporal-blocking group: 3 one stepK_edge launch, 0 masked single-step "
+                         "passes through scratch generations (default: the library's, 3)")
     ap.add_argument("--kstep-variant", type=int, default=None, choices=[0, 1],
                     help="K-step kernel: 0 stepK_stream, 1 stepK_lean (default: the library's)")
     ap.add_argument("--halo-depth", type=int, default=None,

@@ -68,15 +68,12 @@ SIGNATURES = {
     "fdtd_last_error": (C.c_char_p, [_P]),
     "fdtd_bind_buffers": (C.c_int, [_P] * 9),
     "fdtd_plan_frame": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P]),
-    "fdtd_plan_frame_split": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P,
-                                        C.POINTER(C.c_int32), _P]),
     "fdtd_bind_scratch": (C.c_int, [_P, _P, _P, _P]),
     "fdtd_set_temporal_blocking": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_resident": (C.c_int, [_P, C.c_int32, C.c_int64]),
     "fdtd_resident_active": (C.c_int, [_P]),
     "fdtd_set_frame_mode": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_kstep_variant": (C.c_int, [_P, C.c_int32]),
-    "fdtd_set_resident_depth": (C.c_int, [_P, C.c_int32]),
     "fdtd_set_host_row_origin": (C.c_int, [_P, C.c_int64]),
     "fdtd_upload_coeffs": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fdtd_paint_coeffs": (C.c_int, [_P, C.c_int32, C.POINTER(Shape), C.c_double, C.c_double, C.c_double]),
@@ -104,8 +101,6 @@ SIGNATURES = {
     "fdtd_halo_rows": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fdtd_local_rows_halo": (C.c_int64, [C.POINTER(Config), C.c_int32]),
     "fdtd_set_halo_depth": (C.c_int, [_P, C.c_int32]),
-    "fdtd_plan_frame_halo": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P, _P,
-                                       C.POINTER(C.c_int32), _P]),
     "fdtd_plan_edge": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P,
                                  C.POINTER(C.c_int32), _P, C.c_int32]),
     "fdtd_halo_blocks": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),

@@ -6,7 +6,6 @@
 #include "fdtd2d.h"
 #include "kernels.cuh"
 #include "resident.cuh"
-#include "window.cuh"
 #include "edge.cuh"
 
 #include <dlfcn.h>
@@ -62,20 +61,17 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     unsigned char* d_skip = nullptr; unsigned char* d_mask[8] = {};
     std::vector<int2> h_list[8];                 // compact (block column, row tile) launch lists of the frame passes
     int2* d_list[8] = {};
-    std::vector<int2> h_tiles;                   // frame tiles (column tile, row tile) for frame_window (window.cuh)
-    int2* d_tiles = nullptr;
     std::vector<fdtd::EdgeTile> h_edge;          // frame mode 3: the tiles of stepK_edge (edge.cuh), those next to a slab
     fdtd::EdgeTile* d_edge = nullptr;            // interface first (n_edge_near of them)
     size_t d_edge_cap = 0;
     int n_edge_near = 0;
-    size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0, d_tiles_cap = 0;
+    size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
     std::vector<int64_t> row_cells;      // cells the plain K-step kernel advances per tile row (measurement hook)
     int frame_tile_rows = 0, frame_vec = 0, frame_nty = 0;   // the frame passes use smaller tiles than the K-step kernel
     int64_t k_row_lo = 0, k_row_hi = 0;                      // rows the K-step tiles own
     void release() {
         if (d_skip) cudaFree(d_skip);
-        if (d_tiles) cudaFree(d_tiles);
         if (d_edge) cudaFree(d_edge);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
     }
@@ -128,12 +124,10 @@ struct fdtd_ctx {
     void* rs_count = nullptr; void* rs_last = nullptr; void* rs_src = nullptr;   // per-call pulse records on the device
     bool rs_valid = false;
     int rs_stride = 0, res_blocks_max = 0;
-    int resident_depth = 1;          // calls per grid barrier: 1 = step_resident, 2..8 = resident_window (window.cuh)
-    int resw_blocks_max = 0, resw_depth = 0;
 
-    // how the frame of a temporal-blocking group advances: 0 = K masked single-step passes (step_stream), 1 = ONE
-    // frame_window launch next to the K-step kernel, 2 = one frame_window launch behind it
-    int frame_mode = 3;              // (3 = stepK_edge takes every non-plain tile: default since its B200 runs, profiles/r2_sweep_*)
+    // how the non-plain tiles of a temporal-blocking group advance: 3 = ONE stepK_edge launch next to the plain kernel
+    // (default since its B200 runs, profiles/r2_sweep_*), 0 = K masked single-step passes through scratch generations
+    int frame_mode = 3;
     int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
 
@@ -437,17 +431,6 @@ int step_impl(fdtd_ctx* c, int64_t step) {
 // ---- temporal blocking (K steps per HBM pass) ----------------------------------------------------------
 template <typename T> constexpr int kvec() { return sizeof(T) == 8 ? 2 : 4; }     // columns per lane of stepK_stream
 
-// Can frame_window (window.cuh) take the frame tiles of a K-step group of this context?  (Which of them it takes is
-// decided per tile by plan_frame: all of them on a whole grid, all but the interface strips on a y-slab.)
-bool frame_window_usable(const fdtd_ctx* c, int K) {
-    // (deep halos have no pass chain to fall back on: there frame_window is THE frame kernel, whatever the mode says)
-    if ((c->frame_mode == 0 && c->halo_depth <= 1) || K > fdtd::WIN_MAX_CALLS || c->n_src > FDTD_MAX_SRC) return false;
-    for (int p = 0; p < c->n_src; ++p)
-        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0) return false;        // h[:, col-1] wraps to the far column
-    return true;
-}
-template <typename T> int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_t st);
-
 // Frame mode 3: can stepK_edge (edge.cuh) take every non-plain tile of a K-step group of this context?  It handles all
 // walls, pulse kinds, reflectors and probes; what it needs is the whole grid on this GPU or, on a y-slab, halos deep
 // enough for the group (K+1 rows), and no TF/SF "right" line at column 0 (python's h[:, col-1] wraps to the far column).
@@ -463,7 +446,7 @@ bool edge_usable(const fdtd_ctx* c, int K) {
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
 struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
-struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2; bool fused = false;
+struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2;
                    int64_t halo_top = 0, halo_bot = 0; bool edge = false; int edge_rows = 32; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
 
 void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps& m) {
@@ -516,24 +499,6 @@ void plan_frame(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps
                 if (covered) m.h_mask[0][(size_t)fy * ntx1 + t1] = 0;
             }
     }
-    // frame_window (window.cuh) takes every frame tile whose window -- the tile + K+1 rows of apron -- lies inside the
-    // rows this slab OWNS (or beyond a real wall of the grid); the masks then keep only the rest, i.e. the interface
-    // strips of a y-slab, which still need one halo exchange per step and so stay on the masked single-step passes.
-    m.h_tiles.clear();
-    if (g.fused) {
-        const int64_t A = K + 1;
-        for (int ty = 0; ty < ntyF; ++ty) {
-            const int64_t ta = lo + (int64_t)ty * TRF, tb = std::min<int64_t>(ta + TRF, hi);
-            const bool rows_ok = (g.row_begin == 0 || ta - A >= g.row_begin - g.halo_top) &&
-                                 (g.row_end == NR || tb + A <= g.row_end + g.halo_bot);
-            if (!rows_ok) continue;
-            for (int tx = 0; tx < ntx1; ++tx)
-                if (m.h_mask[0][(size_t)ty * ntx1 + tx]) {
-                    m.h_tiles.push_back(make_int2(tx, ty));
-                    m.h_mask[0][(size_t)ty * ntx1 + tx] = 0;
-                }
-        }
-    }
     for (int d = 1; d < K; ++d)                                   // ring d = ring d-1 dilated by one frame tile
         for (int ty = 0; ty < ntyF; ++ty)
             for (int tx = 0; tx < ntx1; ++tx) {
@@ -577,7 +542,6 @@ void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps&
     m.k_row_lo = loK; m.k_row_hi = hiK;
     m.h_skip.assign((size_t)std::max(nty, 1) * ntx2, 1);
     for (int d = 0; d < 8; ++d) { m.h_mask[d].clear(); m.h_list[d].clear(); }
-    m.h_tiles.clear();
     std::vector<fdtd::EdgeTile> near, far;
     const int64_t D = std::max<int64_t>(g.halo_top, g.halo_bot);
     // Edge tiles are single warps that march (rows + 2K + 1) iterations of a slow pipeline: they are cut into pieces of
@@ -623,8 +587,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         key.push_back(live);
     }
     const bool edge = edge_usable(c, K);
-    const bool fused = !edge && frame_window_usable(c, K);
-    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)fused + 2 * (int)edge, c->halo_depth}) {
+    for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)edge, c->halo_depth}) {
         key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
     }
     if (key == m.key && m.d_skip) return 0;
@@ -644,7 +607,7 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
     const bool deep = c->halo_depth > 1;
     const FrameGeom geom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
-                         c->cfg.block_warps, K, kvec<T>(), fused, deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge,
+                         c->cfg.block_warps, K, kvec<T>(), deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge,
                          c->edge_rows};
     if (edge) plan_edge(geom, mods, m); else plan_frame(geom, mods, m);
     const int ntyF = m.frame_nty, ntx1 = m.ntx1;
@@ -672,12 +635,6 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
         }
         m.d_mask_cap = mask_bytes; m.d_list_cap = longest;
     }
-    if (m.d_tiles_cap < m.h_tiles.size()) {
-        if (m.d_tiles) cudaFree(m.d_tiles);
-        CK(cudaMalloc(&m.d_tiles, m.h_tiles.size() * sizeof(int2))); m.d_tiles_cap = m.h_tiles.size();
-    }
-    if (!m.h_tiles.empty())
-        CK(cudaMemcpyAsync(m.d_tiles, m.h_tiles.data(), m.h_tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(m.d_skip, m.h_skip.data(), m.h_skip.size(), cudaMemcpyHostToDevice, c->stream));
     for (int d = 0; d < K && !edge; ++d) {
         CK(cudaMemcpyAsync(m.d_mask[d], m.h_mask[d].data(), mask_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -786,14 +743,7 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
             if (m.nty > 0) launch_stepK_any<T>(PK, c, K);
             if (m.nty > 0) c->stats.kernel_launches++;
             CK(cudaGetLastError());
-            if (!m.h_tiles.empty()) {
-                // frame tiles away from the slab interfaces: K calls in ONE launch from generation A, independent of the
-                // passes and of the K-step kernel (frame mode 1: on the edge stream behind passes 1..K-1; 2: behind the
-                // K-step kernel)
-                if (int rc = launch_frame_window<T>(c, n, K, A, B, c->frame_mode == 1 ? c->edge_stream : c->stream)) return rc;
-                if (c->frame_mode == 1) CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
-            }
-            if (!on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // passes 1..K-1 (and the window launch) done
+            if (!on_edge) CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // passes 1..K-1 done
         }
         StepParams<T> P;
         if (int rc = fill_params<T>(c, P, n + p - 1, src, dst)) return rc;
@@ -873,51 +823,10 @@ int resident_tables(fdtd_ctx* c) {
     return 0;
 }
 
-// calls n .. n+g-1 in ONE cooperative launch with M = resident_depth calls per grid barrier (resident_window)
-template <typename T>
-int resident_window_run(fdtd_ctx* c, int64_t n, int64_t g) {
-    if (int rc = resident_tables<T>(c)) return rc;
-    const int M = c->resident_depth;
-    const int A = c->cur, B = next_gen(c, A);
-    StepParams<T> P;
-    if (int rc = fill_params<T>(c, P, n, A, B)) return rc;
-    P.n_src = 0; P.last_mag = T(0);
-    P.row_lo = 0; P.row_hi = (int)c->cfg.rows + 1;
-    if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
-    int tile_rows = 8, tile_cols = 64;
-    const int apron = fdtd::window_apron(M);
-    const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
-    if (c->resw_depth != M) {
-        int coop = 0, sms = 0, per_sm = 0;
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
-        if (bytes > 48 * 1024)
-            CK(cudaFuncSetAttribute(fdtd::resident_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdtd::resident_window<T>, fdtd::WIN_THREADS, bytes));
-        if (!coop || per_sm < 1) return fail(c, FDTD_ERR_CUDA, "cooperative launch unavailable for resident_window");
-        c->resw_blocks_max = per_sm * sms; c->resw_depth = M;
-    }
-    const int tiles = (int)(((c->cfg.cols + 1 + tile_cols - 1) / tile_cols) * ((c->cfg.rows + 1 + tile_rows - 1) / tile_rows));
-    const int blocks = std::min(tiles, c->resw_blocks_max);
-    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
-    long long first = n;
-    int ns = (int)g, depth = M;
-    void* args[] = {&P, &tile_rows, &tile_cols, &depth, &R, &first, &ns};
-    CK(cudaLaunchCooperativeKernel((void*)fdtd::resident_window<T>, dim3((unsigned)blocks), dim3(fdtd::WIN_THREADS), args, bytes, c->stream));
-    c->stats.kernel_launches++;
-    const int64_t intervals = (g + M - 1) / M;
-    c->cur = (intervals & 1) ? B : A;
-    if (c->n_probe) c->probe_count += g;
-    c->stats.steps += g;
-    c->stats.cell_updates += g * c->owned * c->cfg.cols;
-    return 0;
-}
-
 // calls n .. n+g-1 in ONE cooperative launch
 template <typename T>
 int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
     using G = fdtd::ResGeom;
-    if (c->resident_depth > 1 && g > 1) return resident_window_run<T>(c, n, g);
     if (int rc = resident_tables<T>(c)) return rc;
     const int A = c->cur, B = next_gen(c, A);
     StepParams<T> P;
@@ -951,108 +860,6 @@ int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
 
 int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
     return c->cfg.dtype == FDTD_F64 ? resident_run<double>(c, n, g) : resident_run<float>(c, n, g);
-}
-
-// ---- temporal blocking with the frame in ONE launch (window.cuh) ------------------------------------------
-template <typename T>
-int launch_frame_window(fdtd_ctx* c, int64_t n, int K, int A, int B, cudaStream_t st) {
-    const FrameMaps& m = c->fm[K];
-    if (m.h_tiles.empty()) return 0;
-    if (int rc = resident_tables<T>(c)) return rc;
-    StepParams<T> PF;
-    if (int rc = fill_params<T>(c, PF, n, A, B)) return rc;
-    PF.n_src = 0; PF.last_mag = T(0);                            // the kernel reads the K calls' records itself
-    PF.row_lo = (int)c->cfg.row_begin;
-    PF.row_hi = (int)(c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0));
-    if (c->n_probe) PF.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
-    const int tile_rows = m.frame_tile_rows, tile_cols = 32 * m.frame_vec, apron = fdtd::window_apron(K);
-    const size_t bytes = (size_t)6 * (tile_rows + 2 * apron) * (tile_cols + 2 * apron) * sizeof(T);
-    if (bytes > 200 * 1024) return fail(c, FDTD_ERR_ARG, "frame_window: window does not fit shared memory");
-    if (bytes > 48 * 1024)
-        CK(cudaFuncSetAttribute(fdtd::frame_window<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
-    fdtd::frame_window<T><<<(unsigned)m.h_tiles.size(), fdtd::WIN_THREADS, bytes, st>>>(
-        PF, m.d_tiles, tile_rows, tile_cols, K, R, (long long)n);
-    c->stats.kernel_launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-// A K-step group on a y-slab with deep halos and a communicator (maps built, probe capacity ensured by group_window).
-// Only what lies next to an interface depends on the neighbours, and only that is what they wait for:
-//   main stream : the INTERIOR K-step tile rows -- they read owned rows only, so they start at once
-//   edge stream : (after the previous exchange has landed) the K-step tile rows within D rows of an interface and
-//                 every window tile, on the high-priority stream
-//   comm stream : (after the edge work) the D-row blocks of B to both neighbours -- while the interior still runs
-// The main stream joins the edge stream at the end, so main-stream order again means "all of B written".
-template <typename T>
-int group_window_slab(fdtd_ctx* c, int64_t n, int K, int A, int B) {
-    const FrameMaps& m = c->fm[K];
-    const int TR = c->cfg.tile_rows, D = c->halo_depth;
-    const int e_top = c->cfg.row_begin > 0 ? std::min(m.nty, (D + TR - 1) / TR) : 0;
-    const int e_bot = c->cfg.row_end < c->cfg.rows ? std::min(m.nty - e_top, (D + TR - 1) / TR + 1) : 0;   // (+1: the last tile row may be short)
-    StepParams<T> PK;
-    if (m.nty > 0) {
-        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
-        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
-    }
-    CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this group
-    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
-    CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0));     // the neighbours' rows of A have landed
-    const int n_int = m.nty - e_top - e_bot;
-    if (n_int > 0) { launch_stepK_any<T>(PK, c, K, e_top, n_int, c->stream); c->stats.kernel_launches++; }
-    if (e_top > 0) { launch_stepK_any<T>(PK, c, K, 0, e_top, c->edge_stream); c->stats.kernel_launches++; }
-    if (e_bot > 0) { launch_stepK_any<T>(PK, c, K, m.nty - e_bot, e_bot, c->edge_stream); c->stats.kernel_launches++; }
-    CK(cudaGetLastError());
-    if (int rc = launch_frame_window<T>(c, n, K, A, B, c->edge_stream)) return rc;
-    CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
-    CK(cudaStreamWaitEvent(c->comm_stream, c->ev_bnd, 0));
-    if (int rc = exchange(c, B, c->comm_stream)) return rc;     // ONE exchange per group
-    CK(cudaEventRecord(c->ev_comm, c->comm_stream));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));
-    CK(cudaEventRecord(c->ev_int, c->stream));
-    c->cur = B;
-    if (c->n_probe) c->probe_count += K;
-    c->stats.steps += K;
-    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
-    return 0;
-}
-
-// Steps n .. n+K-1: A -> B.  stepK_stream advances every tile whose K-step cone is plain; frame_window advances every
-// other tile K calls in shared memory from one load of A (tile + K+1 cells of apron).  Both read only A and write
-// disjoint tiles of B (cells of a frame tile that a K-step tile also covers get the same bits from both), so they need
-// no ordering between them and no scratch generations.
-template <typename T>
-int group_window(fdtd_ctx* c, int64_t n, int K) {
-    if (int rc = build_frame_maps<T>(c, n, K)) return rc;
-    const FrameMaps& m = c->fm[K];
-    const int A = c->cur, B = (A + 1) % c->ngen;
-    if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
-    if (c->comm) return group_window_slab<T>(c, n, K, A, B);
-    const bool side = c->frame_mode == 1 && m.nty > 0 && !m.h_tiles.empty();
-    if (side) {
-        CK(cudaEventRecord(c->ev_int, c->stream));              // everything before this group
-        CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
-    }
-    if (m.nty > 0) {
-        StepParams<T> PK;
-        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
-        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
-        launch_stepK_any<T>(PK, c, K);
-        c->stats.kernel_launches++;
-        CK(cudaGetLastError());
-    }
-    if (int rc = launch_frame_window<T>(c, n, K, A, B, side ? c->edge_stream : c->stream)) return rc;
-    if (side) {
-        CK(cudaEventRecord(c->ev_bnd, c->edge_stream));
-        CK(cudaStreamWaitEvent(c->stream, c->ev_bnd, 0));       // main-stream order = "all of B written"
-    }
-    CK(cudaEventRecord(c->ev_int, c->stream));
-    c->cur = B;
-    if (c->n_probe) c->probe_count += K;
-    c->stats.steps += K;
-    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
-    return 0;
 }
 
 // ---- frame mode 3: plain K-step tiles + stepK_edge tiles, nothing else ------------------------------------------------
@@ -1147,20 +954,14 @@ int step_any(fdtd_ctx* c, int64_t step) {
 int group_any(fdtd_ctx* c, int64_t n, int K) {
     const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
     if (edge_usable(c, K)) return c->cfg.dtype == FDTD_F64 ? group_edge<double>(c, n, K) : group_edge<float>(c, n, K);
-    if (c->halo_depth > 1 && !whole) {
-        // deep halos: the slab stores D rows of each neighbour, so a group of K <= D-1 steps needs nothing from them
-        // while it runs -- K-step kernel + frame_window, then one exchange.  No pass chain exists in this mode; a scene
-        // frame_window cannot take (or a deeper group) is stepped call by call instead.
-        if (K <= c->halo_depth - 1 && frame_window_usable(c, K))
-            return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
+    // The fallback, K masked single-step passes through the scratch generations (frame mode 0; a scene stepK_edge cannot
+    // take), exchanges one row per pass on a y-slab: it exists for the one-row halo layout only and needs the scratch.
+    const int kmax = c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1);
+    if ((c->halo_depth > 1 && !whole) || K > kmax) {
         for (int k = 0; k < K; ++k)
             if (int rc = step_any(c, n + k)) return rc;
         return 0;
     }
-    // a whole grid on one GPU: no interface strips, so no pass chain at all; y-slabs go through group_impl, which adds
-    // the window launch to its chain of interface passes
-    if (frame_window_usable(c, K) && !c->comm && whole)
-        return c->cfg.dtype == FDTD_F64 ? group_window<double>(c, n, K) : group_window<float>(c, n, K);
     return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
 }
 
@@ -1334,8 +1135,7 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
 }
 
 static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
-                             fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, bool fused, int32_t* n_window_tiles,
-                             int32_t* window_tiles_xy, int32_t halo_depth = 1) {
+                             fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks) {
     fdtd_ctx* c = nullptr;
     if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes))
         return fail(c, FDTD_ERR_ARG, "bad argument");
@@ -1346,10 +1146,8 @@ static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int
     for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
     const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
-    const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
-    const int64_t hb = (halo_depth > 1 && cfg->row_end < cfg->rows) ? halo_depth : 0;
-    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, fused,
-                         ht, hb}, mods, m);
+    plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, 0, 0},
+               mods, m);
     const int margin = (K + V2 - 1) / V2;
     plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
     plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
@@ -1360,29 +1158,12 @@ static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int
     if (masks)
         for (int d = 0; d < K; ++d)
             std::memcpy(masks + (size_t)d * m.frame_nty * m.ntx1, m.h_mask[d].data(), (size_t)m.frame_nty * m.ntx1);
-    if (n_window_tiles) *n_window_tiles = (int32_t)m.h_tiles.size();
-    if (window_tiles_xy)
-        for (size_t k = 0; k < m.h_tiles.size(); ++k) { window_tiles_xy[2 * k] = m.h_tiles[k].x; window_tiles_xy[2 * k + 1] = m.h_tiles[k].y; }
     return 0;
 }
 
 int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
                     fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks) {
-    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, false, nullptr, nullptr);
-}
-
-int fdtd_plan_frame_split(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
-                          fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, int32_t* n_window_tiles,
-                          int32_t* window_tiles_xy) {
-    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, true, n_window_tiles, window_tiles_xy);
-}
-
-int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes,
-                         const int64_t* boxes, fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks,
-                         int32_t* n_window_tiles, int32_t* window_tiles_xy) {
-    if (halo_depth < 1 || halo_depth > 9) return fail(nullptr, FDTD_ERR_ARG, "halo depth must be 1..9");
-    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks, true, n_window_tiles, window_tiles_xy,
-                             halo_depth);
+    return plan_frame_export(cfg, steps_per_pass, n_boxes, boxes, plan, skip, masks);
 }
 
 int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes, const int64_t* boxes,
@@ -1404,7 +1185,7 @@ int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_
     const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
     const int64_t hb = (halo_depth > 1 && cfg->row_end < cfg->rows) ? halo_depth : 0;
     plan_edge(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, std::max(cfg->block_warps, 1), K, V2,
-                        false, ht, hb, true}, mods, m);
+                        ht, hb, true}, mods, m);
     const int margin = (K + V2 - 1) / V2;
     plan->k_tile_rows = cfg->tile_rows; plan->k_tile_cols = (32 - 2 * margin) * V2; plan->k_load_cols = 32 * V2;
     plan->k_margin_cols = margin * V2; plan->k_tiles_y = m.nty; plan->k_tiles_x = m.ntx2;
@@ -1494,13 +1275,6 @@ int fdtd_set_resident(fdtd_handle c, int32_t enable, int64_t max_cells) {
     return 0;
 }
 
-int fdtd_set_resident_depth(fdtd_handle c, int32_t calls_per_barrier) {
-    if (!c) return FDTD_ERR_ARG;
-    if (calls_per_barrier < 1 || calls_per_barrier > fdtd::WIN_MAX_CALLS) return fail(c, FDTD_ERR_ARG, "calls_per_barrier must be 1..8");
-    c->resident_depth = calls_per_barrier;
-    return 0;
-}
-
 int fdtd_set_kstep_variant(fdtd_handle c, int32_t variant) {
     if (!c) return FDTD_ERR_ARG;
     if (variant < 0 || variant > 1) return fail(c, FDTD_ERR_ARG, "K-step kernel variant must be 0 or 1");
@@ -1510,7 +1284,7 @@ int fdtd_set_kstep_variant(fdtd_handle c, int32_t variant) {
 
 int fdtd_set_frame_mode(fdtd_handle c, int32_t mode) {
     if (!c) return FDTD_ERR_ARG;
-    if (mode < 0 || mode > 3) return fail(c, FDTD_ERR_ARG, "frame mode must be 0, 1, 2 or 3");
+    if (mode != 0 && mode != 3) return fail(c, FDTD_ERR_ARG, "frame mode must be 0 (masked pass chain) or 3 (stepK_edge)");
     c->frame_mode = mode;
     auto_geometry(c);
     for (FrameMaps& m : c->fm) m.key.clear();
@@ -1768,7 +1542,7 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
             }
             n += std::max<int64_t>(g, 1);
         }
-        if (c->frame_mode != 0 || c->halo_depth > 1)     // frame_window reads the pulse records of resident mode
+        if (c->frame_mode != 0)                          // stepK_edge reads the pulse records of resident mode
             if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     }
     if (resident)                                        // upload the pulse records before the timed region, too

@@ -154,8 +154,8 @@ class Engine:
         L.check(self.lib, self.handle, self.lib.fdtd_bind_buffers(self.handle, *[C.c_void_p(b.data_ptr()) for b in self.buffers]))
         self.first_bad = None
         self._keep = None
-        # frame of a temporal-blocking group: 3 = stepK_edge (library default), 0 = masked single-step passes through
-        # scratch generations, 1 / 2 = one frame_window launch next to / behind the K-step kernel
+        # non-plain tiles of a temporal-blocking group: 3 = stepK_edge (library default), 0 = masked single-step passes
+        # through scratch generations
         if frame_mode is None and os.environ.get("FDTD_FRAME_MODE", "") != "":
             frame_mode = int(os.environ["FDTD_FRAME_MODE"])
         if frame_mode is not None:
@@ -173,10 +173,6 @@ class Engine:
             resident = (_resident_default() and temporal <= 1 and kernel == "stream"
                         and not (tile_rows or vec or block_warps))
         self.set_resident(resident)
-        self.resident_depth = 1
-        depth = int(os.environ.get("FDTD_RESIDENT_DEPTH", "1") or 1)      # experiments: calls per grid barrier
-        if depth != 1:
-            self.set_resident_depth(depth)
 
     def set_resident(self, on=True, max_cells=0):
         """run() advances all calls up to the next snapshot in ONE cooperative launch (kernel step_resident; step() = a
@@ -185,11 +181,6 @@ class Engine:
         and slabs keep the per-call / temporal-blocking path.  Same bits either way."""
         L.check(self.lib, self.handle, self.lib.fdtd_set_resident(self.handle, 1 if on else 0, int(max_cells)))
         self.resident = bool(on)
-
-    def set_resident_depth(self, calls_per_barrier):
-        """Resident mode with M calls per grid barrier (kernel resident_window); 1 = step_resident (default)."""
-        L.check(self.lib, self.handle, self.lib.fdtd_set_resident_depth(self.handle, int(calls_per_barrier)))
-        self.resident_depth = int(calls_per_barrier)
 
     def resident_active(self):
         """Would run() use the resident kernel for the scene as it is now?"""

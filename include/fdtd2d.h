@@ -131,11 +131,6 @@ int fdtd_set_temporal_blocking(fdtd_handle h, int32_t steps_per_pass);
  * either way.  fdtd_resident_active reports whether fdtd_run would use it for the current scene (1/0). */
 int fdtd_set_resident(fdtd_handle h, int32_t enable, int64_t max_cells);
 int fdtd_resident_active(fdtd_handle h);
-/* Calls per grid-wide barrier in resident mode: 1 (default) = step_resident; 2..8 = resident_window (csrc/window.cuh):
- * each CTA advances tile + (M+1) cells of apron M calls in shared memory between two barriers, i.e. one barrier, one
- * window load and one store per M calls for a larger window.  Bit-identical.  (Experimental until its first GPU run.) */
-int fdtd_set_resident_depth(fdtd_handle h, int32_t calls_per_barrier);
-
 /* Which K-step kernel fdtd_run launches for the plain tiles of a temporal-blocking group: 1 = stepK_lean (default): the
  * stage pipeline with the row loop unrolled by two and running pointers instead of per-row address arithmetic (about a
  * third fewer issue slots per row); 0 = stepK_stream, the first version of the same pipeline.  Same operations in the
@@ -145,14 +140,11 @@ int fdtd_set_kstep_variant(fdtd_handle h, int32_t variant);
 /* How the tiles the plain K-step kernel leaves out (the FRAME: wall bands and columns, pulse lines, sources, reflectors,
  * probes) advance in a temporal-blocking group:
  *   3  ONE launch of stepK_edge (csrc/edge.cuh) next to the plain kernel (default);
- *   0  K masked single-step launches through the scratch generations (needs fdtd_bind_scratch);
- *   1  ONE launch of frame_window (csrc/window.cuh: each frame tile + K+1 cells of apron advanced K calls in shared
- *      memory from one load of generation A) on a side stream next to the K-step kernel;
- *   2  the same launch queued behind the K-step kernel.
- * Modes 1-3 do not apply (the group silently uses mode 0, or single steps without scratch) when a TF/SF "right" line
- * sits at column 0 or more than 16 pulses exist; on a y-slab mode 3 needs K+1 halo rows (fdtd_set_halo_depth), and in
- * modes 1/2 the frame tiles within K+1 rows of a slab interface stay on the masked passes.  Results are bit-identical in
- * every mode. */
+ *   0  K masked single-step launches through the scratch generations (needs fdtd_bind_scratch).
+ * Mode 3 does not apply (the group silently uses mode 0, or single steps without scratch) when a TF/SF "right" line
+ * sits at column 0 or more than 16 pulses exist, and on a y-slab it needs K+1 halo rows (fdtd_set_halo_depth).  Results
+ * are bit-identical in both modes.  (Round 2 also measured a shared-memory variant, "frame_window", as modes 1/2: bit-exact
+ * but slower than stepK_edge on the B200 -- 512 vs 552 Gcell/s, profiles/r2_sweep_b_summary.txt -- and removed.) */
 int fdtd_set_frame_mode(fdtd_handle h, int32_t mode);
 
 /* The frame plan of temporal blocking as pure host logic (no CUDA call, works without a GPU; used by the tests).
@@ -168,13 +160,6 @@ typedef struct fdtd_frame_plan {
 } fdtd_frame_plan;
 int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
                     fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks);
-
-/* The same plan in frame modes 1/2: window_tiles_xy receives the (column tile, row tile) pairs of the frame tiles that
- * frame_window advances (up to frame_tiles_y * frame_tiles_x pairs; may be NULL), n_window_tiles their number, and
- * masks then cover only the remaining frame tiles -- the interface strips of a y-slab (none on a whole grid). */
-int fdtd_plan_frame_split(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_boxes, const int64_t* boxes,
-                          fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks, int32_t* n_window_tiles,
-                          int32_t* window_tiles_xy);
 
 /* Host arrays handed to fdtd_upload_coeffs / fdtd_set_fields / fdtd_get_fields normally start at global
  * row 0.  A rank that keeps only its slab on the host declares the global row its host arrays start at. */
@@ -267,16 +252,12 @@ int fdtd_halo_rows(fdtd_handle h, void* send_down[3], void* recv_up[3], void** s
  * stores D rows of h/ex/ey (and of the coefficient planes) of EACH neighbouring slab:
  *   local row l  <->  global row  row_begin - (row_begin > 0 ? D : 0) + l,   fdtd_local_rows_halo() rows in all,
  * so a temporal-blocking group of K <= D-1 steps needs nothing from the neighbours while it runs: the K-step kernel
- * reaches the slab's first/last owned row, frame_window (K+1 cells of apron) takes every frame tile, and the D-row blocks
+ * reaches the slab's first/last owned row, stepK_edge takes every other tile (frame mode 3), and the D-row blocks
  * are exchanged ONCE per group (one contiguous D x pitch block per array and direction) instead of one row per step and
  * masked pass.  Call fdtd_set_halo_depth right after fdtd_create, before the buffers are sized and bound; every slab
  * next to an interface must own >= D rows.  Results are bit-identical to depth 1. */
 int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth);
 int fdtd_set_halo_depth(fdtd_handle h, int32_t halo_depth);
-/* fdtd_plan_frame_split for a context with deep halos (pure host logic, no GPU). */
-int fdtd_plan_frame_halo(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes,
-                         const int64_t* boxes, fdtd_frame_plan* plan, uint8_t* skip, uint8_t* masks,
-                         int32_t* n_window_tiles, int32_t* window_tiles_xy);
 /* The tile plan of frame mode 3 as pure host logic (no CUDA call).  Every tile of the slab is a K-step tile: skip
  * (k_tiles_y x k_tiles_x bytes) = 0 for the tiles of the plain K-step kernel; every other tile is listed in edge_tiles
  * as {column tile tx, first row, end row, next-to-an-interface flag} for stepK_edge (csrc/edge.cuh), which folds walls,

@@ -41,7 +41,7 @@ def available():
 
 
 def _build(src, out):
-    deps = [src] + [os.path.join(CSRC, f) for f in ("window.cuh", "resident.cuh", "kernels.cuh")]
+    deps = [src] + [os.path.join(CSRC, f) for f in ("resident.cuh", "kernels.cuh")]
     if os.path.isfile(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     os.makedirs(OUT_DIR, exist_ok=True)
@@ -142,111 +142,3 @@ def emulate(f, setup, times, first_step, n_steps, geom=0, order=0, probe_cells=(
     out = g1 if g else g0
     return (out[0][:NR, :NC].copy(), out[1][:NR + 1, :NC].copy(), out[2][:NR, :NC + 1].copy(),
             probe_out[:n_steps, :len(probe_cells)])
-
-
-# ---- frame_window (csrc/window.cuh) ------------------------------------------------------------------------
-WIN_SRC = os.path.join(HERE, "host_emul", "window_emul.cu")
-WIN_OUT = os.path.join(OUT_DIR, "libwindow_emul.so")
-
-
-class WinEmuScene(C.Structure):
-    _fields_ = [("gen_a", C.c_void_p * 3), ("gen_b", C.c_void_p * 3), ("muc", C.c_void_p), ("epc", C.c_void_p),
-                ("pitch", C.c_int64), ("NR", C.c_int32), ("NC", C.c_int32), ("row_off", C.c_int32), ("lrows", C.c_int32),
-                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("absorb", C.c_int32 * 4),
-                ("S", C.c_double), ("oms", C.c_double), ("n_rect", C.c_int32),
-                ("rh", (C.c_int32 * 4) * MAX_RECT), ("rex", (C.c_int32 * 4) * MAX_RECT), ("rey", (C.c_int32 * 4) * MAX_RECT),
-                ("n_probe", C.c_int32), ("probe_ij", (C.c_int32 * 2) * MAX_PROBE), ("probe_out", C.c_void_p),
-                ("count", C.c_void_p), ("last", C.c_void_p), ("src", C.c_void_p), ("stride", C.c_int32)]
-
-
-_win = None
-
-
-def load_window():
-    global _win
-    if _win is None:
-        _win = C.CDLL(_build(WIN_SRC, WIN_OUT))
-        _win.window_emulate_f64.restype = C.c_int
-        _win.window_emulate_f64.argtypes = [C.POINTER(WinEmuScene), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                            C.c_int, C.c_int, C.c_longlong, C.c_int]
-    return _win
-
-
-def window_emulate(f, setup, times, first_step, K, tiles, tile_rows, tile_cols, order=0, probe_cells=(),
-                   apron=0, row_begin=0, row_end=None, fill=np.nan, poison_halo=False, shrink=-1, halo_depth=1):
-    """Advance the frame tiles `tiles` ([(tx, ty), ...] of the (tile_rows x tile_cols) grid that starts at row
-    `row_begin`) by K calls with the emulated frame_window kernel, reading the oracle-style fields `f` as generation A.
-    With row_begin/row_end the context stores only that y-slab (one halo row above, the ex row below), like the library.
-    shrink: cells the active box loses per call (-1 = the kernel's rule, window.cuh window_margin).
-    poison_halo: the halo rows of generation A (which the library fills by halo exchange) hold NaN instead.
-    halo_depth D >= 2: deep halos (fdtd_set_halo_depth) -- the context stores D valid rows of each neighbouring slab; every
-    other row it does not own holds NaN.
-    Returns (h, ex, ey, probe_records) of generation B as GLOBAL arrays pre-filled with `fill`: cells the kernel did not
-    store keep it."""
-    lib = load_window()
-    NR, NC = f.h.shape
-    row_end = NR if row_end is None else row_end
-    pitch = ((NC + 1 + 31) // 32) * 32
-    deep = halo_depth > 1
-    ht = (halo_depth if row_begin > 0 else 0) if deep else (1 if row_begin > 0 else 0)
-    hb = halo_depth if (deep and row_end < NR) else 0
-    row_off = row_begin - ht
-    lrows = (row_end - row_begin) + ht + hb + 1                          # fdtd_local_rows / fdtd_local_rows_halo
-
-    def plane(a, value=0.0):
-        p = np.full((lrows, pitch), value)
-        if a is not None:
-            n = min(a.shape[0], row_off + lrows) - row_off
-            p[:n, :a.shape[1]] = a[row_off:row_off + n]
-        return p
-    ga = [plane(f.h), plane(f.ex), plane(f.ey)]
-    if row_end < NR and not deep:
-        ga[0][-1, :] = 0.0                                   # the last local row holds ONLY ex[row_end]
-        ga[2][-1, :] = 0.0
-    if row_end < NR and deep:
-        for a in ga:
-            a[-1, :] = np.nan                                # row_end + D is stored but never exchanged
-    if poison_halo:
-        for a in ga:
-            if row_begin > 0:
-                a[0, :] = np.nan
-            if row_end < NR:
-                a[-1, :] = np.nan
-    gb = [plane(None, fill) for _ in range(3)]
-    muc, epc = plane(setup.mu_coef), plane(setup.eps_coef)
-    sc = WinEmuScene()
-    for k in range(3):
-        sc.gen_a[k] = ga[k].ctypes.data
-        sc.gen_b[k] = gb[k].ctypes.data
-    sc.muc, sc.epc, sc.pitch, sc.NR, sc.NC = muc.ctypes.data, epc.ctypes.data, pitch, NR, NC
-    sc.row_off, sc.lrows = row_off, lrows
-    sc.row_lo, sc.row_hi = row_begin, row_end + (1 if row_end == NR else 0)
-    for k, reflect in enumerate(setup.reflect_walls):
-        sc.absorb[k] = 0 if reflect else 1
-    S = setup.courant
-    sc.S, sc.oms = S, 1 - S
-    sc.n_rect = len(setup.reflectors)
-    for r, rect in enumerate(setup.reflectors):
-        for arr, shape in ((sc.rh, (NR, NC)), (sc.rex, (NR + 1, NC)), (sc.rey, (NR, NC + 1))):
-            for q, v in enumerate(clip_rect(rect, *shape)):
-                arr[r][q] = v
-    sc.n_probe = len(probe_cells)
-    for k, (i, j) in enumerate(probe_cells):
-        sc.probe_ij[k][0], sc.probe_ij[k][1] = i, j
-    probe_out = np.full((K, max(len(probe_cells), 1), 3), np.nan)
-    sc.probe_out = probe_out.ctypes.data if probe_cells else None
-    count, last, rec, stride, _ = source_records(setup.pulses, times)
-    if len(setup.pulses):
-        sc.count, sc.last, sc.src, sc.stride = count.ctypes.data, last.ctypes.data, C.addressof(rec), stride
-    t = np.ascontiguousarray(np.asarray(tiles, dtype=np.int32).reshape(-1, 2))
-    rc = lib.window_emulate_f64(C.byref(sc), len(t), t.ctypes.data, tile_rows, tile_cols, K, apron, order, first_step,
-                                shrink)
-    assert rc == 0, "emulation failed"
-
-    def globalise(p, rows, cols):
-        out = np.full((rows, cols), fill)
-        n = min(rows, row_off + lrows) - row_off
-        out[row_off:row_off + n] = p[:n, :cols]
-        return out
-    return (globalise(gb[0], NR, NC), globalise(gb[1], NR + 1, NC), globalise(gb[2], NR, NC + 1),
-            probe_out[:, :len(probe_cells)])

@@ -102,59 +102,6 @@ def test_c5_slab_plan_numbers():
     assert skip.mean() < 0.004
 
 
-def plan_halo(rows, cols, K, depth, tile_rows, boxes, row_begin, row_end, warps=1):
-    lib = L.load()
-    cfg = L.Config()
-    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, row_begin, row_end
-    cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, warps
-    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 4))
-    bp = C.c_void_p(b.ctypes.data) if len(b) else None
-    p, n = L.FramePlan(), C.c_int32(0)
-    assert lib.fdtd_plan_frame_halo(C.byref(cfg), K, depth, len(b), bp, C.byref(p), None, None, C.byref(n), None) == 0
-    skip = np.zeros((max(p.k_tiles_y, 1), p.k_tiles_x), dtype=np.uint8)
-    masks = np.zeros((K, p.frame_tiles_y, p.frame_tiles_x), dtype=np.uint8)
-    xy = np.zeros((max(p.frame_tiles_y * p.frame_tiles_x, 1), 2), dtype=np.int32)
-    assert lib.fdtd_plan_frame_halo(C.byref(cfg), K, depth, len(b), bp, C.byref(p), C.c_void_p(skip.ctypes.data),
-                                    C.c_void_p(masks.ctypes.data), C.byref(n), C.c_void_p(xy.ctypes.data)) == 0
-    return p, skip[:p.k_tiles_y], masks, xy[:n.value]
-
-
-@pytest.mark.parametrize("K", [2, 3, 4, 6, 8])
-@pytest.mark.parametrize("rows,cols,tile_rows,cuts", [(8192, 4096, 48, (0, 2048, 6144, 8192)), (300, 700, 16, (0, 104, 300)),
-                                                      (97, 300, 8, (0, 24, 48, 72, 97))])
-def test_deep_halo_plan_has_no_pass_chain_and_stays_inside_the_stored_rows(K, rows, cols, tile_rows, cuts):
-    """fdtd_set_halo_depth(K+1): per slab, K-step tiles + window tiles cover every owned cell, nothing is left for a pass
-    chain, and neither kind of tile reads a row the slab does not store (owned rows + K+1 halo rows per interface)."""
-    D = K + 1
-    boxes = [(rows // 3, rows // 3, cols // 2, cols // 2), (-(1 << 40), 1 << 40, 7, 7), (rows // 2, rows // 2 + 40, 100, 180)]
-    for b, e in zip(cuts[:-1], cuts[1:]):
-        p, skip, masks, tiles = plan_halo(rows, cols, K, D, tile_rows, boxes, b, e)
-        assert not masks.any()
-        lo, hi = b, e + (1 if e == rows else 0)
-        stored_lo, stored_hi = (b - D if b > 0 else 0), (e + D if e < rows else rows + 1)      # [lo, hi) of valid rows
-        covered = np.zeros((hi - lo, cols + 1), dtype=bool)
-        for ty in range(p.k_tiles_y):
-            ta = p.k_row_lo + ty * p.k_tile_rows
-            tb = min(ta + p.k_tile_rows, p.k_row_hi)
-            for tx in range(p.k_tiles_x):
-                if skip[ty, tx]:
-                    continue
-                assert ta - K >= stored_lo and tb + K - 1 <= stored_hi - 1 and ta >= lo and tb <= e       # rows a stage touches
-                c0 = tx * p.k_tile_cols
-                covered[ta - lo:tb - lo, c0:min(c0 + p.k_tile_cols, cols + 1)] = True
-        for tx, ty in tiles:
-            ta = lo + ty * p.frame_tile_rows
-            tb = min(ta + p.frame_tile_rows, hi)
-            assert (b == 0 or ta - D >= stored_lo) and (e == rows or tb + D <= stored_hi)                  # the window's rows
-            covered[ta - lo:tb - lo, tx * p.frame_tile_cols:(tx + 1) * p.frame_tile_cols] = True
-        assert covered.all(), (K, b, e, int((~covered).sum()))
-        if b > 0:
-            assert p.k_row_lo == b
-    # a depth that does not cover the group keeps the classic plan (interface strips on the chain)
-    p, skip, masks, tiles = plan_halo(rows, cols, K, K, tile_rows, boxes, cuts[1], cuts[2])
-    assert masks[0].any()
-
-
 def test_deep_halo_layout_and_argument_checks():
     lib = L.load()
     cfg = L.Config()
@@ -166,8 +113,3 @@ def test_deep_halo_layout_and_argument_checks():
     cfg.row_begin, cfg.row_end = 60, 100
     assert lib.fdtd_local_rows_halo(C.byref(cfg), 7) == 40 + 7 + 1          # the last slab keeps the ex[rows] row
     assert lib.fdtd_set_halo_depth(None, 3) == -1 and lib.fdtd_halo_blocks(None, None, None, None, None, None) == -1
-    p = L.FramePlan()
-    cfg.tile_rows, cfg.block_warps = 8, 1
-    assert lib.fdtd_plan_frame_halo(C.byref(cfg), 4, 5, 0, None, C.byref(p), None, None, None, None) == 0
-    assert lib.fdtd_plan_frame_halo(C.byref(cfg), 4, 0, 0, None, C.byref(p), None, None, None, None) != 0
-    assert lib.fdtd_plan_frame_halo(C.byref(cfg), 4, 12, 0, None, C.byref(p), None, None, None, None) != 0

@@ -1,7 +1,7 @@
 """GPU: deep halos (fdtd_set_halo_depth, `Engine(halo_depth=K+1)`) -- several slab contexts on ONE device, every
 temporal-blocking group run without any exchange inside it, the D-row blocks copied between the contexts after each
-group (what the library does over NCCL), against the oracle, bitwise.  Written after round 1's GPU budget had run out
-(the layout and the plan are CPU-pinned, tests/test_window_emulation.py); skipped until FDTD_TEST_DEEP_HALO=1."""
+group (what the library does over NCCL), against the oracle, bitwise.  (The layout and the plan are CPU-pinned:
+tests/test_edge_emulation.py, tests/test_slabs.py.)"""
 import os
 
 import numpy as np
@@ -14,7 +14,7 @@ pytestmark = [pytest.mark.gpu]           # first B200 run: round 2 (green); over
 
 
 def _eligible(setup):
-    """frame_window does not take a TF/SF "right" line at column 0 (python's h[:, col-1] wraps)."""
+    """stepK_edge does not take a TF/SF "right" line at column 0 (python's h[:, col-1] wraps)."""
     setup.pulses = [p for p in setup.pulses if not (p.direction == "right" and p.col == 0)]
     return setup
 
@@ -34,10 +34,9 @@ def _copy_blocks(engines):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("frame_mode", [None, 3], ids=["frame_window", "stepK_edge"])
 @pytest.mark.parametrize("world,K,shape,tile_rows", [(2, 4, (300, 700), 16), (3, 6, (400, 900), 16), (2, 2, (97, 300), 8),
                                                     (4, 6, (700, 2100), 48), (3, 8, (500, 1300), 24)])
-def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows, frame_mode):
+def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows):
     from fdtd_em_solver_b200.engine import Engine
     rows, cols = shape
     n_steps = 3 * K + 2
@@ -47,7 +46,7 @@ def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows,
     engines = []
     for b, e_ in SL.split_rows(rows, world):
         e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, row_begin=b, row_end=e_,
-                   temporal=K, tile_rows=tile_rows, halo_depth=K + 1, frame_mode=frame_mode)
+                   temporal=K, tile_rows=tile_rows, halo_depth=K + 1)
         e.upload_coefficients(setup.eps_coef, setup.mu_coef)
         e.set_sources(setup.pulses, times)
         e.set_reflectors(setup.reflectors)
@@ -66,6 +65,6 @@ def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows,
         e.get_fields(out={"h": h, "ex": ex, "ey": ey})
     assert np.array_equal(h, f.h) and np.array_equal(ex, f.ex) and np.array_equal(ey, f.ey)
     launches = [e.stats()["kernel_launches"] for e in engines]
-    assert max(launches) <= 3 * 2 + 2 + 4                     # two launches per group (K-step + window), one per single step
+    assert max(launches) <= 3 * 2 + 2 + 4                     # two launches per group (plain + edge tiles), one per single step
     for e in engines:
         e.close()

@@ -1,10 +1,11 @@
-"""GPU parity of frame_window (fdtd_em_solver_b200/csrc/window.cuh): the frame of a temporal-blocking group advanced
-K calls in ONE launch (fdtd_set_frame_mode 1 = next to the K-step kernel, 2 = behind it) instead of K masked
-single-step passes.  Everything is bit-exact against the oracle (fp64 bar of BASELINE.json: 1e-12 relative L2; what
-is asserted is equality).
+"""GPU parity of frame mode 3 (fdtd_em_solver_b200/csrc/edge.cuh): every tile of a temporal-blocking group that the
+plain K-step kernel leaves out -- wall bands and columns, pulse lines, sources, reflectors, probes -- advanced K calls
+by ONE stepK_edge launch (the K-step register pipeline with those features as tile predicates) instead of K masked
+single-step passes (mode 0, which these tests run beside it).  Everything is bit-exact against the oracle (fp64 bar of
+BASELINE.json: 1e-12 relative L2; what is asserted is equality).
 
-The K-call window algorithm is pinned on the CPU by tests/test_window_emulation.py.  frame_window had no GPU run yet
-when round 1's GPU budget ended, so these tests only run with FDTD_TEST_FRAME_WINDOW=1 and mode 0 stays the default.
+The kernel's device code is pinned on the CPU by tests/test_edge_emulation.py (SIMT emulator).  First B200 run: round 2,
+profiles/r2_first_run_stepK_edge_tests.log.
 """
 import itertools
 import os
@@ -14,7 +15,7 @@ import pytest
 
 from oracle import restated as R, scenarios as SC
 
-pytestmark = [pytest.mark.gpu]           # first B200 run: round 2, profiles/r2_first_run_new_kernels_tests.log (all green)
+pytestmark = [pytest.mark.gpu]
 
 WALLS = list(itertools.product([False, True], repeat=4))
 
@@ -45,10 +46,10 @@ def _without_wrapping_lines(setup):
     return setup
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("temporal", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("shape,tile_rows,warps", [((200, 900), 8, 4), ((131, 517), 4, 2), ((64, 300), 16, 1)])
-def test_k_steps_per_pass_with_the_frame_in_one_launch(shape, tile_rows, warps, temporal, mode):
+def test_k_steps_per_pass_both_frame_modes(shape, tile_rows, warps, temporal, mode):
     rows, cols = shape
     for seed, k in ((1, 0), (2, 3), (4, 5), (5, 2)):
         f, setup, times = SC.random_case(rows, cols, seed, walls=WALLS[(seed * 3) % 16], n_steps=17)
@@ -67,7 +68,8 @@ def test_k_steps_per_pass_with_the_frame_in_one_launch(shape, tile_rows, warps, 
             R.run(f, setup, times)
             e.run(0, len(times))
             groups, rest = divmod(len(times), temporal)
-            assert e.stats()["kernel_launches"] - launches0 <= 2 * groups + 2 * (temporal - 1)   # no K-pass chains
+            if mode == 3:
+                assert e.stats()["kernel_launches"] - launches0 <= 2 * groups + 2 * (temporal - 1)   # no K-pass chains
         _same(e, f, "frame mode %d, K %d, seed %d" % (mode, temporal, seed))
         raw = e.probes()
         for c, (i, j, series) in enumerate(f.raw_probes):
@@ -75,9 +77,10 @@ def test_k_steps_per_pass_with_the_frame_in_one_launch(shape, tile_rows, warps, 
         e.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 3])
 def test_wrapping_line_keeps_the_masked_passes(mode):
-    """A TF/SF "right" line at column 0 is outside the window algorithm: the group silently uses mode 0."""
+    """A TF/SF "right" line at column 0 (python's h[:, col-1] wraps to the far column) is outside stepK_edge: the group
+    silently uses the masked passes, or -- without scratch generations, the default of mode 3 -- single steps."""
     f, setup, times = SC.random_case(131, 517, 3, n_steps=13)          # seed % 3 == 0: has the column-0 line
     assert any(p.direction == "right" and p.col == 0 for p in setup.pulses)
     e = _engine_for(f, setup, times, kernel="stream", tile_rows=8, temporal=4, frame_mode=mode)
@@ -87,13 +90,13 @@ def test_wrapping_line_keeps_the_masked_passes(mode):
     e.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 3])
 def test_fp32_same_bits_as_single_stepping(mode):
     from fdtd_em_solver_b200.engine import Engine
     f, setup, times = SC.random_case(150, 1200, 10, n_steps=13)
     setup = _without_wrapping_lines(setup)
     outs = []
-    for temporal, fm in ((1, 0), (6, mode), (4, mode)):
+    for temporal, fm in ((1, 3), (6, mode), (4, mode)):
         rows, cols = f.h.shape
         S = setup.courant
         e = Engine(rows, cols, courant=S, one_minus_courant=(1 - S), reflect=setup.reflect_walls, dtype="float32",
@@ -108,7 +111,7 @@ def test_fp32_same_bits_as_single_stepping(mode):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 3])
 def test_2048_grid_default_geometry_vs_oracle(mode):
     f, setup, times = SC.random_case(2048, 2048, 21, walls=(False, False, False, False), n_steps=20)
     setup = _without_wrapping_lines(setup)
@@ -120,16 +123,17 @@ def test_2048_grid_default_geometry_vs_oracle(mode):
 
 
 def test_full_size_slab_equals_single_stepping():
-    """BASELINE.json's per-GPU workload (8192 x 65536 fp64, C5 recipe): K = 6 with the frame in one launch must leave
-    the bits of plain single stepping (compared on the device)."""
+    """BASELINE.json's per-GPU workload (8192 x 65536 fp64, C5 recipe) with the library's defaults (K = 8, stepK_lean +
+    stepK_edge, 512-row plain tiles) must leave the bits of plain single stepping (compared on the device)."""
     import torch
     from fdtd_em_solver_b200 import synthetic as SY
     free, total = torch.cuda.mem_get_info()
-    if free < 110 * 2 ** 30:
-        pytest.skip("needs ~100 GB of device memory")
-    rows, cols, n = 8192, 65536, 19
+    if free < 70 * 2 ** 30:
+        pytest.skip("needs ~70 GB of device memory")
+    rows, cols, n = 8192, 65536, 21
     a, _ = SY.make_engine(rows, cols, n_calls=64, temporal=1)
-    b, _ = SY.make_engine(rows, cols, n_calls=64, temporal=6, frame_mode=1)
+    b, _ = SY.make_engine(rows, cols, n_calls=64, temporal=8)
+    assert b.tuning()["frame_mode"] == 3 and b.tuning()["kstep_variant"] == 1 and len(b.buffers) == 8
     a.run(0, n); b.run(0, n)
     for x, y in zip(a.generation_buffers(), b.generation_buffers()):
         assert torch.equal(x, y)

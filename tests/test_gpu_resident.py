@@ -208,59 +208,3 @@ def test_fp32_resident_equals_per_call_path():
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
     assert np.abs(outs[0][0]).max() > 0
-
-
-# ---- resident_window: M calls per grid barrier (csrc/window.cuh) ------------------------------------------------------
-# Pinned on the CPU by tests/test_window_emulation.py; no GPU run yet when round 1's GPU budget ended, so these only run
-# with FDTD_TEST_RESIDENT_DEPTH=1 and depth 1 (step_resident) stays the default.
-depth_gate = pytest.mark.skipif(os.environ.get("FDTD_TEST_RESIDENT_DEPTH", "0") == "0",
-                                reason="resident_window awaits its first GPU run: set FDTD_TEST_RESIDENT_DEPTH=1")
-
-
-@depth_gate
-@pytest.mark.parametrize("depth", [2, 3, 4, 8])
-@pytest.mark.parametrize("shape", [(9, 5), (40, 70), (139, 139), (300, 200)])
-def test_depth_random_cases_run_loop_bitwise(shape, depth):
-    rows, cols = shape
-    for seed, k in ((1, 0), (2, 3), (4, 5), (5, 7)):
-        walls = WALLS[(seed * 5 + rows + cols) % 16]
-        f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=17)
-        setup = _without_wrapping_lines(setup)
-        cells = [(0, 0), (rows // 2, cols // 2), (rows - 1, cols - 1)]
-        f.raw_probes = [(i, j, []) for i, j in cells]
-        e = _engine_for(f, setup, times, resident=True)
-        e.set_resident_depth(depth)
-        e.set_probes(cells)
-        assert e.resident_active()
-        if k:
-            want = np.array(R.run_saving(f, setup, times, k))
-            got = e.run(0, len(times), snapshot_every=k, total_calls=len(times))
-            assert got.shape == want.shape and np.array_equal(got, want), (shape, seed, k)
-        else:
-            R.run(f, setup, times)
-            e.run(0, len(times))
-        _same(e, f, "depth %d shape %s seed %d" % (depth, shape, seed))
-        raw = e.probes()
-        for c, (i, j, series) in enumerate(f.raw_probes):
-            assert np.array_equal(raw[:, c, :], np.array(series)), (shape, seed, c)
-        e.close()
-
-
-@depth_gate
-@pytest.mark.parametrize("depth", [2, 4])
-def test_depth_reference_golden_vectors(depth):
-    from golden_util import load, setup_of, sha
-    from fdtd_em_solver_b200.engine import Engine
-    for name in ("tutorial", "lens", "waveguide", "mixed"):
-        g = load(name)
-        s = setup_of(g)
-        n = int(g["size"])
-        e = Engine(n, courant=s.courant, one_minus_courant=(1 - s.courant), reflect=s.reflect_walls, resident=True)
-        e.set_resident_depth(depth)
-        e.upload_coefficients(g["eps_coef"], g["mu_coef"])
-        e.set_sources(s.pulses, g["times"])
-        e.set_reflectors(s.reflectors)
-        e.run(0, len(g["times"]))
-        h, ex, ey = e.get_fields()
-        assert np.array_equal(h, g["final_h"]) and sha(ex) == str(g["sha_ex"]) and sha(ey) == str(g["sha_ey"]), name
-        e.close()

@@ -203,16 +203,7 @@ def test_c_abi_argument_validation_needs_no_gpu():
     assert lib.fdtd_step(None, 0) == -1 and lib.fdtd_sync(None) == -1 and lib.fdtd_destroy(None) == 0
     assert lib.fdtd_set_temporal_blocking(None, 2) == -1 and lib.fdtd_current_generation(None) == -1
     assert lib.fdtd_set_resident(None, 1, 0) == -1 and lib.fdtd_resident_active(None) == -1
-    assert lib.fdtd_set_resident_depth(None, 2) == -1 and lib.fdtd_set_frame_mode(None, 1) == -1
-    # the split frame plan validates like the plain one
-    plan = L.FramePlan()
-    n = ctypes.c_int32(0)
-    assert lib.fdtd_plan_frame_split(None, 4, 0, None, ctypes.byref(plan), None, None, ctypes.byref(n), None) == -1
-    cfg = L.Config()
-    cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end, cfg.tile_rows, cfg.block_warps = 300, 700, 0, 300, 16, 1
-    assert lib.fdtd_plan_frame_split(ctypes.byref(cfg), 9, 0, None, ctypes.byref(plan), None, None, ctypes.byref(n), None) == -1
-    assert lib.fdtd_plan_frame_split(ctypes.byref(cfg), 4, 0, None, ctypes.byref(plan), None, None, ctypes.byref(n), None) == 0
-    assert n.value > 0 and plan.frame_tile_rows == 8
+    assert lib.fdtd_set_frame_mode(None, 3) == -1 and lib.fdtd_get_tuning(None, None) == -1
 
 
 def test_snapshot_stack_allocator_is_a_plain_float64_array():

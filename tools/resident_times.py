@@ -11,11 +11,10 @@ torch.zeros(1, device="cuda"); torch.cuda.synchronize()
 from fdtd_em_solver_b200 import _lib
 _lib.load()
 
-# FDTD_RESIDENT_DEPTH=M (read by Engine) times resident mode with M calls per grid barrier (kernel resident_window)
 names = sys.argv[1:] or ["waveguide", "lens", "tutorial", "doubleslit"]
 for name in names:
     sc = SC.spec(name)
-    row = dict(config=name, resident_depth=int(os.environ.get("FDTD_RESIDENT_DEPTH", "1") or 1))
+    row = dict(config=name)
     finals = {}
     for resident in (False, True):
         with contextlib.redirect_stdout(io.StringIO()):
