@@ -17,6 +17,7 @@ INCLUDE_DIR = os.path.join(ROOT, "include")
 #   FDTD_LIB_SUFFIX=_cs FDTD_NVCC_EXTRA='-DFDTD_ST_MOD=".cs"'
 LIB_PATH = os.path.join(HERE, "libfdtd2d%s.so" % os.environ.get("FDTD_LIB_SUFFIX", ""))
 NVCC_EXTRA = os.environ.get("FDTD_NVCC_EXTRA", "").split()
+OBJ_DIR = os.path.join(HERE, "_obj%s" % os.environ.get("FDTD_LIB_SUFFIX", ""))     # git-ignored, not needed on the GPU box
 
 F64, F32 = 0, 1
 SRC_POINT, SRC_RIGHT, SRC_LEFT, SRC_UP, SRC_DOWN = 0, 1, 2, 3, 4
@@ -101,14 +102,35 @@ SIGNATURES = {
     "fdtd_halo_rows": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "fdtd_local_rows_halo": (C.c_int64, [C.POINTER(Config), C.c_int32]),
     "fdtd_set_halo_depth": (C.c_int, [_P, C.c_int32]),
-    "fdtd_plan_edge": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(FramePlan), _P,
+    "fdtd_plan_edge": (C.c_int, [C.POINTER(Config), C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(FramePlan), _P,
                                  C.POINTER(C.c_int32), _P, C.c_int32]),
     "fdtd_halo_blocks": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
 }
 
 
+# The library is linked from one host translation unit and the kernel families, each compiled on its own (several of
+# them once per dtype and slice of K): (source, defines, headers it really depends on, tag).  csrc/launch.h is the
+# interface between them.
+_KERNEL_HEADERS = {"k_step.cu": ["kernels.cuh"], "k_stepk.cu": ["kernels.cuh"], "k_resident.cu": ["kernels.cuh", "resident.cuh"],
+                   "k_edge.cu": ["kernels.cuh", "resident.cuh", "edge.cuh"]}
+
+
+def parts():
+    out = [("fdtd2d.cu", [], ["kernels.cuh", "resident.cuh", "edge.cuh"], "host"),
+           ("k_step.cu", [], _KERNEL_HEADERS["k_step.cu"], "step"),
+           ("k_resident.cu", [], _KERNEL_HEADERS["k_resident.cu"], "resident")]
+    for t in ("double", "float"):
+        for lo, hi in ((2, 4), (5, 6), (7, 8)):
+            out.append(("k_stepk.cu", ["-DFDTD_PART_T=" + t, "-DFDTD_K_LO=%d" % lo, "-DFDTD_K_HI=%d" % hi],
+                        _KERNEL_HEADERS["k_stepk.cu"], "stepk_%s_%d_%d" % (t, lo, hi)))
+        for lo, hi in ((2, 3), (4, 5), (6, 6), (7, 7), (8, 8)):
+            out.append(("k_edge.cu", ["-DFDTD_PART_T=" + t, "-DFDTD_K_LO=%d" % lo, "-DFDTD_K_HI=%d" % hi],
+                        _KERNEL_HEADERS["k_edge.cu"], "edge_%s_%d_%d" % (t, lo, hi)))
+    return out
+
+
 def sources():
-    return [os.path.join(SRC_DIR, "fdtd2d.cu")]
+    return sorted({os.path.join(SRC_DIR, src) for src, _, _, _ in parts()})
 
 
 def _stale():
@@ -119,35 +141,66 @@ def _stale():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
+def _object_for(nvcc, part, force, verbose):
+    """Compile one part into OBJ_DIR, named by the hash of everything that determines it; reuse it if it is there."""
+    import hashlib
+    src, defines, headers, tag = part
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + NVCC_EXTRA + defines
+    digest = hashlib.sha256(" ".join(flags).encode())
+    for dep in [os.path.join(SRC_DIR, src), os.path.join(SRC_DIR, "launch.h"), os.path.join(INCLUDE_DIR, "fdtd2d.h")] + \
+            [os.path.join(SRC_DIR, h) for h in headers]:
+        with open(dep, "rb") as fh:
+            digest.update(fh.read())
+    obj = os.path.join(OBJ_DIR, "%s-%s.o" % (tag, digest.hexdigest()[:16]))
+    if os.path.isfile(obj) and not force:
+        return obj, ""
+    for old in os.listdir(OBJ_DIR):                       # one object per part: older versions of this one go
+        if old.startswith(tag + "-") and old.endswith(".o"):
+            os.remove(os.path.join(OBJ_DIR, old))
+    tmp = "%s.tmp.%d" % (obj, os.getpid())
+    cmd = [nvcc] + flags + (["-Xptxas=-v"] if verbose else []) + ["-I", INCLUDE_DIR, "-c", os.path.join(SRC_DIR, src), "-o", tmp]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError("nvcc failed on %s (%s):\n%s%s" % (src, " ".join(defines), res.stdout, res.stderr))
+    os.replace(tmp, obj)
+    return obj, res.stderr
+
+
 def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> fdtd_em_solver_b200/libfdtd2d.so (in tree).
 
-    Safe under torchrun: the build runs under an exclusive file lock (ranks that lose the race find a fresh library when
-    they get the lock and return), and nvcc writes to a per-process temporary that is renamed into place, so no process
-    can ever map a half-written library."""
+    The parts compile in parallel into content-addressed objects (an edit to one kernel family recompiles that family);
+    force=True ignores the object cache.  Safe under torchrun: the build runs under an exclusive file lock (ranks that
+    lose the race find a fresh library when they get the lock and return), and the link writes to a per-process
+    temporary that is renamed into place, so no process can ever map a half-written library."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfdtd2d.so (and there is no CPU fallback)")
     import fcntl
+    from concurrent.futures import ThreadPoolExecutor
     with open(LIB_PATH + ".lock", "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             if not force and not _stale():          # another rank built it while this one waited for the lock
                 return LIB_PATH
+            os.makedirs(OBJ_DIR, exist_ok=True)
+            jobs = int(os.environ.get("FDTD_BUILD_JOBS", "0")) or max(1, min(os.cpu_count() or 1, 16))
+            with ThreadPoolExecutor(jobs) as pool:
+                done = list(pool.map(lambda part: _object_for(nvcc, part, force, verbose), parts()))
             tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
-            cmd = [nvcc] + NVCC_FLAGS + NVCC_EXTRA + ["-I", INCLUDE_DIR] + sources() + ["-o", tmp]
-            if verbose:
-                cmd.insert(1, "-Xptxas=-v")
-            res = subprocess.run(cmd, capture_output=True, text=True)
+            res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + [o for o, _ in done] +
+                                 ["-o", tmp], capture_output=True, text=True)
             if res.returncode != 0:
                 if os.path.exists(tmp):
                     os.remove(tmp)
-                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
             os.replace(tmp, LIB_PATH)
             if verbose:
-                print(res.stderr)
+                print("".join(log for _, log in done))
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH

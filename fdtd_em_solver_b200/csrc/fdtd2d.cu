@@ -4,11 +4,10 @@
 // sm_100a kernels in kernels.cuh.  No CPU fallback exists: every entry point
 // that computes needs a CUDA device.
 #include "fdtd2d.h"
-#include "kernels.cuh"
-#include "resident.cuh"
-#include "edge.cuh"
+#include "launch.h"
 
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -21,6 +20,15 @@ using fdtd::RectI;
 using fdtd::StepParams;
 
 namespace {
+
+// NVTX ranges (the reference has no tracing; these show up in nsys / ncu --nvtx timelines).  Header-only
+// NVTX3: a no-op costing one branch per call unless a tool injected itself into the process.
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 std::string g_create_error;
 
@@ -65,6 +73,8 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     fdtd::EdgeTile* d_edge = nullptr;            // interface first (n_edge_near of them)
     size_t d_edge_cap = 0;
     int n_edge_near = 0;
+    struct EdgeRun { int first, count, flags; };  // consecutive tiles of one class (the kernel instantiation `flags`)
+    std::vector<EdgeRun> edge_runs_near, edge_runs_far;
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
     std::vector<int64_t> row_cells;      // cells the plain K-step kernel advances per tile row (measurement hook)
@@ -113,6 +123,10 @@ struct fdtd_ctx {
     double* snap_dev[2] = {nullptr, nullptr};
     double* snap_pin[2] = {nullptr, nullptr};        // pinned host ring: snapshots reach pageable user memory through it
     struct SnapCopy { double* dst; const double* src; size_t bytes; };
+    // realtime view (fdtd_view_begin / fdtd_view_end): a ring of two decimated pictures of h in flight
+    struct View { double* dev = nullptr; double* pin = nullptr; size_t cap = 0; cudaEvent_t done = nullptr;
+                  int64_t rows = 0, cols = 0; bool pending = false; } view[2];
+    int view_head = 0, view_tail = 0;                // next slot to fill / oldest pending slot
     void* stage = nullptr; size_t stage_bytes = 0;
 
     ncclComm_t comm = nullptr;
@@ -130,6 +144,7 @@ struct fdtd_ctx {
     int frame_mode = 3;
     int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
+    bool edge_class_force = false;   // measurement hook FDTD_EDGE_GENERIC=1: every edge tile through the all-features instantiation
 
     // optional: CUDA events around every launch of the plain K-step kernel on its own stream (bench.py: the roofline
     // line wants the dominant kernel's own duration, measured live in the timed region)
@@ -199,10 +214,9 @@ int h2d_plane(fdtd_ctx* c, void* base, const double* host, int64_t host_ld, int6
         CK(cudaMemcpy2DAsync(c->stage, ncols * 8, src + a * host_ld, host_ld * 8, ncols * 8, m,
                              cudaMemcpyHostToDevice, c->stream));
         dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)std::min<int64_t>(m, 65535));
-        fdtd::plane_from_f64<T><<<grid, 256, 0, c->stream>>>(dst + a * c->pitch, c->pitch,
-                                                             (const double*)c->stage, ncols, (int)m, (int)ncols);
+        CK(fdtd::launch_plane_from_f64<T>(grid, c->stream, dst + a * c->pitch, c->pitch, (const double*)c->stage, ncols,
+                                          (int)m, (int)ncols));
         c->stats.kernel_launches++;
-        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
@@ -223,10 +237,9 @@ int d2h_plane(fdtd_ctx* c, const void* base, double* host, int64_t host_ld, int6
     for (int64_t a = 0; a < n; a += chunk) {
         const int64_t m = std::min(chunk, n - a);
         dim3 block(64, 4), grid((unsigned)((ncols + 63) / 64), (unsigned)std::min<int64_t>((m + 3) / 4, 65535));
-        fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>((double*)c->stage, ncols, src + a * c->pitch, c->pitch,
-                                                             (int)m, (int)ncols, 0, none);
+        CK(fdtd::launch_plane_to_f64<T>(grid, block, c->stream, (double*)c->stage, ncols, src + a * c->pitch, c->pitch,
+                                        (int)m, (int)ncols, 0, none));
         c->stats.kernel_launches++;
-        CK(cudaGetLastError());
         CK(cudaMemcpy2DAsync(dst + a * host_ld, host_ld * 8, c->stage, ncols * 8, ncols * 8, m,
                              cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -272,13 +285,13 @@ int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step, int a, int b) {
     return 0;
 }
 
-template <typename T, int V>
-void launch_stream(const StepParams<T>& P, int WARPS, cudaStream_t s, int n_list) {
+template <typename T>
+cudaError_t launch_stream(const StepParams<T>& P, int V, int WARPS, cudaStream_t s, int n_list) {
     const int ncol_tiles = (P.NC + 1 + 32 * V * WARPS - 1) / (32 * V * WARPS);
     const int nrow_tiles = (P.row_hi - P.row_lo + P.tile_rows - 1) / P.tile_rows;
     dim3 grid((unsigned)ncol_tiles, (unsigned)nrow_tiles);
     if (P.tile_list) grid = dim3((unsigned)n_list, 1);
-    fdtd::step_stream<T, V><<<grid, WARPS * 32, 0, s>>>(P);
+    return fdtd::launch_step_stream<T>(P, V, WARPS, grid, s);
 }
 
 template <typename T>
@@ -289,17 +302,15 @@ int launch_rows(fdtd_ctx* c, StepParams<T>& P, int64_t row_lo, int64_t row_hi, c
     P.row_lo = (int)row_lo; P.row_hi = (int)row_hi;
     if (c->cfg.kernel == FDTD_KERNEL_EXACT) {
         dim3 grid((unsigned)((P.NC + 1 + 255) / 256), (unsigned)std::min<int64_t>(row_hi - row_lo, 65535));
-        fdtd::step_exact<T><<<grid, 256, 0, s>>>(P);
+        CK(fdtd::launch_step_exact<T>(P, grid, s));
     } else {
         const int v = vec_override ? vec_override : c->cfg.vec, w = c->cfg.block_warps;
         constexpr int VA = sizeof(T) == 8 ? 2 : 4, VB = 2 * VA;
         if (w < 1 || w > 8) return fail(c, FDTD_ERR_ARG, "block_warps must be 1..8");
-        if (v == VA) launch_stream<T, VA>(P, w, s, n_list);
-        else if (v == VB) launch_stream<T, VB>(P, w, s, n_list);
-        else return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
+        if (v != VA && v != VB) return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
+        CK(launch_stream<T>(P, v, w, s, n_list));
     }
     c->stats.kernel_launches++;
-    CK(cudaGetLastError());
     return 0;
 }
 
@@ -326,6 +337,7 @@ int nccl_dtype(fdtd_ctx* c) { return c->cfg.dtype == FDTD_F64 ? 8 : 7; }
 // Deep halos: refresh the D rows of h/ex/ey stored from each neighbour with that neighbour's D outermost owned rows
 // of generation g -- one contiguous block of D x pitch elements per array and direction.
 int exchange_deep(fdtd_ctx* c, int g, cudaStream_t s) {
+    Range nvtx("fdtd:halo_exchange_deep");
     const int64_t D = c->halo_depth;
     const size_t es = c->esize, count = (size_t)(D * c->pitch);
     auto row = [&](int f, int64_t grow) { return (char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * es; };
@@ -351,6 +363,7 @@ int exchange_deep(fdtd_ctx* c, int g, cudaStream_t s) {
 int exchange(fdtd_ctx* c, int g, cudaStream_t s) {
     if (!c->comm) return 0;
     if (c->halo_depth > 1) return exchange_deep(c, g, s);
+    Range nvtx("fdtd:halo_exchange");
     const int64_t NC = c->cfg.cols;
     const size_t es = c->esize;
     auto row = [&](int f, int64_t grow) { return (char*)c->gen[g][f] + (size_t)((grow - c->row_off) * c->pitch) * es; };
@@ -377,6 +390,7 @@ int exchange(fdtd_ctx* c, int g, cudaStream_t s) {
 
 template <typename T>
 int step_impl(fdtd_ctx* c, int64_t step) {
+    Range nvtx("fdtd:single_step");
     StepParams<T> P;
     const int dst = next_gen(c, c->cur);
     if (int rc = fill_params<T>(c, P, step, c->cur, dst)) return rc;
@@ -445,7 +459,7 @@ bool edge_usable(const fdtd_ctx* c, int K) {
 
 // Which K-step tiles must NOT be advanced by stepK_stream, and which single-step tiles advance them instead.
 // Pure host logic (no CUDA): also exported as fdtd_plan_frame so that it can be tested without a GPU.
-struct FrameBox { int64_t r0, r1, c0, c1; };                      // inclusive cell box of a wall-less "modifier"
+struct FrameBox { int64_t r0, r1, c0, c1; int what = fdtd::EDGE_SRC | fdtd::EDGE_MISC; };   // inclusive cell box of a wall-less "modifier" (+ what it is, for the edge classes)
 struct FrameGeom { int64_t rows, cols, row_begin, row_end; int tile_rows, block_warps, K, V2;
                    int64_t halo_top = 0, halo_bot = 0; bool edge = false; int edge_rows = 32; };   // rows of h/ex/ey STORED beyond the owned ones (deep halos; 0 = classic)
 
@@ -548,11 +562,19 @@ void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps&
     // at most edge_rows rows, independent of the height of the plain tiles (which like to be tall), so that the few
     // thousand of them spread over the SMs and finish well inside the plain kernel's run.
     const int ER = std::max(g.edge_rows, 1);
+    const int64_t first_stored = std::max<int64_t>(g.row_begin - g.halo_top, 0), last_stored = g.row_end + g.halo_bot - 1;
     auto push = [&](int tx, int64_t ta0, int64_t tb0) {
+        const int64_t jw = (int64_t)tx * OUT - (int64_t)MARGIN * V2;
         for (int64_t ta = ta0; ta < tb0; ta += ER) {
             const int64_t tb = std::min<int64_t>(ta + ER, tb0);
             const bool is_near = (!top_wall && ta < lo + D) || (!bot_wall && tb > g.row_end - D);
-            (is_near ? near : far).push_back(fdtd::EdgeTile{tx, (int)ta, (int)tb, 0});
+            // what the rows / columns this piece marches through (ta-K-1 .. tb+K, jw .. jw+LD-1) touch: its class
+            int need = 0;
+            if (!(ta - K - 1 >= std::max<int64_t>(first_stored, 1) && tb + K <= std::min<int64_t>(NR - 2, last_stored))) need |= fdtd::EDGE_ROWS;
+            if (jw < 1 || jw + LD - 1 > NC - 2) need |= fdtd::EDGE_COLS;
+            for (const FrameBox& q : mods)
+                if (q.r0 <= tb + K && q.r1 >= ta - K - 1 && q.c0 <= jw + LD && q.c1 >= jw - 1) need |= q.what;
+            (is_near ? near : far).push_back(fdtd::EdgeTile{tx, (int)ta, (int)tb, fdtd::edge_class_for(need)});
         }
     };
     if (loK > lo) for (int tx = 0; tx < ntx_e; ++tx) push(tx, lo, loK);
@@ -571,6 +593,17 @@ void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps&
         }
     }
     if (hi > hiK && hiK >= loK) for (int tx = 0; tx < ntx_e; ++tx) push(tx, std::max(hiK, lo), hi);
+    // tiles of one class are launched together: sort each half by class (stable: DRAM likes the row order kept)
+    auto by_class = [](std::vector<fdtd::EdgeTile>& v, std::vector<FrameMaps::EdgeRun>& runs, int base) {
+        std::stable_sort(v.begin(), v.end(), [](const fdtd::EdgeTile& a, const fdtd::EdgeTile& b) { return a.pad < b.pad; });
+        runs.clear();
+        for (size_t k = 0; k < v.size(); ++k) {
+            if (runs.empty() || runs.back().flags != v[k].pad) runs.push_back({base + (int)k, 0, v[k].pad});
+            runs.back().count++;
+        }
+    };
+    by_class(near, m.edge_runs_near, 0);
+    by_class(far, m.edge_runs_far, (int)near.size());
     m.n_edge_near = (int)near.size();
     m.h_edge = near;
     m.h_edge.insert(m.h_edge.end(), far.begin(), far.end());
@@ -596,15 +629,15 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     for (int p = 0; p < c->n_src; ++p) {
         if (!key[p]) continue;
         const fdtd_source& q = c->src[p];
-        if (q.kind == FDTD_SRC_POINT) mods.push_back({q.row, q.row, q.col, q.col});
-        else if (q.kind == FDTD_SRC_RIGHT || q.kind == FDTD_SRC_LEFT) mods.push_back({-BIG, BIG, q.col, q.col});
-        else if (q.kind == FDTD_SRC_UP) mods.push_back({q.row + 1, q.row + 1, -BIG, BIG});
-        else mods.push_back({q.row, q.row, -BIG, BIG});
+        if (q.kind == FDTD_SRC_POINT) mods.push_back({q.row, q.row, q.col, q.col, fdtd::EDGE_SRC});
+        else if (q.kind == FDTD_SRC_RIGHT || q.kind == FDTD_SRC_LEFT) mods.push_back({-BIG, BIG, q.col, q.col, fdtd::EDGE_SRC});
+        else if (q.kind == FDTD_SRC_UP) mods.push_back({q.row + 1, q.row + 1, -BIG, BIG, fdtd::EDGE_SRC});
+        else mods.push_back({q.row, q.row, -BIG, BIG, fdtd::EDGE_SRC});
     }
     for (int r = 0; r < c->n_rect; ++r)
         for (const RectI* b : {&c->rh[r], &c->rex[r], &c->rey[r]})
-            if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1});
-    for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k]});
+            if (b->r1 > b->r0 && b->c1 > b->c0) mods.push_back({b->r0, b->r1 - 1, b->c0, b->c1 - 1, fdtd::EDGE_MISC});
+    for (int k = 0; k < c->n_probe; ++k) mods.push_back({c->probe_i[k], c->probe_i[k], c->probe_j[k], c->probe_j[k], fdtd::EDGE_MISC});
     const bool deep = c->halo_depth > 1;
     const FrameGeom geom{c->cfg.rows, c->cfg.cols, c->cfg.row_begin, c->cfg.row_end, c->cfg.tile_rows,
                          c->cfg.block_warps, K, kvec<T>(), deep ? c->halo_top : 0, deep ? c->halo_bot : 0, edge,
@@ -679,18 +712,7 @@ void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1
     } timed(c, st, K == c->temporal);
     if (timed.on)
         for (int ty = ty0; ty < ty0 + ny && ty < (int)m.row_cells.size(); ++ty) c->kt_cell_steps += m.row_cells[ty] * K;
-    if (c->kstep_variant == 1) {                                 // experimental: fewer issue slots per row (kernels.cuh stepK_lean)
-        constexpr int ring_rows = fdtd::KRing<K>::ROWS > 0 ? fdtd::KRing<K>::ROWS : 4;
-        const size_t lean_bytes = (size_t)w * ring_rows * 5 * 32 * V2 * sizeof(T);
-        if (lean_bytes > 48 * 1024)
-            cudaFuncSetAttribute(fdtd::stepK_lean<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_bytes);
-        fdtd::stepK_lean<T, V2, K><<<grid, w * 32, lean_bytes, st>>>(P, skip, m.ntx2);
-        return;
-    }
-    const size_t ring_bytes = (size_t)w * fdtd::KRing<K>::ROWS * 5 * 32 * V2 * sizeof(T);   // per-warp cp.async prefetch ring
-    if (ring_bytes > 48 * 1024)
-        cudaFuncSetAttribute(fdtd::stepK_stream<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
-    fdtd::stepK_stream<T, V2, K><<<grid, w * 32, ring_bytes, st>>>(P, skip, m.ntx2);
+    fdtd::launch_stepK_k<T, K>(P, c->kstep_variant, w, grid, skip, m.ntx2, st);   // 1 = stepK_lean (default), 0 = stepK_stream
 }
 
 template <typename T>
@@ -713,6 +735,7 @@ void launch_stepK_any(const StepParams<T>& P, fdtd_ctx* c, int K, int ty0 = 0, i
 // With slabs the generation each pass wrote has its halo rows exchanged on the comm stream right after the pass.
 template <typename T>
 int group_impl(fdtd_ctx* c, int64_t n, int K) {
+    Range nvtx("fdtd:k_group_pass_chain");
     if (int rc = build_frame_maps<T>(c, n, K)) return rc;
     const FrameMaps& m = c->fm[K];
     const int A = c->cur, B = (A + 1) % c->ngen;
@@ -826,6 +849,7 @@ int resident_tables(fdtd_ctx* c) {
 // calls n .. n+g-1 in ONE cooperative launch
 template <typename T>
 int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
+    Range nvtx("fdtd:resident_run");
     using G = fdtd::ResGeom;
     if (int rc = resident_tables<T>(c)) return rc;
     const int A = c->cur, B = next_gen(c, A);
@@ -838,7 +862,7 @@ int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
         int coop = 0, sms = 0, per_sm = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->cfg.device));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fdtd::step_resident<T>, fdtd::RES_THREADS, 0));
+        CK(fdtd::resident_blocks_per_sm<T>(&per_sm));
         if (!coop || per_sm < 1) return fail(c, FDTD_ERR_CUDA, "cooperative launch unavailable for step_resident");
         c->res_blocks_max = per_sm * sms;
     }
@@ -846,10 +870,7 @@ int resident_run(fdtd_ctx* c, int64_t n, int64_t g) {
     const int blocks = std::min(tiles, c->res_blocks_max);       // all CTAs co-resident; they stride over the tiles
     T* h1 = (T*)c->gen[B][0]; T* ex1 = (T*)c->gen[B][1]; T* ey1 = (T*)c->gen[B][2];
     fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
-    long long first = n;
-    int ns = (int)g;
-    void* args[] = {&P, &h1, &ex1, &ey1, &R, &first, &ns};
-    CK(cudaLaunchCooperativeKernel((void*)fdtd::step_resident<T>, dim3((unsigned)blocks), dim3(fdtd::RES_THREADS), args, 0, c->stream));
+    CK(fdtd::launch_step_resident<T>(P, h1, ex1, ey1, R, n, (int)g, blocks, c->stream));
     c->stats.kernel_launches++;
     c->cur = (g & 1) ? B : A;
     if (c->n_probe) c->probe_count += g;
@@ -863,17 +884,26 @@ int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
 }
 
 // ---- frame mode 3: plain K-step tiles + stepK_edge tiles, nothing else ------------------------------------------------
-template <typename T, int K>
-void launch_edge_k(const StepParams<T>& P, const fdtd::EdgeTile* tiles, int n, const fdtd::ResSources<T>& R, long long first,
-                   cudaStream_t st) {
-    fdtd::stepK_edge<T, kvec<T>(), K><<<(unsigned)n, 32, 0, st>>>(P, tiles, n, R, first);
+template <typename T>
+cudaError_t launch_edge_any(int K, const StepParams<T>& P, int flags, const fdtd::EdgeTile* tiles, int n,
+                            const fdtd::ResSources<T>& R, long long first, cudaStream_t st) {
+    switch (K) {
+        case 2: return fdtd::launch_edge_k<T, 2>(P, flags, tiles, n, R, first, st);
+        case 3: return fdtd::launch_edge_k<T, 3>(P, flags, tiles, n, R, first, st);
+        case 4: return fdtd::launch_edge_k<T, 4>(P, flags, tiles, n, R, first, st);
+        case 5: return fdtd::launch_edge_k<T, 5>(P, flags, tiles, n, R, first, st);
+        case 6: return fdtd::launch_edge_k<T, 6>(P, flags, tiles, n, R, first, st);
+        case 7: return fdtd::launch_edge_k<T, 7>(P, flags, tiles, n, R, first, st);
+        default: return fdtd::launch_edge_k<T, 8>(P, flags, tiles, n, R, first, st);
+    }
 }
 
-// edge tiles [first_tile, first_tile + n_tiles) of the plan
+// the edge tiles of the plan next to a slab interface (near) or all the others: one launch per tile class in that half
 template <typename T>
-int launch_edge(fdtd_ctx* c, int64_t n, int K, int A, int B, int first_tile, int n_tiles, cudaStream_t st) {
+int launch_edge(fdtd_ctx* c, int64_t n, int K, int A, int B, bool near_half, cudaStream_t st) {
     const FrameMaps& m = c->fm[K];
-    if (n_tiles <= 0) return 0;
+    const std::vector<FrameMaps::EdgeRun>& runs = near_half ? m.edge_runs_near : m.edge_runs_far;
+    if (runs.empty()) return 0;
     if (int rc = resident_tables<T>(c)) return rc;
     StepParams<T> PE;
     if (int rc = fill_params<T>(c, PE, n, A, B)) return rc;
@@ -882,18 +912,10 @@ int launch_edge(fdtd_ctx* c, int64_t n, int K, int A, int B, int first_tile, int
     PE.row_hi = (int)(c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0));
     if (c->n_probe) PE.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
     fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
-    const fdtd::EdgeTile* tiles = m.d_edge + first_tile;
-    switch (K) {
-        case 2: launch_edge_k<T, 2>(PE, tiles, n_tiles, R, n, st); break;
-        case 3: launch_edge_k<T, 3>(PE, tiles, n_tiles, R, n, st); break;
-        case 4: launch_edge_k<T, 4>(PE, tiles, n_tiles, R, n, st); break;
-        case 5: launch_edge_k<T, 5>(PE, tiles, n_tiles, R, n, st); break;
-        case 6: launch_edge_k<T, 6>(PE, tiles, n_tiles, R, n, st); break;
-        case 7: launch_edge_k<T, 7>(PE, tiles, n_tiles, R, n, st); break;
-        default: launch_edge_k<T, 8>(PE, tiles, n_tiles, R, n, st); break;
+    for (const FrameMaps::EdgeRun& run : runs) {                 // costliest class first: it is the one with the longest tiles
+        CK(launch_edge_any<T>(K, PE, c->edge_class_force ? fdtd::EDGE_ALL : run.flags, m.d_edge + run.first, run.count, R, n, st));
+        c->stats.kernel_launches++;
     }
-    c->stats.kernel_launches++;
-    CK(cudaGetLastError());
     return 0;
 }
 
@@ -903,6 +925,7 @@ int launch_edge(fdtd_ctx* c, int64_t n, int K, int A, int B, int first_tile, int
 // previous exchange has landed; the D-row blocks of B leave as soon as they are done, while the interior still runs.
 template <typename T>
 int group_edge(fdtd_ctx* c, int64_t n, int K) {
+    Range nvtx("fdtd:k_group");
     if (int rc = build_frame_maps<T>(c, n, K)) return rc;
     const FrameMaps& m = c->fm[K];
     const int A = c->cur, B = (A + 1) % c->ngen;
@@ -916,7 +939,8 @@ int group_edge(fdtd_ctx* c, int64_t n, int K) {
     CK(cudaEventRecord(c->ev_int, c->stream));                  // everything before this group
     CK(cudaStreamWaitEvent(c->edge_stream, c->ev_int, 0));
     if (!c->comm) {
-        if (int rc = launch_edge<T>(c, n, K, A, B, 0, n_edge, c->edge_stream)) return rc;
+        if (int rc = launch_edge<T>(c, n, K, A, B, true, c->edge_stream)) return rc;
+        if (int rc = launch_edge<T>(c, n, K, A, B, false, c->edge_stream)) return rc;
         if (m.nty > 0) { launch_stepK_any<T>(PK, c, K); c->stats.kernel_launches++; CK(cudaGetLastError()); }
     } else {
         const int TR = c->cfg.tile_rows, D = c->halo_depth;
@@ -924,10 +948,10 @@ int group_edge(fdtd_ctx* c, int64_t n, int K) {
         const int e_bot = c->cfg.row_end < c->cfg.rows ? std::min(m.nty - e_top, (D + TR - 1) / TR + 1) : 0;
         const int n_int = m.nty - e_top - e_bot;
         // tiles away from the interfaces read owned rows only: they start at once
-        if (int rc = launch_edge<T>(c, n, K, A, B, m.n_edge_near, n_edge - m.n_edge_near, c->edge_stream)) return rc;
+        if (int rc = launch_edge<T>(c, n, K, A, B, false, c->edge_stream)) return rc;
         if (n_int > 0) { launch_stepK_any<T>(PK, c, K, e_top, n_int, c->stream); c->stats.kernel_launches++; }
         CK(cudaStreamWaitEvent(c->edge_stream, c->ev_comm, 0)); // the neighbours' rows of A have landed
-        if (int rc = launch_edge<T>(c, n, K, A, B, 0, m.n_edge_near, c->edge_stream)) return rc;
+        if (int rc = launch_edge<T>(c, n, K, A, B, true, c->edge_stream)) return rc;
         if (e_top > 0) { launch_stepK_any<T>(PK, c, K, 0, e_top, c->edge_stream); c->stats.kernel_launches++; }
         if (e_bot > 0) { launch_stepK_any<T>(PK, c, K, m.nty - e_bot, e_bot, c->edge_stream); c->stats.kernel_launches++; }
         CK(cudaGetLastError());
@@ -967,6 +991,7 @@ int group_any(fdtd_ctx* c, int64_t n, int K) {
 
 template <typename T>
 int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, int64_t total_calls) {
+    Range nvtx("fdtd:snapshot");
     fdtd::PatchList pl; pl.n = 0;
     if (next_step < total_calls && next_step < c->table_len) {
         for (int p = 0; p < c->n_src; ++p) {
@@ -981,10 +1006,9 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     const int64_t rows = c->owned, cols = c->cfg.cols;
     CK(cudaStreamWaitEvent(c->stream, c->ev_free[slot], 0));
     dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)std::min<int64_t>((rows + 3) / 4, 65535));
-    fdtd::plane_to_f64<T><<<grid, block, 0, c->stream>>>(c->snap_dev[slot], cols,
-        plane<T>(c->gen[c->cur][0], c, c->cfg.row_begin), c->pitch, (int)rows, (int)cols, (int)c->cfg.row_begin, pl);
+    CK(fdtd::launch_plane_to_f64<T>(grid, block, c->stream, c->snap_dev[slot], cols,
+        plane<T>(c->gen[c->cur][0], c, c->cfg.row_begin), c->pitch, (int)rows, (int)cols, (int)c->cfg.row_begin, pl));
     c->stats.kernel_launches++;
-    CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_packed[slot], c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev_packed[slot], 0));
     // device slot -> pinned host slot (async DMA) -> the caller's array (plain memcpy run by the driver's callback
@@ -1044,6 +1068,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(c, FDTD_ERR_ARG, "bad device ordinal");
     c = new fdtd_ctx();
     c->cfg = *cfg;
+    if (const char* eg = std::getenv("FDTD_EDGE_GENERIC")) c->edge_class_force = std::atoi(eg) != 0;
     if (const char* er = std::getenv("FDTD_EDGE_ROWS")) { const int v = std::atoi(er); if (v >= 1 && v <= 4096) c->edge_rows = v; }
     c->esize = cfg->dtype == FDTD_F64 ? 8 : 4;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
@@ -1113,6 +1138,9 @@ int fdtd_destroy(fdtd_handle c) {
         if (c->snap_pin[s]) cudaFreeHost(c->snap_pin[s]);
         if (c->ev_packed[s]) cudaEventDestroy(c->ev_packed[s]);
         if (c->ev_free[s]) cudaEventDestroy(c->ev_free[s]);
+        if (c->view[s].dev) cudaFree(c->view[s].dev);
+        if (c->view[s].pin) cudaFreeHost(c->view[s].pin);
+        if (c->view[s].done) cudaEventDestroy(c->view[s].done);
     }
     for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm, c->ev_int, c->ev_p3}) if (e) cudaEventDestroy(e);
     for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream, c->edge_stream}) if (s) cudaStreamDestroy(s);
@@ -1167,7 +1195,8 @@ int fdtd_plan_frame(const fdtd_config* cfg, int32_t steps_per_pass, int32_t n_bo
 }
 
 int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes, const int64_t* boxes,
-                   fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles, int32_t* edge_tiles, int32_t max_edge_tiles) {
+                   const int32_t* box_is_pulse, fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles,
+                   int32_t* edge_tiles, int32_t max_edge_tiles) {
     fdtd_ctx* c = nullptr;
     if (!cfg || !plan || steps_per_pass < 2 || steps_per_pass > 8 || n_boxes < 0 || (n_boxes > 0 && !boxes) ||
         halo_depth < 1 || halo_depth > 9)
@@ -1179,7 +1208,9 @@ int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_
     if (!whole && halo_depth < steps_per_pass + 1)
         return fail(c, FDTD_ERR_ARG, "a y-slab needs halos of steps_per_pass + 1 rows for the edge plan");
     std::vector<FrameBox> mods;
-    for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
+    for (int k = 0; k < n_boxes; ++k)
+        mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3],
+                        !box_is_pulse ? (fdtd::EDGE_SRC | fdtd::EDGE_MISC) : (box_is_pulse[k] ? fdtd::EDGE_SRC : fdtd::EDGE_MISC)});
     const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
     const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
@@ -1196,7 +1227,7 @@ int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_
     if (edge_tiles)
         for (size_t k = 0; k < m.h_edge.size() && (int32_t)k < max_edge_tiles; ++k) {
             edge_tiles[4 * k] = m.h_edge[k].tx; edge_tiles[4 * k + 1] = m.h_edge[k].ta; edge_tiles[4 * k + 2] = m.h_edge[k].tb;
-            edge_tiles[4 * k + 3] = (int)k < m.n_edge_near ? 1 : 0;
+            edge_tiles[4 * k + 3] = ((int)k < m.n_edge_near ? 1 : 0) | (m.h_edge[k].pad << 8);
         }
     return 0;
 }
@@ -1304,6 +1335,7 @@ int fdtd_set_host_row_origin(fdtd_handle c, int64_t first_global_row) {
 }
 
 int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_coef, int64_t host_ld) {
+    Range nvtx("fdtd_upload_coeffs");
     NEED_BOUND();
     if (!eps_coef || !mu_coef || host_ld < c->cfg.cols) return fail(c, FDTD_ERR_ARG, "bad coefficient arrays");
     const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off;     // every stored h-row
@@ -1323,13 +1355,12 @@ int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, 
     NEED_BOUND();
     dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
     if (c->cfg.dtype == FDTD_F64)
-        fdtd::synth_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
-            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0);
+        CK(fdtd::launch_synth_coeffs<double>(grid, c->stream, (double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0));
     else
-        fdtd::synth_coeffs<float><<<grid, 256, 0, c->stream>>>((float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
-            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0);
+        CK(fdtd::launch_synth_coeffs<float>(grid, c->stream, (float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
+            (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0));
     c->stats.kernel_launches++;
-    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1349,14 +1380,14 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
     CK(cudaMalloc(&dev, host.size() * sizeof(fdtd::ShapeDev)));
     CK(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(fdtd::ShapeDev), cudaMemcpyHostToDevice, c->stream));
     dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
+    cudaError_t e;
     if (c->cfg.dtype == FDTD_F64)
-        fdtd::paint_coeffs<double><<<grid, 256, 0, c->stream>>>((double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
+        e = fdtd::launch_paint_coeffs<double>(grid, c->stream, (double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
     else
-        fdtd::paint_coeffs<float><<<grid, 256, 0, c->stream>>>((float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
+        e = fdtd::launch_paint_coeffs<float>(grid, c->stream, (float*)c->epc, (float*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
     c->stats.kernel_launches++;
-    cudaError_t e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(c->stream);
     cudaFree(dev);
     if (e != cudaSuccess || e2 != cudaSuccess)
@@ -1385,6 +1416,7 @@ int fdtd_zero_fields(fdtd_handle c) {
 }
 
 int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const double* ey) {
+    Range nvtx("fdtd_set_fields");
     NEED_BOUND();
     if (int rc = quiesce(c)) return rc;
     const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off, NC = c->cfg.cols;
@@ -1404,6 +1436,7 @@ int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const dou
 }
 
 int fdtd_get_fields(fdtd_handle c, double* hh, double* ex, double* ey) {
+    Range nvtx("fdtd_get_fields");
     NEED_BOUND();
     if (int rc = quiesce(c)) return rc;
     const int64_t g0 = c->cfg.row_begin, n = c->owned, NC = c->cfg.cols;
@@ -1506,9 +1539,12 @@ int fdtd_step(fdtd_handle c, int64_t step) {
     return step_any(c, step);
 }
 
-int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
-             double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots) {
+// The run loops of solver.py:288-292 / :331-337.  wait = false (fdtd_run_enqueue): everything is queued on the context's
+// streams and the host returns at once -- consecutive runs chain on the device exactly like the groups of one run do.
+static int run_impl(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
+                    double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots, bool wait) {
     NEED_BOUND();
+    Range nvtx(wait ? "fdtd_run" : "fdtd_run_enqueue");
     if (n_snapshots) *n_snapshots = 0;
     if (n_steps < 0) return fail(c, FDTD_ERR_ARG, "negative step count");
     const bool snaps = snapshot_every > 0 && snapshots_host != nullptr;
@@ -1578,6 +1614,12 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     }
     if (c->comm) cudaStreamWaitEvent(c->stream, c->ev_comm, 0);      // the timed region ends after the last halo landed
     cudaEventRecord(c->ev_t1, c->stream);
+    if (!wait) {
+        if (n_snapshots) *n_snapshots = k;
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        return 0;
+    }
     cudaError_t e1 = cudaStreamSynchronize(c->stream);
     cudaError_t e2 = cudaStreamSynchronize(c->copy_stream);
     cudaError_t e3 = cudaStreamSynchronize(c->comm_stream);
@@ -1589,6 +1631,72 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
     c->stats.last_run_ms = ms;
+    return 0;
+}
+
+int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
+             double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots) {
+    return run_impl(c, first_step, n_steps, snapshot_every, snapshots_host, max_snapshots, total_calls, n_snapshots, true);
+}
+
+int fdtd_run_enqueue(fdtd_handle c, int64_t first_step, int64_t n_steps) {
+    return run_impl(c, first_step, n_steps, 0, nullptr, 0, 0, nullptr, false);
+}
+
+// ---- realtime view (the loop of solver.py:309-329 with batches of calls per frame) --------------------
+int fdtd_view_begin(fdtd_handle c, int32_t row_stride, int32_t col_stride) {
+    NEED_BOUND();
+    Range nvtx("fdtd:view");
+    if (row_stride < 1 || col_stride < 1) return fail(c, FDTD_ERR_ARG, "view strides must be >= 1");
+    fdtd_ctx::View& v = c->view[c->view_head];
+    if (v.pending) return fail(c, FDTD_ERR_STATE, "two views are in flight: fetch one with fdtd_view_end first");
+    // rows of the GLOBAL picture (0, row_stride, 2 row_stride, ...) that this slab owns
+    const int64_t first = (c->cfg.row_begin + row_stride - 1) / row_stride * row_stride;
+    const int64_t rows = first < c->cfg.row_end ? (c->cfg.row_end - 1 - first) / row_stride + 1 : 0;
+    const int64_t cols = (c->cfg.cols - 1) / col_stride + 1;
+    const size_t bytes = (size_t)std::max<int64_t>(rows, 1) * cols * 8;
+    if (bytes > v.cap) {
+        if (v.dev) cudaFree(v.dev);
+        if (v.pin) cudaFreeHost(v.pin);
+        v.dev = v.pin = nullptr; v.cap = 0;
+        CK(cudaMalloc(&v.dev, bytes));
+        CK(cudaHostAlloc(&v.pin, bytes, cudaHostAllocDefault));
+        v.cap = bytes;
+    }
+    if (!v.done) CK(cudaEventCreateWithFlags(&v.done, cudaEventDisableTiming));
+    if (rows > 0) {
+        dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)std::min<int64_t>((rows + 3) / 4, 65535));
+        if (c->cfg.dtype == FDTD_F64)
+            CK(fdtd::launch_plane_view<double>(grid, block, c->stream, v.dev, cols, plane<double>(c->gen[c->cur][0], c, first),
+                                               c->pitch, (int)rows, (int)cols, row_stride, col_stride));
+        else
+            CK(fdtd::launch_plane_view<float>(grid, block, c->stream, v.dev, cols, plane<float>(c->gen[c->cur][0], c, first),
+                                              c->pitch, (int)rows, (int)cols, row_stride, col_stride));
+        c->stats.kernel_launches++;
+        // the copy leaves on the side stream: the next batch of calls, queued behind the pack kernel, runs beside it
+        CK(cudaEventRecord(v.done, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, v.done, 0));
+        CK(cudaMemcpyAsync(v.pin, v.dev, (size_t)rows * cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CK(cudaEventRecord(v.done, c->copy_stream));
+    // the pack kernel of the view after next must not overwrite v.dev before this copy has read it: that kernel is
+    // queued on c->stream only after fdtd_view_end synchronised on v.done, so no extra dependency is needed
+    v.rows = rows; v.cols = cols; v.pending = true;
+    c->view_head ^= 1;
+    return 0;
+}
+
+int fdtd_view_end(fdtd_handle c, double* host_out, int64_t capacity, int64_t* rows, int64_t* cols) {
+    NEED_BOUND();
+    fdtd_ctx::View& v = c->view[c->view_tail];
+    if (!v.pending) return fail(c, FDTD_ERR_STATE, "no view in flight");
+    if (!host_out || capacity < v.rows * v.cols) return fail(c, FDTD_ERR_ARG, "view buffer too small");
+    CK(cudaEventSynchronize(v.done));
+    std::memcpy(host_out, v.pin, (size_t)(v.rows * v.cols) * 8);
+    if (rows) *rows = v.rows;
+    if (cols) *cols = v.cols;
+    v.pending = false;
+    c->view_tail ^= 1;
     return 0;
 }
 

@@ -925,6 +925,17 @@ __global__ void plane_to_f64(double* dst, long long dst_ld, const T* src, long l
     }
 }
 
+// every row_stride-th row / col_stride-th column of a pitched T plane -> dense double plane (the picture of the realtime
+// view; no aliasing patches: plot_and_show draws the field update() returned, solver.py:319-325)
+template <typename T>
+__global__ void plane_view(double* dst, long long dst_ld, const T* src, long long pitch, int rows_out, int cols_out,
+                           int row_stride, int col_stride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols_out) return;
+    for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < rows_out; i += gridDim.y * blockDim.y)
+        dst[(long long)i * dst_ld + j] = (double)src[(long long)i * row_stride * pitch + (long long)j * col_stride];
+}
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
     unsigned long long z = x;

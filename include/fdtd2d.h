@@ -260,12 +260,17 @@ int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth);
 int fdtd_set_halo_depth(fdtd_handle h, int32_t halo_depth);
 /* The tile plan of frame mode 3 as pure host logic (no CUDA call).  Every tile of the slab is a K-step tile: skip
  * (k_tiles_y x k_tiles_x bytes) = 0 for the tiles of the plain K-step kernel; every other tile is listed in edge_tiles
- * as {column tile tx, first row, end row, next-to-an-interface flag} for stepK_edge (csrc/edge.cuh), which folds walls,
+ * as {column tile tx, first row, end row, next-to-an-interface flag | tile class << 8} for stepK_edge (csrc/edge.cuh;
+ * the class is the feature set of the instantiation that runs the tile: 1 grid rows 0 / NR-1 / NR or unstored rows,
+ * 2 grid columns 0 / NC-1 / NC, 4 pulses, 8 reflectors and probes), which folds walls,
  * pulses, reflectors and probes into the same register pipeline -- incl. the K-row bands at the top / bottom wall that
  * the plain tile grid (rows k_row_lo .. k_row_hi) leaves out.  A y-slab needs halo_depth >= steps_per_pass + 1.
- * *n_edge_tiles receives the number of edge tiles; at most max_edge_tiles quadruples are written to edge_tiles. */
+ * box_is_pulse (NULL, or one flag per box) tells a pulse's box (class bit 4) from a reflector / probe box (class bit 8);
+ * NULL counts every box as both.  *n_edge_tiles receives the number of edge tiles; at most max_edge_tiles quadruples are
+ * written to edge_tiles, in launch order (tiles of one class are consecutive within the near and the far half). */
 int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_depth, int32_t n_boxes, const int64_t* boxes,
-                   fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles, int32_t* edge_tiles, int32_t max_edge_tiles);
+                   const int32_t* box_is_pulse, fdtd_frame_plan* plan, uint8_t* skip, int32_t* n_edge_tiles,
+                   int32_t* edge_tiles, int32_t max_edge_tiles);
 /* Block pointers of the current generation for an external transport: send_down = the last D owned rows, recv_down = the
  * D rows stored from the slab below, send_up = the first D owned rows, recv_up = the D rows stored from the slab above
  * (NULL where there is no neighbour); *count = elements per block (D x pitch). */

@@ -115,7 +115,24 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
     return 0;
 }
 
-// One launch of stepK_edge<double, 2, K>: K calls for every listed tile (tiles: n x {tx, ta, tb, 0}).  The pulse records
+}  // extern "C"
+
+// one warp = one edge tile, through the instantiation of its class (edge.cuh EDGE_CLASSES)
+template <int K>
+static int edge_tile_class(int cls, const StepParams<double>& P, const EdgeTile* tl, int n_tiles, const ResSources<double>& R) {
+    switch (cls) {
+        case EDGE_COLS: simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_COLS>(P, tl, n_tiles, R, 0); }); return 0;
+        case EDGE_ROWS: simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_ROWS>(P, tl, n_tiles, R, 0); }); return 0;
+        case EDGE_SRC: simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_SRC>(P, tl, n_tiles, R, 0); }); return 0;
+        case EDGE_COLS | EDGE_SRC: simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_COLS | EDGE_SRC>(P, tl, n_tiles, R, 0); }); return 0;
+        case EDGE_ALL: simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_ALL>(P, tl, n_tiles, R, 0); }); return 0;
+        default: return -2;
+    }
+}
+
+extern "C" {
+
+// One launch of stepK_edge<double, 2, K>: K calls for every listed tile (tiles: n x {tx, ta, tb, class or 0 = all features}).  The pulse records
 // of the K calls come as the device tables of resident mode do: count[K], last[K], src[K][stride].
 int emul_stepK_edge(const StreamScene* sc, int K, const int32_t* tiles, int n_tiles, const int32_t* count, const double* last,
                     const EmuSrc* src, int stride, int n_probe, const int32_t* probe_ij, double* probe_out) {
@@ -139,17 +156,19 @@ int emul_stepK_edge(const StreamScene* sc, int K, const int32_t* tiles, int n_ti
     const EdgeTile* tl = reinterpret_cast<const EdgeTile*>(tiles);
     for (int b = 0; b < n_tiles; ++b) {
         simt::g_block_idx = simt::Idx{(unsigned)b, 0, 0};
+        const int cls = tl[b].pad ? tl[b].pad : (int)EDGE_ALL;   // the instantiation the host launches this tile with
+        int rc = -1;
         switch (K) {
-            case 1: simt::run_warp(0, [&] { stepK_edge<double, 2, 1>(P, tl, n_tiles, R, 0); }); break;
-            case 2: simt::run_warp(0, [&] { stepK_edge<double, 2, 2>(P, tl, n_tiles, R, 0); }); break;
-            case 3: simt::run_warp(0, [&] { stepK_edge<double, 2, 3>(P, tl, n_tiles, R, 0); }); break;
-            case 4: simt::run_warp(0, [&] { stepK_edge<double, 2, 4>(P, tl, n_tiles, R, 0); }); break;
-            case 5: simt::run_warp(0, [&] { stepK_edge<double, 2, 5>(P, tl, n_tiles, R, 0); }); break;
-            case 6: simt::run_warp(0, [&] { stepK_edge<double, 2, 6>(P, tl, n_tiles, R, 0); }); break;
-            case 7: simt::run_warp(0, [&] { stepK_edge<double, 2, 7>(P, tl, n_tiles, R, 0); }); break;
-            case 8: simt::run_warp(0, [&] { stepK_edge<double, 2, 8>(P, tl, n_tiles, R, 0); }); break;
-            default: return -1;
+            case 1: rc = edge_tile_class<1>(cls, P, tl, n_tiles, R); break;
+            case 2: rc = edge_tile_class<2>(cls, P, tl, n_tiles, R); break;
+            case 3: rc = edge_tile_class<3>(cls, P, tl, n_tiles, R); break;
+            case 4: rc = edge_tile_class<4>(cls, P, tl, n_tiles, R); break;
+            case 5: rc = edge_tile_class<5>(cls, P, tl, n_tiles, R); break;
+            case 6: rc = edge_tile_class<6>(cls, P, tl, n_tiles, R); break;
+            case 7: rc = edge_tile_class<7>(cls, P, tl, n_tiles, R); break;
+            case 8: rc = edge_tile_class<8>(cls, P, tl, n_tiles, R); break;
         }
+        if (rc) return rc;
     }
     return 0;
 }

@@ -136,7 +136,8 @@ def stepK_stream(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip, 
 
 
 def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan):
-    """One launch of stepK_edge<double, 2, K>: calls n .. n+K-1 for every listed tile (tx, ta, tb).  Returns the fields
+    """One launch of stepK_edge<double, 2, K>: calls n .. n+K-1 for every listed tile (tx, ta, tb[, class]): a tile with a class
+    runs through that instantiation of the kernel (edge.cuh EDGE_CLASSES), the others through the all-features one.  Returns the fields
     of generation B (cells no tile owns keep `fill`) and the probe records (K, n_probe, 3)."""
     from fdtd_em_solver_b200.engine import build_source_tables
     s = Scene(f, setup, times, n, fill=fill, pad=np.nan)          # NaN outside the arrays: nothing read there may be kept
@@ -155,7 +156,7 @@ def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan):
                 k += 1
         count[m] = k
         lastv[m] = last[n + m] if stride else 0.0
-    tl = np.ascontiguousarray([[tx, ta, tb, 0] for tx, ta, tb in tiles], dtype=np.int32).reshape(-1, 4)
+    tl = np.ascontiguousarray([list(t) + [0] * (4 - len(t)) for t in tiles], dtype=np.int32).reshape(-1, 4)
     pij = np.ascontiguousarray(np.asarray(probes, dtype=np.int32).reshape(-1, 2))
     pout = np.full((K, max(len(pij), 1), 3), np.nan)
     rc = load().emul_stepK_edge(C.byref(s.sc), K, tl.ctypes.data, len(tl), count.ctypes.data, lastv.ctypes.data,

@@ -111,6 +111,7 @@ def test_only_listed_tiles_are_written():
 # ---- the library's own tile plan (fdtd_plan_edge): plain tiles through stepK_lean / stepK_stream, all the others through
 # ---- stepK_edge, together one whole group ------------------------------------------------------------------------------
 def _plan_edge(rows, cols, K, tile_rows, boxes=(), row_begin=0, row_end=None, halo_depth=1):
+    """-> plan, skip map, tiles (tx, ta, tb, next-to-an-interface flag, class).  A box is (r0, r1, c0, c1[, is_pulse])."""
     import ctypes as C
     from fdtd_em_solver_b200 import _lib as L
     lib = L.load()
@@ -118,14 +119,17 @@ def _plan_edge(rows, cols, K, tile_rows, boxes=(), row_begin=0, row_end=None, ha
     cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = rows, cols, row_begin, rows if row_end is None else row_end
     cfg.dtype, cfg.tile_rows, cfg.block_warps = L.F64, tile_rows, 1
     plan = L.FramePlan()
-    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 4))
+    b = np.ascontiguousarray(np.asarray([q[:4] for q in boxes], dtype=np.int64).reshape(-1, 4))
+    kinds = np.ascontiguousarray([q[4] for q in boxes if len(q) > 4], dtype=np.int32)
+    kp = kinds.ctypes.data if len(boxes) and len(kinds) == len(boxes) else None
     n = C.c_int32(0)
-    assert lib.fdtd_plan_edge(C.byref(cfg), K, halo_depth, len(b), b.ctypes.data, C.byref(plan), None, C.byref(n), None, 0) == 0
+    assert lib.fdtd_plan_edge(C.byref(cfg), K, halo_depth, len(b), b.ctypes.data, kp, C.byref(plan), None, C.byref(n), None, 0) == 0
     skip = np.ones((max(plan.k_tiles_y, 1), plan.k_tiles_x), dtype=np.uint8)
     tiles = np.zeros((max(n.value, 1), 4), dtype=np.int32)
-    assert lib.fdtd_plan_edge(C.byref(cfg), K, halo_depth, len(b), b.ctypes.data, C.byref(plan), skip.ctypes.data, C.byref(n),
+    assert lib.fdtd_plan_edge(C.byref(cfg), K, halo_depth, len(b), b.ctypes.data, kp, C.byref(plan), skip.ctypes.data, C.byref(n),
                               tiles.ctypes.data, len(tiles)) == 0
-    return plan, skip, tiles[:n.value]
+    tiles = tiles[:n.value]
+    return plan, skip, np.column_stack([tiles[:, :3], tiles[:, 3] & 1, tiles[:, 3] >> 8])
 
 
 def _boxes(setup, rows, cols):
@@ -134,15 +138,15 @@ def _boxes(setup, rows, cols):
     big = 1 << 40
     out = []
     for p in setup.pulses:
-        if p.direction is None: out.append((p.row, p.row, p.col, p.col))
-        elif p.direction in ("right", "left"): out.append((-big, big, p.col, p.col))
-        elif p.direction == "up": out.append((p.row + 1, p.row + 1, -big, big))
-        else: out.append((p.row, p.row, -big, big))
+        if p.direction is None: out.append((p.row, p.row, p.col, p.col, 1))
+        elif p.direction in ("right", "left"): out.append((-big, big, p.col, p.col, 1))
+        elif p.direction == "up": out.append((p.row + 1, p.row + 1, -big, big, 1))
+        else: out.append((p.row, p.row, -big, big, 1))
     for rect in setup.reflectors:
         for shape in ((rows, cols), (rows + 1, cols), (rows, cols + 1)):
             r0, r1, c0, c1 = clip_rect(rect, *shape)
             if r1 > r0 and c1 > c0:
-                out.append((r0, r1 - 1, c0, c1 - 1))
+                out.append((r0, r1 - 1, c0, c1 - 1, 0))
     return out
 
 
@@ -150,6 +154,7 @@ def _boxes(setup, rows, cols):
 @pytest.mark.parametrize("shape", [(100, 230), (61, 700)])
 def test_plain_plus_edge_tiles_are_one_whole_group(shape, K, tile_rows):
     rows, cols = shape
+    seen_classes = set()
     for seed, walls in ((9, (False,) * 4), (2, (True, False, False, True)), (7, (False, True, True, False))):
         f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=K)
         drop_wrapping_line(setup)
@@ -160,11 +165,13 @@ def test_plain_plus_edge_tiles_are_one_whole_group(shape, K, tile_rows):
         for ty, tx in np.argwhere(skip[:plan.k_tiles_y] == 0):
             ta = plan.k_row_lo + ty * plan.k_tile_rows
             owner[ta:min(ta + plan.k_tile_rows, plan.k_row_hi), tx * out:(tx + 1) * out] += 1
-        for tx, ta, tb, _ in tiles:
+        for tx, ta, tb, _, _ in tiles:
             reach = tx * out - margin * 2 + 64 > cols
             owner[ta:tb, tx * out:(cols + 1 if reach else (tx + 1) * out)] += 1
         assert (owner == 1).all(), np.argwhere(owner != 1)[:5]
-        got_e, _ = E.stepK_edge(f, setup, times, 0, K, [tuple(t[:3]) for t in tiles])
+        seen_classes.update(int(t[4]) for t in tiles)
+        # every tile through the instantiation of ITS class: a feature the planner left out must not have been needed
+        got_e, _ = E.stepK_edge(f, setup, times, 0, K, [(t[0], t[1], t[2], t[4]) for t in tiles])
         got_p = None
         if plan.k_tiles_y > 0 and not skip.all():
             quiet = R.Setup(eps_coef=setup.eps_coef, mu_coef=setup.mu_coef, courant=setup.courant,
@@ -178,6 +185,39 @@ def test_plain_plus_edge_tiles_are_one_whole_group(shape, K, tile_rows):
                 assert not both.any(), name                      # the two launches write disjoint cells
                 a = np.where(np.isnan(a), got_p[k], a)
             assert np.array_equal(a, want), (name, seed, np.argwhere(a != want)[:4])
+    assert seen_classes <= {1, 2, 4, 6, 15}, seen_classes
+
+
+@pytest.mark.parametrize("K,tile_rows", [(2, 8), (4, 16), (6, 16), (8, 24)])
+@pytest.mark.parametrize("line", [None, "right", "left", "down"])
+def test_every_tile_class_is_planned_and_exact(K, tile_rows, line):
+    """A scene shaped like the C5 recipe (walls, one point source, at most one TF/SF line, one reflector, one probe): the
+    planner gives the wall columns, the wall bands, the source tiles and the TF/SF column next to a wall their own cheap
+    instantiations, and the group is still the oracle's, bit for bit."""
+    rows, cols = 150, 520
+    rng = np.random.default_rng(K)
+    f, setup, times = SC.random_case(rows, cols, 11, walls=(False,) * 4, n_steps=K, with_sources=False, with_rects=False)
+    setup.pulses = [R.PulseSpec("table", None, 70, 300, -1.0, 1.0, rng.standard_normal(K))]
+    if line:
+        setup.pulses.append(R.PulseSpec("table", line, 40, 7, -1.0, 1.0, rng.standard_normal(K)))
+    setup.reflectors = [[100, 110, 400, 430]]
+    probes = [(30, 200)]
+    boxes = _boxes(setup, rows, cols) + [(30, 30, 200, 200, 0)]
+    plan, skip, tiles = _plan_edge(rows, cols, K, tile_rows, boxes)
+    classes = {int(t[4]) for t in tiles}
+    assert classes == ({1, 2, 4, 6, 15} if line in ("right", "left") else {1, 2, 4, 15} if line is None else {1, 2, 4, 6, 15}), classes
+    got_e, rec = E.stepK_edge(f, setup, times, 0, K, [(t[0], t[1], t[2], t[4]) for t in tiles], probes=probes)
+    quiet = R.Setup(eps_coef=setup.eps_coef, mu_coef=setup.mu_coef, courant=setup.courant, reflect_walls=setup.reflect_walls,
+                    pulses=[], reflectors=[])
+    got_p = E.stepK_stream(f, quiet, times, 0, K, tile_rows, 1, plan.k_row_lo, plan.k_row_hi, skip, variant=1)
+    want_rec = np.zeros((K, 1, 3))
+    for m, t in enumerate(times):
+        R.leapfrog(f, setup, t)
+        want_rec[m, 0] = (f.h[30, 200], f.ex[30, 200], f.ey[30, 200])
+    for k, (name, want) in enumerate(zip(("h", "ex", "ey"), (f.h, f.ex, f.ey))):
+        a = np.where(np.isnan(got_e[k]), got_p[k], got_e[k])
+        assert np.array_equal(a, want), (name, np.argwhere(a != want)[:4])
+    assert np.array_equal(rec, want_rec)
 
 
 @pytest.mark.parametrize("K", [2, 4, 6, 8])
@@ -197,7 +237,7 @@ def test_edge_plan_on_slabs_with_deep_halos(K):
                 tb = min(ta + plan.k_tile_rows, plan.k_row_hi)
                 owner[ta:tb, tx * out:(tx + 1) * out] += 1
                 assert ta - K >= first and tb + K - 1 <= last
-            for tx, ta, tb, near in tiles:
+            for tx, ta, tb, near, _ in tiles:
                 reach = tx * out - margin * 2 + 64 > cols
                 owner[ta:tb, tx * out:(cols + 1 if reach else (tx + 1) * out)] += 1
                 assert max(ta - K - 1, 0) >= first and min(tb + K, rows) <= last

@@ -65,6 +65,8 @@ def test_deep_halo_slabs_on_one_gpu_match_the_oracle(world, K, shape, tile_rows)
         e.get_fields(out={"h": h, "ex": ex, "ey": ey})
     assert np.array_equal(h, f.h) and np.array_equal(ex, f.ex) and np.array_equal(ey, f.ey)
     launches = [e.stats()["kernel_launches"] for e in engines]
-    assert max(launches) <= 3 * 2 + 2 + 4                     # two launches per group (plain + edge tiles), one per single step
+    # per group: the plain kernel + one stepK_edge launch per tile class (<= 5) in the near and in the far half; one per
+    # single step
+    assert max(launches) <= 3 * (1 + 2 * 5) + 2 + 4
     for e in engines:
         e.close()

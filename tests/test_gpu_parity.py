@@ -242,8 +242,9 @@ def test_temporal_blocking_k_steps_per_pass_bitwise(shape, tile_rows, warps, tem
         else:
             R.run(f, setup, times)
             e.run(0, len(times))
-            if temporal == 2:        # two launches per group (plain + edge tiles; a wrapping TF/SF line: single steps)
-                assert e.stats()["kernel_launches"] - launches0 <= 2 * (len(times) // 2) + len(times) % 2 + len(times)
+            if temporal == 2:        # per group the plain kernel + one stepK_edge launch per tile class present (<= 5); a
+                #                      wrapping TF/SF line: single steps
+                assert e.stats()["kernel_launches"] - launches0 <= 6 * (len(times) // 2) + len(times) % 2 + len(times)
         _same(e, f, "temporal blocking seed %d" % seed)
         raw = e.probes()
         for c, (i, j, series) in enumerate(f.raw_probes):
