@@ -314,6 +314,41 @@ class Engine:
             raise IndexError("index %d is out of bounds for the pulse magnitude table" % bad)
         return snaps
 
+    # ---- realtime view --------------------------------------------------------------
+    def run_enqueue(self, first_step, n_steps):
+        """Queue calls [first_step, first_step+n_steps) and return without waiting (fdtd_run_enqueue).  Returns the number
+        of calls queued: a pulse that outlives its table (App. A-Q10) ends the batch early, and the next batch raises
+        the reference's IndexError."""
+        first_step, n_steps = int(first_step), int(n_steps)
+        if self.first_bad is not None and first_step + n_steps > self.first_bad:
+            if first_step >= self.first_bad:
+                raise IndexError("index %d is out of bounds for the pulse magnitude table" % self.first_bad)
+            n_steps = self.first_bad - first_step
+        L.check(self.lib, self.handle, self.lib.fdtd_run_enqueue(self.handle, first_step, n_steps))
+        return n_steps
+
+    def view_shape(self, row_stride=1, col_stride=1):
+        first = -(-self.row_begin // row_stride) * row_stride
+        rows = (self.row_end - 1 - first) // row_stride + 1 if first < self.row_end else 0
+        return rows, (self.cols - 1) // col_stride + 1
+
+    def view_begin(self, row_stride=1, col_stride=1):
+        """Queue a picture of h[::row_stride, ::col_stride] (this slab's rows of it) behind everything queued so far; its
+        device-to-host copy runs on the side stream, next to whatever is queued after it."""
+        L.check(self.lib, self.handle, self.lib.fdtd_view_begin(self.handle, int(row_stride), int(col_stride)))
+        self._views = getattr(self, "_views", [])
+        self._views.append(self.view_shape(int(row_stride), int(col_stride)))
+
+    def view_end(self):
+        """The oldest picture in flight, as a float64 array (waits for its copy only, not for later work)."""
+        shape = self._views.pop(0)
+        out = np.empty(shape, dtype=np.float64)
+        rows, cols = C.c_int64(0), C.c_int64(0)
+        L.check(self.lib, self.handle, self.lib.fdtd_view_end(self.handle, _ptr(out) if out.size else _ptr(np.empty(1)),
+                                                              max(out.size, 1), C.byref(rows), C.byref(cols)))
+        assert (rows.value, cols.value) == tuple(shape)
+        return out
+
     def sync(self):
         L.check(self.lib, self.handle, self.lib.fdtd_sync(self.handle))
 

@@ -96,6 +96,9 @@ class Solver:
         # reference's one call per frame; n > 1 runs n calls in one device run and shows every n-th field, which keeps
         # the interactive view usable on grids where drawing, not stepping, sets the pace
         self.frame_stride = 1
+        # NOT in the reference either: the picture of the realtime view is h[::d, ::d] (a 65536-column grid on a 1000-pixel
+        # window needs no more); 1 = every cell.  Only the picture is decimated, never the simulation
+        self.view_decimation = 1
 
         self.recorded_energies = []
         self.energy_vector = []
@@ -519,34 +522,82 @@ class Solver:
     _stack = None
 
     def plot_and_show(self):
-        """reference solver.py:309-329: one update per animation frame."""
+        """reference solver.py:309-329: one update per animation frame.  With frame_stride > 1 or view_decimation > 1
+         a frame is a batch of frame_stride calls, and the device runs one batch ahead of the picture:
+        while matplotlib draws the picture of batch k, batch k+1 is stepping and the (decimated) picture of batch k has
+        already left for the host on the copy stream."""
         if _shard.context(self._sharded) is not None:
             raise Exception("realtime plotting is not available in a sharded run: save() and solve(realtime=False)")
         plt = _pyplot()
         import matplotlib.animation as animation
+        stride, dec = max(1, int(self.frame_stride)), max(1, int(self.view_decimation))
         fig, ax1 = plt.subplots(figsize=(6, 6))
-        im = ax1.imshow(self.h, animated=True, extent=[0, self.length_x, self.length_y, 0], vmax=self.pulses_max,
-                        vmin=-self.pulses_max, aspect='auto', cmap='seismic')
+        im = ax1.imshow(self.h if dec == 1 else self.h[::dec, ::dec], animated=True, extent=[0, self.length_x, self.length_y, 0],
+                        vmax=self.pulses_max, vmin=-self.pulses_max, aspect='auto', cmap='seismic')
         ax1.set_aspect('equal', 'box')
         ax1.xaxis.set_ticks_position('top')
         ax1.xaxis.set_label_position('top')
         fig.colorbar(im, ax=ax1)
 
-        stride = max(1, int(self.frame_stride))
-
-        def animate(time):
-            if self.step % self.step_frequency == 0 or stride > 1:
-                fig.suptitle("Time Step = {}".format(self.step))
-            if stride == 1:
+        if stride == 1 and dec == 1:
+            def animate(time):
+                if self.step % self.step_frequency == 0:
+                    fig.suptitle("Time Step = {}".format(self.step))
                 im.set_array(self.update(time))
-            else:                           # `stride` calls in one device run, then one readback for the picture
-                self._run_device(self.time_vector, n_calls=stride)
-                im.set_array(self.h)
-            return im,
+                return im,
+        else:
+            self._sync_engine(self.time_vector)
+            pipe = self._pipeline = {"queued": self.step, "batches": [], "error": None, "first": self.step}
 
-        self._anim = animation.FuncAnimation(fig, animate, frames=self.time_vector[::stride], interval=1, blit=False,
-                                             repeat=False)
-        plt.show()
+            def enqueue():
+                n = min(stride, len(self.time_vector) - pipe["queued"])
+                if n <= 0 or pipe["error"] is not None:
+                    return
+                try:
+                    done = self._engine.run_enqueue(pipe["queued"], n)
+                except IndexError as exc:           # a pulse outliving its table (App. A-Q10): raised at ITS frame
+                    pipe["error"] = exc
+                    return
+                self._host = None
+                self._engine.view_begin(dec, dec)
+                pipe["queued"] += done
+                pipe["batches"].append(done)
+
+            def animate(time):
+                fig.suptitle("Time Step = {}".format(self.step))
+                if not pipe["batches"]:
+                    enqueue()                       # the first frame's own batch
+                if not pipe["batches"]:
+                    if pipe["error"] is not None:
+                        raise pipe["error"]
+                    return im,
+                enqueue()                           # the next frame's batch steps while this frame's picture is drawn
+                im.set_array(self._engine.view_end())
+                self.step += pipe["batches"].pop(0)
+                return im,
+
+        try:
+            self._anim = animation.FuncAnimation(fig, animate, frames=self.time_vector[::stride], interval=1, blit=False,
+                                                 repeat=False)
+            plt.show()
+        finally:
+            self._finish_pipeline()
+
+    _pipeline = None
+
+    def _finish_pipeline(self):
+        """After the realtime view: pictures still in flight are fetched (the window was closed early), the step counter
+        follows the device, and the probe records of the whole view are collected."""
+        pipe, self._pipeline = self._pipeline, None
+        if pipe is None:
+            return
+        while pipe["batches"]:
+            self._engine.view_end()
+            self.step += pipe["batches"].pop(0)
+        self._engine.sync()
+        self._steps_seen = self._engine.stats()["steps"]
+        self._host = None
+        self._collect_probes()
 
     # ------------------------------------------------------------------ persistence
     def save_to_json(self):

@@ -213,6 +213,19 @@ int fdtd_step(fdtd_handle h, int64_t step);
 int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapshot_every,
              double* snapshots_host, int64_t max_snapshots, int64_t total_calls, int64_t* n_snapshots);
 
+/* The realtime view (the reference's plot_and_show loop, solver.py:309-329, with batches of calls per frame).
+ * fdtd_run_enqueue queues calls [first_step, first_step + n_steps) exactly as fdtd_run does (no snapshots) and returns
+ * without waiting; queued runs execute back to back.  fdtd_view_begin queues, behind everything queued so far, a picture
+ * of h -- global rows 0, row_stride, 2 row_stride, ... that this slab owns, columns 0, col_stride, ... -- as float64:
+ * packed on the launch stream, copied to pinned memory on the side stream, so the copy overlaps whatever is queued next.
+ * fdtd_view_end waits for the OLDEST picture in flight and copies it to host_out (capacity in doubles; *rows x *cols,
+ * dense).  At most two pictures are in flight.  Typical frame: run_enqueue(batch k+1); view_begin(); view_end() -> the
+ * picture of batch k is drawn while the device computes batch k+1.  No aliasing patch is applied: the realtime loop
+ * draws the field update() returned, not the saved list (solver.py:323 vs :337). */
+int fdtd_run_enqueue(fdtd_handle h, int64_t first_step, int64_t n_steps);
+int fdtd_view_begin(fdtd_handle h, int32_t row_stride, int32_t col_stride);
+int fdtd_view_end(fdtd_handle h, double* host_out, int64_t capacity, int64_t* rows, int64_t* cols);
+
 /* Launch geometry of the streaming kernel (0 keeps the current value); results never depend on it. */
 int fdtd_set_tuning(fdtd_handle h, int32_t tile_rows, int32_t vec, int32_t block_warps);
 /* What the library runs with (the defaults it picked included): out = {tile_rows, vec, block_warps, steps_per_pass,

@@ -25,6 +25,7 @@ class FakeEngine:
         self.records = []
         self.times = None
         self.closed = False
+        self.views = []
 
     def upload_coefficients(self, eps_coef, mu_coef):
         self.setup.eps_coef, self.setup.mu_coef = np.array(eps_coef), np.array(mu_coef)
@@ -82,6 +83,23 @@ class FakeEngine:
             return np.array(saved)
         out[...] = saved
         return out
+
+    def run_enqueue(self, first_step, n_steps):
+        first_step, n_steps = int(first_step), int(n_steps)
+        if self.first_bad is not None and first_step + n_steps > self.first_bad:
+            if first_step >= self.first_bad:
+                raise IndexError("index %d is out of bounds for the pulse magnitude table" % self.first_bad)
+            n_steps = self.first_bad - first_step
+        for n in range(first_step, first_step + n_steps):
+            self._one(n)
+        return n_steps
+
+    def view_begin(self, row_stride=1, col_stride=1):
+        assert len(self.views) < 2, "at most two pictures in flight"
+        self.views.append(self.f.h[::row_stride, ::col_stride].copy())
+
+    def view_end(self):
+        return self.views.pop(0)
 
     def probes(self):
         return np.array(self.records, dtype=np.float64).reshape(len(self.records), len(self.cells), 3)

@@ -172,6 +172,34 @@ def test_realtime_path_updates_once_per_frame(S, monkeypatch):
     assert s7.step == 61 and len(shown) == len(want) == 9
     assert all(np.array_equal(a, b) for a, b in zip(shown, want))
 
+    # view_decimation = 3: the same run, every third row / column in the picture; the simulation itself is untouched.
+    # With energies recorded: the records of the whole view are collected when it ends
+    del shown[:]
+    f3, setup3, _, _ = SC.restate(sc)
+    s3 = _quiet(SC.drive, S, sc)
+    s3.end_time = 60.5 * s3.dt
+    s3.frame_stride, s3.view_decimation = 7, 3
+    s3.record_energy((1.0, 0.5))
+    _quiet(s3.solve)
+    assert s3.step == 61 and len(shown) == 9 and all(np.array_equal(a, b[::3, ::3]) for a, b in zip(shown, want))
+    assert np.array_equal(s3.h, want[-1]) and len(s3.recorded_energies[0]["energies"]) == 61
+
+    # the window is closed after two frames: the batch that was running ahead is accounted for, nothing is lost
+    del shown[:]
+    def two_frames(fig, func, frames, **k):
+        for frame in list(frames)[:2]:
+            func(frame)
+    monkeypatch.setattr(anim, "FuncAnimation", two_frames)
+    s2 = _quiet(SC.drive, S, sc)
+    s2.end_time = 60.5 * s2.dt
+    s2.frame_stride = 7
+    _quiet(s2.solve)
+    assert len(shown) == 2 and s2.step == 21                 # two shown + the one in flight
+    f2, setup2, _, _ = SC.restate(sc)
+    for t in times[:21]:
+        R.leapfrog(f2, setup2, t)
+    assert np.array_equal(s2.h, f2.h)
+
 
 def test_big_snapshot_stacks_stream_into_the_npy_file(S, monkeypatch, tmp_path):
     """above STREAM_SNAPSHOT_BYTES the stack is an open_memmap of <name>.npy, never a RAM copy +
