@@ -90,6 +90,7 @@ SIGNATURES = {
     "fdtd_step": (C.c_int, [_P, C.c_int64]),
     "fdtd_run": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "fdtd_run_enqueue": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "fdtd_run_streamed": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64]),
     "fdtd_view_begin": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "fdtd_view_end": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fdtd_set_tuning": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),

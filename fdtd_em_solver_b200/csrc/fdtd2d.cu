@@ -75,6 +75,13 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     int n_edge_near = 0;
     struct EdgeRun { int first, count, flags; };  // consecutive tiles of one class (the kernel instantiation `flags`)
     std::vector<EdgeRun> edge_runs_near, edge_runs_far;
+    // fdtd_run_streamed: the same tiles grouped by row band (band = first row / band_rows), a second device copy of the
+    // edge tiles sorted by (band, class)
+    int64_t band_rows = 0;
+    std::vector<int> band_ty0, band_ny;
+    std::vector<std::vector<EdgeRun>> band_runs;
+    fdtd::EdgeTile* d_band = nullptr;
+    size_t d_band_cap = 0;
     size_t d_list_cap = 0, d_skip_cap = 0, d_mask_cap = 0;
     int nty = 0, ntx2 = 0, ntx1 = 0;     // K-step tile grid (nty x ntx2) and frame warp tiles per row (ntx1)
     std::vector<int64_t> row_cells;      // cells the plain K-step kernel advances per tile row (measurement hook)
@@ -83,6 +90,7 @@ struct FrameMaps {                   // per group size K: which tiles the K-step
     void release() {
         if (d_skip) cudaFree(d_skip);
         if (d_edge) cudaFree(d_edge);
+        if (d_band) cudaFree(d_band);
         for (int d = 0; d < 8; ++d) { if (d_mask[d]) cudaFree(d_mask[d]); if (d_list[d]) cudaFree(d_list[d]); }
     }
 };
@@ -127,6 +135,9 @@ struct fdtd_ctx {
     struct View { double* dev = nullptr; double* pin = nullptr; size_t cap = 0; cudaEvent_t done = nullptr;
                   int64_t rows = 0, cols = 0; bool pending = false; } view[2];
     int view_head = 0, view_tail = 0;                // next slot to fill / oldest pending slot
+    // fdtd_run_streamed: device-to-host copies on their own stream (PCIe is full duplex), one event per row band
+    cudaStream_t d2h_stream = nullptr, edge_stream2 = nullptr;
+    std::vector<cudaEvent_t> band_up, band_done, band_edge;
     void* stage = nullptr; size_t stage_bytes = 0;
 
     ncclComm_t comm = nullptr;
@@ -144,6 +155,7 @@ struct fdtd_ctx {
     int frame_mode = 3;
     int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
+    bool maps_pinned = false;        // fdtd_run_streamed: the frame maps in place serve every group of the run
     bool edge_class_force = false;   // measurement hook FDTD_EDGE_GENERIC=1: every edge tile through the all-features instantiation
 
     // optional: CUDA events around every launch of the plain K-step kernel on its own stream (bench.py: the roofline
@@ -609,10 +621,9 @@ void plan_edge(const FrameGeom& g, const std::vector<FrameBox>& mods, FrameMaps&
     m.h_edge.insert(m.h_edge.end(), far.begin(), far.end());
 }
 
-template <typename T>
-int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
-    FrameMaps& m = c->fm[K];
-    // signature: which pulses are live in any step of the group, plus the geometry knobs
+// signature of the frame maps of the group of K calls starting at call n: which pulses are live in any of them, plus the
+// geometry knobs
+std::vector<uint8_t> frame_key(const fdtd_ctx* c, int64_t n, int K) {
     std::vector<uint8_t> key;
     for (int p = 0; p < c->n_src; ++p) {
         uint8_t live = 0;
@@ -623,7 +634,20 @@ int build_frame_maps(fdtd_ctx* c, int64_t n, int K) {
     for (int v : {c->cfg.tile_rows, c->cfg.vec, c->cfg.block_warps, c->n_rect, c->n_probe, K, (int)edge, c->halo_depth}) {
         key.push_back((uint8_t)(v & 0xff)); key.push_back((uint8_t)((v >> 8) & 0xff)); key.push_back((uint8_t)((v >> 16) & 0xff));
     }
+    return key;
+}
+
+// forced_key: a signature that marks MORE pulses live than this group has (fdtd_run_streamed plans once for all groups of a
+// size: a tile near a pulse that is silent in some group is an edge tile there, too -- exact, the kernel reads each call's
+// own records).  While c->maps_pinned, existing maps are used as they are.
+template <typename T>
+int build_frame_maps(fdtd_ctx* c, int64_t n, int K, const std::vector<uint8_t>* forced_key = nullptr) {
+    FrameMaps& m = c->fm[K];
+    if (c->maps_pinned && !forced_key && m.d_skip && !m.key.empty()) return 0;
+    const std::vector<uint8_t> key = forced_key ? *forced_key : frame_key(c, n, K);
+    const bool edge = edge_usable(c, K);
     if (key == m.key && m.d_skip) return 0;
+    m.band_rows = 0;                                             // the band plan of fdtd_run_streamed follows the maps
     std::vector<FrameBox> mods;
     const int64_t BIG = (int64_t)1 << 40;
     for (int p = 0; p < c->n_src; ++p) {
@@ -1142,6 +1166,11 @@ int fdtd_destroy(fdtd_handle c) {
         if (c->view[s].pin) cudaFreeHost(c->view[s].pin);
         if (c->view[s].done) cudaEventDestroy(c->view[s].done);
     }
+    for (cudaEvent_t e : c->band_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->band_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->band_edge) cudaEventDestroy(e);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->edge_stream2) cudaStreamDestroy(c->edge_stream2);
     for (cudaEvent_t e : {c->ev_t0, c->ev_t1, c->ev_bnd, c->ev_comm, c->ev_int, c->ev_p3}) if (e) cudaEventDestroy(e);
     for (cudaStream_t s : {c->stream, c->copy_stream, c->comm_stream, c->edge_stream}) if (s) cudaStreamDestroy(s);
     delete c;
@@ -1641,6 +1670,288 @@ int fdtd_run(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t snapsho
 
 int fdtd_run_enqueue(fdtd_handle c, int64_t first_step, int64_t n_steps) {
     return run_impl(c, first_step, n_steps, 0, nullptr, 0, 0, nullptr, false);
+}
+
+}  // extern "C"
+
+// ---- streamed solve: upload -> calls -> download as one pipeline over row bands (end-to-end path) ------------
+// The band plan of a group size: tile rows and edge tiles grouped by band = first row / band_rows.
+template <typename T>
+static int build_band_plan(fdtd_ctx* c, int K, int64_t band_rows, int n_bands) {
+    FrameMaps& m = c->fm[K];
+    if (m.band_rows == band_rows && (int)m.band_ty0.size() == n_bands) return 0;
+    auto band_of = [&](int64_t row) { return (int)std::min<int64_t>(std::max<int64_t>(row, 0) / band_rows, n_bands - 1); };
+    m.band_ty0.assign(n_bands, 0); m.band_ny.assign(n_bands, 0);
+    for (int ty = m.nty - 1; ty >= 0; --ty) {
+        const int b = band_of(m.k_row_lo + (int64_t)ty * c->cfg.tile_rows);
+        m.band_ty0[b] = ty; m.band_ny[b]++;
+    }
+    std::vector<fdtd::EdgeTile> sorted = m.h_edge;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](const fdtd::EdgeTile& x, const fdtd::EdgeTile& y) {
+        const int bx = band_of(x.ta), by = band_of(y.ta);
+        return bx != by ? bx < by : x.pad < y.pad;
+    });
+    m.band_runs.assign(n_bands, {});
+    for (size_t k = 0; k < sorted.size(); ++k) {
+        auto& runs = m.band_runs[band_of(sorted[k].ta)];
+        if (runs.empty() || runs.back().flags != sorted[k].pad) runs.push_back({(int)k, 0, sorted[k].pad});
+        runs.back().count++;
+    }
+    if (m.d_band_cap < sorted.size()) {
+        if (m.d_band) cudaFree(m.d_band);
+        m.d_band = nullptr; m.d_band_cap = 0;
+        CK(cudaMalloc(&m.d_band, sorted.size() * sizeof(fdtd::EdgeTile))); m.d_band_cap = sorted.size();
+    }
+    if (!sorted.empty()) CK(cudaMemcpy(m.d_band, sorted.data(), sorted.size() * sizeof(fdtd::EdgeTile), cudaMemcpyHostToDevice));
+    m.band_rows = band_rows;
+    return 0;
+}
+
+constexpr int NOT_STREAMED = 0x5eed;                             // run_streamed: this run does not fit the pipeline
+
+// calls n .. n+K-1 for the tiles of one row band: generation A -> B.  The plain tiles go to the launch stream, the edge
+// tiles to one of two side streams (by band parity); they are tied together by one event per band (band_edge[b] = "the
+// edge tiles of the latest group on band b are done"), so the launch stream never waits for the edge tiles of the unit
+// it has just queued -- only for those of the previous group on the bands b-1, b, b+1 that the unit reads (or overwrites
+// what they read).  probe_base = index of the group's first probe record.
+template <typename T>
+static int band_group(fdtd_ctx* c, int64_t n, int K, int A, int B, int band, int n_bands, int64_t probe_base) {
+    const FrameMaps& m = c->fm[K];
+    cudaStream_t es = (band & 1) ? c->edge_stream2 : c->edge_stream;
+    const int b0 = std::max(band - 1, 0), b1 = std::min(band + 1, n_bands - 1);
+    const bool has_edge = !m.band_runs[band].empty();
+    if (has_edge) {
+        CK(cudaEventRecord(c->ev_int, c->stream));               // the plain tiles of the previous group
+        CK(cudaStreamWaitEvent(es, c->ev_int, 0));
+        for (int nb = b0; nb <= b1; ++nb)                        // its edge tiles on the neighbouring bands (other stream)
+            if (nb != band) CK(cudaStreamWaitEvent(es, c->band_edge[nb], 0));
+        StepParams<T> PE;
+        if (int rc = fill_params<T>(c, PE, n, A, B)) return rc;
+        PE.n_src = 0; PE.last_mag = T(0);
+        PE.row_lo = (int)c->cfg.row_begin;
+        PE.row_hi = (int)(c->cfg.row_end + (c->cfg.row_end == c->cfg.rows ? 1 : 0));
+        if (c->n_probe) PE.probe_out = c->probe_dev + (size_t)probe_base * c->n_probe * 3;
+        fdtd::ResSources<T> R{(const int*)c->rs_count, (const T*)c->rs_last, (const fdtd::SrcStep<T>*)c->rs_src, c->rs_stride};
+        for (const FrameMaps::EdgeRun& run : m.band_runs[band]) {
+            CK(launch_edge_any<T>(K, PE, run.flags, m.d_band + run.first, run.count, R, n, es));
+            c->stats.kernel_launches++;
+        }
+    }
+    if (m.band_ny[band] > 0) {
+        for (int nb = b0; nb <= b1; ++nb) CK(cudaStreamWaitEvent(c->stream, c->band_edge[nb], 0));
+        StepParams<T> PK;
+        if (int rc = fill_params<T>(c, PK, n, A, B)) return rc;
+        PK.n_src = 0; PK.n_rect = 0; PK.n_probe = 0; PK.row_lo = (int)m.k_row_lo; PK.row_hi = (int)m.k_row_hi;
+        launch_stepK_any<T>(PK, c, K, m.band_ty0[band], m.band_ny[band], c->stream);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    if (has_edge) CK(cudaEventRecord(c->band_edge[band], es));
+    return 0;
+}
+
+// fdtd_upload_coeffs + (fdtd_zero_fields) + fdtd_run + fdtd_get_fields(h) with the three stages overlapped.  The grid is cut
+// into row bands; band b's coefficient rows go up on the copy stream, and as soon as band b+1 has landed the first group
+// of calls runs on band b, the second group on band b-1, ... (a group on band b needs the previous group on bands b-1,
+// b, b+1 -- K-step cones are at most K+1 rows deep -- so groups advance along diagonals of the (band, group) plane, all on
+// the launch stream, in an order that is also safe for the two ping-pong generations).  Behind the last group of a band
+// its rows of h leave on a second copy stream, while the bands below are still uploading / stepping: PCIe carries both
+// directions at once.  Long runs sweep diagonally only through their first and last n_bands - 1 groups; the groups in
+// between are whole-grid launches (fdtd_run's).  Bit-identical to the four separate calls.
+template <typename T>
+static int run_streamed(fdtd_ctx* c, const double* eps, const double* mu, int64_t host_ld, bool zero, int64_t first_step,
+                        int64_t n_steps, double* h_out, int64_t out_ld) {
+    Range nvtx("fdtd_run_streamed");
+    const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
+    // the groups of the run, as fdtd_run forms them
+    struct Group { int64_t n; int K; };
+    std::vector<Group> groups;
+    const int kmax = c->temporal;
+    for (int64_t n = first_step; n < first_step + n_steps;) {
+        int64_t g = std::min<int64_t>(kmax, first_step + n_steps - n);
+        if (c->n_src > 0) g = std::min<int64_t>(g, c->table_len - n);
+        if (g < 1) return fail(c, FDTD_ERR_RANGE, "step " + std::to_string(n) + " outside the source tables (length " +
+                                                      std::to_string(c->table_len) + ")");
+        groups.push_back({n, (int)g});
+        n += g;
+    }
+    if (groups.size() >= 2 && groups.back().K == 1) {            // no single step at the end: 8 + 1 -> 7 + 2, 2 + 1 -> 3
+        Group& prev = groups[groups.size() - 2];
+        if (prev.K >= 3) { prev.K -= 1; groups.back().n -= 1; groups.back().K = 2; }
+        else { prev.K += 1; groups.pop_back(); }
+    }
+    // one tile plan per group size, for the pulses live in ANY group of that size
+    std::vector<uint8_t> keys[9];
+    for (const Group& g : groups) {
+        if (g.K < 2 || !edge_usable(c, g.K)) return NOT_STREAMED;
+        const std::vector<uint8_t> key = frame_key(c, g.n, g.K);
+        if (keys[g.K].empty()) keys[g.K] = key;
+        else for (int p = 0; p < c->n_src; ++p) keys[g.K][p] |= key[p];
+    }
+    const int TR = c->cfg.tile_rows;
+    // Bands: whole tile rows, at least 2 K + 2 rows (a K-step cone reaches into the neighbouring band only), and about
+    // `want` of them -- few enough that one band fills the GPU a couple of times over (a band unit is its own launch),
+    // enough that the copies come in pieces.  FDTD_STREAM_BANDS overrides the count (measurement hook).
+    int want = 16;                                               // (B200, C5 slab, 20 calls: 4 / 8 / 16 bands -> 45 / 53 / 57.5 Gcell/s end to end)
+    if (const char* wb = std::getenv("FDTD_STREAM_BANDS")) { const int v = std::atoi(wb); if (v >= 2 && v <= 64) want = v; }
+    const int64_t total_ty = (NR + TR - 1) / TR;
+    const int64_t H = (int64_t)TR * std::max<int64_t>((2 * 8 + 2 + TR - 1) / TR, (total_ty + want - 1) / want);
+    const int NB = (int)((NR + H - 1) / H);
+    if (NB < 2 || (c->ngen != 2 && c->cur > 1)) return NOT_STREAMED;
+    struct TwoGenerations {                                      // ping-pong between two generations only, also where
+        fdtd_ctx* c; int saved;                                  // group_edge picks the next one
+        explicit TwoGenerations(fdtd_ctx* c_) : c(c_), saved(c_->ngen) { c->ngen = 2; }
+        ~TwoGenerations() { c->ngen = saved; }
+    } two(c);
+    for (const Group& g : groups) {
+        if (int rc = build_frame_maps<T>(c, g.n, g.K, &keys[g.K])) return rc;
+        if (int rc = build_band_plan<T>(c, g.K, H, NB)) return rc;
+    }
+    struct PinnedMaps {
+        fdtd_ctx* c;
+        explicit PinnedMaps(fdtd_ctx* c_) : c(c_) { c->maps_pinned = true; }
+        ~PinnedMaps() { c->maps_pinned = false; }
+    } pinned(c);
+    if (int rc = resident_tables<T>(c)) return rc;
+    if (int rc = ensure_probe_capacity(c, n_steps)) return rc;
+    if (!c->d2h_stream) CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    if (!c->edge_stream2) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        CK(cudaStreamCreateWithPriority(&c->edge_stream2, cudaStreamNonBlocking, prio_hi));
+    }
+    while ((int)c->band_up.size() < NB) {
+        cudaEvent_t e1, e2, e3;
+        CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); c->band_up.push_back(e1);
+        CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); c->band_done.push_back(e2);
+        CK(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming)); c->band_edge.push_back(e3);
+    }
+    if (int rc = quiesce(c)) return rc;
+    CK(cudaStreamSynchronize(c->copy_stream));
+    if (zero) {
+        for (int g = 0; g < c->ngen; ++g)
+            for (int f = 0; f < 3; ++f)
+                CK(cudaMemsetAsync(c->gen[g][f], 0, (size_t)c->lrows * c->pitch * c->esize, c->stream));
+        c->cur = 0;
+    }
+    CK(cudaEventRecord(c->ev_t0, c->stream));
+    const int G = (int)groups.size();
+    const int gen0 = c->cur, gen1 = (c->cur + 1) % c->ngen;
+    std::vector<int64_t> probe_base(G);
+    for (int g = 0, acc = 0; g < G; ++g) { probe_base[g] = c->probe_count + acc; acc += groups[g].K; }
+    auto upload = [&](int b) -> int {
+        const int64_t r0 = (int64_t)b * H, r1 = std::min<int64_t>(r0 + H, NR);
+        if (r1 > r0) {
+            CK(cudaMemcpy2DAsync(plane<T>(c->epc, c, r0), c->pitch * 8, eps + (r0 - c->host_row0) * host_ld, host_ld * 8, NC * 8,
+                                 r1 - r0, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaMemcpy2DAsync(plane<T>(c->muc, c, r0), c->pitch * 8, mu + (r0 - c->host_row0) * host_ld, host_ld * 8, NC * 8,
+                                 r1 - r0, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CK(cudaEventRecord(c->band_up[b], c->copy_stream));
+        return 0;
+    };
+    // Rows of h that are final once the LAST group has run on bands 0 .. b: a row r < (b+1) H belongs to a tile that starts
+    // at or above it, i.e. in a band <= b.
+    auto rows_done = [&](int b) -> int64_t { return b + 1 == NB ? NR : std::min<int64_t>((int64_t)(b + 1) * H, NR); };
+    int64_t copied = 0;                                          // rows of h already on their way to the host
+    auto download = [&](int b) -> int {
+        if (!h_out) return 0;
+        const int64_t upto = rows_done(b);
+        if (upto <= copied) return 0;
+        CK(cudaEventRecord(c->band_done[b], c->stream));         // the band's plain tiles of the last group ...
+        CK(cudaStreamWaitEvent(c->d2h_stream, c->band_done[b], 0));
+        CK(cudaStreamWaitEvent(c->d2h_stream, c->band_edge[b], 0));   // ... and its edge tiles
+        const int final_gen = (G % 2 == 0) ? gen0 : gen1;
+        CK(cudaMemcpy2DAsync(h_out + (copied - c->host_row0) * out_ld, out_ld * 8, plane<T>(c->gen[final_gen][0], c, copied),
+                             c->pitch * 8, NC * 8, upto - copied, cudaMemcpyDeviceToHost, c->d2h_stream));
+        copied = upto;
+        return 0;
+    };
+    // diagonal sweep over groups [g0, g1): band + (group - g0) = d
+    auto sweep = [&](int g0, int g1, bool up, bool down) -> int {
+        const int ng = g1 - g0;
+        for (int d = 0; d <= NB + ng; ++d) {
+            if (up && d < NB) if (int rc = upload(d)) return rc;
+            for (int k = 0; k < ng; ++k) {
+                const int b = d - 1 - k, g = g0 + k;
+                if (b < 0 || b >= NB) continue;
+                if (up && k == 0) CK(cudaStreamWaitEvent(c->stream, c->band_up[std::min(b + 1, NB - 1)], 0));
+                const int A = (g % 2 == 0) ? gen0 : gen1, B = (g % 2 == 0) ? gen1 : gen0;
+                if (int rc = band_group<T>(c, groups[g].n, groups[g].K, A, B, b, NB, probe_base[g])) return rc;
+                if (down && g == G - 1) if (int rc = download(b)) return rc;
+            }
+        }
+        return 0;
+    };
+    auto join = [&]() -> int {                                   // the launch stream behind every edge tile queued so far
+        for (int b = 0; b < NB; ++b) CK(cudaStreamWaitEvent(c->stream, c->band_edge[b], 0));
+        return 0;
+    };
+    // A band unit is its own launch and fills the GPU only 1-2 times over, so swept groups run at about 0.4 of the speed of
+    // whole-grid groups (B200: 16 ms instead of 6.2 ms per 8-call group on the C5 slab).  That is free while the copies
+    // are the longer pole -- up to about 14 groups of 8 calls against the 0.23 s the three planes take over PCIe -- and a
+    // loss beyond: long runs sweep only their first and last `wing` groups (200 calls: 295 vs 261 Gcell/s end to end).
+    int wing = std::min(NB - 1, 4), sweep_all_upto = 14;
+    if (const char* wg = std::getenv("FDTD_STREAM_WING")) { const int v = std::atoi(wg); if (v >= 1 && v <= 64) { wing = v; sweep_all_upto = 2 * v; } }
+    int rc = 0;
+    if (G <= std::max(sweep_all_upto, 2 * wing)) rc = sweep(0, G, true, true);
+    else {
+        rc = sweep(0, wing, true, false);
+        if (!rc) rc = join();
+        for (int g = wing; g < G - wing && !rc; ++g) {
+            c->cur = (g % 2 == 0) ? gen0 : gen1;
+            const int64_t pc = c->probe_count;
+            c->probe_count = probe_base[g];
+            rc = group_edge<T>(c, groups[g].n, groups[g].K);
+            c->probe_count = pc;
+            c->stats.steps -= groups[g].K;                       // accounted once, below
+            c->stats.cell_updates -= (int64_t)groups[g].K * c->owned * c->cfg.cols;
+        }
+        if (!rc) rc = sweep(G - wing, G, false, true);
+    }
+    if (!rc) rc = join();
+    if (rc) return rc;
+    c->cur = (G % 2 == 0) ? gen0 : gen1;
+    if (c->n_probe) c->probe_count += n_steps;
+    c->stats.steps += n_steps;
+    c->stats.cell_updates += n_steps * c->owned * c->cfg.cols;
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    if (int q = quiesce(c)) return q;
+    CK(cudaStreamSynchronize(c->edge_stream2));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->d2h_stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+    c->stats.last_run_ms = ms;
+    return 0;
+}
+
+extern "C" {
+
+int fdtd_run_streamed(fdtd_handle c, const double* eps_coef, const double* mu_coef, int64_t host_ld, int32_t zero_fields,
+                      int64_t first_step, int64_t n_steps, double* h_out, int64_t out_ld) {
+    NEED_BOUND();
+    if (!eps_coef || !mu_coef || host_ld < c->cfg.cols || n_steps < 0 || (h_out && out_ld < c->cfg.cols))
+        return fail(c, FDTD_ERR_ARG, "bad argument");
+    // The pipeline serves the case it was built for: float64, the whole grid on this GPU, temporal blocking with stepK_edge.
+    // Everything else takes the same four steps one after the other.
+    const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
+    if (c->cfg.dtype == FDTD_F64 && whole && !c->comm && c->temporal >= 2 && c->cfg.kernel == FDTD_KERNEL_STREAM &&
+        !resident_eligible(c) && n_steps >= 2) {
+        const int rc = run_streamed<double>(c, eps_coef, mu_coef, host_ld, zero_fields != 0, first_step, n_steps, h_out, out_ld);
+        if (rc != NOT_STREAMED) return rc;
+    }
+    if (const char* strict = std::getenv("FDTD_STREAMED_STRICT"))            // test hook: the caller expected the pipeline
+        if (std::atoi(strict)) return fail(c, FDTD_ERR_STATE, "fdtd_run_streamed: this run does not fit the pipeline");
+    if (int rc = fdtd_upload_coeffs(c, eps_coef, mu_coef, host_ld)) return rc;
+    if (zero_fields) if (int rc = fdtd_zero_fields(c)) return rc;
+    if (int rc = fdtd_run(c, first_step, n_steps, 0, nullptr, 0, first_step + n_steps, nullptr)) return rc;
+    if (h_out) {
+        if (int rc = quiesce(c)) return rc;
+        if (int rc = d2h_plane<double>(c, c->gen[c->cur][0], h_out, out_ld, c->cfg.row_begin, c->owned, c->cfg.cols)) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
 }
 
 // ---- realtime view (the loop of solver.py:309-329 with batches of calls per frame) --------------------

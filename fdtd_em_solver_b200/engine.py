@@ -314,6 +314,28 @@ class Engine:
             raise IndexError("index %d is out of bounds for the pulse magnitude table" % bad)
         return snaps
 
+    def run_streamed(self, eps_coef, mu_coef, first_step, n_steps, zero_fields=True, want_h=True, h_out=None):
+        """upload_coefficients + zero_fields + run + get_fields("h") as one pipeline over row bands (fdtd_run_streamed):
+        the coefficient rows travel up while the calls already run on the bands above, h travels back behind each band's
+        last call.  Returns h (global shape, owned rows written) or None.  Pinned host arrays (torch pin_memory, or
+        cudaHostRegister-ed numpy) make the copies asynchronous; ordinary numpy arrays work without the overlap."""
+        e, m = _f64(eps_coef), _f64(mu_coef)
+        if e.shape != (self.rows, self.cols) or m.shape != (self.rows, self.cols):
+            raise ValueError("coefficient arrays must be (rows, cols)")
+        first_step, n_steps = int(first_step), int(n_steps)
+        bad = None
+        if self.first_bad is not None and first_step + n_steps > self.first_bad:
+            bad = self.first_bad
+            n_steps = max(0, bad - first_step)
+        h = None
+        if want_h:
+            h = np.zeros((self.rows, self.cols)) if h_out is None else h_out
+        L.check(self.lib, self.handle, self.lib.fdtd_run_streamed(self.handle, _ptr(e), _ptr(m), self.cols, 1 if zero_fields else 0,
+                                                                  first_step, n_steps, _ptr(h), self.cols))
+        if bad is not None:
+            raise IndexError("index %d is out of bounds for the pulse magnitude table" % bad)
+        return h
+
     # ---- realtime view (SURVEY.md 8(f)-3) --------------------------------------------------------------
     def run_enqueue(self, first_step, n_steps):
         """Queue calls [first_step, first_step+n_steps) and return without waiting (fdtd_run_enqueue).  Returns the number

@@ -118,6 +118,8 @@ class Solver:
         self._engine_key = None
         self._host = None           # (h, ex, ey) host copies valid for the current step, or None
         self._pending = None        # host fields to upload before the next step
+        self._pending_is_zero = False
+        self._host_h = None         # h alone, when a streamed run brought it back with its last calls
         self._probe_seen = 0
 
     # ------------------------------------------------------------------ sizing
@@ -129,6 +131,7 @@ class Solver:
         self.size = int(self.length_x / self.ds)
         n = self.size
         self._pending = (np.zeros((n, n)), np.zeros((n + 1, n)), np.zeros((n, n + 1)))
+        self._pending_is_zero = True
         self._host = self._pending
         self.steps = int(self.end_time / self.dt)
 
@@ -149,7 +152,8 @@ class Solver:
             self._host = got
         return self._host
 
-    h = property(lambda self: None if self.size is None else self._fetch()[0])
+    h = property(lambda self: None if self.size is None else (self._host_h if self._host_h is not None and self._host is None
+                                                               else self._fetch()[0]))
     ex = property(lambda self: None if self.size is None else self._fetch()[1])
     ey = property(lambda self: None if self.size is None else self._fetch()[2])
 
@@ -157,6 +161,7 @@ class Solver:
         cur = list(self._fetch())
         cur[k] = np.array(value, dtype=np.float64)
         self._host = self._pending = tuple(cur)
+        self._pending_is_zero = False
 
     h = h.setter(lambda self, v: self._set_field(0, v))
     ex = ex.setter(lambda self, v: self._set_field(1, v))
@@ -254,8 +259,11 @@ class Solver:
         self.eps_coefficient_arr = (self.dt / self.ds) * (1 / self.material.eps_arr)
         self.mu_coefficient_arr = (self.dt / self.ds) * (1 / self.material.mu_arr)
 
-    def _sync_engine(self, times):
-        """(Re)build the device state from the host-side description when it changed."""
+    def _sync_engine(self, times, defer_coefficients=False):
+        """(Re)build the device state from the host-side description when it changed.  defer_coefficients: the caller
+        sends host coefficient planes itself, pipelined with the run (Engine.run_streamed); returns True if they are
+        still to be sent."""
+        deferred = False
         courant = (C * self.dt / self.ds)                    # evaluated exactly as solver.py:221 does
         sh = _shard.context(self._sharded)
         temporal = self._temporal_block
@@ -294,6 +302,8 @@ class Solver:
         if static != self._static_key:
             if isinstance(self.eps_coefficient_arr, tuple):          # painted on the device from the recorded shapes
                 e.paint_coefficients(self.material.ops, self.dt / self.ds)
+            elif defer_coefficients:
+                deferred = True
             else:
                 e.upload_coefficients(self.eps_coefficient_arr, self.mu_coefficient_arr)
             e.set_reflectors(self.reflectors if self.reflect else [])
@@ -302,8 +312,13 @@ class Solver:
             self._static_key = static
             self._probe_seen = 0
         if self._pending is not None:
-            e.set_fields(*self._pending)
+            if self._pending_is_zero:                   # fresh fields (update_constants): cleared on the device, not sent
+                e.zero_fields()
+            else:
+                e.set_fields(*self._pending)
             self._pending = None
+            self._pending_is_zero = False
+        return deferred
 
     def _collect_probes(self):
         """Energy formula of reference solver.py:251-255, evaluated on the host from raw device probes; and the h
@@ -377,12 +392,17 @@ class Solver:
 
     def _run_device(self, times, snapshot_every=0, n_calls=None):
         """The loops of solver.py:288-292 / :331-337 for calls self.step .. len(times)-1 (or the next n_calls of them)."""
-        self._sync_engine(times)
+        # a run without snapshots on a grid beyond resident mode's reach: coefficient upload, calls and the read of h are one
+        # pipelined library call (Engine.run_streamed) instead of three
+        streamed = (not snapshot_every and n_calls is None and _shard.context(self._sharded) is None
+                    and (self.size + 1) ** 2 > 512 * 512 and self._dtype in ("float64", np.float64))
+        deferred = self._sync_engine(times, defer_coefficients=streamed)
         first = self.step
         n = len(times) - first
         if n_calls is not None:
             n = max(0, min(n, int(n_calls)))
         self._host = None
+        self._host_h = None
         def account(collect):
             done = self._engine.stats()["steps"]
             self.step = first + (done - self._steps_seen)
@@ -391,8 +411,17 @@ class Solver:
                 self._collect_probes()
 
         try:
-            stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
-                                     alloc=self._snapshot_alloc if snapshot_every else None)
+            if deferred:
+                stack = None
+                try:
+                    self._host_h = self._engine.run_streamed(self.eps_coefficient_arr, self.mu_coefficient_arr, first, n,
+                                                             zero_fields=False)
+                except BaseException:
+                    self._static_key = None             # the coefficient planes may not have arrived: send them again
+                    raise
+            else:
+                stack = self._engine.run(first, n, snapshot_every, total_calls=len(times),
+                                         alloc=self._snapshot_alloc if snapshot_every else None)
         except IndexError:
             # a pulse outliving its table (App. A-Q10): found on the host from the same tables on every rank, so the
             # collective probe gather of a sharded run is still matched; the records up to the failing call are kept

@@ -223,6 +223,17 @@ int fdtd_run(fdtd_handle h, int64_t first_step, int64_t n_steps, int64_t snapsho
  * picture of batch k is drawn while the device computes batch k+1.  No aliasing patch is applied: the realtime loop
  * draws the field update() returned, not the saved list (solver.py:323 vs :337). */
 int fdtd_run_enqueue(fdtd_handle h, int64_t first_step, int64_t n_steps);
+/* fdtd_upload_coeffs + (zero_fields: fdtd_zero_fields) + fdtd_run(first_step, n_steps) + fdtd_get_fields(h) as ONE pipeline
+ * over row bands: band b's coefficient rows travel to the device while the calls already run on the bands above it, and a
+ * band's rows of h travel back behind its last call while the bands below are still stepping -- PCIe busy in both
+ * directions, the stepping hidden behind it (the whole-job path of Solver.solve(solve_only=True) followed by a read of
+ * solver.h, solver.py:278-292).  h_out (may be NULL: no download) receives the owned rows of h, out_ld doubles per row,
+ * addressed like fdtd_get_fields (see fdtd_set_host_row_origin).  Pinned host memory makes the copies asynchronous;
+ * pageable memory works, without the overlap.  Pipelined for float64, the whole grid on one GPU, temporal blocking >= 2;
+ * any other configuration runs the four steps one after the other.  Bit-identical to them either way. */
+int fdtd_run_streamed(fdtd_handle h, const double* eps_coef, const double* mu_coef, int64_t host_ld, int32_t zero_fields,
+                      int64_t first_step, int64_t n_steps, double* h_out, int64_t out_ld);
+
 int fdtd_view_begin(fdtd_handle h, int32_t row_stride, int32_t col_stride);
 int fdtd_view_end(fdtd_handle h, double* host_out, int64_t capacity, int64_t* rows, int64_t* cols);
 

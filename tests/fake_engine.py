@@ -52,6 +52,9 @@ class FakeEngine:
         self.f.ex = np.array(ex) if ex is not None else z.ex
         self.f.ey = np.array(ey) if ey is not None else z.ey
 
+    def zero_fields(self):
+        self.set_fields()
+
     def get_fields(self, which="hxy", out=None):
         return self.f.h.copy(), self.f.ex.copy(), self.f.ey.copy()
 
@@ -83,6 +86,14 @@ class FakeEngine:
             return np.array(saved)
         out[...] = saved
         return out
+
+    def run_streamed(self, eps_coef, mu_coef, first_step, n_steps, zero_fields=True, want_h=True, h_out=None):
+        self.upload_coefficients(eps_coef, mu_coef)
+        self.streamed_runs = getattr(self, "streamed_runs", 0) + 1
+        if zero_fields:
+            self.set_fields()
+        self.run(first_step, n_steps)
+        return self.f.h.copy() if want_h else None
 
     def run_enqueue(self, first_step, n_steps):
         first_step, n_steps = int(first_step), int(n_steps)
@@ -168,6 +179,9 @@ class FakeSlabEngine:
         whole = R.Fields(np.array(h) if h is not None else z.h, np.array(ex) if ex is not None else z.ex,
                          np.array(ey) if ey is not None else z.ey)
         self.fl, self.off = OS.make_slab(whole, self.row_begin, self.row_end)      # owned rows + halo rows only
+
+    def zero_fields(self):
+        self.set_fields()
 
     def _own(self):
         ht = self.row_begin - self.off
