@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libfdtd2d%s.so" % os.environ.get("FDTD_LIB_SUFFIX
 NVCC_EXTRA = os.environ.get("FDTD_NVCC_EXTRA", "").split()
 OBJ_DIR = os.path.join(HERE, "_obj%s" % os.environ.get("FDTD_LIB_SUFFIX", ""))     # git-ignored, not needed on the GPU box
 
-F64, F32 = 0, 1
+F64, F32, F32X = 0, 1, 2       # F32X: fp32 hi + bf16 lo field storage, float64 coefficients and arithmetic
 SRC_POINT, SRC_RIGHT, SRC_LEFT, SRC_UP, SRC_DOWN = 0, 1, 2, 3, 4
 KERNEL_EXACT, KERNEL_STREAM = 0, 1
 DIRECTION_KIND = {None: SRC_POINT, "right": SRC_RIGHT, "left": SRC_LEFT, "up": SRC_UP, "down": SRC_DOWN}
@@ -130,6 +130,8 @@ def parts():
         for lo, hi in ((2, 3), (4, 5), (6, 6), (7, 7), (8, 8)):
             out.append(("k_edge.cu", ["-DFDTD_PART_T=" + t, "-DFDTD_K_LO=%d" % lo, "-DFDTD_K_HI=%d" % hi],
                         _KERNEL_HEADERS["k_edge.cu"], "edge_%s_%d_%d" % (t, lo, hi)))
+    for lo, hi in ((1, 3), (4, 6), (7, 8)):
+        out.append(("k_split.cu", ["-DFDTD_K_LO=%d" % lo, "-DFDTD_K_HI=%d" % hi], _KERNEL_HEADERS["k_edge.cu"], "split_%d_%d" % (lo, hi)))
     return out
 
 

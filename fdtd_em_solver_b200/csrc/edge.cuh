@@ -80,11 +80,15 @@ inline void edge_syncwarp() { (void)__shfl_sync(0xffffffffu, 0, 0); }       // t
 __device__ __forceinline__ void edge_syncwarp() { __syncwarp(); }
 #endif
 
-template <typename T, int V, int K, int F>
+// SPLIT = 1 (T = double): the fields live in split storage (kernels.cuh: fp32 hi plane + bf16 lo plane, dtype FDTD_F32X).
+// Loads decode, stores encode, and every value a call would have stored is rounded to the storage format on its way to
+// the next stage (split_round), so that a group of K calls gives exactly the bits of K single calls.
+template <typename T, int V, int K, int F, int SPLIT = 0>
 __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const EdgeRec<T>* rec, EdgeWallState<T, V, K>* W,
                                               int ta, int tb, int jw, int lane) {
     constexpr bool ROWS = (F & EDGE_ROWS) != 0, COLS = (F & EDGE_COLS) != 0, SRC = (F & EDGE_SRC) != 0,
                    MISC = (F & EDGE_MISC) != 0;
+    static_assert(!SPLIT || sizeof(T) == 8, "split storage computes in double");
     const unsigned full = 0xffffffffu;
     constexpr int MARGIN = KGeom<K, V>::MARGIN;
     const int NR = P.NR, NC = P.NC;
@@ -112,11 +116,30 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
         }
 
     auto row_in = [&](int i) { return i >= 0 && i <= NR && i >= P.row_off && i < P.row_off + P.lrows; };
-    auto ldrow = [&](T (&r)[V], const T* a, int i) {
+    auto ldrow = [&](T (&r)[V], const T* a, int i) {          // a coefficient row
         if (col_in && row_in(i)) ldvec<T, V>(r, a + (long long)(i - P.row_off) * pitch + j);
         else {
 #pragma unroll
             for (int v = 0; v < V; ++v) r[v] = T(0);
+        }
+    };
+    auto ldfield = [&](T (&r)[V], const T* a, int i) {        // a row of h / ex / ey
+        if (!SPLIT) { ldrow(r, a, i); return; }
+        if (col_in && row_in(i)) {
+            const long long at = (long long)(i - P.row_off) * pitch + j;
+            const float* hi = reinterpret_cast<const float*>(a) + at;
+            const unsigned short* lo = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(a) + P.split_lo_off) + at;
+#pragma unroll
+            for (int v = 0; v < V; ++v) r[v] = (T)split_decode(hi[v], lo[v]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) r[v] = T(0);
+        }
+    };
+    auto stored = [&](T (&x)[V]) {                            // a call's final values, as the next call will read them
+        if (SPLIT) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[v] = (T)split_round((double)x[v]);
         }
     };
     // value of the column to the right / left of element v (own register or the neighbour lane's)
@@ -161,11 +184,11 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
     // rows up on its first hop (ex[NR] <- ex_pre[NR-1] <- hn[NR-2]); below, the delayed store needs iteration tb+K-1, which
     // also gives the up wall its second row (ex[0] <- ex_pre[1] <- ex[2])
     const int t_first = max(ta - K - 1, 0), t_last = tb + K - 1;
-    ldrow(Lh[0], P.h, t_first); ldrow(Lex[0], P.ex, t_first); ldrow(Ley[0], P.ey, t_first);
+    ldfield(Lh[0], P.h, t_first); ldfield(Lex[0], P.ex, t_first); ldfield(Ley[0], P.ey, t_first);
     ldrow(Cmu[0], P.muc, t_first); ldrow(Cep[0], P.epc, t_first);
     // the row below stage 1's row is loaded one iteration ahead of its use, so its latency hides behind K stages of work
     T nh[V], nex[V], ney[V], nmu[V], nep[V];
-    ldrow(nh, P.h, t_first + 1); ldrow(nex, P.ex, t_first + 1); ldrow(ney, P.ey, t_first + 1);
+    ldfield(nh, P.h, t_first + 1); ldfield(nex, P.ex, t_first + 1); ldfield(ney, P.ey, t_first + 1);
     ldrow(nmu, P.muc, t_first + 1); ldrow(nep, P.epc, t_first + 1);
 
     for (int t = t_first; t <= t_last; ++t) {
@@ -174,7 +197,7 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
 #pragma unroll
         for (int v = 0; v < V; ++v) { ph[v] = nh[v]; pex[v] = nex[v]; pey[v] = ney[v]; fmu[v] = nmu[v]; fep[v] = nep[v]; }
         if (t < t_last) {
-            ldrow(nh, P.h, t + 2); ldrow(nex, P.ex, t + 2); ldrow(ney, P.ey, t + 2);
+            ldfield(nh, P.h, t + 2); ldfield(nex, P.ex, t + 2); ldfield(ney, P.ey, t + 2);
             ldrow(nmu, P.muc, t + 2); ldrow(nep, P.epc, t + 2);
         }
 #pragma unroll
@@ -260,6 +283,7 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
                         }
                     }
                     lr_and_rects(Lex[s], Ley[s], 0);
+                    stored(Lex[s]); stored(Ley[s]);
                 }
                 // own row: down wall (:226-227) from what this stage left in W at the row above
 #pragma unroll
@@ -302,6 +326,9 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
                     if (wr && c == NC - 1) fh[v] = add(mul(ho[v], oms), mul(hol[v], S));
                 }
             }
+            // fh, fx, fy are what this call leaves in the arrays for row r (row 0's E values: one iteration later, above)
+            stored(fh);
+            if (!ROWS || r != 0) { stored(fx); stored(fy); }
             // L[s] holds the FINAL values of row r-1 after call s: probes (:246-255), then its consumer -- stage s+1
             // in the next trip of this loop, or the store below
             if (MISC && P.n_probe && storing && r - 1 >= ta && r - 1 < tb) {
@@ -339,7 +366,22 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
             T* const hq = P.hn + (long long)(q - P.row_off) * pitch;
             T* const exq_ = P.exn + (long long)(q - P.row_off) * pitch;
             T* const eyq_ = P.eyn + (long long)(q - P.row_off) * pitch;
-            if (!ROWS && !COLS) {                                // every stored cell exists in all three arrays
+            if (SPLIT) {
+                const long long at = (long long)(q - P.row_off) * pitch;
+                auto put = [&](T* base, int c, T x) {
+                    float hi; unsigned short lo;
+                    split_encode((double)x, hi, lo);
+                    reinterpret_cast<float*>(base)[at + c] = hi;
+                    reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(base) + P.split_lo_off)[at + c] = lo;
+                };
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int c = j + v;
+                    if (q < NR && c < NC) put(P.hn, c, Lh[K][v]);
+                    if (c < NC) put(P.exn, c, Lex[K][v]);
+                    if (q < NR && c <= NC) put(P.eyn, c, Ley[K][v]);
+                }
+            } else if (!ROWS && !COLS) {                         // every stored cell exists in all three arrays
                 stvec<T, V>(hq + j, Lh[K]); stvec<T, V>(exq_ + j, Lex[K]); stvec<T, V>(eyq_ + j, Ley[K]);
             } else {
 #pragma unroll
@@ -364,7 +406,7 @@ __device__ __forceinline__ void run_tile_edge(const StepParams<T>& P, const Edge
 
 // One warp per edge tile.  P: generation A in h/ex/ey, generation B in hn/exn/eyn, probe_out = record of call
 // first_step (call s of the group writes record s); R: the per-call pulse records of resident mode.
-template <typename T, int V, int K, int F>
+template <typename T, int V, int K, int F, int SPLIT = 0>
 __global__ void __launch_bounds__(32) stepK_edge(const __grid_constant__ StepParams<T> P, const EdgeTile* __restrict__ tiles,
                                                  int n_tiles, const ResSources<T> R, long long first_step) {
 #if defined(FDTD_HOST_EMUL)
@@ -391,9 +433,9 @@ __global__ void __launch_bounds__(32) stepK_edge(const __grid_constant__ StepPar
     }
     const EdgeTile tl = tiles[blockIdx.x];
 #if defined(FDTD_HOST_EMUL)
-    run_tile_edge<T, V, K, F>(P, rec, &wall, tl.ta, tl.tb, tl.tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+    run_tile_edge<T, V, K, F, SPLIT>(P, rec, &wall, tl.ta, tl.tb, tl.tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 #else
-    run_tile_edge<T, V, K, F>(P, rec, wall_p, tl.ta, tl.tb, tl.tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+    run_tile_edge<T, V, K, F, SPLIT>(P, rec, wall_p, tl.ta, tl.tb, tl.tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 #endif
 }
 

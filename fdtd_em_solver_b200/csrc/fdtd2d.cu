@@ -155,6 +155,9 @@ struct fdtd_ctx {
     int frame_mode = 3;
     int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
+    // split field storage (dtype FDTD_F32X): every tile is a stepK_edge tile; one tile list per group size
+    bool split = false;
+    struct SplitTiles { fdtd::EdgeTile* dev = nullptr; int n = 0; } split_tiles[9];
     bool maps_pinned = false;        // fdtd_run_streamed: the frame maps in place serve every group of the run
     bool edge_class_force = false;   // measurement hook FDTD_EDGE_GENERIC=1: every edge tile through the all-features instantiation
 
@@ -294,6 +297,7 @@ int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step, int a, int b) {
     for (int k = 0; k < c->n_probe; ++k) { P.probe_i[k] = c->probe_i[k]; P.probe_j[k] = c->probe_j[k]; }
     P.probe_out = nullptr;
     P.tile_mask = nullptr; P.mask_stride = 0; P.tile_list = nullptr;
+    P.split_lo_off = c->split ? (long long)c->lrows * c->pitch * 4 : 0;
     return 0;
 }
 
@@ -818,7 +822,7 @@ int group_impl(fdtd_ctx* c, int64_t n, int K) {
 
 // ---- resident mode: many steps per cooperative launch (resident.cuh) ------------------------------------
 bool resident_eligible(const fdtd_ctx* c) {
-    if (!c->resident || c->comm || c->cfg.kernel != FDTD_KERNEL_STREAM) return false;
+    if (!c->resident || c->comm || c->cfg.kernel != FDTD_KERNEL_STREAM || c->split) return false;
     if (c->cfg.row_begin != 0 || c->cfg.row_end != c->cfg.rows) return false;            // whole grid on this GPU
     if ((c->cfg.rows + 1) * (c->cfg.cols + 1) > c->resident_max_cells) return false;
     if (c->n_src > FDTD_MAX_SRC) return false;
@@ -995,11 +999,119 @@ int group_edge(fdtd_ctx* c, int64_t n, int K) {
     return 0;
 }
 
+// ---- split field storage (dtype FDTD_F32X) ----------------------------------------------------------------------------------
+// Fields: fp32 hi plane + bf16 lo plane per buffer (6 bytes per value, 32 significant bits); coefficients, pulse tables and
+// arithmetic: float64, in the reference's operation order.  One kernel family runs this mode: stepK_edge with every
+// feature (edge.cuh, SPLIT = 1), for every tile of the grid, K = 1 .. 8 calls per launch with the bits of single calls.
+float* split_hi(fdtd_ctx* c, void* base, int64_t global_row) { return (float*)base + (global_row - c->row_off) * c->pitch; }
+unsigned short* split_lo(fdtd_ctx* c, void* base, int64_t global_row) {
+    return (unsigned short*)((char*)base + (size_t)c->lrows * c->pitch * 4) + (global_row - c->row_off) * c->pitch;
+}
+
+int split_h2d_field(fdtd_ctx* c, void* base, const double* host, int64_t host_ld, int64_t g0, int64_t n, int64_t ncols) {
+    if (n <= 0 || !host) return 0;
+    const double* src = host + (g0 - c->host_row0) * host_ld;
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(32 << 20) / (ncols * 8));
+    if (int rc = ensure_stage(c, (size_t)std::min(chunk, n) * ncols * 8)) return rc;
+    for (int64_t a = 0; a < n; a += chunk) {
+        const int64_t m = std::min(chunk, n - a);
+        CK(cudaMemcpy2DAsync(c->stage, ncols * 8, src + a * host_ld, host_ld * 8, ncols * 8, m, cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((unsigned)((ncols + 255) / 256), (unsigned)std::min<int64_t>(m, 65535));
+        CK(fdtd::launch_split_from_f64(grid, c->stream, split_hi(c, base, g0 + a), split_lo(c, base, g0 + a), c->pitch,
+                                       (const double*)c->stage, ncols, (int)m, (int)ncols));
+        c->stats.kernel_launches++;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int split_d2h_field(fdtd_ctx* c, void* base, double* host, int64_t host_ld, int64_t g0, int64_t n, int64_t ncols) {
+    if (n <= 0 || !host) return 0;
+    double* dst = host + (g0 - c->host_row0) * host_ld;
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(32 << 20) / (ncols * 8));
+    if (int rc = ensure_stage(c, (size_t)std::min(chunk, n) * ncols * 8)) return rc;
+    fdtd::PatchList none; none.n = 0;
+    for (int64_t a = 0; a < n; a += chunk) {
+        const int64_t m = std::min(chunk, n - a);
+        dim3 block(64, 4), grid((unsigned)((ncols + 63) / 64), (unsigned)std::min<int64_t>((m + 3) / 4, 65535));
+        CK(fdtd::launch_split_to_f64(grid, block, c->stream, (double*)c->stage, ncols, split_hi(c, base, g0 + a),
+                                     split_lo(c, base, g0 + a), c->pitch, (int)m, (int)ncols, 1, 1, 0, none));
+        c->stats.kernel_launches++;
+        CK(cudaMemcpy2DAsync(dst + a * host_ld, host_ld * 8, c->stage, ncols * 8, ncols * 8, m, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// the tiles of a group of K calls: the whole index space (rows 0 .. NR, columns 0 .. NC), every tile with every feature
+int split_plan(fdtd_ctx* c, int K) {
+    fdtd_ctx::SplitTiles& t = c->split_tiles[K];
+    if (t.dev) return 0;
+    const int V2 = 2, MARGIN = (K + V2 - 1) / V2, OUT = (32 - 2 * MARGIN) * V2, LD = 32 * V2;
+    const int64_t NR = c->cfg.rows, NC = c->cfg.cols;
+    int ntx = (int)((NC + 1 + OUT - 1) / OUT);
+    while (ntx > 1 && (int64_t)(ntx - 2) * OUT - (int64_t)MARGIN * V2 + LD > NC) --ntx;    // that tile owns everything right of it
+    // tile height: a tile marches rows + 2 K + 1 iterations of a latency-bound pipeline, so short tiles waste work and
+    // tall ones leave a small grid with too few warps; aim at about four warps per resident-warp slot of the GPU
+    int64_t er = (NR + 1) * ntx / (4 * 1184);
+    er = std::max<int64_t>(8, std::min<int64_t>(64, er));
+    if (const char* e = std::getenv("FDTD_SPLIT_ROWS")) { const int v = std::atoi(e); if (v >= 1 && v <= 4096) er = v; }
+    std::vector<fdtd::EdgeTile> tiles;
+    for (int64_t ta = 0; ta < NR + 1; ta += er)
+        for (int tx = 0; tx < ntx; ++tx)
+            tiles.push_back(fdtd::EdgeTile{tx, (int)ta, (int)std::min<int64_t>(ta + er, NR + 1), fdtd::EDGE_ALL});
+    CK(cudaMalloc(&t.dev, tiles.size() * sizeof(fdtd::EdgeTile)));
+    CK(cudaMemcpy(t.dev, tiles.data(), tiles.size() * sizeof(fdtd::EdgeTile), cudaMemcpyHostToDevice));
+    t.n = (int)tiles.size();
+    return 0;
+}
+
+// calls n .. n+K-1 (K = 1 .. 8): generation A -> B in one launch
+int split_group(fdtd_ctx* c, int64_t n, int K) {
+    Range nvtx("fdtd:split_group");
+    for (int p = 0; p < c->n_src; ++p)
+        if (c->src[p].kind == FDTD_SRC_RIGHT && c->src[p].col == 0)
+            return fail(c, FDTD_ERR_ARG, "split storage (FDTD_F32X) does not take a TF/SF \"right\" line at column 0");
+    if (c->n_src > FDTD_MAX_SRC) return fail(c, FDTD_ERR_ARG, "split storage (FDTD_F32X) takes at most 16 pulses");
+    if (int rc = split_plan(c, K)) return rc;
+    if (int rc = resident_tables<double>(c)) return rc;
+    if (c->n_probe) if (int rc = ensure_probe_capacity(c, K)) return rc;
+    const int A = c->cur, B = (A + 1) % 2;
+    StepParams<double> P;
+    if (int rc = fill_params<double>(c, P, n, A, B)) return rc;
+    P.n_src = 0; P.last_mag = 0.0;                               // the kernel reads each call's records itself
+    P.row_lo = 0; P.row_hi = (int)c->cfg.rows + 1;
+    if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
+    fdtd::ResSources<double> R{(const int*)c->rs_count, (const double*)c->rs_last, (const fdtd::SrcStep<double>*)c->rs_src, c->rs_stride};
+    const fdtd_ctx::SplitTiles& t = c->split_tiles[K];
+    cudaError_t e;
+    switch (K) {
+        case 1: e = fdtd::launch_edge_split_k<1>(P, t.dev, t.n, R, n, c->stream); break;
+        case 2: e = fdtd::launch_edge_split_k<2>(P, t.dev, t.n, R, n, c->stream); break;
+        case 3: e = fdtd::launch_edge_split_k<3>(P, t.dev, t.n, R, n, c->stream); break;
+        case 4: e = fdtd::launch_edge_split_k<4>(P, t.dev, t.n, R, n, c->stream); break;
+        case 5: e = fdtd::launch_edge_split_k<5>(P, t.dev, t.n, R, n, c->stream); break;
+        case 6: e = fdtd::launch_edge_split_k<6>(P, t.dev, t.n, R, n, c->stream); break;
+        case 7: e = fdtd::launch_edge_split_k<7>(P, t.dev, t.n, R, n, c->stream); break;
+        case 8: e = fdtd::launch_edge_split_k<8>(P, t.dev, t.n, R, n, c->stream); break;
+        default: return fail(c, FDTD_ERR_ARG, "split group of 1..8 calls");
+    }
+    CK(e);
+    c->stats.kernel_launches++;
+    c->cur = B;
+    if (c->n_probe) c->probe_count += K;
+    c->stats.steps += K;
+    c->stats.cell_updates += (int64_t)K * c->owned * c->cfg.cols;
+    return 0;
+}
+
 int step_any(fdtd_ctx* c, int64_t step) {
+    if (c->split) return split_group(c, step, 1);
     return c->cfg.dtype == FDTD_F64 ? step_impl<double>(c, step) : step_impl<float>(c, step);
 }
 
 int group_any(fdtd_ctx* c, int64_t n, int K) {
+    if (c->split) return split_group(c, n, K);
     const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
     if (edge_usable(c, K)) return c->cfg.dtype == FDTD_F64 ? group_edge<double>(c, n, K) : group_edge<float>(c, n, K);
     // The fallback, K masked single-step passes through the scratch generations (frame mode 0; a scene stepK_edge cannot
@@ -1030,6 +1142,11 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     const int64_t rows = c->owned, cols = c->cfg.cols;
     CK(cudaStreamWaitEvent(c->stream, c->ev_free[slot], 0));
     dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)std::min<int64_t>((rows + 3) / 4, 65535));
+    if (c->split) {
+        CK(fdtd::launch_split_to_f64(grid, block, c->stream, c->snap_dev[slot], cols, split_hi(c, c->gen[c->cur][0], c->cfg.row_begin),
+                                     split_lo(c, c->gen[c->cur][0], c->cfg.row_begin), c->pitch, (int)rows, (int)cols, 1, 1,
+                                     (int)c->cfg.row_begin, pl));
+    } else
     CK(fdtd::launch_plane_to_f64<T>(grid, block, c->stream, c->snap_dev[slot], cols,
         plane<T>(c->gen[c->cur][0], c, c->cfg.row_begin), c->pitch, (int)rows, (int)cols, (int)c->cfg.row_begin, pl));
     c->stats.kernel_launches++;
@@ -1082,7 +1199,9 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
         return fail(c, FDTD_ERR_ARG, "bad slab row range");
     const bool whole = cfg->row_begin == 0 && cfg->row_end == cfg->rows;
     if (!whole && cfg->row_end - cfg->row_begin < 2) return fail(c, FDTD_ERR_ARG, "a slab must own at least 2 rows");
-    if (cfg->dtype != FDTD_F64 && cfg->dtype != FDTD_F32) return fail(c, FDTD_ERR_ARG, "bad dtype");
+    if (cfg->dtype != FDTD_F64 && cfg->dtype != FDTD_F32 && cfg->dtype != FDTD_F32X) return fail(c, FDTD_ERR_ARG, "bad dtype");
+    if (cfg->dtype == FDTD_F32X && !whole)
+        return fail(c, FDTD_ERR_ARG, "split storage (FDTD_F32X) runs on one GPU: y-slabs are not available in this mode");
     if (cfg->kernel != FDTD_KERNEL_EXACT && cfg->kernel != FDTD_KERNEL_STREAM) return fail(c, FDTD_ERR_ARG, "bad kernel");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1094,7 +1213,8 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->cfg = *cfg;
     if (const char* eg = std::getenv("FDTD_EDGE_GENERIC")) c->edge_class_force = std::atoi(eg) != 0;
     if (const char* er = std::getenv("FDTD_EDGE_ROWS")) { const int v = std::atoi(er); if (v >= 1 && v <= 4096) c->edge_rows = v; }
-    c->esize = cfg->dtype == FDTD_F64 ? 8 : 4;
+    c->esize = cfg->dtype == FDTD_F64 ? 8 : (cfg->dtype == FDTD_F32X ? 6 : 4);     // bytes per FIELD value (F32X: 4 hi + 2 lo)
+    c->split = cfg->dtype == FDTD_F32X;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
     if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
     c->cfg.pitch = c->pitch;
@@ -1166,6 +1286,7 @@ int fdtd_destroy(fdtd_handle c) {
         if (c->view[s].pin) cudaFreeHost(c->view[s].pin);
         if (c->view[s].done) cudaEventDestroy(c->view[s].done);
     }
+    for (auto& t : c->split_tiles) if (t.dev) cudaFree(t.dev);
     for (cudaEvent_t e : c->band_up) cudaEventDestroy(e);
     for (cudaEvent_t e : c->band_done) cudaEventDestroy(e);
     for (cudaEvent_t e : c->band_edge) cudaEventDestroy(e);
@@ -1369,7 +1490,7 @@ int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_c
     if (!eps_coef || !mu_coef || host_ld < c->cfg.cols) return fail(c, FDTD_ERR_ARG, "bad coefficient arrays");
     const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off;     // every stored h-row
     int rc;
-    if (c->cfg.dtype == FDTD_F64) {
+    if (c->cfg.dtype != FDTD_F32) {                      // float64 coefficient planes (also under split field storage)
         if ((rc = h2d_plane<double>(c, c->epc, eps_coef, host_ld, g0, n, c->cfg.cols))) return rc;
         if ((rc = h2d_plane<double>(c, c->muc, mu_coef, host_ld, g0, n, c->cfg.cols))) return rc;
     } else {
@@ -1383,7 +1504,7 @@ int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_c
 int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, double epsilon0, double mu0) {
     NEED_BOUND();
     dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
-    if (c->cfg.dtype == FDTD_F64)
+    if (c->cfg.dtype != FDTD_F32)
         CK(fdtd::launch_synth_coeffs<double>(grid, c->stream, (double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0));
     else
@@ -1410,7 +1531,7 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
     CK(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(fdtd::ShapeDev), cudaMemcpyHostToDevice, c->stream));
     dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(c->lrows, 65535));
     cudaError_t e;
-    if (c->cfg.dtype == FDTD_F64)
+    if (c->cfg.dtype != FDTD_F32)
         e = fdtd::launch_paint_coeffs<double>(grid, c->stream, (double*)c->epc, (double*)c->muc, c->pitch, (int)c->lrows,
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, dev, n, eps_background, mu_background, dt_over_ds);
     else
@@ -1451,7 +1572,11 @@ int fdtd_set_fields(fdtd_handle c, const double* hh, const double* ex, const dou
     const int64_t g0 = c->row_off, n = c->cfg.row_end + c->halo_bot - c->row_off, NC = c->cfg.cols;
     const int a = c->cur;
     int rc;
-    if (c->cfg.dtype == FDTD_F64) {
+    if (c->split) {
+        if ((rc = split_h2d_field(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = split_h2d_field(c, c->gen[a][1], ex, NC, g0, n + 1, NC))) return rc;
+        if ((rc = split_h2d_field(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    } else if (c->cfg.dtype == FDTD_F64) {
         if ((rc = h2d_plane<double>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
         if ((rc = h2d_plane<double>(c, c->gen[a][1], ex, NC, g0, n + 1, NC))) return rc;
         if ((rc = h2d_plane<double>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
@@ -1472,7 +1597,11 @@ int fdtd_get_fields(fdtd_handle c, double* hh, double* ex, double* ey) {
     const int64_t nex = n + (c->cfg.row_end == c->cfg.rows ? 1 : 0);
     const int a = c->cur;
     int rc;
-    if (c->cfg.dtype == FDTD_F64) {
+    if (c->split) {
+        if ((rc = split_d2h_field(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
+        if ((rc = split_d2h_field(c, c->gen[a][1], ex, NC, g0, nex, NC))) return rc;
+        if ((rc = split_d2h_field(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
+    } else if (c->cfg.dtype == FDTD_F64) {
         if ((rc = d2h_plane<double>(c, c->gen[a][0], hh, NC, g0, n, NC))) return rc;
         if ((rc = d2h_plane<double>(c, c->gen[a][1], ex, NC, g0, nex, NC))) return rc;
         if ((rc = d2h_plane<double>(c, c->gen[a][2], ey, NC + 1, g0, n, NC + 1))) return rc;
@@ -1590,10 +1719,11 @@ static int run_impl(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t 
     // steps per group: what the caller asked for, what the bound scratch generations allow, and -- on a slab with deep
     // halos -- what the halos cover (a group of K steps reads K+1 rows of the neighbours)
     int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? c->temporal : 1;
+    if (c->split) kmax_pre = 8;          // split storage: a group of K calls has the bits of K single calls and needs no extra buffers
     if (c->halo_depth > 1 && !(c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)) kmax_pre = std::min(kmax_pre, c->halo_depth - 1);
     if (kmax_pre >= 2 && !edge_usable(c, kmax_pre))      // only the pass chain needs the scratch generations
         kmax_pre = std::min(kmax_pre, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1));
-    if (kmax_pre >= 2 && !resident) {
+    if (kmax_pre >= 2 && !resident && !c->split) {
         // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
         bool seen[9] = {};
         for (int64_t n = first_step; n < first_step + n_steps;) {
@@ -1635,7 +1765,7 @@ static int run_impl(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t 
         if (snaps && (n + 1) % snapshot_every == 0) {
             if (k >= max_snapshots) { rc = fail(c, FDTD_ERR_ARG, "snapshot buffer too small"); break; }
             double* dst = snapshots_host + (size_t)k * c->owned * c->cfg.cols;
-            rc = c->cfg.dtype == FDTD_F64 ? snapshot_impl<double>(c, (int)(k & 1), dst, n + 1, total_calls)
+            rc = c->cfg.dtype != FDTD_F32 ? snapshot_impl<double>(c, (int)(k & 1), dst, n + 1, total_calls)
                                           : snapshot_impl<float>(c, (int)(k & 1), dst, n + 1, total_calls);
             if (rc) break;
             ++k;
@@ -1948,7 +2078,11 @@ int fdtd_run_streamed(fdtd_handle c, const double* eps_coef, const double* mu_co
     if (int rc = fdtd_run(c, first_step, n_steps, 0, nullptr, 0, first_step + n_steps, nullptr)) return rc;
     if (h_out) {
         if (int rc = quiesce(c)) return rc;
-        if (int rc = d2h_plane<double>(c, c->gen[c->cur][0], h_out, out_ld, c->cfg.row_begin, c->owned, c->cfg.cols)) return rc;
+        int rc;
+        if (c->split) rc = split_d2h_field(c, c->gen[c->cur][0], h_out, out_ld, c->cfg.row_begin, c->owned, c->cfg.cols);
+        else if (c->cfg.dtype == FDTD_F64) rc = d2h_plane<double>(c, c->gen[c->cur][0], h_out, out_ld, c->cfg.row_begin, c->owned, c->cfg.cols);
+        else rc = d2h_plane<float>(c, c->gen[c->cur][0], h_out, out_ld, c->cfg.row_begin, c->owned, c->cfg.cols);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
@@ -1977,7 +2111,12 @@ int fdtd_view_begin(fdtd_handle c, int32_t row_stride, int32_t col_stride) {
     if (!v.done) CK(cudaEventCreateWithFlags(&v.done, cudaEventDisableTiming));
     if (rows > 0) {
         dim3 block(64, 4), grid((unsigned)((cols + 63) / 64), (unsigned)std::min<int64_t>((rows + 3) / 4, 65535));
-        if (c->cfg.dtype == FDTD_F64)
+        if (c->split) {
+            fdtd::PatchList none; none.n = 0;
+            CK(fdtd::launch_split_to_f64(grid, block, c->stream, v.dev, cols, split_hi(c, c->gen[c->cur][0], first),
+                                         split_lo(c, c->gen[c->cur][0], first), c->pitch, (int)rows, (int)cols, row_stride,
+                                         col_stride, 0, none));
+        } else if (c->cfg.dtype == FDTD_F64)
             CK(fdtd::launch_plane_view<double>(grid, block, c->stream, v.dev, cols, plane<double>(c->gen[c->cur][0], c, first),
                                                c->pitch, (int)rows, (int)cols, row_stride, col_stride));
         else
@@ -2098,6 +2237,7 @@ int fdtd_comm_unique_id(void* out128) {
 int fdtd_comm_init(fdtd_handle c, const void* unique_id128, int32_t rank, int32_t nranks) {
     if (!c || !unique_id128) return FDTD_ERR_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, FDTD_ERR_ARG, "bad rank/nranks");
+    if (c->split) return fail(c, FDTD_ERR_ARG, "split storage (FDTD_F32X) runs on one GPU");
     std::string err;
     if (!g_nccl.load(err)) return fail(c, FDTD_ERR_COMM, err);
     CK(cudaSetDevice(c->cfg.device));

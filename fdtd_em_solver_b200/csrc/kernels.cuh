@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define FDTD_MAX_SRC 16
 #define FDTD_MAX_RECT 24
@@ -78,7 +79,43 @@ struct StepParams {
     const unsigned char* tile_mask;   // optional: [row tile][warp tile] != 0 -> compute, else skip (temporal-blocking frame)
     const int2* tile_list;            // optional compact launch: blockIdx.x -> (block column, row tile)
     int mask_stride;
+    // split storage (dtype FDTD_F32X, T = double): h/ex/ey/hn/exn/eyn point at the fp32 "hi" plane of their buffer, the
+    // bf16 "lo" plane of the same buffer starts split_lo_off BYTES behind it; 0 = plain storage.  Last on purpose: the
+    // offsets of every other field, and with them the code of the kernels that do not read it, stay what they were.
+    long long split_lo_off;
 };
+
+// ---- split field storage: value ~ hi + lo, hi = fp32(value), lo = bf16(fp32(value - hi)), both round-to-nearest-even.
+// 32 bits of significand in 6 bytes.  Bit operations only for the bf16 half, so that the device, the CPU emulator and
+// the numpy oracle (oracle/split_storage.py) produce the same bits.
+#if defined(FDTD_HOST_EMUL)
+#define FDTD_HD inline
+#else
+#define FDTD_HD __host__ __device__ __forceinline__
+#endif
+FDTD_HD unsigned short split_bf16_bits(float f) {
+    unsigned int u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (unsigned short)(u >> 16);       // inf / nan: truncate
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+FDTD_HD float split_bf16_value(unsigned short b) {
+    const unsigned int u = (unsigned int)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+FDTD_HD void split_encode(double x, float& hi, unsigned short& lo) {
+    hi = (float)x;
+    lo = split_bf16_bits((float)(x - (double)hi));
+}
+FDTD_HD double split_decode(float hi, unsigned short lo) { return (double)hi + (double)split_bf16_value(lo); }
+FDTD_HD double split_round(double x) {                         // what a value becomes on its way through storage
+    float hi; unsigned short lo;
+    split_encode(x, hi, lo);
+    return split_decode(hi, lo);
+}
 
 __device__ __forceinline__ bool inside(const RectI& r, int i, int j) {
     return i >= r.r0 && i < r.r1 && j >= r.c0 && j < r.c1;

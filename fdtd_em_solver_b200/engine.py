@@ -111,13 +111,16 @@ class Engine:
         row_end = rows if row_end is None else row_end
         self.rows, self.cols, self.row_begin, self.row_end = int(rows), int(cols), int(row_begin), int(row_end)
         self.owned = self.row_end - self.row_begin
-        self.dtype = np.dtype(dtype)
+        # "float32x": fields stored as fp32 hi + bf16 lo planes (6 bytes per value), float64 coefficients and arithmetic
+        # (include/fdtd2d.h FDTD_F32X) -- the reduced-storage mode that keeps 1e-5 on long runs; one GPU, whole grid
+        self.split = str(dtype) == "float32x"
+        self.dtype = np.dtype("float64") if self.split else np.dtype(dtype)
         if self.dtype not in (np.dtype("float64"), np.dtype("float32")):
-            raise ValueError("dtype must be float64 or float32")
+            raise ValueError("dtype must be float64, float32 or float32x")
         cfg = L.Config()
         cfg.rows, cfg.cols, cfg.row_begin, cfg.row_end = self.rows, self.cols, self.row_begin, self.row_end
         cfg.pitch = 0
-        cfg.dtype = L.F64 if self.dtype == np.float64 else L.F32
+        cfg.dtype = L.F32X if self.split else (L.F64 if self.dtype == np.float64 else L.F32)
         cfg.device = int(device)
         for k in range(4):
             cfg.reflect[k] = 1 if reflect[k] else 0
@@ -149,7 +152,11 @@ class Engine:
         dev = torch.device("cuda", int(device))
         self.device = dev
         # the ONLY role torch plays: owner of the device buffers
-        self.buffers = [torch.zeros((self.lrows, self.pitch), dtype=tdt, device=dev) for _ in range(8)]
+        if self.split:      # six field buffers of hi (4 B) + lo (2 B) planes, two float64 coefficient planes
+            self.buffers = [torch.zeros((self.lrows * self.pitch * 6,), dtype=torch.uint8, device=dev) for _ in range(6)] + \
+                           [torch.zeros((self.lrows, self.pitch), dtype=torch.float64, device=dev) for _ in range(2)]
+        else:
+            self.buffers = [torch.zeros((self.lrows, self.pitch), dtype=tdt, device=dev) for _ in range(8)]
         torch.cuda.synchronize(dev)
         L.check(self.lib, self.handle, self.lib.fdtd_bind_buffers(self.handle, *[C.c_void_p(b.data_ptr()) for b in self.buffers]))
         self.first_bad = None

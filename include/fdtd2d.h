@@ -42,7 +42,15 @@ enum fdtd_status {
     FDTD_ERR_COMM = -5      /* NCCL halo transport failed / unavailable     */
 };
 
-enum fdtd_dtype { FDTD_F64 = 0, FDTD_F32 = 1 };
+/* FDTD_F64: the parity mode (bit-identical to the reference).  FDTD_F32: everything in float32, 32 bytes per cell-update, the
+ * throughput mode; its error grows with the length of the run (field-STORAGE rounding) and leaves the 1e-5 gate on long
+ * runs.  FDTD_F32X ("float32x"): the fields are stored as an fp32 "hi" plane plus a bf16 "lo" plane (6 bytes per value, 32
+ * significant bits: each field buffer holds local_rows x pitch floats followed by local_rows x pitch uint16), the
+ * coefficient planes, the pulse tables and ALL arithmetic are float64 in the reference's operation order; 52 bytes per
+ * cell-update (3 fields x 6 B x 2 + 2 coefficients x 8 B) instead of 64, 1e-5 relative L2 held on every snapshot of the
+ * reference's scripts.  One GPU, one kernel family (stepK_edge with every feature, up to 8 calls per launch, the bits of
+ * single calls); no TF/SF "right" line at column 0. */
+enum fdtd_dtype { FDTD_F64 = 0, FDTD_F32 = 1, FDTD_F32X = 2 };
 
 /* Pulse.get_direction(): None / "right" / "left" / "up" / "down" (solver.py:484, :176-217). */
 enum fdtd_source_kind { FDTD_SRC_POINT = 0, FDTD_SRC_RIGHT = 1, FDTD_SRC_LEFT = 2, FDTD_SRC_UP = 3, FDTD_SRC_DOWN = 4 };

@@ -8,12 +8,16 @@ mkdir -p gpurun_out
 O=gpurun_out/r2m_n${N}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531"
 timeout 900 $TR tools/slab_check.py --big > ${O}_slab_check.log 2>&1; echo "slab_check rc=$?"; tail -3 ${O}_slab_check.log
+if [ -z "$LEAN" ]; then      # LEAN=1 (the 8-GPU call, charged 8x): what the smaller calls already showed is left out
 timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -k "nccl or sharded or torchrun" > ${O}_multi_gpu_tests.log 2>&1; echo "multi tests rc=$?"; tail -2 ${O}_multi_gpu_tests.log
+fi
 timeout 300 python bench.py --no-cpu --no-e2e --steps 200 > ${O}_bench_samebox_n1_f64.json 2> ${O}_bench_samebox_n1_f64.err; echo "n1 rc=$?"
 timeout 400 $TR bench.py --gpus $N --no-cpu > ${O}_bench_weak_f64.json 2> ${O}_bench_weak_f64.err; echo "weak f64 rc=$?"
 timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --steps 20 --warmup 5 > ${O}_bench_weak_f64_20steps.json 2> ${O}_bench_weak_f64_20steps.err; echo "20 steps rc=$?"
 timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --dtype f32 > ${O}_bench_weak_f32.json 2> ${O}_bench_weak_f32.err; echo "weak f32 rc=$?"
+if [ -z "$LEAN" ]; then
 timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --halo-depth 1 --frame-mode 0 --temporal 6 --steps 198 > ${O}_bench_weak_f64_onerow_halos_k6.json 2> ${O}_bench_weak_f64_onerow_halos_k6.err; echo "one-row halos rc=$?"
+fi
 if [ "$N" -ge 2 ]; then
   timeout 300 $TR bench.py --gpus $N --no-cpu --no-e2e --dtype f32 --total-rows 65536 --steps 200 > ${O}_bench_strong_f32.json 2> ${O}_bench_strong_f32.err; echo "strong f32 rc=$?"
 fi
@@ -27,7 +31,7 @@ python - <<PY
 import json, glob
 for f in sorted(glob.glob("${O}_bench_*.json")):
     try:
-        d = json.load(open(f)); r = d.get("roofline") or {}
+        d = json.loads(open(f).read().strip().splitlines()[-1]); r = d.get("roofline") or {}
         print(f.split("_bench_")[1], "n", d["n_gpus"], round(d["value"], 1), "ms/step", round(d["ms_per_step"], 4), "e2e", (d.get("e2e") or {}).get("value"),
               "halo", (d.get("halo") or d.get("nvlink") or {}))
     except Exception as e:
