@@ -35,7 +35,8 @@ import numpy as np  # noqa: E402
 
 ROWS_PER_GPU = 8192
 COLS = 65536
-BYTES_PER_CELL = {"f64": 64, "f32": 32}      # 5 words read + 3 written
+# 5 words read + 3 written; f32x = split field storage: 3 fields x 6 B x 2 + 2 float64 coefficients
+BYTES_PER_CELL = {"f64": 64, "f32": 32, "f32x": 52}
 METRIC = "Gcell-updates/s (2D Yee leapfrog, C5 synthetic slab)"
 CPU_SAMPLE = (512, 65536)           # rows x cols of the CPU arm's sample: a thin slab of the real rows
 
@@ -242,13 +243,15 @@ def workload_config(args, n_gpus, engine=None):
             args.temporal, kvec, frame, args.tile_rows, args.warps)
     else:
         kernel = "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)
+    if args.dtype == "f32x":
+        kernel = "stepK_edge<double,2,8,all features,split storage>: every tile of the grid, 8 steps per launch"
     return {"workload": "C5 synthetic: %d x %d Yee grid (%d rows per GPU, y-slab sharded), heterogeneous eps_r=1+3u "
                         "(splitmix64), mu_r=1, 4 absorbing walls, 1 point source per slab + 1 TF/SF line at col 7"
                         % (ROWS_PER_GPU * n_gpus, COLS, ROWS_PER_GPU),
             "rows": ROWS_PER_GPU * n_gpus, "cols": COLS, "rows_per_gpu": ROWS_PER_GPU,
             "l2": "inputs_exceed_l2 (%d arrays x %.1f GiB per GPU, no flush needed)"
                   % (n_arrays,
-                     ROWS_PER_GPU * COLS * (8 if args.dtype == "f64" else 4) / 2 ** 30),
+                     ROWS_PER_GPU * COLS * {"f64": 8, "f32": 4, "f32x": 6}[args.dtype] / 2 ** 30),
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "y-slab x%d, %d halo rows of h/ex/ey each way ONCE per K-step group over NCCL"
                             % (n_gpus, halo) if halo > 1 else
@@ -265,7 +268,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000,
                     help="timed leapfrog steps (BASELINE.json's config 5 runs 10 000; 1000 keeps the default run short)")
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32", "f32x"],
+                    help="f32x: fp32 hi + bf16 lo field storage, float64 coefficients and arithmetic (1 GPU)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tile-rows", type=int, default=0, help="rows per warp tile (0 = library default for the chosen --temporal)")
     ap.add_argument("--vec", type=int, default=0)
@@ -321,7 +325,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
     rows = ROWS_PER_GPU * n_gpus
-    dtype = "float64" if args.dtype == "f64" else "float32"
+    dtype = {"f64": "float64", "f32": "float32", "f32x": "float32x"}[args.dtype]
     n_calls = 8 * (args.steps + args.warmup) + 256
     e, _ = SY.make_engine(rows, COLS, dtype=dtype, n_calls=n_calls, row_begin=rank * ROWS_PER_GPU,
                           row_end=(rank + 1) * ROWS_PER_GPU, slab_edges=(rank * ROWS_PER_GPU,), device=local_rank,
@@ -504,6 +508,12 @@ def main():
         alg_bytes = ROWS_PER_GPU * COLS * bpc
         kname = "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
             tname, args.vec, "; 3 launches with halo overlap" if n_gpus > 1 else "")
+    if args.dtype == "f32x":
+        # one launch = 8 steps of the whole slab through stepK_edge with split storage; 52 algorithmic bytes per cell-update
+        launch_ms = ms / args.steps * 8
+        alg_bytes = ROWS_PER_GPU * COLS * bpc * 8
+        kname = ("fdtd::stepK_edge<double,2,8,15,1>: split field storage (fp32 hi + bf16 lo), one launch advances the whole "
+                 "slab 8 steps; launch time = whole-step time x 8 (the only kernel of the step)")
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": args.steps,

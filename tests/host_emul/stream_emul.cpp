@@ -117,6 +117,12 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
 
 }  // extern "C"
 
+// split storage: every tile through the all-features instantiation with SPLIT = 1
+template <int K>
+static void edge_tile_split(const StepParams<double>& P, const EdgeTile* tl, int n_tiles, const ResSources<double>& R) {
+    simt::run_warp(0, [&] { stepK_edge<double, 2, K, EDGE_ALL, 1>(P, tl, n_tiles, R, 0); });
+}
+
 // one warp = one edge tile, through the instantiation of its class (edge.cuh EDGE_CLASSES)
 template <int K>
 static int edge_tile_class(int cls, const StepParams<double>& P, const EdgeTile* tl, int n_tiles, const ResSources<double>& R) {
@@ -135,7 +141,8 @@ extern "C" {
 // One launch of stepK_edge<double, 2, K>: K calls for every listed tile (tiles: n x {tx, ta, tb, class or 0 = all features}).  The pulse records
 // of the K calls come as the device tables of resident mode do: count[K], last[K], src[K][stride].
 int emul_stepK_edge(const StreamScene* sc, int K, const int32_t* tiles, int n_tiles, const int32_t* count, const double* last,
-                    const EmuSrc* src, int stride, int n_probe, const int32_t* probe_ij, double* probe_out) {
+                    const EmuSrc* src, int stride, int n_probe, const int32_t* probe_ij, double* probe_out,
+                    long long split_lo_off) {
     StepParams<double> P;
     fill(P, *sc);
     P.n_src = 0;                                                 // the kernel reads the records itself
@@ -158,6 +165,21 @@ int emul_stepK_edge(const StreamScene* sc, int K, const int32_t* tiles, int n_ti
         simt::g_block_idx = simt::Idx{(unsigned)b, 0, 0};
         const int cls = tl[b].pad ? tl[b].pad : (int)EDGE_ALL;   // the instantiation the host launches this tile with
         int rc = -1;
+        if (split_lo_off) {                                      // split storage (FDTD_F32X): the planes are hi / lo pairs
+            P.split_lo_off = split_lo_off;
+            switch (K) {
+                case 1: edge_tile_split<1>(P, tl, n_tiles, R); break;
+                case 2: edge_tile_split<2>(P, tl, n_tiles, R); break;
+                case 3: edge_tile_split<3>(P, tl, n_tiles, R); break;
+                case 4: edge_tile_split<4>(P, tl, n_tiles, R); break;
+                case 5: edge_tile_split<5>(P, tl, n_tiles, R); break;
+                case 6: edge_tile_split<6>(P, tl, n_tiles, R); break;
+                case 7: edge_tile_split<7>(P, tl, n_tiles, R); break;
+                case 8: edge_tile_split<8>(P, tl, n_tiles, R); break;
+                default: return -1;
+            }
+            continue;
+        }
         switch (K) {
             case 1: rc = edge_tile_class<1>(cls, P, tl, n_tiles, R); break;
             case 2: rc = edge_tile_class<2>(cls, P, tl, n_tiles, R); break;

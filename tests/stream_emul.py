@@ -65,7 +65,7 @@ def load():
         _lib.emul_stepK_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.emul_stepK_edge.restype = C.c_int
         _lib.emul_stepK_edge.argtypes = [C.POINTER(StreamScene), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
     return _lib
 
 
@@ -135,7 +135,31 @@ def stepK_stream(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip, 
     return s.result()
 
 
-def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan):
+def _split_planes(a, pitch, rows, hi_fill):
+    """A field as the library stores it under FDTD_F32X: (rows x pitch) float32 hi plane, then the uint16 lo plane."""
+    hi = np.full((rows, pitch), hi_fill, dtype=np.float32)
+    lo = np.zeros((rows, pitch), dtype=np.uint16)
+    if a is not None:
+        x = np.asarray(a, dtype=np.float64)
+        h32 = x.astype(np.float32)
+        r32 = (x - h32.astype(np.float64)).astype(np.float32)
+        u = r32.view(np.uint32).astype(np.uint64)
+        bits = (np.where((u & 0x7F800000) != 0x7F800000, u + 0x7FFF + ((u >> 16) & 1), u) >> 16).astype(np.uint16)
+        hi[:x.shape[0], :x.shape[1]] = h32
+        lo[:x.shape[0], :x.shape[1]] = bits
+    buf = np.empty(rows * pitch * 6, dtype=np.uint8)
+    buf[:rows * pitch * 4] = hi.view(np.uint8).ravel()
+    buf[rows * pitch * 4:] = lo.view(np.uint8).ravel()
+    return buf
+
+
+def _split_values(buf, pitch, rows):
+    hi = buf[:rows * pitch * 4].view(np.float32).reshape(rows, pitch)
+    lo = buf[rows * pitch * 4:].view(np.uint16).reshape(rows, pitch)
+    return hi.astype(np.float64) + (lo.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan, split=False):
     """One launch of stepK_edge<double, 2, K>: calls n .. n+K-1 for every listed tile (tx, ta, tb[, class]): a tile with a class
     runs through that instantiation of the kernel (edge.cuh EDGE_CLASSES), the others through the all-features one.  Returns the fields
     of generation B (cells no tile owns keep `fill`) and the probe records (K, n_probe, 3)."""
@@ -159,7 +183,21 @@ def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan):
     tl = np.ascontiguousarray([list(t) + [0] * (4 - len(t)) for t in tiles], dtype=np.int32).reshape(-1, 4)
     pij = np.ascontiguousarray(np.asarray(probes, dtype=np.int32).reshape(-1, 2))
     pout = np.full((K, max(len(pij), 1), 3), np.nan)
+    lo_off = 0
+    if split:
+        # split=True: generation A holds the fields as split storage keeps them, generation B (hi planes NaN) receives the
+        # encoded results; the coefficient planes stay float64
+        rows, pitch = s.NR + 1, s.sc.pitch
+        lo_off = rows * pitch * 4
+        a_planes = [_split_planes(x, pitch, rows, np.nan) for x in (f.h, f.ex, f.ey)]
+        b_planes = [_split_planes(None, pitch, rows, fill) for _ in range(3)]
+        for k in range(3):
+            s.sc.a[k], s.sc.b[k] = a_planes[k].ctypes.data, b_planes[k].ctypes.data
     rc = load().emul_stepK_edge(C.byref(s.sc), K, tl.ctypes.data, len(tl), count.ctypes.data, lastv.ctypes.data,
-                                C.cast(recs, C.c_void_p), stride, len(pij), pij.ctypes.data, pout.ctypes.data)
+                                C.cast(recs, C.c_void_p), stride, len(pij), pij.ctypes.data, pout.ctypes.data, lo_off)
     assert rc == 0
+    if split:
+        NR, NC = s.NR, s.NC
+        vals = [_split_values(b, pitch, rows) for b in b_planes]
+        return (vals[0][:NR, :NC].copy(), vals[1][:NR + 1, :NC].copy(), vals[2][:NR, :NC + 1].copy()), pout[:, :len(pij)]
     return s.result(), pout[:, :len(pij)]

@@ -243,3 +243,29 @@ def test_edge_plan_on_slabs_with_deep_halos(K):
                 assert max(ta - K - 1, 0) >= first and min(tb + K, rows) <= last
                 assert bool(near) == ((b > 0 and ta < b + D) or (e < rows and tb > e - D))
             assert (owner[lo:hi] == 1).all() and (owner[:lo] == 0).all() and (owner[hi:] == 0).all()
+
+
+# ---- split field storage (dtype FDTD_F32X): the same kernel with SPLIT = 1, held to oracle/split_storage.py ---------------
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("shape,heights", [((33, 40), (7, 5, 12)), ((40, 130), (9,)), ((26, 200), (4, 11))])
+def test_split_storage_group_of_k_calls_has_the_bits_of_k_stored_calls(shape, heights, K):
+    """fp32 hi + bf16 lo field planes, float64 coefficients and arithmetic: a launch that advances K calls must leave what
+    K calls with a store and a load between them leave -- every value the next call reads passes through split_round."""
+    from oracle import split_storage as SS
+    rows, cols = shape
+    for seed in (0, 1, 5):
+        walls = WALLS[(seed * 7 + rows + cols + K) % 16]
+        f, setup, times = SC.random_case(rows, cols, seed, walls=walls, n_steps=2 * K + 1)
+        drop_wrapping_line(setup)
+        SS.store(f)                                            # the device holds the fields in split storage
+        cells = [(0, 0), (rows // 2, cols // 3), (rows - 1, cols - 1)]
+        tiles = all_tiles(rows, cols, K, heights)
+        for n in (0, K):
+            got, rec = E.stepK_edge(f, setup, times, n, K, tiles, probes=cells, split=True)
+            want_rec = np.zeros((K, len(cells), 3))
+            for m, t in enumerate(times[n:n + K]):
+                SS.leapfrog(f, setup, t)
+                for k, (i, j) in enumerate(cells):
+                    want_rec[m, k] = (f.h[i, j], f.ex[i, j], f.ey[i, j])
+            check(got, f, "split storage: shape %s seed %d walls %s K %d group at %d" % (shape, seed, walls, K, n))
+            assert np.array_equal(rec, want_rec)
