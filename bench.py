@@ -548,7 +548,13 @@ def main():
     if os.path.isfile(traffic_file):
         try:
             rf = line["roofline"]
-            rf["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+            tf = json.load(open(traffic_file))
+            rf["traffic"] = tf["dram_bytes_per_launch"]
+            if tf.get("algorithmic_bytes_per_launch") and alg_bytes < 0.98 * tf["algorithmic_bytes_per_launch"]:
+                # the captured launch covered the whole slab; this run's launches cover fewer tiles each (deep halos on
+                # y-slabs: interior tile rows and interface tile rows are separate launches) -- same bytes per tile
+                rf["traffic"] = tf["dram_bytes_per_launch"] * alg_bytes / tf["algorithmic_bytes_per_launch"]
+                rf["traffic_scaled_from"] = tf["dram_bytes_per_launch"]
             # DRAM-level view of the same launch: the ncu bytes over the live launch time.  With temporal blocking the
             # algorithmic fraction above exceeds 1 by design; THIS one cannot, and says how close the pass is to the bus.
             rf["dram_achieved"] = rf["traffic"] / (rf["launch_ms"] * 1e-3) / 1e9          # the kernel's own event time

@@ -34,6 +34,11 @@ def leapfrog(f, s, time):
     """One call: the reference's update on the stored fields, results back through storage."""
     R.leapfrog(f, s, time)
     store(f)
+    # record_energy (solver.py:246-255) reads the arrays the call LEFT: in this mode those are the stored values
+    for i, j, series in f.probes:
+        series[-1] = 0.5 * ((s.eps[i][j] * (f.ex[i][j] ** 2 + f.ey[i][j] ** 2) + s.mu[i][j] * f.h[i][j] ** 2))
+    for i, j, series in f.raw_probes:
+        series[-1] = (f.h[i][j], f.ex[i][j], f.ey[i][j])
 
 
 def run(f, s, times):
