@@ -45,6 +45,8 @@ if __name__ == "__main__":
                if not keep or any(s in names[k] for s in keep)}
         old = json.load(open(MANIFEST)) if os.path.exists(MANIFEST) else {}
         old.setdefault("kernels", {}).update(rec)
+        # kernels that no longer exist in the build (renamed / re-templated / removed) cannot be "unchanged": drop them
+        old["kernels"] = {k: v for k, v in old["kernels"].items() if k in hashes}
         old["nvcc_flags"] = _lib.NVCC_FLAGS
         json.dump(old, open(MANIFEST, "w"), indent=1, sort_keys=True)
         print("recorded %d kernels in %s" % (len(rec), MANIFEST))
