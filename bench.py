@@ -244,7 +244,9 @@ def workload_config(args, n_gpus, engine=None):
     else:
         kernel = "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)
     if args.dtype == "f32x":
-        kernel = "stepK_edge<double,2,8,all features,split storage>: every tile of the grid, 8 steps per launch"
+        kernel = ("stepK_lean_split<%d> (plain tiles: fp32 hi + bf16 lo planes, float64 arithmetic, %d steps per HBM pass) + "
+                  "stepK_edge<double,2,%d,all features,split> for the wall / source / reflector tiles; tile_rows=%d warps=%d"
+                  % (args.temporal, args.temporal, args.temporal, args.tile_rows, args.warps))
     return {"workload": "C5 synthetic: %d x %d Yee grid (%d rows per GPU, y-slab sharded), heterogeneous eps_r=1+3u "
                         "(splitmix64), mu_r=1, 4 absorbing walls, 1 point source per slab + 1 TF/SF line at col 7"
                         % (ROWS_PER_GPU * n_gpus, COLS, ROWS_PER_GPU),
@@ -508,12 +510,10 @@ def main():
         alg_bytes = ROWS_PER_GPU * COLS * bpc
         kname = "fdtd::step_stream<%s,%d> (one launch per step per GPU%s)" % (
             tname, args.vec, "; 3 launches with halo overlap" if n_gpus > 1 else "")
-    if args.dtype == "f32x":
-        # one launch = 8 steps of the whole slab through stepK_edge with split storage; 52 algorithmic bytes per cell-update
-        launch_ms = ms / args.steps * 8
-        alg_bytes = ROWS_PER_GPU * COLS * bpc * 8
-        kname = ("fdtd::stepK_edge<double,2,8,15,1>: split field storage (fp32 hi + bf16 lo), one launch advances the whole "
-                 "slab 8 steps; launch time = whole-step time x 8 (the only kernel of the step)")
+    if args.dtype == "f32x" and args.temporal > 1 and kt["launches"] > 0:
+        kname = ("fdtd::stepK_lean_split<%d>: split field storage (fp32 hi + bf16 lo planes, 6 B per field value, float64 "
+                 "coefficients and arithmetic): 52 algorithmic bytes per cell-update; one launch advances its tiles %d steps"
+                 % (args.temporal, args.temporal))
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": args.steps,

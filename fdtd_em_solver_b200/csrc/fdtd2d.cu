@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using fdtd::RectI;
@@ -157,6 +158,7 @@ struct fdtd_ctx {
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
     // split field storage (dtype FDTD_F32X): every tile is a stepK_edge tile; one tile list per group size
     bool split = false;
+    bool split_all_edge = false;         // FDTD_SPLIT_ALL_EDGE=1: every tile through stepK_edge (the first version of the mode)
     struct SplitTiles { fdtd::EdgeTile* dev = nullptr; int n = 0; } split_tiles[9];
     bool maps_pinned = false;        // fdtd_run_streamed: the frame maps in place serve every group of the run
     bool edge_class_force = false;   // measurement hook FDTD_EDGE_GENERIC=1: every edge tile through the all-features instantiation
@@ -740,6 +742,12 @@ void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1
     } timed(c, st, K == c->temporal);
     if (timed.on)
         for (int ty = ty0; ty < ty0 + ny && ty < (int)m.row_cells.size(); ++ty) c->kt_cell_steps += m.row_cells[ty] * K;
+    if constexpr (sizeof(T) == 8) {
+        if (c->split) {                                          // split storage: the lean pipeline on hi / lo planes
+            fdtd::launch_stepK_split_k<K>(P, w, grid, skip, m.ntx2, st);
+            return;
+        }
+    }
     fdtd::launch_stepK_k<T, K>(P, c->kstep_variant, w, grid, skip, m.ntx2, st);   // 1 = stepK_lean (default), 0 = stepK_stream
 }
 
@@ -912,9 +920,28 @@ int resident_any(fdtd_ctx* c, int64_t n, int64_t g) {
 }
 
 // ---- frame mode 3: plain K-step tiles + stepK_edge tiles, nothing else ------------------------------------------------
+inline cudaError_t launch_edge_split_any(int K, const StepParams<double>& P, const fdtd::EdgeTile* tiles, int n,
+                                         const fdtd::ResSources<double>& R, long long first, cudaStream_t st) {
+    switch (K) {
+        case 1: return fdtd::launch_edge_split_k<1>(P, tiles, n, R, first, st);
+        case 2: return fdtd::launch_edge_split_k<2>(P, tiles, n, R, first, st);
+        case 3: return fdtd::launch_edge_split_k<3>(P, tiles, n, R, first, st);
+        case 4: return fdtd::launch_edge_split_k<4>(P, tiles, n, R, first, st);
+        case 5: return fdtd::launch_edge_split_k<5>(P, tiles, n, R, first, st);
+        case 6: return fdtd::launch_edge_split_k<6>(P, tiles, n, R, first, st);
+        case 7: return fdtd::launch_edge_split_k<7>(P, tiles, n, R, first, st);
+        case 8: return fdtd::launch_edge_split_k<8>(P, tiles, n, R, first, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <typename T>
 cudaError_t launch_edge_any(int K, const StepParams<T>& P, int flags, const fdtd::EdgeTile* tiles, int n,
                             const fdtd::ResSources<T>& R, long long first, cudaStream_t st) {
+    if constexpr (sizeof(T) == 8) {
+        // split storage (P.split_lo_off != 0) has ONE edge instantiation, the one with every feature
+        if (P.split_lo_off) return launch_edge_split_any(K, P, tiles, n, R, first, st);
+    }
     switch (K) {
         case 2: return fdtd::launch_edge_k<T, 2>(P, flags, tiles, n, R, first, st);
         case 3: return fdtd::launch_edge_k<T, 3>(P, flags, tiles, n, R, first, st);
@@ -1084,18 +1111,8 @@ int split_group(fdtd_ctx* c, int64_t n, int K) {
     if (c->n_probe) P.probe_out = c->probe_dev + (size_t)c->probe_count * c->n_probe * 3;
     fdtd::ResSources<double> R{(const int*)c->rs_count, (const double*)c->rs_last, (const fdtd::SrcStep<double>*)c->rs_src, c->rs_stride};
     const fdtd_ctx::SplitTiles& t = c->split_tiles[K];
-    cudaError_t e;
-    switch (K) {
-        case 1: e = fdtd::launch_edge_split_k<1>(P, t.dev, t.n, R, n, c->stream); break;
-        case 2: e = fdtd::launch_edge_split_k<2>(P, t.dev, t.n, R, n, c->stream); break;
-        case 3: e = fdtd::launch_edge_split_k<3>(P, t.dev, t.n, R, n, c->stream); break;
-        case 4: e = fdtd::launch_edge_split_k<4>(P, t.dev, t.n, R, n, c->stream); break;
-        case 5: e = fdtd::launch_edge_split_k<5>(P, t.dev, t.n, R, n, c->stream); break;
-        case 6: e = fdtd::launch_edge_split_k<6>(P, t.dev, t.n, R, n, c->stream); break;
-        case 7: e = fdtd::launch_edge_split_k<7>(P, t.dev, t.n, R, n, c->stream); break;
-        case 8: e = fdtd::launch_edge_split_k<8>(P, t.dev, t.n, R, n, c->stream); break;
-        default: return fail(c, FDTD_ERR_ARG, "split group of 1..8 calls");
-    }
+    if (K < 1 || K > 8) return fail(c, FDTD_ERR_ARG, "split group of 1..8 calls");
+    cudaError_t e = launch_edge_split_any(K, P, t.dev, t.n, R, n, c->stream);
     CK(e);
     c->stats.kernel_launches++;
     c->cur = B;
@@ -1111,7 +1128,9 @@ int step_any(fdtd_ctx* c, int64_t step) {
 }
 
 int group_any(fdtd_ctx* c, int64_t n, int K) {
-    if (c->split) return split_group(c, n, K);
+    // split storage: plain tiles through stepK_lean_split, the others through stepK_edge<.., split> (group_edge); a scene
+    // stepK_edge cannot take ends in split_group, which says so
+    if (c->split) return (edge_usable(c, K) && !c->split_all_edge) ? group_edge<double>(c, n, K) : split_group(c, n, K);
     const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
     if (edge_usable(c, K)) return c->cfg.dtype == FDTD_F64 ? group_edge<double>(c, n, K) : group_edge<float>(c, n, K);
     // The fallback, K masked single-step passes through the scratch generations (frame mode 0; a scene stepK_edge cannot
@@ -1123,6 +1142,29 @@ int group_any(fdtd_ctx* c, int64_t n, int K) {
         return 0;
     }
     return c->cfg.dtype == FDTD_F64 ? group_impl<double>(c, n, K) : group_impl<float>(c, n, K);
+}
+
+// pinned ring slot -> the caller's (pageable) snapshot array, on the driver's callback thread.  A C5-sized snapshot is
+// 4.3 GB whose destination pages are touched for the first time here: one memcpy thread moves about 4 GB/s, far below the
+// 50 GB/s the DMA before it delivers, so big copies are cut into 2 MiB-aligned chunks for up to 8 threads
+// (FDTD_SNAPSHOT_THREADS).  The reference scripts' snapshots (0.15 - 0.8 MB) stay a plain memcpy.
+void snapshot_copy(void* dst, const void* src, size_t bytes) {
+    static const unsigned want = [] {
+        unsigned n = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = std::getenv("FDTD_SNAPSHOT_THREADS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) n = (unsigned)v; }
+        return n;
+    }();
+    const size_t min_chunk = (size_t)32 << 20;
+    const unsigned n = (unsigned)std::min<size_t>(want, bytes / min_chunk);
+    if (n <= 1) { std::memcpy(dst, src, bytes); return; }
+    const size_t chunk = ((bytes / n) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n; ++t) {
+        const size_t lo = std::min(bytes, t * chunk), hi = std::min(bytes, (t + 1) * chunk);
+        if (hi > lo) pool.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    std::memcpy(dst, src, std::min(bytes, chunk));
+    for (std::thread& th : pool) th.join();
 }
 
 template <typename T>
@@ -1160,7 +1202,7 @@ int snapshot_impl(fdtd_ctx* c, int slot, double* host_dst, int64_t next_step, in
     auto* job = new fdtd_ctx::SnapCopy{host_dst, c->snap_pin[slot], (size_t)rows * cols * 8};
     cudaError_t he = cudaLaunchHostFunc(c->copy_stream, [](void* p) {
         auto* j = static_cast<fdtd_ctx::SnapCopy*>(p);
-        std::memcpy(j->dst, j->src, j->bytes);
+        snapshot_copy(j->dst, j->src, j->bytes);
         delete j;
     }, job);
     if (he != cudaSuccess) { delete job; return fail(c, FDTD_ERR_CUDA, std::string("cudaLaunchHostFunc: ") + cudaGetErrorString(he)); }
@@ -1189,6 +1231,8 @@ int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth) {
 
 const char* fdtd_last_error(fdtd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static void auto_geometry(fdtd_ctx* c);
+
 int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     fdtd_ctx* c = nullptr;
     if (!cfg || !out) return fail(c, FDTD_ERR_ARG, "null argument");
@@ -1215,6 +1259,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     if (const char* er = std::getenv("FDTD_EDGE_ROWS")) { const int v = std::atoi(er); if (v >= 1 && v <= 4096) c->edge_rows = v; }
     c->esize = cfg->dtype == FDTD_F64 ? 8 : (cfg->dtype == FDTD_F32X ? 6 : 4);     // bytes per FIELD value (F32X: 4 hi + 2 lo)
     c->split = cfg->dtype == FDTD_F32X;
+    if (const char* e = std::getenv("FDTD_SPLIT_ALL_EDGE")) c->split_all_edge = std::atoi(e) != 0;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
     if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
     c->cfg.pitch = c->pitch;
@@ -1227,7 +1272,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
         // SHORT tiles -- 6 rows keep all resident CTAs inside a narrow band of rows, which is what DRAM likes.
         // Small grids (the script configs, N = 139..442) get narrow single-warp tiles so that the launch
         // still spreads over the 148 SMs.
-        const int va = cfg->dtype == FDTD_F64 ? 2 : 4;
+        const int va = cfg->dtype != FDTD_F32 ? 2 : 4;
         const int64_t wide_tiles = ((cfg->cols + 1 + 128 * va - 1) / (128 * va)) * ((c->owned + 5) / 6);
         const bool small = wide_tiles < 2 * 148;
         if (c->cfg.vec <= 0) c->cfg.vec = small ? va : 4;     // 4 columns per lane: 256-bit (f64) / 128-bit (f32) accesses
@@ -1242,6 +1287,12 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
                 c->cfg.tile_rows = (int)std::min<int64_t>(16, std::max<int64_t>(4, c->owned / want_row_tiles));
             }
         }
+    }
+    if (c->split) {
+        // split storage always runs groups of up to 8 calls per launch (a group has the bits of single calls and needs no
+        // extra buffers), so its launch geometry is the K = 8 one from the start; fdtd_set_temporal_blocking may lower K
+        c->temporal = 8;
+        auto_geometry(c);
     }
     auto bail = [&](cudaError_t ee, const char* what) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(ee);
@@ -1322,7 +1373,7 @@ static int plan_frame_export(const fdtd_config* cfg, int32_t steps_per_pass, int
         return fail(c, FDTD_ERR_ARG, "bad geometry");
     std::vector<FrameBox> mods;
     for (int k = 0; k < n_boxes; ++k) mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3]});
-    const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+    const int V2 = cfg->dtype != FDTD_F32 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
     plan_frame(FrameGeom{cfg->rows, cfg->cols, cfg->row_begin, cfg->row_end, cfg->tile_rows, cfg->block_warps, K, V2, 0, 0},
                mods, m);
@@ -1361,7 +1412,7 @@ int fdtd_plan_edge(const fdtd_config* cfg, int32_t steps_per_pass, int32_t halo_
     for (int k = 0; k < n_boxes; ++k)
         mods.push_back({boxes[4 * k], boxes[4 * k + 1], boxes[4 * k + 2], boxes[4 * k + 3],
                         !box_is_pulse ? (fdtd::EDGE_SRC | fdtd::EDGE_MISC) : (box_is_pulse[k] ? fdtd::EDGE_SRC : fdtd::EDGE_MISC)});
-    const int V2 = cfg->dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+    const int V2 = cfg->dtype != FDTD_F32 ? 2 : 4, K = steps_per_pass;
     FrameMaps m;
     const int64_t ht = (halo_depth > 1 && cfg->row_begin > 0) ? halo_depth : 0;
     const int64_t hb = (halo_depth > 1 && cfg->row_end < cfg->rows) ? halo_depth : 0;
@@ -1408,7 +1459,7 @@ static void auto_geometry(fdtd_ctx* c) {
         if (c->frame_mode == 3 && rows_for_k_edge[steps_per_pass] > tr) {
             // ... as long as the plain tiles still fill the GPU several times over (8 single-warp CTAs per SM at 250
             // registers): a grid much smaller than the 8192 x 65536 slab keeps shorter tiles
-            const int V2 = c->cfg.dtype == FDTD_F64 ? 2 : 4, K = steps_per_pass;
+            const int V2 = c->cfg.dtype != FDTD_F32 ? 2 : 4, K = steps_per_pass;
             const int64_t out_cols = (32 - 2 * ((K + V2 - 1) / V2)) * V2;
             const int64_t ntx = (c->cfg.cols + 1 + out_cols - 1) / out_cols;
             const int64_t want_nty = (4 * 8 * 148 + ntx - 1) / ntx;
@@ -1719,11 +1770,10 @@ static int run_impl(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t 
     // steps per group: what the caller asked for, what the bound scratch generations allow, and -- on a slab with deep
     // halos -- what the halos cover (a group of K steps reads K+1 rows of the neighbours)
     int kmax_pre = (c->cfg.kernel == FDTD_KERNEL_STREAM) ? c->temporal : 1;
-    if (c->split) kmax_pre = 8;          // split storage: a group of K calls has the bits of K single calls and needs no extra buffers
     if (c->halo_depth > 1 && !(c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows)) kmax_pre = std::min(kmax_pre, c->halo_depth - 1);
     if (kmax_pre >= 2 && !edge_usable(c, kmax_pre))      // only the pass chain needs the scratch generations
         kmax_pre = std::min(kmax_pre, c->ngen >= 4 ? 8 : (c->ngen == 3 ? 2 : 1));
-    if (kmax_pre >= 2 && !resident && !c->split) {
+    if (kmax_pre >= 2 && !resident && !(c->split && (c->split_all_edge || !edge_usable(c, kmax_pre)))) {
         // Build the frame maps of every group size this run will use BEFORE the timed region (host work + a sync each).
         bool seen[9] = {};
         for (int64_t n = first_step; n < first_step + n_steps;) {
@@ -1732,13 +1782,13 @@ static int run_impl(fdtd_handle c, int64_t first_step, int64_t n_steps, int64_t 
             if (c->n_src > 0) g = std::min<int64_t>(g, c->table_len - n);
             if (g >= 2 && !seen[g]) {
                 seen[g] = true;
-                const int rc0 = c->cfg.dtype == FDTD_F64 ? build_frame_maps<double>(c, n, (int)g) : build_frame_maps<float>(c, n, (int)g);
+                const int rc0 = c->cfg.dtype != FDTD_F32 ? build_frame_maps<double>(c, n, (int)g) : build_frame_maps<float>(c, n, (int)g);
                 if (rc0) return rc0;
             }
             n += std::max<int64_t>(g, 1);
         }
         if (c->frame_mode != 0)                          // stepK_edge reads the pulse records of resident mode
-            if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
+            if (int rc0 = c->cfg.dtype != FDTD_F32 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
     }
     if (resident)                                        // upload the pulse records before the timed region, too
         if (int rc0 = c->cfg.dtype == FDTD_F64 ? resident_tables<double>(c) : resident_tables<float>(c)) return rc0;
@@ -2152,7 +2202,7 @@ int fdtd_view_end(fdtd_handle c, double* host_out, int64_t capacity, int64_t* ro
 
 int fdtd_set_tuning(fdtd_handle c, int32_t tile_rows, int32_t vec, int32_t block_warps) {
     if (!c) return FDTD_ERR_ARG;
-    const int va = c->cfg.dtype == FDTD_F64 ? 2 : 4;
+    const int va = c->cfg.dtype != FDTD_F32 ? 2 : 4;
     if (vec && vec != va && vec != 2 * va) return fail(c, FDTD_ERR_ARG, "unsupported vec (2/4 for f64, 4/8 for f32)");
     if (block_warps < 0 || block_warps > 8 || tile_rows < 0) return fail(c, FDTD_ERR_ARG, "bad tuning");
     if (tile_rows) { c->cfg.tile_rows = tile_rows; c->auto_tile_rows = false; }

@@ -17,11 +17,22 @@ cudaError_t launch_edge_split_k(const StepParams<double>& P, const EdgeTile* til
     return cudaGetLastError();
 }
 
-#define FDTD_INSTANTIATE(K) \
+// the plain tiles of a K-step group under split storage (kernels.cuh stepK_lean_split), K = 2 .. 8
+template <int K>
+cudaError_t launch_stepK_split_k(const StepParams<double>& P, int warps, dim3 grid, const unsigned char* skip, int ntx2,
+                                 cudaStream_t st) {
+    const size_t ring_bytes = (size_t)warps * 4 * SplitRing::SLOT;
+    stepK_lean_split<K><<<grid, warps * 32, ring_bytes, st>>>(P, skip, ntx2);
+    return cudaGetLastError();
+}
+
+#define FDTD_INSTANTIATE_EDGE(K) \
     template cudaError_t launch_edge_split_k<K>(const StepParams<double>&, const EdgeTile*, int, const ResSources<double>&, \
                                                 long long, cudaStream_t);
+#define FDTD_INSTANTIATE(K) FDTD_INSTANTIATE_EDGE(K) \
+    template cudaError_t launch_stepK_split_k<K>(const StepParams<double>&, int, dim3, const unsigned char*, int, cudaStream_t);
 #if FDTD_K_LO <= 1 && 1 <= FDTD_K_HI
-FDTD_INSTANTIATE(1)
+FDTD_INSTANTIATE_EDGE(1)                                         // single calls have no plain tiles (all-edge launch)
 
 // dense float64 rows -> split planes of a pitched buffer (hi at `hi`, lo at `lo`)
 __global__ void split_from_f64(float* hi, unsigned short* lo, long long pitch, const double* src, long long src_ld, int rows,
@@ -84,5 +95,6 @@ FDTD_INSTANTIATE(7)
 FDTD_INSTANTIATE(8)
 #endif
 #undef FDTD_INSTANTIATE
+#undef FDTD_INSTANTIATE_EDGE
 
 }  // namespace fdtd

@@ -21,6 +21,7 @@
 // the association order is the reference's, so fp64 results are bit-identical to the reference.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -94,11 +95,17 @@ struct StepParams {
 #define FDTD_HD __host__ __device__ __forceinline__
 #endif
 FDTD_HD unsigned short split_bf16_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    // one F2FP instead of eight integer instructions; the same bits for every finite value and for +-inf (both are
+    // round-to-nearest-even on the bit pattern), a NaN becomes the canonical one -- no stored field is ever NaN
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+#else
     unsigned int u;
     memcpy(&u, &f, 4);
     if ((u & 0x7f800000u) == 0x7f800000u) return (unsigned short)(u >> 16);       // inf / nan: truncate
     u += 0x7fffu + ((u >> 16) & 1u);
     return (unsigned short)(u >> 16);
+#endif
 }
 FDTD_HD float split_bf16_value(unsigned short b) {
     const unsigned int u = (unsigned int)b << 16;
@@ -111,10 +118,40 @@ FDTD_HD void split_encode(double x, float& hi, unsigned short& lo) {
     lo = split_bf16_bits((float)(x - (double)hi));
 }
 FDTD_HD double split_decode(float hi, unsigned short lo) { return (double)hi + (double)split_bf16_value(lo); }
+// (double)(float)x without a conversion instruction: x rounded (to nearest, ties to even) to 24 significant bits on the
+// exponent range of float32, by adding and subtracting M = 1.5 * 2^(e + 29), e = the exponent of x clamped to float32's
+// smallest normal exponent -- the sum lies in M's binade, whose spacing 2^(e - 23) is float32's for x (2^-149 under the
+// clamp, the subnormal spacing), M is an even multiple of that spacing, so the rounding of the sum IS the rounding of x;
+// the sign is copied back so that a value that rounds to zero keeps its sign as the conversion does.  Equal to
+// (double)(float)x for every |x| <= FLT_MAX (beyond it the conversion gives inf; no stored field is).  Why: on sm_100 the
+// conversions with a 64-bit side run on the XU pipe at 16 lanes per clock and SM, a quarter of the FP64 pipe's DADD rate;
+// ncu showed the first split K-step kernel 87 % XU-bound (profiles/r2j_ncu_full_stepK_lean_split_raw.csv).
+FDTD_HD double split_round_hi(double x) {
+    unsigned long long u;
+    memcpy(&u, &x, 8);
+    const unsigned int top = (unsigned int)(u >> 32);
+    unsigned int e = top & 0x7ff00000u;
+    e = e < (897u << 20) ? (897u << 20) : e;
+    const unsigned long long mb = (unsigned long long)(e + (29u << 20) + 0x00080000u) << 32;
+    double M;
+    memcpy(&M, &mb, 8);
+#if defined(__CUDA_ARCH__)
+    const double r = __dsub_rn(__dadd_rn(x, M), M);
+#else
+    volatile double t = x + M;                                   // one rounding each, whatever the host compiler's flags
+    const double r = t - M;
+#endif
+    unsigned long long v;
+    memcpy(&v, &r, 8);
+    v = (v & 0x7fffffffffffffffull) | (u & 0x8000000000000000ull);
+    double out;
+    memcpy(&out, &v, 8);
+    return out;
+}
 FDTD_HD double split_round(double x) {                         // what a value becomes on its way through storage
-    float hi; unsigned short lo;
-    split_encode(x, hi, lo);
-    return split_decode(hi, lo);
+    const double hi = split_round_hi(x);                        // == (double)(float)x
+    const float lo = split_bf16_value(split_bf16_bits((float)(x - hi)));
+    return hi + (double)lo;
 }
 
 __device__ __forceinline__ bool inside(const RectI& r, int i, int j) {
@@ -648,9 +685,17 @@ template <int K> struct KRing { static constexpr int ROWS = (K <= 2) ? 0 : 4; };
 
 #if defined(FDTD_HOST_EMUL)          // the copy lands at once: ordering bugs around wait_group are not modelled
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 16); }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 8); }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) { __builtin_memcpy(smem, gmem, 4); }
 __device__ __forceinline__ void cp_async_commit() {}
 template <int N> __device__ __forceinline__ void cp_async_wait() {}
 #else
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -932,6 +977,177 @@ __global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(co
     if (ta >= tb) return;
     constexpr int RING = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;      // K = 2 prefetches through the ring here, too
     run_tileK_lean<T, V, K, RING>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+}
+
+// ---------------------------------------------------------------------------
+// stepK_lean_split: stepK_lean on SPLIT field storage (dtype FDTD_F32X: every field value = fp32 hi + bf16 lo, 6 bytes;
+// float64 coefficient planes, float64 arithmetic in the reference's order).  The plain tiles of a K-step group in this
+// mode; stepK_edge<.., SPLIT = 1> takes the others.  Same lane geometry, stage pipeline and ring as stepK_lean, with
+//   * a ring slot of 2 x 16 B (mu, ep) + 3 x 8 B (hi pairs of h, ex, ey) + 3 x 4 B (lo pairs) per lane,
+//   * loads decoded (hi + lo, exact in double), the last stage's outputs encoded on their way to generation B,
+//   * every value one call hands to the next -- a stage's (h, ex, ey) outputs -- rounded through the storage format
+//     (split_round), because a launch of K calls must leave the bits K stored calls leave (oracle/split_storage.py).
+//     Inside a call nothing is rounded: ex / ey are computed from the unrounded new h, as the reference computes them.
+// Algorithmic traffic: 3 x 6 B read + 3 x 6 B written + 2 x 8 B coefficients = 52 B per cell per K steps.
+// ---------------------------------------------------------------------------
+struct SplitRing {                                               // byte offsets inside one ring slot of one warp
+    static constexpr int MU = 0, EP = 512, HI = 1024, LO = 1024 + 3 * 256, SLOT = 1024 + 3 * 256 + 3 * 128;
+};
+
+template <int K, int RING>
+__device__ __forceinline__ void run_tileK_lean_split(const StepParams<double>& P, int ta, int tb, int jw, int lane) {
+    typedef double T;
+    constexpr int V = 2;
+    const unsigned full = 0xffffffffu;
+    constexpr int MARGIN = KGeom<K, V>::MARGIN;
+    const int j = jw + lane * V;
+    const long long pitch = P.pitch;
+    const int i_first = ta - K + 1, i_last = tb + K - 2;
+    const long long o_first = (long long)(i_first - P.row_off) * pitch + j;      // element offset of row i_first
+    const long long lo_off = P.split_lo_off;
+    const float* const h_hi = reinterpret_cast<const float*>(P.h);
+    const float* const ex_hi = reinterpret_cast<const float*>(P.ex);
+    const float* const ey_hi = reinterpret_cast<const float*>(P.ey);
+    const unsigned short* const h_lo = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(P.h) + lo_off);
+    const unsigned short* const ex_lo = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(P.ex) + lo_off);
+    const unsigned short* const ey_lo = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(P.ey) + lo_off);
+    auto decode2 = [](T (&x)[V], const float* hi, const unsigned short* lo) {
+        x[0] = split_decode(hi[0], lo[0]); x[1] = split_decode(hi[1], lo[1]);
+    };
+
+    T ex0c[V];
+    T hnp[K][V];
+    T Lh[K][V], Lex[K][V], Ley[K][V];
+    T Cmu[K][V], Cep[K][V];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int v = 0; v < V; ++v) hnp[s][v] = Lh[s][v] = Lex[s][v] = Ley[s][v] = Cmu[s][v] = Cep[s][v] = T(0);
+    {   // prologue: hn_1 of row ta-K and ex0 of row ta-K+1 (as run_tileK_lean)
+        T h[V], mu[V], exm[V], ey[V];
+        decode2(h, h_hi + o_first - pitch, h_lo + o_first - pitch);
+        ldvec<T, V>(mu, P.muc + o_first - pitch);
+        decode2(exm, ex_hi + o_first - pitch, ex_lo + o_first - pitch);
+        decode2(ex0c, ex_hi + o_first, ex_lo + o_first);
+        decode2(ey, ey_hi + o_first - pitch, ey_lo + o_first - pitch);
+        const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+            hnp[0][v] = add(h[v], mul(mu[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
+        }
+    }
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    unsigned char* const ring = ring_raw + (size_t)(threadIdx.x >> 5) * (RING * SplitRing::SLOT);
+    int i_issue = i_first;
+    long long o_issue = o_first;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (i_issue <= i_last) {
+            unsigned char* slot = ring + s_issue * SplitRing::SLOT;
+            cp_async16(slot + SplitRing::MU + lane * 16, P.muc + o_issue);
+            cp_async16(slot + SplitRing::EP + lane * 16, P.epc + o_issue);
+            cp_async8(slot + SplitRing::HI + 0 * 256 + lane * 8, h_hi + o_issue);
+            cp_async8(slot + SplitRing::HI + 1 * 256 + lane * 8, ex_hi + o_issue + pitch);
+            cp_async8(slot + SplitRing::HI + 2 * 256 + lane * 8, ey_hi + o_issue);
+            cp_async4(slot + SplitRing::LO + 0 * 128 + lane * 4, h_lo + o_issue);
+            cp_async4(slot + SplitRing::LO + 1 * 128 + lane * 4, ex_lo + o_issue + pitch);
+            cp_async4(slot + SplitRing::LO + 2 * 128 + lane * 4, ey_lo + o_issue);
+        }
+        cp_async_commit();
+        ++i_issue; o_issue += pitch;
+        s_issue = (s_issue + 1 == RING) ? 0 : s_issue + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < RING; ++d) issue();
+    int s_read = 0;
+    long long o_store = o_first - (long long)(K - 1) * pitch;    // offset of row i-(K-1), the row the last stage produces
+    float* const hn_hi = reinterpret_cast<float*>(P.hn);
+    float* const exn_hi = reinterpret_cast<float*>(P.exn);
+    float* const eyn_hi = reinterpret_cast<float*>(P.eyn);
+    unsigned short* const hn_lo = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(P.hn) + lo_off);
+    unsigned short* const exn_lo = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(P.exn) + lo_off);
+    unsigned short* const eyn_lo = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(P.eyn) + lo_off);
+    auto put2 = [](float* hi, unsigned short* lo, const T (&x)[V]) {
+        float2 a; ushort2 b;
+        split_encode(x[0], a.x, b.x); split_encode(x[1], a.y, b.y);
+        *reinterpret_cast<float2*>(hi) = a; *reinterpret_cast<ushort2*>(lo) = b;
+    };
+    constexpr int ROW_UNROLL = FDTD_LEAN_UNROLL;
+#pragma unroll ROW_UNROLL
+    for (int i = i_first; i <= i_last; ++i) {
+        Row<T, V> cur;
+        cp_async_wait<RING - 1>();
+        {
+            const unsigned char* slot = ring + s_read * SplitRing::SLOT;
+            const double2 m2 = *reinterpret_cast<const double2*>(slot + SplitRing::MU + lane * 16);
+            const double2 e2 = *reinterpret_cast<const double2*>(slot + SplitRing::EP + lane * 16);
+            cur.mu[0] = m2.x; cur.mu[1] = m2.y; cur.ep[0] = e2.x; cur.ep[1] = e2.y;
+            const float2 a = *reinterpret_cast<const float2*>(slot + SplitRing::HI + 0 * 256 + lane * 8);
+            const float2 b = *reinterpret_cast<const float2*>(slot + SplitRing::HI + 1 * 256 + lane * 8);
+            const float2 c = *reinterpret_cast<const float2*>(slot + SplitRing::HI + 2 * 256 + lane * 8);
+            const ushort2 la = *reinterpret_cast<const ushort2*>(slot + SplitRing::LO + 0 * 128 + lane * 4);
+            const ushort2 lb = *reinterpret_cast<const ushort2*>(slot + SplitRing::LO + 1 * 128 + lane * 4);
+            const ushort2 lc = *reinterpret_cast<const ushort2*>(slot + SplitRing::LO + 2 * 128 + lane * 4);
+            cur.h[0] = split_decode(a.x, la.x); cur.h[1] = split_decode(a.y, la.y);
+            cur.exn[0] = split_decode(b.x, lb.x); cur.exn[1] = split_decode(b.y, lb.y);
+            cur.ey[0] = split_decode(c.x, lc.x); cur.ey[1] = split_decode(c.y, lc.y);
+        }
+        T oh[V], oex[V], oey[V];
+        auto stage = [&](const T (&h)[V], const T (&exc)[V], const T (&exn)[V], const T (&ey)[V], const T (&mu)[V],
+                         const T (&ep)[V], T (&hp)[V]) {
+            const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+                oh[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
+            }
+            const T lf = __shfl_up_sync(full, oh[V - 1], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T hl = (v == 0) ? lf : oh[v > 0 ? v - 1 : 0];
+                oex[v] = add(exc[v], mul(ep[v], sub(oh[v], hp[v])));
+                oey[v] = sub(ey[v], mul(ep[v], sub(oh[v], hl)));
+                hp[v] = oh[v];                                    // the same call's next row reads the UNROUNDED new h
+            }
+        };
+        stage(cur.h, ex0c, cur.exn, cur.ey, cur.mu, cur.ep, hnp[0]);
+#pragma unroll
+        for (int s = 1; s < K; ++s) {
+            T ph[V], pex[V], pey[V];                             // what call s left in the arrays: through the storage format
+#pragma unroll
+            for (int v = 0; v < V; ++v) { ph[v] = split_round(oh[v]); pex[v] = split_round(oex[v]); pey[v] = split_round(oey[v]); }
+            stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }
+        }
+        if (i - (K - 1) >= ta && lane >= MARGIN && lane < 32 - MARGIN) {
+            put2(hn_hi + o_store, hn_lo + o_store, oh); put2(exn_hi + o_store, exn_lo + o_store, oex);
+            put2(eyn_hi + o_store, eyn_lo + o_store, oey);
+        }
+        o_store += pitch;
+#pragma unroll
+        for (int s = K - 1; s >= 2; --s)
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
+        s_read = (s_read + 1 == RING) ? 0 : s_read + 1;
+        issue();                                                 // refill the slot just consumed
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 2) stepK_lean_split(const __grid_constant__ StepParams<double> P,
+                                                           const unsigned char* __restrict__ skip, int skip_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tx >= skip_stride) return;
+    if (skip[(long long)blockIdx.y * skip_stride + tx]) return;
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    run_tileK_lean_split<K, 4>(P, ta, tb, tx * KGeom<K, 2>::OUT - KGeom<K, 2>::MARGIN * 2, lane);
 }
 
 // ---------------------------------------------------------------------------

@@ -35,9 +35,12 @@ template <typename T, int K> cudaError_t launch_stepK_k(const StepParams<T>& P, 
 template <typename T, int K> cudaError_t launch_edge_k(const StepParams<T>& P, int flags, const EdgeTile* tiles, int n,
                                                        const ResSources<T>& R, long long first, cudaStream_t st);
 
-// ---- k_split.cu: split field storage (FDTD_F32X) -- stepK_edge<double, 2, K, EDGE_ALL, split> for K = 1 .. 8, conversions ----
+// ---- k_split.cu: split field storage (FDTD_F32X) -- stepK_edge<double, 2, K, EDGE_ALL, split> for K = 1 .. 8, the plain
+// K-step kernel stepK_lean_split<K> for K = 2 .. 8, conversions ----
 template <int K> cudaError_t launch_edge_split_k(const StepParams<double>& P, const EdgeTile* tiles, int n,
                                                  const ResSources<double>& R, long long first, cudaStream_t st);
+template <int K> cudaError_t launch_stepK_split_k(const StepParams<double>& P, int warps, dim3 grid, const unsigned char* skip,
+                                                  int ntx2, cudaStream_t st);
 cudaError_t launch_split_from_f64(dim3 grid, cudaStream_t s, float* hi, unsigned short* lo, long long pitch, const double* src,
                                   long long src_ld, int rows, int cols);
 cudaError_t launch_split_to_f64(dim3 grid, dim3 block, cudaStream_t s, double* dst, long long dst_ld, const float* hi,

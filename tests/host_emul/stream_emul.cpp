@@ -115,6 +115,36 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
     return 0;
 }
 
+// One launch of stepK_lean_split<K> (kernels.cuh): the plain tiles of a K-step group under split field storage.  The
+// scene's a[] / b[] point at split buffers (fp32 hi plane, then the bf16 lo plane split_lo_off bytes behind it).
+int emul_stepK_lean_split(const StreamScene* sc, int K, int tile_rows, int warps, int row_lo, int row_hi,
+                          const unsigned char* skip, int tiles_x, int tiles_y, long long split_lo_off) {
+    StepParams<double> P;
+    fill(P, *sc);
+    P.n_src = 0; P.n_rect = 0;
+    P.row_lo = row_lo; P.row_hi = row_hi; P.tile_rows = tile_rows;
+    P.split_lo_off = split_lo_off;
+    const int gx = (tiles_x + warps - 1) / warps;
+    simt::g_block_dim = simt::Idx{(unsigned)(warps * 32), 1, 1};
+    simt::g_grid_dim = simt::Idx{(unsigned)gx, (unsigned)tiles_y, 1};
+    for (int by = 0; by < tiles_y; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            simt::g_block_idx = simt::Idx{(unsigned)bx, (unsigned)by, 0};
+            for (int w = 0; w < warps; ++w)
+                switch (K) {
+                    case 2: simt::run_warp(w, [&] { stepK_lean_split<2>(P, skip, tiles_x); }); break;
+                    case 3: simt::run_warp(w, [&] { stepK_lean_split<3>(P, skip, tiles_x); }); break;
+                    case 4: simt::run_warp(w, [&] { stepK_lean_split<4>(P, skip, tiles_x); }); break;
+                    case 5: simt::run_warp(w, [&] { stepK_lean_split<5>(P, skip, tiles_x); }); break;
+                    case 6: simt::run_warp(w, [&] { stepK_lean_split<6>(P, skip, tiles_x); }); break;
+                    case 7: simt::run_warp(w, [&] { stepK_lean_split<7>(P, skip, tiles_x); }); break;
+                    case 8: simt::run_warp(w, [&] { stepK_lean_split<8>(P, skip, tiles_x); }); break;
+                    default: return -1;
+                }
+        }
+    return 0;
+}
+
 }  // extern "C"
 
 // split storage: every tile through the all-features instantiation with SPLIT = 1

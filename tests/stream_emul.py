@@ -63,6 +63,9 @@ def load():
         _lib.emul_step_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5
         _lib.emul_stepK_stream.restype = C.c_int
         _lib.emul_stepK_stream.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.emul_stepK_lean_split.restype = C.c_int
+        _lib.emul_stepK_lean_split.argtypes = [C.POINTER(StreamScene)] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int,
+                                                                                         C.c_longlong]
         _lib.emul_stepK_edge.restype = C.c_int
         _lib.emul_stepK_edge.argtypes = [C.POINTER(StreamScene), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
@@ -157,6 +160,24 @@ def _split_values(buf, pitch, rows):
     hi = buf[:rows * pitch * 4].view(np.float32).reshape(rows, pitch)
     lo = buf[rows * pitch * 4:].view(np.uint16).reshape(rows, pitch)
     return hi.astype(np.float64) + (lo.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+def stepK_lean_split(f, setup, times, n, K, tile_rows, warps, row_lo, row_hi, skip):
+    """One launch of stepK_lean_split<K>: the plain tiles of the frame plan under split field storage.  f holds the fields as
+    storage keeps them; returns generation B decoded (cells no tile stored are NaN)."""
+    s = Scene(f, setup, times, n)
+    skip = np.ascontiguousarray(skip, dtype=np.uint8)
+    rows, pitch = s.NR + 1, s.sc.pitch
+    a_planes = [_split_planes(x, pitch, rows, np.nan) for x in (f.h, f.ex, f.ey)]
+    b_planes = [_split_planes(None, pitch, rows, np.nan) for _ in range(3)]
+    for k in range(3):
+        s.sc.a[k], s.sc.b[k] = a_planes[k].ctypes.data, b_planes[k].ctypes.data
+    rc = load().emul_stepK_lean_split(C.byref(s.sc), K, tile_rows, warps, row_lo, row_hi, skip.ctypes.data,
+                                      skip.shape[1], skip.shape[0], C.c_longlong(rows * pitch * 4))
+    assert rc == 0
+    vals = [_split_values(b, pitch, rows) for b in b_planes]
+    NR, NC = s.NR, s.NC
+    return vals[0][:NR, :NC].copy(), vals[1][:NR + 1, :NC].copy(), vals[2][:NR, :NC + 1].copy()
 
 
 def stepK_edge(f, setup, times, n, K, tiles, probes=(), fill=np.nan, split=False):

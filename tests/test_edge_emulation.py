@@ -269,3 +269,38 @@ def test_split_storage_group_of_k_calls_has_the_bits_of_k_stored_calls(shape, he
                     want_rec[m, k] = (f.h[i, j], f.ex[i, j], f.ey[i, j])
             check(got, f, "split storage: shape %s seed %d walls %s K %d group at %d" % (shape, seed, walls, K, n))
             assert np.array_equal(rec, want_rec)
+
+
+@pytest.mark.parametrize("K,tile_rows", [(2, 8), (3, 12), (5, 16), (8, 24), (8, 9)])
+def test_split_storage_group_on_the_library_plan_plain_and_edge_tiles(K, tile_rows):
+    """What fdtd_run launches for a group under split storage: the plain tiles of the frame plan through stepK_lean_split
+    (kernels.cuh), every other tile through stepK_edge<.., split>; together they write every cell once, with the bits of K
+    stored calls -- two consecutive groups, so the second one starts from stored values the first one produced."""
+    from oracle import split_storage as SS
+    rows, cols = 150, 520
+    rng = np.random.default_rng(K)
+    f, setup, times = SC.random_case(rows, cols, 11, walls=(False, True, False, False), n_steps=2 * K, with_sources=False,
+                                     with_rects=False)
+    setup.pulses = [R.PulseSpec("table", None, 70, 300, -1.0, 1.0, rng.standard_normal(2 * K)),
+                    R.PulseSpec("table", "right", 40, 7, -1.0, 1.0, rng.standard_normal(2 * K))]
+    setup.reflectors = [[100, 110, 400, 430]]
+    probes = [(30, 200)]
+    boxes = _boxes(setup, rows, cols) + [(30, 30, 200, 200, 0)]
+    plan, skip, tiles = _plan_edge(rows, cols, K, tile_rows, boxes)
+    assert (skip == 0).any() and len(tiles) > 0                 # the group really has both kinds of tiles
+    quiet = R.Setup(eps_coef=setup.eps_coef, mu_coef=setup.mu_coef, courant=setup.courant, reflect_walls=setup.reflect_walls,
+                    pulses=[], reflectors=[])
+    SS.store(f)
+    for n in (0, K):
+        got_e, rec = E.stepK_edge(f, setup, times, n, K, [(t[0], t[1], t[2]) for t in tiles], probes=probes, split=True)
+        got_p = E.stepK_lean_split(f, quiet, times, n, K, tile_rows, 1, plan.k_row_lo, plan.k_row_hi, skip)
+        want_rec = np.zeros((K, 1, 3))
+        for m, t in enumerate(times[n:n + K]):
+            SS.leapfrog(f, setup, t)
+            want_rec[m, 0] = (f.h[30, 200], f.ex[30, 200], f.ey[30, 200])
+        for k, (name, want) in enumerate(zip(("h", "ex", "ey"), (f.h, f.ex, f.ey))):
+            both = ~np.isnan(got_e[k]) & ~np.isnan(got_p[k])
+            assert not both.any(), (name, "written twice", np.argwhere(both)[:4])
+            a = np.where(np.isnan(got_e[k]), got_p[k], got_e[k])
+            assert np.array_equal(a, want), (name, n, np.argwhere(a != want)[:4])
+        assert np.array_equal(rec, want_rec)
