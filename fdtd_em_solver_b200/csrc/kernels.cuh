@@ -118,21 +118,21 @@ FDTD_HD void split_encode(double x, float& hi, unsigned short& lo) {
     lo = split_bf16_bits((float)(x - (double)hi));
 }
 FDTD_HD double split_decode(float hi, unsigned short lo) { return (double)hi + (double)split_bf16_value(lo); }
-// (double)(float)x without a conversion instruction: x rounded (to nearest, ties to even) to 24 significant bits on the
-// exponent range of float32, by adding and subtracting M = 1.5 * 2^(e + 29), e = the exponent of x clamped to float32's
+// (double)(float)x without a conversion instruction: x rounded (to nearest, ties to even) to 53 - shift significant bits
+// (24 for shift = 29) on the exponent range of float32, by adding and subtracting M = 1.5 * 2^(e + shift), e = the exponent of x clamped to float32's
 // smallest normal exponent -- the sum lies in M's binade, whose spacing 2^(e - 23) is float32's for x (2^-149 under the
 // clamp, the subnormal spacing), M is an even multiple of that spacing, so the rounding of the sum IS the rounding of x;
 // the sign is copied back so that a value that rounds to zero keeps its sign as the conversion does.  Equal to
 // (double)(float)x for every |x| <= FLT_MAX (beyond it the conversion gives inf; no stored field is).  Why: on sm_100 the
 // conversions with a 64-bit side run on the XU pipe at 16 lanes per clock and SM, a quarter of the FP64 pipe's DADD rate;
 // ncu showed the first split K-step kernel 87 % XU-bound (profiles/r2j_ncu_full_stepK_lean_split_raw.csv).
-FDTD_HD double split_round_hi(double x) {
+FDTD_HD double split_round_sig(double x, unsigned int shift) {  // 29: to float32's 24 bits; 45: to bfloat16's 8 bits
     unsigned long long u;
     memcpy(&u, &x, 8);
     const unsigned int top = (unsigned int)(u >> 32);
     unsigned int e = top & 0x7ff00000u;
     e = e < (897u << 20) ? (897u << 20) : e;
-    const unsigned long long mb = (unsigned long long)(e + (29u << 20) + 0x00080000u) << 32;
+    const unsigned long long mb = (unsigned long long)(e + (shift << 20) + 0x00080000u) << 32;
     double M;
     memcpy(&M, &mb, 8);
 #if defined(__CUDA_ARCH__)
@@ -147,6 +147,15 @@ FDTD_HD double split_round_hi(double x) {
     double out;
     memcpy(&out, &v, 8);
     return out;
+}
+FDTD_HD double split_round_hi(double x) { return split_round_sig(x, 29u); }
+// The same value with NO conversion instruction at all: the bf16 half is float32(x - hi) rounded once more to 8 bits, both
+// as magic-number additions (bfloat16 has float32's exponent range, so the same clamp applies).  Four DADDs instead of two
+// XU conversions: the K-step kernel gives some values of a stage to each pipe (FDTD_SPLIT_XU_PER_STAGE).
+FDTD_HD double split_round_fp64(double x) {
+    const double hi = split_round_sig(x, 29u);
+    const double lo = split_round_sig(split_round_sig(x - hi, 29u), 45u);
+    return hi + lo;
 }
 FDTD_HD double split_round(double x) {                         // what a value becomes on its way through storage
     const double hi = split_round_hi(x);                        // == (double)(float)x
@@ -990,6 +999,9 @@ __global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(co
 //     Inside a call nothing is rounded: ex / ey are computed from the unrounded new h, as the reference computes them.
 // Algorithmic traffic: 3 x 6 B read + 3 x 6 B written + 2 x 8 B coefficients = 52 B per cell per K steps.
 // ---------------------------------------------------------------------------
+#ifndef FDTD_SPLIT_XU_PER_STAGE
+#define FDTD_SPLIT_XU_PER_STAGE 5          // of the 6 values a stage hands on (B200 sweep 0..6: 191 204 211 217 224 211 Gcell/s, profiles/r2l_*)
+#endif
 struct SplitRing {                                               // byte offsets inside one ring slot of one warp
     static constexpr int MU = 0, EP = 512, HI = 1024, LO = 1024 + 3 * 256, SLOT = 1024 + 3 * 256 + 3 * 128;
 };
@@ -1116,7 +1128,13 @@ __device__ __forceinline__ void run_tileK_lean_split(const StepParams<double>& P
         for (int s = 1; s < K; ++s) {
             T ph[V], pex[V], pey[V];                             // what call s left in the arrays: through the storage format
 #pragma unroll
-            for (int v = 0; v < V; ++v) { ph[v] = split_round(oh[v]); pex[v] = split_round(oex[v]); pey[v] = split_round(oey[v]); }
+            for (int v = 0; v < V; ++v) {
+                // six values per stage: the first FDTD_SPLIT_XU_PER_STAGE of (h0, ex0, ey0, h1, ex1, ey1) take the bf16 half
+                // through two XU conversions, the others through four more DADDs -- same bits, two pipes kept busy
+                ph[v] = (3 * v + 0 < FDTD_SPLIT_XU_PER_STAGE) ? split_round(oh[v]) : split_round_fp64(oh[v]);
+                pex[v] = (3 * v + 1 < FDTD_SPLIT_XU_PER_STAGE) ? split_round(oex[v]) : split_round_fp64(oex[v]);
+                pey[v] = (3 * v + 2 < FDTD_SPLIT_XU_PER_STAGE) ? split_round(oey[v]) : split_round_fp64(oey[v]);
+            }
             stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
 #pragma unroll
             for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }

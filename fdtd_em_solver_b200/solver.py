@@ -9,7 +9,10 @@ What moved to the device: Solver.update (:169-257) and the run loops of
 Solver.solve (:288-292, :319-337) -- see engine.py / csrc/.
 
 Extra, optional constructor keywords (defaults keep reference scripts
-unchanged): dtype="float64"|"float32", device=0, kernel="stream"|"exact",
+unchanged): dtype="float64"|"float32"|"float32x" (float32x: fields stored as
+fp32 hi + bf16 lo pairs, float64 arithmetic -- the reduced-precision mode that
+stays within 1e-5 of the reference on every snapshot; one GPU), device=0,
+kernel="stream"|"exact",
 material_on_device=False (paint eps/mu on the GPU from the recorded shapes),
 temporal_block=None (leapfrog steps per HBM pass in solve(); 2..8 = temporal
 blocking, bit-identical results; None = 8 on grids beyond 512 x 512 cells,

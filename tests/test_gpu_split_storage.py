@@ -81,8 +81,8 @@ def test_runs_snapshots_and_probes_bitwise_against_the_split_oracle(snap):
         raw = e.probes()
         for c, (i, j, series) in enumerate(f.raw_probes):
             assert np.array_equal(raw[:, c, :], np.array(series)), (seed, c)
-        if snap in (0, 8):                   # groups of up to 8 calls: a plain-tile launch + the edge-tile launches (+ helpers)
-            assert e.stats()["kernel_launches"] < n_steps
+        if snap in (0, 8):                   # 29 calls = 3 groups of 8 + one of 5, each a plain-tile launch + the edge-tile
+            assert e.stats()["kernel_launches"] < 2 * n_steps       # launches of its near / far halves (+ snapshot packs)
         e.close()
 
 
