@@ -238,8 +238,10 @@ def workload_config(args, n_gpus, engine=None):
     kvec = 2 if args.dtype == "f64" else 4
     if args.temporal > 1:
         frame = {0: "masked step_stream frame passes", 3: "stepK_edge for the wall / source / reflector tiles"}[frame_mode]
+        umu = engine is not None and variant == 1 and engine.uniform_mu()
         kernel = "%s<%s,%d,%d> (%d steps per HBM pass, %d columns per lane) + %s; tile_rows=%d warps=%d" % (
-            "stepK_lean" if variant == 1 else "stepK_stream", "double" if args.dtype == "f64" else "float", kvec, args.temporal,
+            ("stepK_lean_umu" if umu else "stepK_lean") if variant == 1 else "stepK_stream",
+            "double" if args.dtype == "f64" else "float", kvec, args.temporal,
             args.temporal, kvec, frame, args.tile_rows, args.warps)
     else:
         kernel = "step_stream vec=%d tile_rows=%d warps=%d" % (args.vec, args.tile_rows, args.warps)
@@ -260,7 +262,8 @@ def workload_config(args, n_gpus, engine=None):
                             "y-slab x%d, 3 halo rows down + 1 up per step over NCCL" % n_gpus),
             "kernel": kernel,
             "temporal_blocking": args.temporal,
-            "frame_mode": frame_mode, "kstep_variant": variant, "halo_depth": halo}
+            "frame_mode": frame_mode, "kstep_variant": variant, "halo_depth": halo,
+            "uniform_mu": bool(engine is not None and engine.uniform_mu())}
 
 
 def main():
@@ -504,7 +507,11 @@ def main():
         alg_bytes = kt["cell_updates"] / kt["launches"] * bpc
         kname = ("fdtd::%s<%s,%d,%d>: one launch advances its tiles %d steps (algorithmic bytes are counted per step, so "
                  "frac > 1 is the temporal-blocking gain; the DRAM-level view is traffic / dram_frac)"
-                 % ("stepK_lean" if e.kstep_variant == 1 else "stepK_stream", tname, kvec, args.temporal, args.temporal))
+                 % (("stepK_lean_umu" if e.uniform_mu() else "stepK_lean") if e.kstep_variant == 1 else "stepK_stream",
+                    tname, kvec, args.temporal, args.temporal))
+        if e.kstep_variant == 1 and e.uniform_mu():
+            kname += ("; mu_coef is one value everywhere (mu_r = 1, the C5 recipe), found by a device scan: the kernel streams "
+                      "7 words per cell and pass instead of 8 -- algorithmic bytes stay SURVEY.md's 64 B per cell-update")
     else:
         launch_ms = ms / args.steps
         alg_bytes = ROWS_PER_GPU * COLS * bpc
@@ -544,7 +551,8 @@ def main():
         line["halo"] = {"bytes_sent_per_step_per_gpu": halo_bytes / max(1, st["steps"]),
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s%s.json" % (
-        args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else "", "_lean" if e.kstep_variant == 1 else ""))
+        args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else "",
+        ("_lean_umu" if e.uniform_mu() else "_lean") if e.kstep_variant == 1 else ""))
     if os.path.isfile(traffic_file):
         try:
             rf = line["roofline"]

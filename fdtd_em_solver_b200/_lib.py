@@ -98,6 +98,8 @@ SIGNATURES = {
     "fdtd_sync": (C.c_int, [_P]),
     "fdtd_kernel_timing": (C.c_int, [_P, C.c_int32]),
     "fdtd_kernel_timing_fetch": (C.c_int, [_P, C.POINTER(C.c_int32), _D, _D, _D, C.POINTER(C.c_int64)]),
+    "fdtd_rescan_coeffs": (C.c_int, [_P]),
+    "fdtd_uniform_mu": (C.c_int, [_P]),
     "fdtd_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "fdtd_current_generation": (C.c_int, [_P]),
     "fdtd_comm_unique_id": (C.c_int, [_P]),

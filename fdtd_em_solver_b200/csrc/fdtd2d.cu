@@ -157,6 +157,11 @@ struct fdtd_ctx {
     int kstep_variant = 1;           // 0 = stepK_stream, 1 = stepK_lean (same bits, fewer issue slots; default since round 2)
     int edge_rows = 32;              // rows per stepK_edge tile (experiment hook: FDTD_EDGE_ROWS)
     // split field storage (dtype FDTD_F32X): every tile is a stepK_edge tile; one tile list per group size
+    // uniform mu_coef plane (mu_r = 1 everywhere: every script of the reference, the C5 recipe): found by a device scan
+    // whenever the coefficients arrive; the plain K-step kernel then reads the value from its parameters (stepK_lean_umu)
+    bool mu_uniform = false, mu_uniform_enable = true, mu_scanned = false;
+    double mu_uniform_value = 0.0;
+    void* scan_dev = nullptr;            // {T value (8 bytes), int differs}
     bool split = false;
     bool split_all_edge = false;         // FDTD_SPLIT_ALL_EDGE=1: every tile through stepK_edge (the first version of the mode)
     struct SplitTiles { fdtd::EdgeTile* dev = nullptr; int n = 0; } split_tiles[9];
@@ -300,7 +305,36 @@ int fill_params(fdtd_ctx* c, StepParams<T>& P, int64_t step, int a, int b) {
     P.probe_out = nullptr;
     P.tile_mask = nullptr; P.mask_stride = 0; P.tile_list = nullptr;
     P.split_lo_off = c->split ? (long long)c->lrows * c->pitch * 4 : 0;
+    P.mu_uniform = (T)c->mu_uniform_value;
     return 0;
+}
+
+// Does every stored cell of the mu_coef plane hold one value?  (Rows: every h-row this context stores, halos included;
+// columns 0 .. NC-1 -- what any plain K-step tile can load.)  One pass over the plane, about a millisecond for 4 GB.
+template <typename T>
+int scan_mu_uniform_t(fdtd_ctx* c) {
+    c->mu_uniform = false;
+    c->mu_scanned = true;
+    if (!c->mu_uniform_enable || !c->muc) return 0;
+    const int64_t rows = std::min<int64_t>(c->cfg.row_end + c->halo_bot, c->cfg.rows) - c->row_off;
+    if (rows < 1) return 0;
+    if (!c->scan_dev) CK(cudaMalloc(&c->scan_dev, 16));
+    CK(cudaMemsetAsync(c->scan_dev, 0, 16, c->stream));
+    dim3 grid((unsigned)((c->cfg.cols + 255) / 256), (unsigned)std::min<int64_t>(rows, 4096));
+    CK(fdtd::launch_plane_uniform<T>(grid, c->stream, (const T*)c->muc, c->pitch, (int)rows, (int)c->cfg.cols,
+                                     (T*)c->scan_dev, (int*)((char*)c->scan_dev + 8)));
+    c->stats.kernel_launches++;
+    unsigned char host[16];
+    CK(cudaMemcpyAsync(host, c->scan_dev, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int differs; T value;
+    std::memcpy(&value, host, sizeof(T)); std::memcpy(&differs, host + 8, 4);
+    c->mu_uniform = differs == 0;
+    c->mu_uniform_value = (double)value;
+    return 0;
+}
+int scan_mu_uniform(fdtd_ctx* c) {
+    return c->cfg.dtype != FDTD_F32 ? scan_mu_uniform_t<double>(c) : scan_mu_uniform_t<float>(c);
 }
 
 template <typename T>
@@ -748,7 +782,8 @@ void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1
             return;
         }
     }
-    fdtd::launch_stepK_k<T, K>(P, c->kstep_variant, w, grid, skip, m.ntx2, st);   // 1 = stepK_lean (default), 0 = stepK_stream
+    // 1 = stepK_lean (default; 2 = the same on a uniform mu_coef plane, picked here), 0 = stepK_stream
+    fdtd::launch_stepK_k<T, K>(P, (c->kstep_variant == 1 && c->mu_uniform) ? 2 : c->kstep_variant, w, grid, skip, m.ntx2, st);
 }
 
 template <typename T>
@@ -1232,6 +1267,7 @@ int64_t fdtd_local_rows_halo(const fdtd_config* cfg, int32_t halo_depth) {
 const char* fdtd_last_error(fdtd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 static void auto_geometry(fdtd_ctx* c);
+static int quiesce(fdtd_ctx* c);
 
 int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     fdtd_ctx* c = nullptr;
@@ -1260,6 +1296,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->esize = cfg->dtype == FDTD_F64 ? 8 : (cfg->dtype == FDTD_F32X ? 6 : 4);     // bytes per FIELD value (F32X: 4 hi + 2 lo)
     c->split = cfg->dtype == FDTD_F32X;
     if (const char* e = std::getenv("FDTD_SPLIT_ALL_EDGE")) c->split_all_edge = std::atoi(e) != 0;
+    if (const char* e = std::getenv("FDTD_UNIFORM_MU")) c->mu_uniform_enable = std::atoi(e) != 0;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
     if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
     c->cfg.pitch = c->pitch;
@@ -1338,6 +1375,7 @@ int fdtd_destroy(fdtd_handle c) {
         if (c->view[s].done) cudaEventDestroy(c->view[s].done);
     }
     for (auto& t : c->split_tiles) if (t.dev) cudaFree(t.dev);
+    if (c->scan_dev) cudaFree(c->scan_dev);
     for (cudaEvent_t e : c->band_up) cudaEventDestroy(e);
     for (cudaEvent_t e : c->band_done) cudaEventDestroy(e);
     for (cudaEvent_t e : c->band_edge) cudaEventDestroy(e);
@@ -1360,6 +1398,7 @@ int fdtd_bind_buffers(fdtd_handle c, void* h0, void* h1, void* ex0, void* ex1, v
     c->gen[0][0] = h0; c->gen[1][0] = h1; c->gen[0][1] = ex0; c->gen[1][1] = ex1; c->gen[0][2] = ey0; c->gen[1][2] = ey1;
     c->epc = eps_coef; c->muc = mu_coef;
     c->bound = true; c->cur = 0;
+    c->mu_uniform = false;                                       // nothing is known about freshly bound planes
     return 0;
 }
 
@@ -1549,7 +1588,7 @@ int fdtd_upload_coeffs(fdtd_handle c, const double* eps_coef, const double* mu_c
         if ((rc = h2d_plane<float>(c, c->muc, mu_coef, host_ld, g0, n, c->cfg.cols))) return rc;
     }
     CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return scan_mu_uniform(c);
 }
 
 int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, double epsilon0, double mu0) {
@@ -1563,7 +1602,7 @@ int fdtd_fill_synthetic_coeffs(fdtd_handle c, uint64_t seed, double dt_over_ds, 
             (int)c->cfg.cols, (int)c->row_off, (int)c->cfg.rows, c->cfg.cols, seed, dt_over_ds, epsilon0, mu0));
     c->stats.kernel_launches++;
     CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return scan_mu_uniform(c);
 }
 
 int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double eps_background, double mu_background,
@@ -1593,8 +1632,18 @@ int fdtd_paint_coeffs(fdtd_handle c, int32_t n, const fdtd_shape* shapes, double
     cudaFree(dev);
     if (e != cudaSuccess || e2 != cudaSuccess)
         return fail(c, FDTD_ERR_CUDA, std::string("paint_coeffs: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
-    return 0;
+    return scan_mu_uniform(c);
 }
+
+// The library remembers one property of the coefficient planes (a uniform mu_coef plane lets the K-step kernel skip that
+// stream).  It is re-established by every entry point that writes the planes; a caller that writes the caller-owned
+// tensors directly says so here.
+int fdtd_rescan_coeffs(fdtd_handle c) {
+    NEED_BOUND();
+    if (int rc = quiesce(c)) return rc;
+    return scan_mu_uniform(c);
+}
+int fdtd_uniform_mu(fdtd_handle c) { return c ? (c->mu_uniform ? 1 : 0) : FDTD_ERR_ARG; }
 
 // Host-side accessors must not race with work still in flight on the side streams (a halo block of the last exchange
 // landing after an upload, a frame / edge launch still writing): they wait for all of them first.
@@ -2078,6 +2127,9 @@ static int run_streamed(fdtd_ctx* c, const double* eps, const double* mu, int64_
     else {
         rc = sweep(0, wing, true, false);
         if (!rc) rc = join();
+        // every coefficient row has landed by now (the sweep's groups waited for their bands): the scan of the mu_coef
+        // plane can run here, so that the whole-grid groups and the final sweep take the kernel without that stream
+        if (!rc) rc = scan_mu_uniform(c);
         for (int g = wing; g < G - wing && !rc; ++g) {
             c->cur = (g % 2 == 0) ? gen0 : gen1;
             const int64_t pc = c->probe_count;
@@ -2118,8 +2170,12 @@ int fdtd_run_streamed(fdtd_handle c, const double* eps_coef, const double* mu_co
     const bool whole = c->cfg.row_begin == 0 && c->cfg.row_end == c->cfg.rows;
     if (c->cfg.dtype == FDTD_F64 && whole && !c->comm && c->temporal >= 2 && c->cfg.kernel == FDTD_KERNEL_STREAM &&
         !resident_eligible(c) && n_steps >= 2) {
+        // the coefficient rows arrive while the first groups already run: nothing is known about the plane until the end
+        // (long runs scan once all rows have landed, behind their first groups; short ones at the end, for the next run)
+        c->mu_uniform = false;
+        c->mu_scanned = false;
         const int rc = run_streamed<double>(c, eps_coef, mu_coef, host_ld, zero_fields != 0, first_step, n_steps, h_out, out_ld);
-        if (rc != NOT_STREAMED) return rc;
+        if (rc != NOT_STREAMED) return rc ? rc : (c->mu_scanned ? 0 : scan_mu_uniform(c));
     }
     if (const char* strict = std::getenv("FDTD_STREAMED_STRICT"))            // test hook: the caller expected the pipeline
         if (std::atoi(strict)) return fail(c, FDTD_ERR_STATE, "fdtd_run_streamed: this run does not fit the pipeline");

@@ -41,6 +41,12 @@ cudaError_t launch_plane_view(dim3 grid, dim3 block, cudaStream_t s, double* dst
 }
 
 template <typename T>
+cudaError_t launch_plane_uniform(dim3 grid, cudaStream_t s, const T* src, long long pitch, int rows, int cols, T* out, int* differs) {
+    plane_uniform<T><<<grid, 256, 0, s>>>(src, pitch, rows, cols, out, differs);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_synth_coeffs(dim3 grid, cudaStream_t s, T* epc, T* muc, long long pitch, int lrows, int cols, int row_off,
                                 int NR, long long NC, unsigned long long seed, double dtds, double eps0, double mu0) {
     synth_coeffs<T><<<grid, 256, 0, s>>>(epc, muc, pitch, lrows, cols, row_off, NR, NC, seed, dtds, eps0, mu0);
@@ -61,6 +67,7 @@ cudaError_t launch_paint_coeffs(dim3 grid, cudaStream_t s, T* epc, T* muc, long 
     template cudaError_t launch_plane_to_f64<T>(dim3, dim3, cudaStream_t, double*, long long, const T*, long long, int, int, int, \
                                                 const PatchList&); \
     template cudaError_t launch_plane_view<T>(dim3, dim3, cudaStream_t, double*, long long, const T*, long long, int, int, int, int); \
+    template cudaError_t launch_plane_uniform<T>(dim3, cudaStream_t, const T*, long long, int, int, T*, int*); \
     template cudaError_t launch_synth_coeffs<T>(dim3, cudaStream_t, T*, T*, long long, int, int, int, int, long long, \
                                                 unsigned long long, double, double, double); \
     template cudaError_t launch_paint_coeffs<T>(dim3, cudaStream_t, T*, T*, long long, int, int, int, int, const ShapeDev*, int, \

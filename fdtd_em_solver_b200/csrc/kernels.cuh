@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <string.h>
+#include <type_traits>
 
 #define FDTD_MAX_SRC 16
 #define FDTD_MAX_RECT 24
@@ -84,6 +85,10 @@ struct StepParams {
     // bf16 "lo" plane of the same buffer starts split_lo_off BYTES behind it; 0 = plain storage.  Last on purpose: the
     // offsets of every other field, and with them the code of the kernels that do not read it, stay what they were.
     long long split_lo_off;
+    // uniform mu_coef (every stored cell of the plane holds this value -- mu_r = 1 everywhere, as in all of the reference's
+    // scripts and the C5 recipe; detected on the device when the coefficients arrive): stepK_lean_umu reads it from here
+    // instead of streaming the plane.  Behind split_lo_off for the same reason.
+    T mu_uniform;
 };
 
 // ---- split field storage: value ~ hi + lo, hi = fp32(value), lo = bf16(fp32(value - hi)), both round-to-nearest-even.
@@ -861,7 +866,7 @@ __global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_stream(cons
 //   * every global address is a running pointer advanced by one pitch per row, and the ring slot is a wrapping counter.
 // Same operations in the same order on the same operands => bit-identical to stepK_stream.
 // ---------------------------------------------------------------------------
-template <typename T, int V, int K, int RING>
+template <typename T, int V, int K, int RING, int UMU = 0>
 __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
     const unsigned full = 0xffffffffu;
     constexpr int MARGIN = KGeom<K, V>::MARGIN;
@@ -881,7 +886,13 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
         for (int v = 0; v < V; ++v) hnp[s][v] = Lh[s][v] = Lex[s][v] = Ley[s][v] = Cmu[s][v] = Cep[s][v] = T(0);
     {   // prologue: hn_1 of row ta-K and ex0 of row ta-K+1 (same as run_tileK)
         T h[V], mu[V], exm[V], ey[V];
-        ldvec<T, V>(h, P.h + o_first - pitch); ldvec<T, V>(mu, P.muc + o_first - pitch); ldvec<T, V>(exm, P.ex + o_first - pitch);
+        ldvec<T, V>(h, P.h + o_first - pitch); ldvec<T, V>(exm, P.ex + o_first - pitch);
+        if constexpr (UMU) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) mu[v] = P.mu_uniform;
+        } else {
+            ldvec<T, V>(mu, P.muc + o_first - pitch);
+        }
         ldvec<T, V>(ex0c, P.ex + o_first); ldvec<T, V>(ey, P.ey + o_first - pitch);
         const T nb = __shfl_down_sync(full, ey[0], 1);
 #pragma unroll
@@ -900,7 +911,8 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
     auto issue = [&]() {
         if (i_issue <= i_last) {
             T* slot = ring + s_issue * SLOT;
-            cp_async16(slot + 0 * 32 * V, P.h + o_issue); cp_async16(slot + 1 * 32 * V, P.muc + o_issue);
+            cp_async16(slot + 0 * 32 * V, P.h + o_issue);
+            if constexpr (!UMU) cp_async16(slot + 1 * 32 * V, P.muc + o_issue);
             cp_async16(slot + 2 * 32 * V, P.epc + o_issue); cp_async16(slot + 3 * 32 * V, P.ex + o_issue + pitch);
             cp_async16(slot + 4 * 32 * V, P.ey + o_issue);
         }
@@ -923,7 +935,8 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
             const T* slot = ring + s_read * SLOT;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                cur.h[v] = slot[0 * 32 * V + v]; cur.mu[v] = slot[1 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
+                cur.h[v] = slot[0 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
+                if constexpr (UMU) cur.mu[v] = P.mu_uniform; else cur.mu[v] = slot[1 * 32 * V + v];
                 cur.exn[v] = slot[3 * 32 * V + v]; cur.ey[v] = slot[4 * 32 * V + v];
             }
         }
@@ -951,7 +964,8 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
             T ph[V], pex[V], pey[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) { ph[v] = oh[v]; pex[v] = oex[v]; pey[v] = oey[v]; }
-            stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
+            if constexpr (UMU) stage(Lh[s], Lex[s], pex, Ley[s], cur.mu, Cep[s], hnp[s]);       // the plane is one value
+            else stage(Lh[s], Lex[s], pex, Ley[s], Cmu[s], Cep[s], hnp[s]);
 #pragma unroll
             for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }
         }
@@ -962,9 +976,9 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
 #pragma unroll
         for (int s = K - 1; s >= 2; --s)
 #pragma unroll
-            for (int v = 0; v < V; ++v) { Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
+            for (int v = 0; v < V; ++v) { if constexpr (!UMU) Cmu[s][v] = Cmu[s - 1][v]; Cep[s][v] = Cep[s - 1][v]; }
 #pragma unroll
-        for (int v = 0; v < V; ++v) { Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
+        for (int v = 0; v < V; ++v) { if constexpr (!UMU) Cmu[1][v] = cur.mu[v]; Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
         s_read = (s_read + 1 == RING) ? 0 : s_read + 1;
         issue();                                                 // refill the slot just consumed
     }
@@ -986,6 +1000,24 @@ __global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(co
     if (ta >= tb) return;
     constexpr int RING = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;      // K = 2 prefetches through the ring here, too
     run_tileK_lean<T, V, K, RING>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+}
+
+// stepK_lean with a UNIFORM mu_coef plane (P.mu_uniform): four streams per row instead of five -- 7 words per cell and pass
+// instead of 8 -- and no coefficient delay line for mu (32 registers at K = 8).  The host launches it only after a device
+// scan has found every stored cell of the plane equal (fdtd2d.cu: scan_mu_uniform); the value is the plane's, so the bits
+// are those of stepK_lean.
+template <typename T, int V, int K>
+__global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean_umu(const __grid_constant__ StepParams<T> P,
+                                                         const unsigned char* __restrict__ skip, int skip_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tx >= skip_stride) return;
+    if (skip[(long long)blockIdx.y * skip_stride + tx]) return;
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    constexpr int RING = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;
+    run_tileK_lean<T, V, K, RING, 1>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -1205,6 +1237,21 @@ __global__ void plane_view(double* dst, long long dst_ld, const T* src, long lon
     if (j >= cols_out) return;
     for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < rows_out; i += gridDim.y * blockDim.y)
         dst[(long long)i * dst_ld + j] = (double)src[(long long)i * row_stride * pitch + (long long)j * col_stride];
+}
+
+// Is a plane one value?  out[0] receives src[0]; *differs is set (never cleared) when any of rows x cols differs from it.
+// Bitwise comparison: +0 and -0 count as different, NaN equals the same NaN.
+template <typename T>
+__global__ void plane_uniform(const T* src, long long pitch, int rows, int cols, T* out, int* differs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    typedef typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned int>::type Bits;
+    const Bits* const bits = reinterpret_cast<const Bits*>(src);
+    const Bits first = bits[0];
+    if (j == 0 && blockIdx.y == 0) out[0] = src[0];
+    bool diff = false;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) diff |= bits[(long long)i * pitch + j] != first;
+    if (diff) *differs = 1;
 }
 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {

@@ -20,6 +20,8 @@ template <typename T> cudaError_t launch_plane_to_f64(dim3 grid, dim3 block, cud
 template <typename T> cudaError_t launch_plane_view(dim3 grid, dim3 block, cudaStream_t s, double* dst, long long dst_ld,
                                                     const T* src, long long pitch, int rows_out, int cols_out, int row_stride,
                                                     int col_stride);
+template <typename T> cudaError_t launch_plane_uniform(dim3 grid, cudaStream_t s, const T* src, long long pitch, int rows, int cols,
+                                                       T* out, int* differs);
 template <typename T> cudaError_t launch_synth_coeffs(dim3 grid, cudaStream_t s, T* epc, T* muc, long long pitch, int lrows,
                                                       int cols, int row_off, int NR, long long NC, unsigned long long seed,
                                                       double dtds, double eps0, double mu0);

@@ -402,6 +402,14 @@ class Engine:
                                                                         C.byref(hi), C.byref(cu)))
         return dict(launches=n.value, total_ms=tot.value, min_ms=lo.value, max_ms=hi.value, cell_updates=cu.value)
 
+    def uniform_mu(self):
+        """True when the library found the mu_coef plane uniform and runs the K-step kernel without that stream."""
+        return int(self.lib.fdtd_uniform_mu(self.handle)) == 1
+
+    def rescan_coefficients(self):
+        """After writing self.buffers[6] / [7] (the coefficient planes) directly."""
+        L.check(self.lib, self.handle, self.lib.fdtd_rescan_coeffs(self.handle))
+
     def stats(self):
         s = L.Stats()
         L.check(self.lib, self.handle, self.lib.fdtd_get_stats(self.handle, C.byref(s)))

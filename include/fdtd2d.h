@@ -187,6 +187,15 @@ int fdtd_fill_synthetic_coeffs(fdtd_handle h, uint64_t seed, double dt_over_ds, 
 int fdtd_paint_coeffs(fdtd_handle h, int32_t n, const fdtd_shape* shapes, double eps_background, double mu_background,
                       double dt_over_ds);
 
+/* One property of the coefficient planes is remembered by the library: a UNIFORM mu_coef plane (mu_r = 1 everywhere, as in
+ * every script of the reference and in the C5 recipe) lets the plain K-step kernel read the value from its parameters
+ * instead of streaming the plane (7 words per cell and pass instead of 8; same bits).  fdtd_upload_coeffs,
+ * fdtd_fill_synthetic_coeffs, fdtd_paint_coeffs and fdtd_run_streamed establish it with one device pass over the plane;
+ * a caller that writes the caller-owned coefficient tensors directly calls fdtd_rescan_coeffs afterwards.
+ * fdtd_uniform_mu reports it (1/0).  FDTD_UNIFORM_MU=0 in the environment keeps the general kernel. */
+int fdtd_rescan_coeffs(fdtd_handle h);
+int fdtd_uniform_mu(fdtd_handle h);
+
 /* self.h / self.ex / self.ey (solver.py:101-103).  GLOBAL host arrays, any pointer may be NULL
  * (set: zero-fill that field; get: skip it).  set also loads the halo rows; get writes owned rows only. */
 int fdtd_set_fields(fdtd_handle h, const double* hh, const double* ex, const double* ey);

@@ -144,9 +144,10 @@ def test_more_tiles_than_co_resident_blocks():
     e.set_resident(True, max_cells=1 << 22)
     assert e.resident_active()
     R.run(f, setup, times)
+    launches0 = e.stats()["kernel_launches"]              # the coefficient upload's scan of the mu_coef plane is a launch
     e.run(0, len(times))
     _same(e, f, "strided tiles")
-    assert e.stats()["kernel_launches"] == 1
+    assert e.stats()["kernel_launches"] - launches0 == 1
     e.close()
 
 
