@@ -1006,8 +1006,13 @@ __global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean(co
 // instead of 8 -- and no coefficient delay line for mu (32 registers at K = 8).  The host launches it only after a device
 // scan has found every stored cell of the plane equal (fdtd2d.cu: scan_mu_uniform); the value is the plane's, so the bits
 // are those of stepK_lean.
+#ifdef FDTD_UMU_MAXNREG                    // build knob for the occupancy sweep: cap the registers of the K >= 7 instantiations
+#define FDTD_UMU_BOUNDS(K) __maxnreg__((K) >= 7 ? FDTD_UMU_MAXNREG : 168)
+#else
+#define FDTD_UMU_BOUNDS(K) __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS)
+#endif
 template <typename T, int V, int K>
-__global__ void __launch_bounds__(128, KBoundsLean<K>::MIN_BLOCKS) stepK_lean_umu(const __grid_constant__ StepParams<T> P,
+__global__ void FDTD_UMU_BOUNDS(K) stepK_lean_umu(const __grid_constant__ StepParams<T> P,
                                                          const unsigned char* __restrict__ skip, int skip_stride) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
