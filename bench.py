@@ -39,6 +39,8 @@ COLS = 65536
 BYTES_PER_CELL = {"f64": 64, "f32": 32, "f32x": 52}
 METRIC = "Gcell-updates/s (2D Yee leapfrog, C5 synthetic slab)"
 CPU_SAMPLE = (512, 65536)           # rows x cols of the CPU arm's sample: a thin slab of the real rows
+# the plain K-step kernel the library launches when the mu_coef plane is uniform (FDTD_SKEW=0 keeps the un-skewed pipeline)
+UMU_KERNEL = "stepK_lean_umu" if os.environ.get("FDTD_SKEW", "1") == "0" else "stepK_skew_umu"
 
 
 def measured_peak_gbs():
@@ -240,7 +242,7 @@ def workload_config(args, n_gpus, engine=None):
         frame = {0: "masked step_stream frame passes", 3: "stepK_edge for the wall / source / reflector tiles"}[frame_mode]
         umu = engine is not None and variant == 1 and engine.uniform_mu()
         kernel = "%s<%s,%d,%d> (%d steps per HBM pass, %d columns per lane) + %s; tile_rows=%d warps=%d" % (
-            ("stepK_lean_umu" if umu else "stepK_lean") if variant == 1 else "stepK_stream",
+            (UMU_KERNEL if umu else "stepK_lean") if variant == 1 else "stepK_stream",
             "double" if args.dtype == "f64" else "float", kvec, args.temporal,
             args.temporal, kvec, frame, args.tile_rows, args.warps)
     else:
@@ -507,7 +509,7 @@ def main():
         alg_bytes = kt["cell_updates"] / kt["launches"] * bpc
         kname = ("fdtd::%s<%s,%d,%d>: one launch advances its tiles %d steps (algorithmic bytes are counted per step, so "
                  "frac > 1 is the temporal-blocking gain; the DRAM-level view is traffic / dram_frac)"
-                 % (("stepK_lean_umu" if e.uniform_mu() else "stepK_lean") if e.kstep_variant == 1 else "stepK_stream",
+                 % ((UMU_KERNEL if e.uniform_mu() else "stepK_lean") if e.kstep_variant == 1 else "stepK_stream",
                     tname, kvec, args.temporal, args.temporal))
         if e.kstep_variant == 1 and e.uniform_mu():
             kname += ("; mu_coef is one value everywhere (mu_r = 1, the C5 recipe), found by a device scan: the kernel streams "
@@ -552,7 +554,7 @@ def main():
                         "nvlink_frac_of_900GBs": (halo_bytes / max(1, st["steps"])) / (ms / args.steps * 1e-3) / 900e9}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_%s%s%s.json" % (
         args.dtype, "_temporal%d" % args.temporal if args.temporal > 1 else "",
-        ("_lean_umu" if e.uniform_mu() else "_lean") if e.kstep_variant == 1 else ""))
+        (("_skew_umu" if UMU_KERNEL == "stepK_skew_umu" else "_lean_umu") if e.uniform_mu() else "_lean") if e.kstep_variant == 1 else ""))
     if os.path.isfile(traffic_file):
         try:
             rf = line["roofline"]

@@ -160,6 +160,7 @@ struct fdtd_ctx {
     // uniform mu_coef plane (mu_r = 1 everywhere: every script of the reference, the C5 recipe): found by a device scan
     // whenever the coefficients arrive; the plain K-step kernel then reads the value from its parameters (stepK_lean_umu)
     bool mu_uniform = false, mu_uniform_enable = true, mu_scanned = false;
+    bool skew = true;                    // stepK_skew_umu (the stage chain cut: 788 vs 769 Gcell/s) for a uniform plane; FDTD_SKEW=0: stepK_lean_umu
     double mu_uniform_value = 0.0;
     void* scan_dev = nullptr;            // {T value (8 bytes), int differs}
     bool split = false;
@@ -783,7 +784,8 @@ void launch_stepK(const StepParams<T>& P0, fdtd_ctx* c, int ty0 = 0, int ny = -1
         }
     }
     // 1 = stepK_lean (default; 2 = the same on a uniform mu_coef plane, picked here), 0 = stepK_stream
-    fdtd::launch_stepK_k<T, K>(P, (c->kstep_variant == 1 && c->mu_uniform) ? 2 : c->kstep_variant, w, grid, skip, m.ntx2, st);
+    const int variant = (c->kstep_variant == 1 && c->mu_uniform) ? (c->skew && K >= 4 ? 3 : 2) : c->kstep_variant;
+    fdtd::launch_stepK_k<T, K>(P, variant, w, grid, skip, m.ntx2, st);
 }
 
 template <typename T>
@@ -1297,6 +1299,7 @@ int fdtd_create(const fdtd_config* cfg, fdtd_handle* out) {
     c->split = cfg->dtype == FDTD_F32X;
     if (const char* e = std::getenv("FDTD_SPLIT_ALL_EDGE")) c->split_all_edge = std::atoi(e) != 0;
     if (const char* e = std::getenv("FDTD_UNIFORM_MU")) c->mu_uniform_enable = std::atoi(e) != 0;
+    if (const char* e = std::getenv("FDTD_SKEW")) c->skew = std::atoi(e) != 0;
     c->pitch = cfg->pitch ? cfg->pitch : fdtd_default_pitch(cfg->cols, cfg->dtype);
     if (c->pitch < cfg->cols + 1 || c->pitch % 32) { delete c; c = nullptr; return fail(c, FDTD_ERR_ARG, "pitch must be >= cols+1 and a multiple of 32"); }
     c->cfg.pitch = c->pitch;

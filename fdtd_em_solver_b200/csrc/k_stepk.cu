@@ -12,6 +12,13 @@ template <typename T, int K>
 cudaError_t launch_stepK_k(const StepParams<T>& P, int variant, int warps, dim3 grid, const unsigned char* skip, int ntx2,
                            cudaStream_t st) {
     constexpr int V2 = sizeof(T) == 8 ? 2 : 4;
+    if (variant == 3) {                                          // ... with the stage chain cut (kernels.cuh stepK_skew_umu)
+        const size_t lean_bytes = (size_t)warps * 4 * 5 * 32 * V2 * sizeof(T);
+        if (lean_bytes > 48 * 1024)
+            cudaFuncSetAttribute(stepK_skew_umu<T, V2, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_bytes);
+        stepK_skew_umu<T, V2, K><<<grid, warps * 32, lean_bytes, st>>>(P, skip, ntx2);
+        return cudaGetLastError();
+    }
     if (variant == 2) {                                          // stepK_lean on a uniform mu_coef plane (P.mu_uniform)
         constexpr int ring_rows = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;
         const size_t lean_bytes = (size_t)warps * ring_rows * 5 * 32 * V2 * sizeof(T);

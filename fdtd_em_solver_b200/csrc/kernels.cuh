@@ -38,6 +38,9 @@
 #ifndef FDTD_LEAN_UNROLL
 #define FDTD_LEAN_UNROLL 2
 #endif
+#ifndef FDTD_LEAN_UNROLL_BIG             // row-loop unroll of the K >= 7 instantiations of the lean / skew pipelines (B200, K = 8,
+#define FDTD_LEAN_UNROLL_BIG 4           // unroll 2 -> 4: general 684 -> 699, uniform mu 754 -> 769, skewed 773 -> 788 Gcell/s)
+#endif
 #ifndef FDTD_LEAN_MIN_BLOCKS_K6
 #define FDTD_LEAN_MIN_BLOCKS_K6 3
 #endif
@@ -926,7 +929,7 @@ __device__ __forceinline__ void run_tileK_lean(const StepParams<T>& P, int ta, i
     long long o_store = o_first - (long long)(K - 1) * pitch;    // offset of row i-(K-1), the row the last stage produces
     // 2: the latch copies rename (K = 6: 367 -> 263 instructions per row); 2*(K-1) would also rename the coefficient delay
     // line (-> ~242) at five times the code size -- a build knob for the GPU sweep: FDTD_NVCC_EXTRA=-DFDTD_LEAN_UNROLL=10
-    constexpr int ROW_UNROLL = FDTD_LEAN_UNROLL;
+    constexpr int ROW_UNROLL = (K >= 7) ? FDTD_LEAN_UNROLL_BIG : FDTD_LEAN_UNROLL;
 #pragma unroll ROW_UNROLL
     for (int i = i_first; i <= i_last; ++i) {
         Row<T, V> cur;
@@ -1023,6 +1026,164 @@ __global__ void FDTD_UMU_BOUNDS(K) stepK_lean_umu(const __grid_constant__ StepPa
     if (ta >= tb) return;
     constexpr int RING = KRing<K>::ROWS > 0 ? KRing<K>::ROWS : 4;
     run_tileK_lean<T, V, K, RING, 1>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
+}
+
+// ---------------------------------------------------------------------------
+// stepK_skew_umu: stepK_lean_umu with the stage chain CUT.  In the lean pipeline stage s+1 reads the ex row that stage s
+// produces in the same iteration, so the K stages of a row form one dependency chain of 7 K DADD/DMUL; with two warps per
+// scheduler that leaves about six independent operations in flight and the FP64 pipe at 65 % (ncu: top stall "wait",
+// profiles/r2m_ncu_full_stepK_lean_umu_f64_k8_raw.csv).  At a SKEWED boundary (bit s of SKEW: between stages s and s+1)
+// the consumer runs one more row behind: it takes (h, ex, ey) of its row from what stage s left TWO iterations ago and the
+// ex of the row below from what it left in the previous one -- nothing from this iteration -- so the chain falls apart into
+// independent pieces that the scheduler interleaves.  Price per skewed boundary: one more latched row (3 V values) and
+// one more entry of the coefficient delay line; the registers come from the mu delay line this variant does not have.
+// Same operations on the same operands in the same order per cell: the bits of stepK_lean.
+// ---------------------------------------------------------------------------
+template <int SKEW> __host__ __device__ constexpr int skew_count(int upto) {       // skewed boundaries among 1 .. upto
+    int n = 0;
+    for (int b = 1; b <= upto; ++b) n += (SKEW >> b) & 1;
+    return n;
+}
+
+template <typename T, int V, int K, int RING, int SKEW>
+__device__ __forceinline__ void run_tileK_skew_umu(const StepParams<T>& P, int ta, int tb, int jw, int lane) {
+    const unsigned full = 0xffffffffu;
+    constexpr int MARGIN = KGeom<K, V>::MARGIN;
+    constexpr int NSK = skew_count<SKEW>(K - 1);                 // rows the last stage trails behind the lean pipeline's
+    static_assert(RING > 0 && V * sizeof(T) == 16, "prefetches through the cp.async ring");
+    const int j = jw + lane * V;
+    const long long pitch = P.pitch;
+    const int i_first = ta - K + 1, i_last = tb + K - 2;
+    const long long o_first = (long long)(i_first - P.row_off) * pitch + j;      // element offset of row i_first
+
+    T ex0c[V], muU[V];
+    T hnp[K][V];
+    T Lh[K][V], Lex[K][V], Ley[K][V];                            // what stage s left in the previous iteration
+    T Mh[K][V], Mex[K][V], Mey[K][V];                            // ... and in the one before (skewed boundaries only)
+    T Cep[K + NSK][V];                                           // Cep[k] = eps_coef of row i - k
+#pragma unroll
+    for (int v = 0; v < V; ++v) muU[v] = P.mu_uniform;
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+        for (int v = 0; v < V; ++v) hnp[s][v] = Lh[s][v] = Lex[s][v] = Ley[s][v] = Mh[s][v] = Mex[s][v] = Mey[s][v] = T(0);
+#pragma unroll
+    for (int s = 0; s < K + NSK; ++s)
+#pragma unroll
+        for (int v = 0; v < V; ++v) Cep[s][v] = T(0);
+    {   // prologue: hn_1 of row ta-K and ex0 of row ta-K+1 (same as run_tileK)
+        T h[V], exm[V], ey[V];
+        ldvec<T, V>(h, P.h + o_first - pitch); ldvec<T, V>(exm, P.ex + o_first - pitch);
+        ldvec<T, V>(ex0c, P.ex + o_first); ldvec<T, V>(ey, P.ey + o_first - pitch);
+        const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+            hnp[0][v] = add(h[v], mul(muU[v], sub(sub(ex0c[v], exm[v]), sub(eyr, ey[v]))));
+        }
+    }
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    constexpr int SLOT = 5 * 32 * V;                             // the lean kernel's slot layout (the mu part stays unused)
+    T* const ring = reinterpret_cast<T*>(ring_raw) + (size_t)(threadIdx.x >> 5) * (RING * SLOT) + lane * V;
+    int i_issue = i_first;
+    long long o_issue = o_first;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (i_issue <= i_last) {
+            T* slot = ring + s_issue * SLOT;
+            cp_async16(slot + 0 * 32 * V, P.h + o_issue);
+            cp_async16(slot + 2 * 32 * V, P.epc + o_issue); cp_async16(slot + 3 * 32 * V, P.ex + o_issue + pitch);
+            cp_async16(slot + 4 * 32 * V, P.ey + o_issue);
+        }
+        cp_async_commit();
+        ++i_issue; o_issue += pitch;
+        s_issue = (s_issue + 1 == RING) ? 0 : s_issue + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < RING; ++d) issue();
+    int s_read = 0;
+    long long o_store = o_first - (long long)(K - 1 + NSK) * pitch;      // row the last stage produces in iteration i_first
+    constexpr int ROW_UNROLL = (K >= 7) ? FDTD_LEAN_UNROLL_BIG : FDTD_LEAN_UNROLL;
+    // NSK more iterations than the lean loop: the rows beyond i_last that stage 1 then "loads" are whatever the ring holds;
+    // nothing that is stored depends on them
+#pragma unroll ROW_UNROLL
+    for (int i = i_first; i <= i_last + NSK; ++i) {
+        Row<T, V> cur;
+        cp_async_wait<RING - 1>();
+        {
+            const T* slot = ring + s_read * SLOT;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                cur.h[v] = slot[0 * 32 * V + v]; cur.ep[v] = slot[2 * 32 * V + v];
+                cur.exn[v] = slot[3 * 32 * V + v]; cur.ey[v] = slot[4 * 32 * V + v];
+            }
+        }
+        T oh[V], oex[V], oey[V];
+        auto stage = [&](const T (&h)[V], const T (&exc)[V], const T (&exn)[V], const T (&ey)[V], const T (&mu)[V],
+                         const T (&ep)[V], T (&hp)[V]) {
+            const T nb = __shfl_down_sync(full, ey[0], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T eyr = (v + 1 < V) ? ey[v + 1 < V ? v + 1 : 0] : nb;
+                oh[v] = add(h[v], mul(mu[v], sub(sub(exn[v], exc[v]), sub(eyr, ey[v]))));
+            }
+            const T lf = __shfl_up_sync(full, oh[V - 1], 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T hl = (v == 0) ? lf : oh[v > 0 ? v - 1 : 0];
+                oex[v] = add(exc[v], mul(ep[v], sub(oh[v], hp[v])));
+                oey[v] = sub(ey[v], mul(ep[v], sub(oh[v], hl)));
+                hp[v] = oh[v];
+            }
+        };
+        stage(cur.h, ex0c, cur.exn, cur.ey, muU, cur.ep, hnp[0]);
+#pragma unroll
+        for (int s = 1; s < K; ++s) {
+            T ph[V], pex[V], pey[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { ph[v] = oh[v]; pex[v] = oex[v]; pey[v] = oey[v]; }
+            const int d = s + skew_count<SKEW>(s);               // stage s+1 works on row i - d (a constant after unrolling)
+            if ((SKEW >> s) & 1) {
+                stage(Mh[s], Mex[s], Lex[s], Mey[s], muU, Cep[d], hnp[s]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { Mh[s][v] = Lh[s][v]; Mex[s][v] = Lex[s][v]; Mey[s][v] = Ley[s][v]; }
+            } else {
+                stage(Lh[s], Lex[s], pex, Ley[s], muU, Cep[d], hnp[s]);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Lh[s][v] = ph[v]; Lex[s][v] = pex[v]; Ley[s][v] = pey[v]; }
+        }
+        if (i - (K - 1 + NSK) >= ta && lane >= MARGIN && lane < 32 - MARGIN) {
+            stvec<T, V>(P.hn + o_store, oh); stvec<T, V>(P.exn + o_store, oex); stvec<T, V>(P.eyn + o_store, oey);
+        }
+        o_store += pitch;
+#pragma unroll
+        for (int s = K - 1 + NSK; s >= 2; --s)
+#pragma unroll
+            for (int v = 0; v < V; ++v) Cep[s][v] = Cep[s - 1][v];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { Cep[1][v] = cur.ep[v]; ex0c[v] = cur.exn[v]; }
+        s_read = (s_read + 1 == RING) ? 0 : s_read + 1;
+        issue();
+    }
+}
+
+#ifndef FDTD_SKEW_MASK
+#define FDTD_SKEW_MASK 0x48                  // boundaries 3|4 and 6|7: three chains of 3 + 3 + 2 stages at K = 8
+#endif
+template <int K> struct KSkew { static constexpr int MASK = FDTD_SKEW_MASK & ((1 << K) - 2); };
+
+template <typename T, int V, int K>
+__global__ void __launch_bounds__(128, 1) stepK_skew_umu(const __grid_constant__ StepParams<T> P,
+                                                        const unsigned char* __restrict__ skip, int skip_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tx >= skip_stride) return;
+    if (skip[(long long)blockIdx.y * skip_stride + tx]) return;
+    const int ta = P.row_lo + blockIdx.y * P.tile_rows;
+    const int tb = min(ta + P.tile_rows, P.row_hi);
+    if (ta >= tb) return;
+    run_tileK_skew_umu<T, V, K, 4, KSkew<K>::MASK>(P, ta, tb, tx * KGeom<K, V>::OUT - KGeom<K, V>::MARGIN * V, lane);
 }
 
 // ---------------------------------------------------------------------------

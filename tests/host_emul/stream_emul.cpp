@@ -87,6 +87,20 @@ int emul_stepK_stream(const StreamScene* sc, int K, int tile_rows, int warps, in
         for (int bx = 0; bx < gx; ++bx) {
             simt::g_block_idx = simt::Idx{(unsigned)bx, (unsigned)by, 0};
             for (int w = 0; w < warps; ++w) {
+                if (variant == 3) {                              // stepK_skew_umu: uniform plane + the stage chain cut
+                    P.mu_uniform = sc->muc[0];
+                    switch (K) {
+                        case 2: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 2>(P, skip, tiles_x); }); break;
+                        case 3: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 3>(P, skip, tiles_x); }); break;
+                        case 4: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 4>(P, skip, tiles_x); }); break;
+                        case 5: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 5>(P, skip, tiles_x); }); break;
+                        case 6: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 6>(P, skip, tiles_x); }); break;
+                        case 7: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 7>(P, skip, tiles_x); }); break;
+                        case 8: simt::run_warp(w, [&] { stepK_skew_umu<double, 2, 8>(P, skip, tiles_x); }); break;
+                        default: return -1;
+                    }
+                    continue;
+                }
                 if (variant == 2) {                              // stepK_lean_umu: the value of the (uniform) plane, as the host passes it
                     P.mu_uniform = sc->muc[0];
                     switch (K) {

@@ -44,9 +44,13 @@ def _uniform(setup):
     return setup
 
 
+@pytest.mark.parametrize("skew", [0, 1], ids=["stepK_lean_umu", "stepK_skew_umu"])
 @pytest.mark.parametrize("temporal", [2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("shape,tile_rows,warps", [((200, 900), 8, 4), ((131, 517), 5, 2), ((300, 1500), 0, 0)])
-def test_uniform_mu_groups_bitwise_against_the_oracle(shape, tile_rows, warps, temporal):
+def test_uniform_mu_groups_bitwise_against_the_oracle(shape, tile_rows, warps, temporal, skew, monkeypatch):
+    """skew: FDTD_SKEW picks between the two kernels for a uniform plane -- the lean pipeline, and the one whose stage chain
+    is cut at two boundaries (kernels.cuh stepK_skew_umu); the library's default is whichever the B200 measured faster."""
+    monkeypatch.setenv("FDTD_SKEW", str(skew))
     rows, cols = shape
     for seed, k in ((1, 0), (2, 3), (3, 5)):
         f, setup, times = SC.random_case(rows, cols, seed, walls=WALLS[(seed * 3) % 16], n_steps=17)
@@ -155,3 +159,19 @@ def test_streamed_runs_learn_the_property_at_the_end():
     R.run(f, setup, times)
     _same(e, f, "streamed 16 calls + 8 calls on the fast path")
     e.close()
+
+
+@pytest.mark.parametrize("skew", [0, 1])
+def test_c5_slab_sized_columns_and_tall_tiles(skew, monkeypatch):
+    """The geometry bench.py runs (512-row plain tiles, 32-row edge tiles, K = 8) on a grid tall enough for several tile
+    rows, against single stepping on the device."""
+    from fdtd_em_solver_b200 import synthetic as SY
+    monkeypatch.setenv("FDTD_SKEW", str(skew))
+    e8, _ = SY.make_engine(2048, 4096, dtype="float64", n_calls=128, temporal=8, tile_rows=512)
+    e1, _ = SY.make_engine(2048, 4096, dtype="float64", n_calls=128, temporal=1)
+    assert e8.uniform_mu() and e8.tuning()["tile_rows"] == 512
+    e8.run(0, 43)
+    e1.run(0, 43)
+    for a, b in zip(e8.get_fields(), e1.get_fields()):
+        assert np.array_equal(a, b)
+    e8.close(); e1.close()

@@ -56,7 +56,7 @@ def _plan(rows, cols, K, tile_rows, warps):
     return plan, skip
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["stepK_stream", "stepK_lean", "stepK_lean_umu"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["stepK_stream", "stepK_lean", "stepK_lean_umu", "stepK_skew_umu"])
 @pytest.mark.parametrize("K,tile_rows", [(2, 8), (3, 12), (4, 16), (5, 7), (6, 16), (7, 9), (8, 24)])
 def test_stepK_plain_tiles_bitwise(K, tile_rows, variant):
     """The K-stage pipeline on every tile the frame plan leaves to it: K calls in one pass == K oracle calls.  Both the
@@ -64,7 +64,7 @@ def test_stepK_plain_tiles_bitwise(K, tile_rows, variant):
     exercise the remainder of the unrolled loop)."""
     rows, cols = 100, 230
     f, setup, times = SC.random_case(rows, cols, 9, n_steps=K, with_sources=False, with_rects=False)
-    if variant == 2:              # stepK_lean_umu: the mu_coef plane is ONE value, which the kernel takes from its parameters
+    if variant >= 2:              # stepK_lean_umu / stepK_skew_umu: the mu_coef plane is ONE value, taken from the parameters
         setup.mu_coef = np.full_like(setup.mu_coef, setup.mu_coef[3, 5])
     plan, skip = _plan(rows, cols, K, tile_rows, 2)
     assert plan.k_tiles_y > 0 and not skip.all()
