@@ -684,9 +684,10 @@ __global__ void __launch_bounds__(FDTD_LAUNCH_BOUNDS) step_stream(const __grid_c
 // ---------------------------------------------------------------------------
 // Temporal blocking: K leapfrog steps per HBM pass (generation A -> generation B = A + K steps), K = 2 .. 8.
 //
-// Only for tiles whose K-step dependency cone touches no wall, source, reflector, probe or slab interface; the
-// host marks all other tiles in `skip` and advances them with K masked single-step launches through scratch
-// generations (fdtd2d.cu: group_impl).  Per warp: 32 lanes x V columns are LOADED; stage 1 (step n) is computed for
+// Only for tiles whose K-step dependency cone touches no wall, source, reflector or probe (the PLAIN tiles); the host
+// marks all other tiles in `skip` and gives them to stepK_edge (edge.cuh; fdtd2d.cu: group_edge) -- or, in the fallback
+// frame mode 0, advances them with K masked single-step launches through scratch generations (group_impl).
+// Per warp: 32 lanes x V columns are LOADED; stage 1 (step n) is computed for
 // the row just loaded, stage s (step n+s-1) trails s-1 rows behind, fed from register latches that hold the
 // previous stage's last output row and from a register delay line of the coefficient rows; only stage K is stored.
 // The first and last ceil(K/V) lanes are sacrificial halo lanes (their neighbour values are garbage, which moves
@@ -860,12 +861,12 @@ __global__ void __launch_bounds__(128, KBounds<K>::MIN_BLOCKS) stepK_stream(cons
 }
 
 // ---------------------------------------------------------------------------
-// stepK_lean: the same K-stage pipeline with fewer issue slots per row (EXPERIMENTAL: CPU-pinned through
-// tests/host_emul/simt.h, not yet run on a GPU; selected with fdtd_set_kstep_variant(h, 1), stepK_stream stays the
-// default).  The shipped row loop of stepK_stream<double,2,6> issues 367 instructions per row, of which only 132 are
+// stepK_lean: the same K-stage pipeline with fewer issue slots per row -- the default plain-tile kernel since its B200
+// runs in round 2 (K = 8: 552 vs 468 Gcell/s for stepK_stream, profiles/r2_sweep_b_summary.txt; fdtd_set_kstep_variant(h, 0)
+// selects stepK_stream).  The row loop of stepK_stream<double,2,6> issues 367 instructions per row, of which only 132 are
 // the DADD/DMUL of the update: 125 are register moves (latch and delay-line copies) and ~70 are address arithmetic
 // ((i - row_off) * pitch per array and row, ring slot modulo) -- profiles/r1_stepK_unroll_sass_mix.txt.  Here
-//   * the row loop is unrolled by two, so the latch copies become register renaming (ptxas: 125 -> 29 moves per row),
+//   * the row loop is unrolled (by two; by four for K >= 7), so the latch copies become register renaming (ptxas: 125 -> 29 moves per row),
 //   * every global address is a running pointer advanced by one pitch per row, and the ring slot is a wrapping counter.
 // Same operations in the same order on the same operands => bit-identical to stepK_stream.
 // ---------------------------------------------------------------------------

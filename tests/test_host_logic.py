@@ -204,6 +204,7 @@ def test_c_abi_argument_validation_needs_no_gpu():
     assert lib.fdtd_set_temporal_blocking(None, 2) == -1 and lib.fdtd_current_generation(None) == -1
     assert lib.fdtd_set_resident(None, 1, 0) == -1 and lib.fdtd_resident_active(None) == -1
     assert lib.fdtd_set_frame_mode(None, 3) == -1 and lib.fdtd_get_tuning(None, None) == -1
+    assert lib.fdtd_uniform_mu(None) == -1 and lib.fdtd_rescan_coeffs(None) == -1
 
 
 def test_snapshot_stack_allocator_is_a_plain_float64_array():
