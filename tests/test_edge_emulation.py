@@ -304,3 +304,29 @@ def test_split_storage_group_on_the_library_plan_plain_and_edge_tiles(K, tile_ro
             a = np.where(np.isnan(got_e[k]), got_p[k], got_e[k])
             assert np.array_equal(a, want), (name, n, np.argwhere(a != want)[:4])
         assert np.array_equal(rec, want_rec)
+
+
+@pytest.mark.parametrize("variant", [2, 3], ids=["stepK_lean_umu", "stepK_skew_umu"])
+@pytest.mark.parametrize("K,tile_rows", [(3, 12), (5, 16), (8, 24), (8, 7)])
+def test_whole_group_with_the_uniform_mu_kernels(K, tile_rows, variant):
+    """The group fdtd_run launches when the mu_coef plane is one value: the plain tiles through stepK_lean_umu or
+    stepK_skew_umu (value from the kernel parameters; the skewed pipeline runs extra drain iterations per tile), every other
+    tile through stepK_edge, which still reads the plane.  Two consecutive groups, every cell written once, oracle's bits."""
+    rows, cols = 120, 410
+    f, setup, times = SC.random_case(rows, cols, 13, walls=(False, True, False, False), n_steps=2 * K)
+    drop_wrapping_line(setup)
+    setup.mu_coef = np.full_like(setup.mu_coef, setup.mu_coef[1, 1])
+    plan, skip, tiles = _plan_edge(rows, cols, K, tile_rows, _boxes(setup, rows, cols))
+    assert plan.k_tiles_y > 0 and not skip.all() and len(tiles) > 0
+    quiet = R.Setup(eps_coef=setup.eps_coef, mu_coef=setup.mu_coef, courant=setup.courant, reflect_walls=setup.reflect_walls,
+                    pulses=[], reflectors=[])
+    for n in (0, K):
+        got_e, _ = E.stepK_edge(f, setup, times, n, K, [(t[0], t[1], t[2], t[4]) for t in tiles])
+        got_p = E.stepK_stream(f, quiet, times, n, K, tile_rows, 1, plan.k_row_lo, plan.k_row_hi, skip, variant=variant)
+        for t in times[n:n + K]:
+            R.leapfrog(f, setup, t)
+        for k, (name, want) in enumerate(zip(("h", "ex", "ey"), (f.h, f.ex, f.ey))):
+            both = ~np.isnan(got_e[k]) & ~np.isnan(got_p[k])
+            assert not both.any(), name
+            a = np.where(np.isnan(got_e[k]), got_p[k], got_e[k])
+            assert np.array_equal(a, want), (name, n, np.argwhere(a != want)[:4])
