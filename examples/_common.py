@@ -13,7 +13,8 @@ def options(description, default_name):
     ap.add_argument("--name", default=default_name, help="basename of the .npy / .txt the run writes")
     ap.add_argument("--show", action="store_true", help="realtime matplotlib view instead of saving (needs a display)")
     ap.add_argument("--time-scale", type=float, default=1.0, help="shorten the simulated time (1.0 = the reference's)")
-    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32", "float32x"],
+                    help="float32x: fp32 hi + bf16 lo field storage with float64 arithmetic (stays within 1e-5 of float64)")
     return ap.parse_args()
 
 
